@@ -1,0 +1,206 @@
+/*
+ * vmap.h -- C ABI of the B200-native scan-insertion path ("libvmap_b200.so").
+ *
+ * This is the drop-in boundary that sits UNDER volumetric_mapping::OctomapWorld: the reference
+ * has no FFI layer of its own, so every entry point below names the C++ member
+ * it replaces in /root/reference (paths relative to that tree).  Plain pointers, sizes and PODs
+ * only; every function returns a vmap_status (never throws); per-point geometric failures are
+ * silent, exactly like the reference (out-of-bounds ray -> nothing inserted).
+ *
+ * All "host" pointers are ordinary (pageable or pinned) host memory; functions with a `_dev`
+ * suffix take CUDA device pointers on the handle's device instead.  A handle is
+ * thread-compatible: one mutating call in flight per handle.
+ */
+#ifndef VMAP_VMAP_H_
+#define VMAP_VMAP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VMAP_API
+#else
+#define VMAP_API __attribute__((visibility("default")))
+#endif
+
+typedef enum vmap_status {
+  VMAP_OK = 0,
+  VMAP_ERR_INVALID_ARGUMENT = 1,
+  VMAP_ERR_CUDA = 2,          /* a CUDA runtime call failed; see vmap_last_error()            */
+  VMAP_ERR_CAPACITY = 3,      /* device map could not grow (out of device memory / hard cap)  */
+  VMAP_ERR_NO_DEVICE = 4,     /* no usable CUDA device: there is NO CPU fallback              */
+  VMAP_ERR_BUFFER_TOO_SMALL = 5,
+  VMAP_ERR_NOT_CAPTURED = 6,  /* debug key capture was not enabled for the last scan          */
+  VMAP_ERR_DIST = 7           /* multi-GPU exchange failure                                   */
+} vmap_status;
+
+/* CellStatus of volumetric_map_base/include/volumetric_map_base/world_base.h:54 */
+enum { VMAP_CELL_FREE = 0, VMAP_CELL_OCCUPIED = 1, VMAP_CELL_UNKNOWN = 2 };
+
+/* volumetric_mapping::OctomapParameters, octomap_world/include/octomap_world/octomap_world.h:54-109
+ * (same fields, order, defaults; bools widened to int32). */
+typedef struct vmap_params {
+  double resolution;              /* 0.15 */
+  double probability_hit;         /* 0.65 */
+  double probability_miss;        /* 0.4  */
+  double threshold_min;           /* 0.12 */
+  double threshold_max;           /* 0.97 */
+  double threshold_occupancy;     /* 0.7  */
+  int32_t filter_speckles;        /* 1 (unused by the path) */
+  int32_t _pad0;
+  double max_free_space;          /* 0.0 = no free-space filter (octomap_world.cc:189,215) */
+  double min_height_free_space;   /* 0.0 */
+  double sensor_max_range;        /* 5.0; negative disables (octomap_world.cc:184) */
+  double visualize_min_z;
+  double visualize_max_z;
+  int32_t treat_unknown_as_occupied; /* 1 */
+  int32_t change_detection_enabled;  /* 0 (unused by the path) */
+} vmap_params;
+
+/* How per-scan key-set construction (octomap::KeySet free_cells / occupied_cells,
+ * octomap_world.cc:126,150) is realised on the device. */
+enum {
+  VMAP_DEDUPE_BITMASK = 0, /* per-8^3-block 512-bit free/occupied masks OR-ed in L2 (default) */
+  VMAP_DEDUPE_SORT = 1     /* emit packed keys, radix sort + unique, occupied-wins            */
+};
+
+/* Device-side sizing; everything grows on demand, these are starting points. 0 = default. */
+typedef struct vmap_config {
+  int32_t device;             /* CUDA device ordinal; -1 = current device                    */
+  int32_t dedupe_mode;        /* VMAP_DEDUPE_*                                               */
+  uint64_t initial_blocks;    /* voxel-block pool capacity (8^3 voxels = 2 KiB each)         */
+  uint64_t max_blocks;        /* hard cap for growth; 0 = limited by device memory only      */
+  uint64_t initial_scan_points;
+  uint64_t initial_scan_keys; /* sort mode: packed-key buffer capacity                       */
+} vmap_config;
+
+/* Counters of the most recent insert call (the metric's numerators). */
+typedef struct vmap_scan_stats {
+  uint64_t points_in;        /* points / pixels handed in                                    */
+  uint64_t points_valid;     /* finite (cloud) or valid-disparity (image) points             */
+  uint64_t points_in_range;  /* castRay's range predicate true (octomap_world.cc:184-185)    */
+  uint64_t rays_cast;        /* points not skipped by the occupied_cells test (:133,:168)    */
+  uint64_t traversals;       /* keys produced by computeRayKeys over all cast rays           */
+  uint64_t occupied_emitted; /* occupied_cells->insert calls (:206)                          */
+  uint64_t unique_free;      /* |free_cells| after the erase loop (:252-254)                 */
+  uint64_t unique_occupied;  /* |occupied_cells|                                             */
+  uint64_t longest_ray;      /* max keys of one ray                                          */
+  uint64_t blocks_touched;   /* voxel blocks updated by this scan                            */
+  uint64_t blocks_total;     /* voxel blocks resident in the map after this scan             */
+  uint64_t retries;          /* times the scan was re-run after a device-side grow           */
+  double gpu_ms;             /* device time of the scan's kernels (CUDA events)              */
+  /* the same, split by stage (CUDA events on the handle's stream between the kernels):        */
+  double front_ms;           /* K1  transform / projection / classification                  */
+  double resolve_ms;         /* K1b skip rule, cast-ray list, occupied marks                 */
+  double walk_ms;            /* K2  DDA walk + key-set construction                          */
+  double update_ms;          /* K4  log-odds update of the touched voxel blocks              */
+} vmap_scan_stats;
+
+typedef struct vmap vmap;
+
+VMAP_API const char* vmap_version(void);
+/* Fills OctomapParameters' constructor defaults (octomap_world.h:56-69). */
+VMAP_API void vmap_default_params(vmap_params* p);
+VMAP_API void vmap_default_config(vmap_config* c);
+
+/* OctomapWorld::OctomapWorld(const OctomapParameters&)  (octomap_world.cc:53-56). */
+VMAP_API int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out);
+VMAP_API int vmap_destroy(vmap* h);
+/* OctomapWorld::resetMap  (octomap_world.cc:75-80). */
+VMAP_API int vmap_reset(vmap* h);
+/* OctomapWorld::setOctomapParameters (octomap_world.cc:84-104): a changed resolution resets the
+ * map, everything else is applied to the existing map. */
+VMAP_API int vmap_set_params(vmap* h, const vmap_params* params);
+/* OctomapWorld::getOctomapParameters (octomap_world.cc:106-108). */
+VMAP_API int vmap_get_params(const vmap* h, vmap_params* params);
+/* Message of the last failing call on this handle (h == NULL: last vmap_create failure). */
+VMAP_API const char* vmap_last_error(const vmap* h);
+
+/* OctomapWorld::insertPointcloudIntoMapImpl (octomap_world.cc:110-141), reached from
+ * WorldBase::insertPointcloud (world_base.cc:182-213).
+ *   xyz, n, stride_bytes : n points, 3 floats each, stride_bytes apart (16 for pcl::PointXYZ)
+ *   is_dense             : pcl cloud.is_dense; when 0, non-finite points are dropped first
+ *   T_rowmajor           : Transformation::getTransformationMatrix(), row-major 4x4 double
+ *   xyz_world_out        : optional (may be NULL).  The reference mutates the caller's cloud in
+ *                          place (NaN compaction + world-frame transform, :115-119); when
+ *                          non-NULL the device result is written back here with the same
+ *                          stride (may alias xyz) and *n_out receives the new point count. */
+VMAP_API int vmap_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes,
+                                    int is_dense, const double T_rowmajor[16],
+                                    float* xyz_world_out, size_t* n_out);
+/* Same, points already resident on the handle's device (tightly packed when stride is 12). */
+VMAP_API int vmap_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n,
+                                        size_t stride_bytes, const double T_rowmajor[16]);
+
+/* OctomapWorld::insertProjectedDisparityIntoMapImpl (octomap_world.cc:143-175): CV_32FC3 image
+ * of sensor-frame points, rows x cols, row_pitch_bytes between rows; sensor_to_world given as
+ * unit quaternion (w,x,y,z) + translation, the form the reference evaluates (:162). */
+VMAP_API int vmap_insert_projected(vmap* h, const float* xyz_hw3, int rows, int cols,
+                                   size_t row_pitch_bytes, const double q_wxyz[4],
+                                   const double t[3]);
+/* WorldBase::insertDisparityImage(cv::Mat) (world_base.cc:51-87) fused with the above:
+ * Q down-sampling fix-up (:55-69), cv::reprojectImageTo3D(..., handleMissingValues=true) (:75),
+ * then insertion.  disparity is CV_32FC1; Q_full row-major 4x4; full_image_width =
+ * full_image_size.x(). */
+VMAP_API int vmap_insert_disparity(vmap* h, const float* disparity, int rows, int cols,
+                                   size_t row_pitch_bytes, const double Q_full_rowmajor[16],
+                                   double full_image_width, const double q_wxyz[4],
+                                   const double t[3]);
+VMAP_API int vmap_insert_disparity_dev(vmap* h, const float* d_disparity, int rows, int cols,
+                                       size_t row_pitch_bytes, const double Q_full_rowmajor[16],
+                                       double full_image_width, const double q_wxyz[4],
+                                       const double t[3]);
+/* Projection only (cv::reprojectImageTo3D semantics), for parity tests of kernel 1. */
+VMAP_API int vmap_reproject(vmap* h, const float* disparity, int rows, int cols,
+                            size_t row_pitch_bytes, const double Q_rowmajor[16],
+                            float* xyz_hw3_out);
+
+/* OctomapWorld::updateOccupancy(KeySet* free_cells, KeySet* occupied_cells)
+ * (octomap_world.cc:238-264); also called by OctomapManager::loadOctomapCallback
+ * (octomap_manager.cc:332-341).  Keys are 3 x uint16 (octomap::OcTreeKey). */
+VMAP_API int vmap_apply_keys(vmap* h, const uint16_t* free_k3, size_t n_free,
+                             const uint16_t* occ_k3, size_t n_occ);
+
+/* OctomapWorld::getCellStatusPoint (octomap_world.cc:346-360), batched: n points (3 doubles
+ * each) -> n status bytes (VMAP_CELL_*). */
+VMAP_API int vmap_query_points(vmap* h, const double* xyz, size_t n, uint8_t* status);
+VMAP_API int vmap_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status);
+/* OctomapWorld::getLineStatus (octomap_world.cc:395-418), batched: n segments (start xyz, end
+ * xyz = 6 doubles each) -> n status bytes. */
+VMAP_API int vmap_query_lines(vmap* h, const double* start_end_xyz6, size_t n, uint8_t* status);
+VMAP_API int vmap_query_lines_dev(vmap* h, const double* d_start_end_xyz6, size_t n,
+                                  uint8_t* d_status);
+
+/* Finest-level leaves (what octree_->begin_leafs() would visit after expanding pruned nodes):
+ * used by the on-demand export to octomap::OcTree for the unchanged publish/save paths
+ * (octomap_world.cc:820-856) and by the parity tests. */
+VMAP_API int vmap_leaf_count(vmap* h, size_t* n);
+VMAP_API int vmap_export_leaves(vmap* h, uint16_t* keys_k3, float* logodds, size_t capacity,
+                                size_t* n);
+/* Inverse (loadOctomapFromFile / setOctomapFromMsg feed): sets leaf values, no clamping. */
+VMAP_API int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds, size_t n);
+
+/* Per-scan counters of the last insert / apply call. */
+VMAP_API int vmap_last_scan_stats(const vmap* h, vmap_scan_stats* stats);
+/* Parity hook: when enabled, the next inserts keep their final free / occupied key sets. */
+VMAP_API int vmap_set_debug_capture(vmap* h, int enabled);
+VMAP_API int vmap_debug_last_scan_keys(vmap* h, uint16_t* free_k3, size_t free_capacity,
+                                       size_t* n_free, uint16_t* occ_k3, size_t occ_capacity,
+                                       size_t* n_occ);
+/* (float)log(p/(1-p)) constants in effect: hit, miss, clamp min, clamp max, occupancy. */
+VMAP_API int vmap_logodds_constants(const vmap* h, float out5[5]);
+/* cudaStream_t all of the handle's work is enqueued on (for CUDA-event timing by callers). */
+VMAP_API void* vmap_stream(vmap* h);
+/* Number of kernel launches issued by this handle since creation (bench.py gpu_launches). */
+VMAP_API uint64_t vmap_kernel_launches(const vmap* h);
+/* Device memory currently held by the handle, bytes. */
+VMAP_API uint64_t vmap_device_bytes(const vmap* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VMAP_VMAP_H_ */

@@ -1,0 +1,54 @@
+"""In-tree build of libvmap_b200.so (nvcc, sm_100a only).  No JIT cache: the .so sits next to
+this file so it travels with the repository snapshot to the GPU box."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libvmap_b200.so")
+SOURCES = ["vmap.cu"]
+DEPS = ["vmap.cu", "vmap_device.cuh", "vmap_kernels.cuh", "vmap_sort.cuh", "vmap_sort_host.inl",
+        os.path.join("..", "..", "include", "vmap", "vmap.h")]
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    # bit-exact parity: no FMA contraction anywhere (the kernels also use explicit *_rn
+    # intrinsics on every order-sensitive operation)
+    "-fmad=false",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "-shared",
+]
+
+
+def nvcc_path():
+    p = shutil.which("nvcc")
+    if p:
+        return p
+    p = "/usr/local/cuda/bin/nvcc"
+    if os.path.exists(p):
+        return p
+    raise RuntimeError("nvcc not found: libvmap_b200.so cannot be built (there is no CPU fallback)")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    subprocess.check_call(cmd, cwd=HERE)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,1032 @@
+// vmap.cu -- host side of libvmap_b200.so: the C ABI of include/vmap/vmap.h, device memory
+// management for the voxel-block map, and the launch sequences of the scan-insertion and query
+// kernels (vmap_kernels.cuh).  There is no CPU fallback anywhere in this file: without a CUDA
+// device vmap_create fails with VMAP_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/vmap/vmap.h"
+#include "vmap_kernels.cuh"
+#include "vmap_sort.cuh"
+
+namespace {
+
+using namespace vmapdev;
+
+thread_local std::string g_create_error;
+
+struct DevBuf {  // grow-only device buffer
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct vmap {
+  vmap_params params;
+  vmap_config cfg;
+  DevParams P;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // per-kernel timing marks
+  bool evk_set[5] = {false, false, false, false, false};
+
+  // voxel-block map
+  MapView m{};
+  uint64_t table_cap = 0;
+  uint64_t pool_cap = 0;
+  uint32_t epoch = 0;
+
+  // per-scan scratch
+  ScanBuffers sb{};
+  size_t scan_cap = 0;
+  size_t first_cap = 0;
+  Counters* d_cnt = nullptr;
+  Counters* h_cnt = nullptr;     // pinned
+  Persist* h_persist = nullptr;  // pinned
+  DevBuf in;                     // staged input (points / image / keys / query coordinates)
+  DevBuf out;                    // staged output (statuses, exported leaves)
+  DevBuf aux;                    // second staged input / output
+  SortBuffers sort{};            // VMAP_DEDUPE_SORT scratch
+
+  // multi-GPU sharding (vmap_set_shard): rays r with r % world == rank are walked here; blocks
+  // are owned by owner_of(block) (vmap_device.cuh)
+  int shard_rank = 0, shard_world = 1;
+
+  // parity hook
+  bool capture = false;
+  bool captured = false;
+  DevBuf cap_free, cap_occ;
+  uint32_t* d_cap_n = nullptr;  // [2]
+  uint32_t h_cap_n[2] = {0, 0};
+
+  vmap_scan_stats stats{};
+  mutable std::string err;
+  uint64_t launches = 0;
+  uint64_t dev_bytes = 0;
+};
+
+namespace {
+
+#define VM_CUDA(h, expr)                                                                    \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                       \
+      return (e__ == cudaErrorMemoryAllocation) ? VMAP_ERR_CAPACITY : VMAP_ERR_CUDA;        \
+    }                                                                                       \
+  } while (0)
+
+#define VM_TRY(expr)                 \
+  do {                               \
+    int s__ = (expr);                \
+    if (s__ != VMAP_OK) return s__;  \
+  } while (0)
+
+int fail(const vmap* h, int code, const char* msg) {
+  h->err = msg;
+  return code;
+}
+
+int dev_alloc(vmap* h, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) return VMAP_OK;
+  VM_CUDA(h, cudaMalloc(p, bytes));
+  h->dev_bytes += bytes;
+  return VMAP_OK;
+}
+void dev_free(vmap* h, void* p, size_t bytes) {
+  if (p) {
+    cudaFree(p);
+    h->dev_bytes -= bytes;
+  }
+}
+int ensure(vmap* h, DevBuf* b, size_t bytes) {
+  if (bytes <= b->cap) return VMAP_OK;
+  // in-flight work may still reference the old buffer
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  dev_free(h, b->p, b->cap);
+  b->p = nullptr;
+  b->cap = 0;
+  size_t want = std::max(bytes, (size_t)4096);
+  want = (want + (want >> 2) + 255) & ~(size_t)255;
+  VM_TRY(dev_alloc(h, &b->p, want));
+  b->cap = want;
+  return VMAP_OK;
+}
+
+uint64_t next_pow2(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+float logodds(double p) { return (float)std::log(p / (1 - p)); }  // octomap_utils.h
+
+void derive_params(vmap* h) {
+  const vmap_params& p = h->params;
+  DevParams& P = h->P;
+  P.res = p.resolution;
+  P.res_factor = 1.0 / p.resolution;
+  P.max_range = p.sensor_max_range;
+  P.max_free_space = p.max_free_space;
+  P.min_height_free_space = p.min_height_free_space;
+  // setProbHit/Miss, setClampingThresMin/Max, setOccupancyThres (octomap_world.cc:94-98)
+  P.hit = logodds(p.probability_hit);
+  P.miss = logodds(p.probability_miss);
+  P.cmin = logodds(p.threshold_min);
+  P.cmax = logodds(p.threshold_max);
+  P.occ_thres = logodds(p.threshold_occupancy);
+  P.treat_unknown_as_occupied = p.treat_unknown_as_occupied ? 1 : 0;
+  P.free_filter = (p.max_free_space != 0.0) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// map storage
+// ---------------------------------------------------------------------------------------------
+size_t table_bytes_per_entry() {
+  return sizeof(unsigned long long) + sizeof(uint32_t) * (1 + 2 * kMaskWords + 1);
+}
+
+int alloc_table(vmap* h, uint64_t cap, MapView* out) {
+  MapView v = h->m;
+  VM_TRY(dev_alloc(h, (void**)&v.keys, cap * sizeof(unsigned long long)));
+  VM_TRY(dev_alloc(h, (void**)&v.slot, cap * sizeof(uint32_t)));
+  VM_TRY(dev_alloc(h, (void**)&v.free_mask, cap * kMaskWords * sizeof(uint32_t)));
+  VM_TRY(dev_alloc(h, (void**)&v.occ_mask, cap * kMaskWords * sizeof(uint32_t)));
+  VM_TRY(dev_alloc(h, (void**)&v.touched, cap * sizeof(uint32_t)));
+  VM_CUDA(h, cudaMemsetAsync(v.keys, 0xFF, cap * sizeof(unsigned long long), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(v.slot, 0xFF, cap * sizeof(uint32_t), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(v.free_mask, 0, cap * kMaskWords * sizeof(uint32_t), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(v.occ_mask, 0, cap * kMaskWords * sizeof(uint32_t), h->stream));
+  v.cap_mask = (uint32_t)(cap - 1);
+  *out = v;
+  return VMAP_OK;
+}
+void free_table(vmap* h, const MapView& v, uint64_t cap) {
+  dev_free(h, v.keys, cap * sizeof(unsigned long long));
+  dev_free(h, v.slot, cap * sizeof(uint32_t));
+  dev_free(h, v.free_mask, cap * kMaskWords * sizeof(uint32_t));
+  dev_free(h, v.occ_mask, cap * kMaskWords * sizeof(uint32_t));
+  dev_free(h, v.touched, cap * sizeof(uint32_t));
+}
+
+// Double the hash table.  Only legal when no scan marks are pending (masks all zero).
+int grow_table(vmap* h) {
+  const uint64_t old_cap = h->table_cap;
+  const uint64_t new_cap = old_cap * 2;
+  if (new_cap > (1ull << 31)) return fail(h, VMAP_ERR_CAPACITY, "voxel-block table limit (2^31 entries) reached");
+  MapView nv;
+  VM_TRY(alloc_table(h, new_cap, &nv));
+  k_rehash<<<(unsigned)((old_cap + 255) / 256), 256, 0, h->stream>>>(
+      h->m.keys, h->m.slot, (uint32_t)old_cap, nv.keys, nv.slot, nv.cap_mask);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  free_table(h, h->m, old_cap);
+  h->m = nv;
+  h->table_cap = new_cap;
+  return VMAP_OK;
+}
+
+int grow_pool(vmap* h, uint64_t need_blocks) {
+  uint64_t new_cap = h->pool_cap;
+  while (new_cap < need_blocks) new_cap *= 2;
+  if (h->cfg.max_blocks && new_cap > h->cfg.max_blocks) {
+    if (need_blocks > h->cfg.max_blocks)
+      return fail(h, VMAP_ERR_CAPACITY, "voxel-block pool would exceed vmap_config.max_blocks");
+    new_cap = h->cfg.max_blocks;
+  }
+  if (new_cap >= 0xFFFFFFFFull) return fail(h, VMAP_ERR_CAPACITY, "voxel-block pool limit reached");
+  float* np_ = nullptr;
+  const size_t blk = (size_t)kBlockVoxels * sizeof(float);
+  VM_TRY(dev_alloc(h, (void**)&np_, new_cap * blk));
+  VM_CUDA(h, cudaMemcpyAsync(np_, h->m.pool, h->pool_cap * blk, cudaMemcpyDeviceToDevice, h->stream));
+  VM_CUDA(h, cudaMemsetAsync((char*)np_ + h->pool_cap * blk, 0xFF, (new_cap - h->pool_cap) * blk, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  dev_free(h, h->m.pool, h->pool_cap * blk);
+  h->m.pool = np_;
+  h->pool_cap = new_cap;
+  h->m.pool_cap = (uint32_t)new_cap;
+  return VMAP_OK;
+}
+
+int init_map(vmap* h) {
+  const uint64_t blocks = h->cfg.initial_blocks ? h->cfg.initial_blocks : (1ull << 17);
+  h->pool_cap = std::max<uint64_t>(blocks, 64);
+  if (h->cfg.max_blocks) h->pool_cap = std::min(h->pool_cap, h->cfg.max_blocks);
+  h->table_cap = next_pow2(h->pool_cap * 2);
+  h->m = MapView{};
+  VM_TRY(alloc_table(h, h->table_cap, &h->m));
+  const size_t blk = (size_t)kBlockVoxels * sizeof(float);
+  VM_TRY(dev_alloc(h, (void**)&h->m.pool, h->pool_cap * blk));
+  VM_CUDA(h, cudaMemsetAsync(h->m.pool, 0xFF, h->pool_cap * blk, h->stream));
+  VM_TRY(dev_alloc(h, (void**)&h->m.persist, sizeof(Persist)));
+  VM_CUDA(h, cudaMemsetAsync(h->m.persist, 0, sizeof(Persist), h->stream));
+  h->m.pool_cap = (uint32_t)h->pool_cap;
+  h->epoch = 0;
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+void free_map(vmap* h) {
+  if (h->table_cap) free_table(h, h->m, h->table_cap);
+  dev_free(h, h->m.pool, h->pool_cap * kBlockVoxels * sizeof(float));
+  dev_free(h, h->m.persist, sizeof(Persist));
+  h->m = MapView{};
+  h->table_cap = h->pool_cap = 0;
+}
+
+// Advance the scan epoch (entries whose stored epoch differs are "not yet touched this scan").
+int next_epoch(vmap* h) {
+  if (h->epoch >= kEpochMax) {
+    k_reset_epochs<<<(unsigned)((h->table_cap + 255) / 256), 256, 0, h->stream>>>(h->m.keys, (uint32_t)h->table_cap);
+    h->launches++;
+    VM_CUDA(h, cudaGetLastError());
+    h->epoch = 0;
+  }
+  h->epoch++;
+  h->m.epoch = h->epoch;
+  return VMAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-scan scratch
+// ---------------------------------------------------------------------------------------------
+int ensure_scan(vmap* h, size_t n) {
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "more than 2^31-1 points in one scan");
+  if (n <= h->scan_cap && h->scan_cap) return VMAP_OK;
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  ScanBuffers& sb = h->sb;
+  const size_t oc = h->scan_cap, ofc = h->first_cap;
+  dev_free(h, sb.world, oc * 12);
+  dev_free(h, sb.ray_end, oc * 12);
+  dev_free(h, sb.key, oc * 8);
+  dev_free(h, sb.flags, oc);
+  dev_free(h, sb.rays, oc * 4);
+  dev_free(h, sb.first_keys, ofc * 8);
+  dev_free(h, sb.first_idx, ofc * 4);
+  sb = ScanBuffers{};
+  h->scan_cap = h->first_cap = 0;
+  size_t cap = std::max<size_t>(n + (n >> 2), std::max<uint64_t>(h->cfg.initial_scan_points, 16384));
+  const size_t fc = (size_t)next_pow2(2 * cap);
+  VM_TRY(dev_alloc(h, (void**)&sb.world, cap * 12));
+  VM_TRY(dev_alloc(h, (void**)&sb.ray_end, cap * 12));
+  VM_TRY(dev_alloc(h, (void**)&sb.key, cap * 8));
+  VM_TRY(dev_alloc(h, (void**)&sb.flags, cap));
+  VM_TRY(dev_alloc(h, (void**)&sb.rays, cap * 4));
+  VM_TRY(dev_alloc(h, (void**)&sb.first_keys, fc * 8));
+  VM_TRY(dev_alloc(h, (void**)&sb.first_idx, fc * 4));
+  sb.first_mask = (uint32_t)(fc - 1);
+  h->scan_cap = cap;
+  h->first_cap = fc;
+  return VMAP_OK;
+}
+
+int begin_scan_scratch(vmap* h, size_t n) {
+  // size the first-index table to the scan (power of two >= 2n) so clearing stays proportional
+  const size_t fc = std::min(h->first_cap, (size_t)next_pow2(std::max<size_t>(2 * n, 1024)));
+  h->sb.first_mask = (uint32_t)(fc - 1);
+  VM_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->min_disparity_ord, 0xFF, sizeof(uint32_t), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->sb.first_keys, 0xFF, fc * 8, h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->sb.first_idx, 0xFF, fc * 4, h->stream));
+  return VMAP_OK;
+}
+
+int read_counters(vmap* h) {
+  VM_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaMemcpyAsync(h->h_persist, h->m.persist, sizeof(Persist), cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+// Stage marks for vmap_scan_stats.{front,resolve,walk,update}_ms: 0 = scan start, 1 = after the
+// front-end kernel, 2 = after resolve, 3 = after the walk (key-set complete), 4 = after update.
+int mark_stage(vmap* h, int i) {
+  VM_CUDA(h, cudaEventRecord(h->evk[i], h->stream));
+  h->evk_set[i] = true;
+  return VMAP_OK;
+}
+
+unsigned grid_for(size_t n, unsigned block) { return (unsigned)std::max<size_t>(1, (n + block - 1) / block); }
+
+int g_sm_count(int device) {
+  static int cached[64] = {0};
+  if (device < 0 || device >= 64) device = 0;
+  if (!cached[device]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    cached[device] = v > 0 ? v : 148;
+  }
+  return cached[device];
+}
+
+// Parity hook: count the scan's key sets, size the capture buffers, then expand the masks.
+int launch_capture(vmap* h) {
+  if (!h->capture) return VMAP_OK;
+  for (int pass = 0; pass < 2; pass++) {
+    VM_CUDA(h, cudaMemsetAsync(h->d_cap_n, 0, 2 * sizeof(uint32_t), h->stream));
+    k_capture_keys<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(
+        h->m, h->d_cnt, (uint16_t*)h->cap_free.p, h->d_cap_n, pass ? (uint32_t)(h->cap_free.cap / 6) : 0u,
+        (uint16_t*)h->cap_occ.p, h->d_cap_n + 1, pass ? (uint32_t)(h->cap_occ.cap / 6) : 0u);
+    h->launches++;
+    VM_CUDA(h, cudaGetLastError());
+    if (pass == 0) {
+      VM_CUDA(h, cudaMemcpyAsync(h->h_cap_n, h->d_cap_n, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+      VM_CUDA(h, cudaStreamSynchronize(h->stream));
+      VM_TRY(ensure(h, &h->cap_free, (size_t)h->h_cap_n[0] * 6 + 6));
+      VM_TRY(ensure(h, &h->cap_occ, (size_t)h->h_cap_n[1] * 6 + 6));
+    }
+  }
+  return VMAP_OK;
+}
+
+int launch_update(vmap* h) {
+  k_update<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->P, h->m, h->d_cnt);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  return VMAP_OK;
+}
+
+int clear_marks(vmap* h) {
+  k_clear_masks<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->m, h->d_cnt);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  return VMAP_OK;
+}
+
+// Runs  mark() -> [capture] -> update  with the grow-and-retry protocol.
+//   mark() enqueues everything up to and including the kernels that set block masks.
+template <class Mark>
+int run_scan(vmap* h, size_t n_points, Mark&& mark) {
+  VM_TRY(next_epoch(h));
+  uint64_t retries = 0;
+  float ms_total = 0.f;
+  for (;;) {
+    VM_TRY(begin_scan_scratch(h, n_points));
+    for (bool& b : h->evk_set) b = false;
+    VM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    VM_TRY(mark_stage(h, 0));
+    VM_TRY(mark());
+    VM_TRY(mark_stage(h, 3));
+    VM_TRY(launch_capture(h));
+    if (h->capture) VM_TRY(mark_stage(h, 3));
+    VM_TRY(launch_update(h));
+    VM_TRY(mark_stage(h, 4));
+    VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    VM_TRY(read_counters(h));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    ms_total += ms;
+    bool redo = false;
+    if (h->h_cnt->overflow_table) {
+      // the table filled up mid-scan: drop this scan's marks, double the table, run it again
+      VM_TRY(clear_marks(h));
+      VM_TRY(grow_table(h));  // resets every entry's epoch to 0
+      redo = true;
+    } else if (h->h_cnt->overflow_pool) {
+      VM_TRY(clear_marks(h));
+      VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_entries));
+      // epochs are still the current one: give the re-run a fresh epoch so blocks are re-listed
+      VM_TRY(next_epoch(h));
+      redo = true;
+    }
+    if (!redo) break;
+    if (++retries > 40) return fail(h, VMAP_ERR_CAPACITY, "scan could not be applied after repeated growth");
+  }
+  // keep the load factor <= 1/2 so probes stay short
+  while ((uint64_t)h->h_persist->n_entries * 2 > h->table_cap) VM_TRY(grow_table(h));
+  const Counters& c = *h->h_cnt;
+  vmap_scan_stats& s = h->stats;
+  s.points_valid = c.points_valid;
+  s.points_in_range = c.points_in_range;
+  s.rays_cast = c.rays_cast;
+  s.traversals = c.traversals;
+  s.occupied_emitted = c.occupied_emitted;
+  s.unique_free = c.unique_free;
+  s.unique_occupied = c.unique_occupied;
+  s.longest_ray = c.longest_ray;
+  s.blocks_touched = c.n_touched;
+  s.blocks_total = h->h_persist->n_slots;
+  s.retries = retries;
+  s.gpu_ms = ms_total;
+  auto span = [&](int a, int b) -> double {
+    float v = 0.f;
+    if (!h->evk_set[a] || !h->evk_set[b]) return 0.0;
+    if (cudaEventElapsedTime(&v, h->evk[a], h->evk[b]) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+    return (double)v;
+  };
+  s.front_ms = span(0, 1);
+  s.resolve_ms = span(1, 2);
+  s.walk_ms = h->evk_set[2] ? span(2, 3) : span(0, 3);
+  s.update_ms = span(3, 4);
+  h->captured = h->capture;
+  return VMAP_OK;
+}
+
+void fill_transform_matrix(Transform* T, const double M[16]) {
+  std::memset(T, 0, sizeof(*T));
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 4; c++) T->m[4 * r + c] = M[4 * r + c];
+  // pointEigenToOctomap(T_G_sensor.getPosition())  (octomap_world.cc:120-121)
+  T->origin[0] = (float)M[3];
+  T->origin[1] = (float)M[7];
+  T->origin[2] = (float)M[11];
+}
+
+void fill_transform_quat(Transform* T, const double q[4], const double t[3]) {
+  std::memset(T, 0, sizeof(*T));
+  for (int i = 0; i < 4; i++) T->q[i] = q[i];
+  for (int i = 0; i < 3; i++) T->t[i] = t[i];
+  // sensor_origin = T_G_sensor * Vector3d::Zero()  (octomap_world.cc:146-148): Eigen's
+  // _transformVector on the zero vector, evaluated with the same operation order.
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double v[3] = {0.0, 0.0, 0.0};
+  double uv[3] = {y * v[2] - z * v[1], z * v[0] - x * v[2], x * v[1] - y * v[0]};
+  for (int i = 0; i < 3; i++) uv[i] += uv[i];
+  const double c[3] = {y * uv[2] - z * uv[1], z * uv[0] - x * uv[2], x * uv[1] - y * uv[0]};
+  for (int i = 0; i < 3; i++) T->origin[i] = (float)(((v[i] + w * uv[i]) + c[i]) + t[i]);
+}
+
+// K1b + K2 of the bitmask mode (everything after the front-end kernel).
+int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
+  VM_TRY(mark_stage(h, 1));
+  k_resolve<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, h->m, h->d_cnt, (uint32_t)n, 1);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  VM_TRY(mark_stage(h, 2));
+  if (h->P.free_filter)
+    k_walk_mask<true><<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->m, h->d_cnt, T.origin[0], T.origin[1], T.origin[2]);
+  else
+    k_walk_mask<false><<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->m, h->d_cnt, T.origin[0], T.origin[1], T.origin[2]);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  return VMAP_OK;
+}
+
+// VMAP_DEDUPE_SORT: K1b (no occupied marks) -> emit packed keys -> radix sort -> unique with
+// occupied-wins -> set block masks from the unique keys (vmap_sort.cuh).
+int launch_resolve_and_sort(vmap* h, size_t n, const Transform& T);
+
+int launch_after_front(vmap* h, size_t n, const Transform& T) {
+  if (h->cfg.dedupe_mode == VMAP_DEDUPE_SORT) return launch_resolve_and_sort(h, n, T);
+  return launch_resolve_and_walk(h, n, T);
+}
+
+int insert_cloud_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_dense,
+                        const double Tm[16]) {
+  Transform T;
+  fill_transform_matrix(&T, Tm);
+  VM_TRY(ensure_scan(h, n));
+  h->stats = vmap_scan_stats{};
+  h->stats.points_in = n;
+  if (n == 0) {
+    // updateOccupancy on two empty sets: nothing changes
+    h->h_cap_n[0] = h->h_cap_n[1] = 0;
+    h->captured = h->capture;
+    return VMAP_OK;
+  }
+  return run_scan(h, n, [&]() -> int {
+    k_front_cloud<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, d_in, (uint32_t)n,
+                                                          (uint32_t)stride, is_dense);
+    h->launches++;
+    VM_CUDA(h, cudaGetLastError());
+    return launch_after_front(h, n, T);
+  });
+}
+
+}  // namespace
+
+#include "vmap_sort_host.inl"
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* vmap_version(void) { return "volumetric_mapping_b200 0.1 (sm_100a)"; }
+
+void vmap_default_params(vmap_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->resolution = 0.15;
+  p->probability_hit = 0.65;
+  p->probability_miss = 0.4;
+  p->threshold_min = 0.12;
+  p->threshold_max = 0.97;
+  p->threshold_occupancy = 0.7;
+  p->filter_speckles = 1;
+  p->max_free_space = 0.0;
+  p->min_height_free_space = 0.0;
+  p->sensor_max_range = 5.0;
+  p->visualize_min_z = -1.7976931348623157e308;  // -std::numeric_limits<double>::max()
+  p->visualize_max_z = 1.7976931348623157e308;
+  p->treat_unknown_as_occupied = 1;
+  p->change_detection_enabled = 0;
+}
+
+void vmap_default_config(vmap_config* c) {
+  if (!c) return;
+  std::memset(c, 0, sizeof(*c));
+  c->device = -1;
+  c->dedupe_mode = VMAP_DEDUPE_BITMASK;
+}
+
+const char* vmap_last_error(const vmap* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out) {
+  if (!out) {
+    g_create_error = "vmap_create: out is NULL";
+    return VMAP_ERR_INVALID_ARGUMENT;
+  }
+  *out = nullptr;
+  vmap_params p;
+  if (params) p = *params; else vmap_default_params(&p);
+  vmap_config c;
+  if (config) c = *config; else vmap_default_config(&c);
+  if (!(p.resolution > 0.0) || !std::isfinite(p.resolution)) {
+    g_create_error = "vmap_create: resolution must be positive";
+    return VMAP_ERR_INVALID_ARGUMENT;
+  }
+  if (c.dedupe_mode != VMAP_DEDUPE_BITMASK && c.dedupe_mode != VMAP_DEDUPE_SORT) {
+    g_create_error = "vmap_create: unknown dedupe_mode";
+    return VMAP_ERR_INVALID_ARGUMENT;
+  }
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0) {
+    g_create_error = std::string("vmap_create: no CUDA device (") + cudaGetErrorString(e) +
+                     "); this library has no CPU fallback";
+    cudaGetLastError();
+    return VMAP_ERR_NO_DEVICE;
+  }
+  int dev = c.device;
+  if (dev < 0) {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  }
+  if (dev >= n_dev) {
+    g_create_error = "vmap_create: device ordinal out of range";
+    return VMAP_ERR_INVALID_ARGUMENT;
+  }
+  vmap* h = new (std::nothrow) vmap();
+  if (!h) {
+    g_create_error = "vmap_create: out of host memory";
+    return VMAP_ERR_CAPACITY;
+  }
+  h->params = p;
+  h->cfg = c;
+  h->device = dev;
+  derive_params(h);
+  auto bail = [&](int code) {
+    g_create_error = h->err;
+    vmap_destroy(h);
+    return code;
+  };
+  auto cuda_ok = [&](cudaError_t ce, const char* what) {
+    if (ce == cudaSuccess) return true;
+    h->err = std::string(what) + ": " + cudaGetErrorString(ce);
+    return false;
+  };
+  if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return bail(VMAP_ERR_CUDA);
+  if (!cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(VMAP_ERR_CUDA);
+  if (!cuda_ok(cudaEventCreate(&h->ev0), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
+  if (!cuda_ok(cudaEventCreate(&h->ev1), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
+  for (auto& e : h->evk)
+    if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
+  if (!cuda_ok(cudaMallocHost((void**)&h->h_cnt, sizeof(Counters)), "cudaMallocHost")) return bail(VMAP_ERR_CUDA);
+  if (!cuda_ok(cudaMallocHost((void**)&h->h_persist, sizeof(Persist)), "cudaMallocHost")) return bail(VMAP_ERR_CUDA);
+  std::memset(h->h_cnt, 0, sizeof(Counters));
+  std::memset(h->h_persist, 0, sizeof(Persist));
+  int s = dev_alloc(h, (void**)&h->d_cnt, sizeof(Counters));
+  if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_cap_n, 2 * sizeof(uint32_t));
+  if (s == VMAP_OK) s = init_map(h);
+  if (s != VMAP_OK) return bail(s);
+  *out = h;
+  return VMAP_OK;
+}
+
+int vmap_destroy(vmap* h) {
+  if (!h) return VMAP_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_map(h);
+  ScanBuffers& sb = h->sb;
+  cudaFree(sb.world); cudaFree(sb.ray_end); cudaFree(sb.key); cudaFree(sb.flags); cudaFree(sb.rays);
+  cudaFree(sb.first_keys); cudaFree(sb.first_idx);
+  cudaFree(h->in.p); cudaFree(h->out.p); cudaFree(h->aux.p);
+  cudaFree(h->cap_free.p); cudaFree(h->cap_occ.p);
+  cudaFree(h->d_cnt); cudaFree(h->d_cap_n);
+  sort_free(h);
+  if (h->h_cnt) cudaFreeHost(h->h_cnt);
+  if (h->h_persist) cudaFreeHost(h->h_persist);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto& e : h->evk)
+    if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return VMAP_OK;
+}
+
+int vmap_reset(vmap* h) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  // octree_->clear(): keep the allocations, forget every block
+  VM_CUDA(h, cudaMemsetAsync(h->m.keys, 0xFF, h->table_cap * sizeof(unsigned long long), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->m.slot, 0xFF, h->table_cap * sizeof(uint32_t), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->m.free_mask, 0, h->table_cap * kMaskWords * sizeof(uint32_t), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->m.occ_mask, 0, h->table_cap * kMaskWords * sizeof(uint32_t), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->m.pool, 0xFF, h->pool_cap * kBlockVoxels * sizeof(float), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->m.persist, 0, sizeof(Persist), h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->epoch = 0;
+  h->stats = vmap_scan_stats{};
+  h->captured = false;
+  return VMAP_OK;
+}
+
+int vmap_set_params(vmap* h, const vmap_params* params) {
+  if (!h || !params) return VMAP_ERR_INVALID_ARGUMENT;
+  if (!(params->resolution > 0.0) || !std::isfinite(params->resolution))
+    return fail(h, VMAP_ERR_INVALID_ARGUMENT, "resolution must be positive");
+  const bool new_res = params->resolution != h->params.resolution;  // octomap_world.cc:85
+  h->params = *params;
+  derive_params(h);
+  if (new_res) return vmap_reset(h);
+  return VMAP_OK;
+}
+
+int vmap_get_params(const vmap* h, vmap_params* params) {
+  if (!h || !params) return VMAP_ERR_INVALID_ARGUMENT;
+  *params = h->params;
+  return VMAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// insertion
+// ---------------------------------------------------------------------------------------------
+int vmap_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n, size_t stride_bytes,
+                               const double T_rowmajor[16]) {
+  if (!h || (!d_xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  return insert_cloud_common(h, reinterpret_cast<const uint8_t*>(d_xyz), n, stride_bytes, 1, T_rowmajor);
+}
+
+int vmap_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes, int is_dense,
+                           const double T_rowmajor[16], float* xyz_world_out, size_t* n_out) {
+  if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (n_out) *n_out = n;
+  if (n) {
+    const size_t bytes = (n - 1) * stride_bytes + 12;
+    VM_TRY(ensure(h, &h->in, bytes));
+    VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  VM_TRY(insert_cloud_common(h, (const uint8_t*)h->in.p, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor));
+  if (n && (xyz_world_out || (n_out && !is_dense))) {
+    // the reference leaves the NaN-compacted, world-frame cloud in the caller's buffer
+    std::vector<float> w(n * 3);
+    std::vector<uint8_t> f(n);
+    VM_CUDA(h, cudaMemcpyAsync(w.data(), h->sb.world, n * 12, cudaMemcpyDeviceToHost, h->stream));
+    VM_CUDA(h, cudaMemcpyAsync(f.data(), h->sb.flags, n, cudaMemcpyDeviceToHost, h->stream));
+    VM_CUDA(h, cudaStreamSynchronize(h->stream));
+    size_t j = 0;
+    for (size_t i = 0; i < n; i++) {
+      if (!(f[i] & kFlagValid)) continue;
+      if (xyz_world_out) {
+        float* o = reinterpret_cast<float*>(reinterpret_cast<char*>(xyz_world_out) + j * stride_bytes);
+        o[0] = w[3 * i]; o[1] = w[3 * i + 1]; o[2] = w[3 * i + 2];
+      }
+      j++;
+    }
+    if (n_out) *n_out = j;
+  }
+  return VMAP_OK;
+}
+
+static int insert_image_common(vmap* h, const uint8_t* d_img, int rows, int cols, size_t pitch,
+                               const double* Q /* null: image is CV_32FC3 */, const double q[4],
+                               const double t[3]) {
+  Transform T;
+  fill_transform_quat(&T, q, t);
+  const size_t n = (size_t)rows * (size_t)cols;
+  VM_TRY(ensure_scan(h, n));
+  h->stats = vmap_scan_stats{};
+  h->stats.points_in = n;
+  if (n == 0) {
+    h->h_cap_n[0] = h->h_cap_n[1] = 0;
+    h->captured = h->capture;
+    return VMAP_OK;
+  }
+  QMat Qm;
+  if (Q) std::memcpy(Qm.q, Q, sizeof(Qm.q)); else std::memset(Qm.q, 0, sizeof(Qm.q));
+  return run_scan(h, n, [&]() -> int {
+    if (Q) {
+      k_min_disparity<<<g_sm_count(h->device) * 4, 256, 0, h->stream>>>(h->d_cnt, d_img, rows, cols, pitch);
+      h->launches++;
+      VM_CUDA(h, cudaGetLastError());
+      k_front_disparity<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, Qm, d_img, rows, cols, pitch, nullptr);
+    } else {
+      k_front_projected<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, d_img, rows, cols, pitch);
+    }
+    h->launches++;
+    VM_CUDA(h, cudaGetLastError());
+    return launch_after_front(h, n, T);
+  });
+}
+
+static int check_image_args(vmap* h, const void* img, int rows, int cols, size_t pitch, size_t px_bytes,
+                            const double* q, const double* t) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  if (rows < 0 || cols < 0 || !q || !t) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bad image arguments");
+  if ((size_t)rows * (size_t)cols && !img) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "null image");
+  if (pitch < (size_t)cols * px_bytes || (pitch & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "row pitch too small or not a multiple of 4");
+  return VMAP_OK;
+}
+
+int vmap_insert_projected(vmap* h, const float* xyz_hw3, int rows, int cols, size_t row_pitch_bytes,
+                          const double q_wxyz[4], const double t[3]) {
+  VM_TRY(check_image_args(h, xyz_hw3, rows, cols, row_pitch_bytes, 12, q_wxyz, t));
+  VM_CUDA(h, cudaSetDevice(h->device));
+  const size_t bytes = (size_t)rows * row_pitch_bytes;
+  if (bytes) {
+    VM_TRY(ensure(h, &h->in, bytes));
+    VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz_hw3, bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  return insert_image_common(h, (const uint8_t*)h->in.p, rows, cols, row_pitch_bytes, nullptr, q_wxyz, t);
+}
+
+// world_base.cc:55-69
+static void fixup_q(const double Q_full[16], double full_image_width, int cols, double Q[16]) {
+  std::memcpy(Q, Q_full, 16 * sizeof(double));
+  const double downsampling_factor = full_image_width / cols;
+  if (std::fabs(downsampling_factor - 1.0) > 1e-6) {
+    const double downsampling_squared = downsampling_factor * downsampling_factor;
+    Q[0] /= downsampling_factor;
+    Q[3] /= downsampling_squared;
+    Q[5] /= downsampling_factor;
+    Q[7] /= downsampling_squared;
+    Q[11] /= downsampling_squared;
+    Q[14] /= downsampling_factor;
+    Q[15] /= downsampling_factor;
+  }
+}
+
+int vmap_insert_disparity_dev(vmap* h, const float* d_disparity, int rows, int cols,
+                              size_t row_pitch_bytes, const double Q_full_rowmajor[16],
+                              double full_image_width, const double q_wxyz[4], const double t[3]) {
+  VM_TRY(check_image_args(h, d_disparity, rows, cols, row_pitch_bytes, 4, q_wxyz, t));
+  if (!Q_full_rowmajor) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "null Q");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  double Q[16];
+  fixup_q(Q_full_rowmajor, full_image_width, cols > 0 ? cols : 1, Q);
+  return insert_image_common(h, (const uint8_t*)d_disparity, rows, cols, row_pitch_bytes, Q, q_wxyz, t);
+}
+
+int vmap_insert_disparity(vmap* h, const float* disparity, int rows, int cols, size_t row_pitch_bytes,
+                          const double Q_full_rowmajor[16], double full_image_width,
+                          const double q_wxyz[4], const double t[3]) {
+  VM_TRY(check_image_args(h, disparity, rows, cols, row_pitch_bytes, 4, q_wxyz, t));
+  if (!Q_full_rowmajor) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "null Q");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  const size_t bytes = (size_t)rows * row_pitch_bytes;
+  if (bytes) {
+    VM_TRY(ensure(h, &h->in, bytes));
+    VM_CUDA(h, cudaMemcpyAsync(h->in.p, disparity, bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  double Q[16];
+  fixup_q(Q_full_rowmajor, full_image_width, cols > 0 ? cols : 1, Q);
+  return insert_image_common(h, (const uint8_t*)h->in.p, rows, cols, row_pitch_bytes, Q, q_wxyz, t);
+}
+
+int vmap_reproject(vmap* h, const float* disparity, int rows, int cols, size_t row_pitch_bytes,
+                   const double Q_rowmajor[16], float* xyz_hw3_out) {
+  const double qi[4] = {1, 0, 0, 0}, ti[3] = {0, 0, 0};
+  VM_TRY(check_image_args(h, disparity, rows, cols, row_pitch_bytes, 4, qi, ti));
+  if (!Q_rowmajor || !xyz_hw3_out) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  const size_t n = (size_t)rows * cols;
+  if (!n) return VMAP_OK;
+  const size_t bytes = (size_t)rows * row_pitch_bytes;
+  VM_TRY(ensure(h, &h->in, bytes));
+  VM_TRY(ensure(h, &h->out, n * 12));
+  VM_CUDA(h, cudaMemcpyAsync(h->in.p, disparity, bytes, cudaMemcpyHostToDevice, h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->min_disparity_ord, 0xFF, sizeof(uint32_t), h->stream));
+  k_min_disparity<<<g_sm_count(h->device) * 4, 256, 0, h->stream>>>(h->d_cnt, (const uint8_t*)h->in.p, rows, cols, row_pitch_bytes);
+  QMat Qm;
+  std::memcpy(Qm.q, Q_rowmajor, sizeof(Qm.q));
+  Transform T;
+  std::memset(&T, 0, sizeof(T));
+  k_front_disparity<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, Qm, (const uint8_t*)h->in.p, rows, cols,
+                                                            row_pitch_bytes, (float*)h->out.p);
+  h->launches += 2;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaMemcpyAsync(xyz_hw3_out, h->out.p, n * 12, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+int vmap_apply_keys(vmap* h, const uint16_t* free_k3, size_t n_free, const uint16_t* occ_k3, size_t n_occ) {
+  if (!h || (!free_k3 && n_free) || (!occ_k3 && n_occ)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n_free > 0x7FFFFFFFull || n_occ > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many keys");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  h->stats = vmap_scan_stats{};
+  if (n_free + n_occ == 0) return VMAP_OK;
+  VM_TRY(ensure_scan(h, 1));
+  VM_TRY(ensure(h, &h->in, n_free * 6));
+  VM_TRY(ensure(h, &h->aux, n_occ * 6));
+  if (n_free) VM_CUDA(h, cudaMemcpyAsync(h->in.p, free_k3, n_free * 6, cudaMemcpyHostToDevice, h->stream));
+  if (n_occ) VM_CUDA(h, cudaMemcpyAsync(h->aux.p, occ_k3, n_occ * 6, cudaMemcpyHostToDevice, h->stream));
+  return run_scan(h, 1, [&]() -> int {
+    if (n_occ) {
+      k_mark_keys<<<grid_for(n_occ, 256), 256, 0, h->stream>>>(h->m, h->d_cnt, (const uint16_t*)h->aux.p, (uint32_t)n_occ, 1);
+      h->launches++;
+    }
+    if (n_free) {
+      k_mark_keys<<<grid_for(n_free, 256), 256, 0, h->stream>>>(h->m, h->d_cnt, (const uint16_t*)h->in.p, (uint32_t)n_free, 0);
+      h->launches++;
+    }
+    VM_CUDA(h, cudaGetLastError());
+    return VMAP_OK;
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// queries
+// ---------------------------------------------------------------------------------------------
+int vmap_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status) {
+  if (!h || ((!d_xyz || !d_status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query points");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (!n) return VMAP_OK;
+  k_query_points<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->m, d_xyz, (uint32_t)n, d_status);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+int vmap_query_points(vmap* h, const double* xyz, size_t n, uint8_t* status) {
+  if (!h || ((!xyz || !status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (!n) return VMAP_OK;
+  VM_TRY(ensure(h, &h->in, n * 24));
+  VM_TRY(ensure(h, &h->out, n));
+  VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
+  VM_TRY(vmap_query_points_dev(h, (const double*)h->in.p, n, (uint8_t*)h->out.p));
+  VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+int vmap_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_status) {
+  if (!h || ((!d_ab || !d_status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query segments");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (!n) return VMAP_OK;
+  k_query_lines<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->m, d_ab, (uint32_t)n, d_status);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+int vmap_query_lines(vmap* h, const double* ab, size_t n, uint8_t* status) {
+  if (!h || ((!ab || !status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (!n) return VMAP_OK;
+  VM_TRY(ensure(h, &h->in, n * 48));
+  VM_TRY(ensure(h, &h->out, n));
+  VM_CUDA(h, cudaMemcpyAsync(h->in.p, ab, n * 48, cudaMemcpyHostToDevice, h->stream));
+  VM_TRY(vmap_query_lines_dev(h, (const double*)h->in.p, n, (uint8_t*)h->out.p));
+  VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// leaves in / out
+// ---------------------------------------------------------------------------------------------
+static int count_leaves(vmap* h, uint16_t* d_k3, float* d_val, uint32_t cap, size_t* n) {
+  VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_leaves, 0, sizeof(uint32_t), h->stream));
+  k_export<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->m, h->d_cnt, d_k3, d_val, cap);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  uint32_t v = 0;
+  VM_CUDA(h, cudaMemcpyAsync(&v, &h->d_cnt->n_leaves, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  *n = v;
+  return VMAP_OK;
+}
+
+int vmap_leaf_count(vmap* h, size_t* n) {
+  if (!h || !n) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  return count_leaves(h, nullptr, nullptr, 0, n);
+}
+
+int vmap_export_leaves(vmap* h, uint16_t* keys_k3, float* logodds_out, size_t capacity, size_t* n) {
+  if (!h || !n) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  size_t total = 0;
+  VM_TRY(count_leaves(h, nullptr, nullptr, 0, &total));
+  *n = total;
+  if (total == 0) return VMAP_OK;
+  if (capacity < total || !keys_k3 || !logodds_out) return fail(h, VMAP_ERR_BUFFER_TOO_SMALL, "export buffers too small; *n holds the leaf count");
+  VM_TRY(ensure(h, &h->out, total * 6));
+  VM_TRY(ensure(h, &h->aux, total * 4));
+  size_t again = 0;
+  VM_TRY(count_leaves(h, (uint16_t*)h->out.p, (float*)h->aux.p, (uint32_t)total, &again));
+  VM_CUDA(h, cudaMemcpyAsync(keys_k3, h->out.p, total * 6, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaMemcpyAsync(logodds_out, h->aux.p, total * 4, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in, size_t n) {
+  if (!h || ((!keys_k3 || !logodds_in) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many leaves");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (!n) return VMAP_OK;
+  VM_TRY(ensure(h, &h->in, n * 6));
+  VM_TRY(ensure(h, &h->aux, n * 4));
+  VM_CUDA(h, cudaMemcpyAsync(h->in.p, keys_k3, n * 6, cudaMemcpyHostToDevice, h->stream));
+  VM_CUDA(h, cudaMemcpyAsync(h->aux.p, logodds_in, n * 4, cudaMemcpyHostToDevice, h->stream));
+  for (int attempt = 0; attempt < 40; attempt++) {
+    VM_TRY(next_epoch(h));
+    VM_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+    k_touch_keys<<<grid_for(n, 256), 256, 0, h->stream>>>(h->m, h->d_cnt, (const uint16_t*)h->in.p, (uint32_t)n);
+    k_assign_slots<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->m, h->d_cnt);
+    k_write_leaves<<<grid_for(n, 256), 256, 0, h->stream>>>(h->m, h->d_cnt, (const uint16_t*)h->in.p, (const float*)h->aux.p, (uint32_t)n);
+    h->launches += 3;
+    VM_CUDA(h, cudaGetLastError());
+    VM_TRY(read_counters(h));
+    if (h->h_cnt->overflow_table) {
+      VM_TRY(grow_table(h));
+      continue;
+    }
+    if (h->h_cnt->overflow_pool) {
+      VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_entries));
+      continue;
+    }
+    while ((uint64_t)h->h_persist->n_entries * 2 > h->table_cap) VM_TRY(grow_table(h));
+    return VMAP_OK;
+  }
+  return fail(h, VMAP_ERR_CAPACITY, "import could not be applied after repeated growth");
+}
+
+// ---------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------
+int vmap_last_scan_stats(const vmap* h, vmap_scan_stats* stats) {
+  if (!h || !stats) return VMAP_ERR_INVALID_ARGUMENT;
+  *stats = h->stats;
+  return VMAP_OK;
+}
+
+int vmap_set_debug_capture(vmap* h, int enabled) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  h->capture = enabled != 0;
+  if (!h->capture) h->captured = false;
+  return VMAP_OK;
+}
+
+int vmap_debug_last_scan_keys(vmap* h, uint16_t* free_k3, size_t free_capacity, size_t* n_free,
+                              uint16_t* occ_k3, size_t occ_capacity, size_t* n_occ) {
+  if (!h || !n_free || !n_occ) return VMAP_ERR_INVALID_ARGUMENT;
+  if (!h->captured) return fail(h, VMAP_ERR_NOT_CAPTURED, "debug capture was not enabled for the last scan");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  *n_free = h->h_cap_n[0];
+  *n_occ = h->h_cap_n[1];
+  if (!free_k3 && !occ_k3) return VMAP_OK;  // size query
+  if (free_capacity < *n_free || occ_capacity < *n_occ) return fail(h, VMAP_ERR_BUFFER_TOO_SMALL, "key buffers too small");
+  if (*n_free) VM_CUDA(h, cudaMemcpyAsync(free_k3, h->cap_free.p, *n_free * 6, cudaMemcpyDeviceToHost, h->stream));
+  if (*n_occ) VM_CUDA(h, cudaMemcpyAsync(occ_k3, h->cap_occ.p, *n_occ * 6, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+int vmap_logodds_constants(const vmap* h, float out5[5]) {
+  if (!h || !out5) return VMAP_ERR_INVALID_ARGUMENT;
+  out5[0] = h->P.hit; out5[1] = h->P.miss; out5[2] = h->P.cmin; out5[3] = h->P.cmax; out5[4] = h->P.occ_thres;
+  return VMAP_OK;
+}
+
+void* vmap_stream(vmap* h) { return h ? (void*)h->stream : nullptr; }
+uint64_t vmap_kernel_launches(const vmap* h) { return h ? h->launches : 0; }
+uint64_t vmap_device_bytes(const vmap* h) { return h ? h->dev_bytes : 0; }
+
+}  // extern "C"

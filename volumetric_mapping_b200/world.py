@@ -1,0 +1,240 @@
+"""Host-side mirror of volumetric_mapping::OctomapWorld for the scan-insertion path.
+
+Method names and argument meaning follow the reference class
+(octomap_world/include/octomap_world/octomap_world.h:119-256 and
+volumetric_map_base/include/volumetric_map_base/world_base.h:50-235); every call goes through
+the C ABI of include/vmap/vmap.h into the CUDA kernels.  numpy arrays stand in for
+pcl::PointCloud / cv::Mat / Eigen types, a (q_wxyz, t) pair or a 4x4 matrix for
+kindr::minimal::QuatTransformation.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import VmapError
+
+DEDUPE_BITMASK = 0
+DEDUPE_SORT = 1
+
+# CellStatus (world_base.h:54)
+kFree, kOccupied, kUnknown = 0, 1, 2
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def quat_to_matrix(q_wxyz, t):
+    """QuatTransformation::getTransformationMatrix(): Eigen::Quaterniond::toRotationMatrix()
+    (same association order) with the translation in the last column."""
+    w, x, y, z = (float(v) for v in q_wxyz)
+    tx, ty, tz = 2.0 * x, 2.0 * y, 2.0 * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    T = np.eye(4, dtype=np.float64)
+    T[0, 0] = 1.0 - (tyy + tzz); T[0, 1] = txy - twz; T[0, 2] = txz + twy
+    T[1, 0] = txy + twz; T[1, 1] = 1.0 - (txx + tzz); T[1, 2] = tyz - twx
+    T[2, 0] = txz - twy; T[2, 1] = tyz + twx; T[2, 2] = 1.0 - (txx + tyy)
+    T[0, 3], T[1, 3], T[2, 3] = (float(v) for v in t)
+    return T
+
+
+class OctomapWorld:
+    """GPU-resident OctomapWorld (insertion + point/line queries)."""
+
+    def __init__(self, params=None, device=-1, dedupe_mode=DEDUPE_BITMASK, initial_blocks=0,
+                 max_blocks=0, **param_overrides):
+        self._L = _capi.lib()
+        if params is None:
+            params = _capi.default_params(**param_overrides)
+        elif param_overrides:
+            raise TypeError("pass either params or keyword overrides")
+        cfg = _capi.default_config(device=device, dedupe_mode=dedupe_mode,
+                                   initial_blocks=initial_blocks, max_blocks=max_blocks)
+        h = C.c_void_p()
+        st = self._L.vmap_create(C.byref(params), C.byref(cfg), C.byref(h))
+        if st != 0:
+            raise VmapError(st, (self._L.vmap_last_error(None) or b"").decode())
+        self._h = h
+
+    # -- plumbing -----------------------------------------------------------------------
+    def _check(self, st):
+        if st != 0:
+            raise VmapError(st, (self._L.vmap_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.vmap_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    # -- map management (octomap_world.cc:75-108) -----------------------------------------
+    def resetMap(self):
+        self._check(self._L.vmap_reset(self._h))
+
+    def setOctomapParameters(self, params):
+        self._check(self._L.vmap_set_params(self._h, C.byref(params)))
+
+    def getOctomapParameters(self):
+        p = _capi.Params()
+        self._check(self._L.vmap_get_params(self._h, C.byref(p)))
+        return p
+
+    # -- insertion ----------------------------------------------------------------------
+    def insertPointcloud(self, T, xyz, is_dense=True):
+        """WorldBase::insertPointcloud -> insertPointcloudIntoMapImpl (octomap_world.cc:110-141).
+        T: 4x4 getTransformationMatrix().  Returns the cloud as the reference leaves it in the
+        caller's buffer (NaN-compacted when !is_dense, world frame)."""
+        cloud = np.array(xyz, dtype=np.float32, order="C").reshape(-1, 3)
+        Tm = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        n_out = C.c_size_t(0)
+        self._check(self._L.vmap_insert_pointcloud(self._h, cloud.ctypes.data, cloud.shape[0], 12,
+                                                   int(bool(is_dense)), _dptr(Tm),
+                                                   cloud.ctypes.data, C.byref(n_out)))
+        return cloud[: n_out.value]
+
+    def insertPointcloudFast(self, T, xyz):
+        """Same insertion without the in-place write-back of the transformed cloud."""
+        cloud = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        Tm = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        self._check(self._L.vmap_insert_pointcloud(self._h, cloud.ctypes.data, cloud.shape[0], 12,
+                                                   1, _dptr(Tm), None, None))
+
+    def insertPointcloudDevice(self, T, data_ptr, n, stride_bytes=12):
+        """Points already in device memory (e.g. a torch tensor's data_ptr())."""
+        Tm = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        self._check(self._L.vmap_insert_pointcloud_dev(self._h, C.c_void_p(int(data_ptr)), int(n),
+                                                       int(stride_bytes), _dptr(Tm)))
+
+    def insertProjectedDisparity(self, q_wxyz, t, xyz_hw3):
+        """insertProjectedDisparityIntoMapImpl (octomap_world.cc:143-175)."""
+        img = np.ascontiguousarray(xyz_hw3, dtype=np.float32)
+        rows, cols = img.shape[:2]
+        q = np.ascontiguousarray(q_wxyz, dtype=np.float64)
+        tt = np.ascontiguousarray(t, dtype=np.float64)
+        self._check(self._L.vmap_insert_projected(self._h, img.ctypes.data, rows, cols, cols * 12,
+                                                  _dptr(q), _dptr(tt)))
+
+    def insertDisparityImage(self, q_wxyz, t, disparity, Q_full, full_image_width):
+        """WorldBase::insertDisparityImage(cv::Mat) (world_base.cc:51-87)."""
+        d = np.ascontiguousarray(disparity, dtype=np.float32)
+        rows, cols = d.shape
+        Q = np.ascontiguousarray(Q_full, dtype=np.float64).reshape(16)
+        q = np.ascontiguousarray(q_wxyz, dtype=np.float64)
+        tt = np.ascontiguousarray(t, dtype=np.float64)
+        self._check(self._L.vmap_insert_disparity(self._h, d.ctypes.data, rows, cols, cols * 4,
+                                                  _dptr(Q), float(full_image_width), _dptr(q),
+                                                  _dptr(tt)))
+
+    def insertDisparityImageDevice(self, q_wxyz, t, data_ptr, rows, cols, Q_full, full_image_width,
+                                   row_pitch_bytes=None):
+        Q = np.ascontiguousarray(Q_full, dtype=np.float64).reshape(16)
+        q = np.ascontiguousarray(q_wxyz, dtype=np.float64)
+        tt = np.ascontiguousarray(t, dtype=np.float64)
+        pitch = cols * 4 if row_pitch_bytes is None else int(row_pitch_bytes)
+        self._check(self._L.vmap_insert_disparity_dev(self._h, C.c_void_p(int(data_ptr)), rows,
+                                                      cols, pitch, _dptr(Q),
+                                                      float(full_image_width), _dptr(q), _dptr(tt)))
+
+    def reprojectImageTo3D(self, disparity, Q):
+        d = np.ascontiguousarray(disparity, dtype=np.float32)
+        rows, cols = d.shape
+        Qm = np.ascontiguousarray(Q, dtype=np.float64).reshape(16)
+        out = np.zeros((rows, cols, 3), dtype=np.float32)
+        self._check(self._L.vmap_reproject(self._h, d.ctypes.data, rows, cols, cols * 4, _dptr(Qm),
+                                           out.ctypes.data))
+        return out
+
+    def updateOccupancy(self, free_k3, occ_k3):
+        """updateOccupancy(KeySet*, KeySet*) (octomap_world.cc:238-264)."""
+        f = np.ascontiguousarray(free_k3, dtype=np.uint16).reshape(-1, 3)
+        o = np.ascontiguousarray(occ_k3, dtype=np.uint16).reshape(-1, 3)
+        self._check(self._L.vmap_apply_keys(self._h, f.ctypes.data, f.shape[0], o.ctypes.data,
+                                            o.shape[0]))
+
+    # -- queries ------------------------------------------------------------------------
+    def getCellStatusPoint(self, xyz):
+        p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(p.shape[0], dtype=np.uint8)
+        self._check(self._L.vmap_query_points(self._h, p.ctypes.data, p.shape[0], out.ctypes.data))
+        return out
+
+    def getLineStatus(self, start_end_xyz6):
+        p = np.ascontiguousarray(start_end_xyz6, dtype=np.float64).reshape(-1, 6)
+        out = np.zeros(p.shape[0], dtype=np.uint8)
+        self._check(self._L.vmap_query_lines(self._h, p.ctypes.data, p.shape[0], out.ctypes.data))
+        return out
+
+    def getCellStatusPointDevice(self, xyz_ptr, n, status_ptr):
+        self._check(self._L.vmap_query_points_dev(self._h, C.c_void_p(int(xyz_ptr)), int(n),
+                                                  C.c_void_p(int(status_ptr))))
+
+    def getLineStatusDevice(self, ab_ptr, n, status_ptr):
+        self._check(self._L.vmap_query_lines_dev(self._h, C.c_void_p(int(ab_ptr)), int(n),
+                                                 C.c_void_p(int(status_ptr))))
+
+    # -- leaves / introspection ---------------------------------------------------------
+    def leaf_count(self):
+        n = C.c_size_t(0)
+        self._check(self._L.vmap_leaf_count(self._h, C.byref(n)))
+        return int(n.value)
+
+    def export_leaves(self):
+        n = self.leaf_count()
+        k = np.zeros((n, 3), dtype=np.uint16)
+        v = np.zeros(n, dtype=np.float32)
+        got = C.c_size_t(0)
+        self._check(self._L.vmap_export_leaves(self._h, k.ctypes.data, v.ctypes.data, n,
+                                               C.byref(got)))
+        return k[: got.value], v[: got.value]
+
+    def import_leaves(self, keys_k3, logodds):
+        k = np.ascontiguousarray(keys_k3, dtype=np.uint16).reshape(-1, 3)
+        v = np.ascontiguousarray(logodds, dtype=np.float32).reshape(-1)
+        assert k.shape[0] == v.shape[0]
+        self._check(self._L.vmap_import_leaves(self._h, k.ctypes.data, v.ctypes.data, k.shape[0]))
+
+    def set_debug_capture(self, enabled=True):
+        self._check(self._L.vmap_set_debug_capture(self._h, int(bool(enabled))))
+
+    def last_scan_keys(self):
+        nf, no = C.c_size_t(0), C.c_size_t(0)
+        self._check(self._L.vmap_debug_last_scan_keys(self._h, None, 0, C.byref(nf), None, 0,
+                                                      C.byref(no)))
+        f = np.zeros((nf.value, 3), dtype=np.uint16)
+        o = np.zeros((no.value, 3), dtype=np.uint16)
+        if nf.value or no.value:
+            self._check(self._L.vmap_debug_last_scan_keys(
+                self._h, f.ctypes.data if nf.value else None, nf.value, C.byref(nf),
+                o.ctypes.data if no.value else None, no.value, C.byref(no)))
+        return f, o
+
+    def last_scan_stats(self):
+        s = _capi.ScanStats()
+        self._check(self._L.vmap_last_scan_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def logodds_constants(self):
+        out = (C.c_float * 5)()
+        self._check(self._L.vmap_logodds_constants(self._h, out))
+        return np.array(list(out), dtype=np.float32)
+
+    def stream(self):
+        return int(self._L.vmap_stream(self._h) or 0)
+
+    def kernel_launches(self):
+        return int(self._L.vmap_kernel_launches(self._h))
+
+    def device_bytes(self):
+        return int(self._L.vmap_device_bytes(self._h))
