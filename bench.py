@@ -14,8 +14,9 @@ input and new map blocks.
 Per-step timing is done on the device with CUDA events recorded on the library's own stream
 (vmap_scan_stats.gpu_ms, bracketing exactly the scan's kernels); a 256 MiB buffer is
 overwritten between steps so no step starts with its map blocks in L2.  N > 1: one process per
-GPU (torchrun), scans are dealt round-robin to ranks and each rank builds the map shard of its
-own scans ... see DESIGN.md "Multi-GPU".
+GPU (torchrun); ONE map, sharded by voxel-block owner over the ranks.  A step is one ROUND of N
+scans: rank r generates scan (step*N + r), block records are exchanged all-to-all over NCCL
+inside the library, and every shard applies the round's scans in order (DESIGN.md "Multi-GPU").
 """
 import argparse
 import ctypes as C
@@ -219,8 +220,8 @@ def run_b200(args):
 
     K, W = args.steps, args.warmup
     total = K + W
-    # weak scaling: every rank inserts its own K+W scans (rank r takes scans r, r+world, ...)
-    # into its own map shard (DESIGN.md "Multi-GPU": independent map shards, no collective).
+    # weak scaling: a step is one round of `world` scans of the SAME trajectory and map; rank r
+    # generates scan step*world + r, every shard applies the round in scan order.
     scans = [scenes.trajectory_scan(rank + world * i, resolution=RESOLUTION) for i in range(total)]
     n_pts = scans[0]["points"].shape[0]
     dev_pts = [torch.from_numpy(s["points"]).cuda() for s in scans]
@@ -234,8 +235,14 @@ def run_b200(args):
 
     def run(kind):
         """kind: 'dev' (inputs resident in HBM) or 'host' (pinned host buffers, H2D inside)."""
-        w = vm.OctomapWorld(resolution=RESOLUTION, sensor_max_range=MAX_RANGE,
-                            initial_blocks=1 << 19, device=local_rank)
+        if world > 1:
+            from volumetric_mapping_b200 import sharded
+            sw = sharded.ShardedOctomapWorld(rank, world, local_rank, resolution=RESOLUTION,
+                                             sensor_max_range=MAX_RANGE, initial_blocks=1 << 18)
+            w = sw.local
+        else:
+            w = vm.OctomapWorld(resolution=RESOLUTION, sensor_max_range=MAX_RANGE,
+                                initial_blocks=1 << 19, device=local_rank)
         launches0 = None
         stats, gpu_ms, wall_ms = [], [], []
         sampler = ClockSampler(local_rank)
@@ -249,7 +256,15 @@ def run_b200(args):
             flush.fill_(i & 0xFF)            # evict the map from L2 between steps
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            if kind == "dev":
+            if world > 1:
+                if i >= W:
+                    dist.barrier()          # rounds start together; wall clock is per round
+                    t0 = time.perf_counter()
+                if kind == "dev":
+                    w.dist_insert_pointcloud_device(scans[i]["T"], dev_pts[i].data_ptr(), n_pts)
+                else:
+                    w.dist_insert_pointcloud(scans[i]["T"], pinned[i].numpy())
+            elif kind == "dev":
                 w.insertPointcloudDevice(scans[i]["T"], dev_pts[i].data_ptr(), n_pts)
             else:
                 w.insertPointcloudFast(scans[i]["T"], pinned[i].numpy())
@@ -264,7 +279,10 @@ def run_b200(args):
         launches = w.kernel_launches() - launches0
         out = {"stats": stats, "gpu_ms": gpu_ms, "wall_ms": wall_ms, "launches": launches,
                "clocks": clocks, "device_bytes": w.device_bytes()}
-        w.close()
+        if world > 1:
+            sw.close()
+        else:
+            w.close()
         return out
 
     dev = run("dev")
@@ -323,8 +341,9 @@ def run_b200(args):
                        "traversals_per_step": trav / K / world,
                        "l2": "256 MiB buffer overwritten between steps (L2 flushed)",
                        "timing": "CUDA events on the library stream around each scan's kernels",
-                       "sharding": "replicas only: rank r inserts scans r, r+N, ... into its "
-                                   "own map" if world > 1 else "single GPU"},
+                       "sharding": ("one map sharded by 8^3-block owner over %d ranks; step = "
+                                    "round of %d scans, NCCL all-to-all of block records"
+                                    % (world, world)) if world > 1 else "single GPU"},
             "scans_per_s": K * world / t_dev,
             "e2e": {"value": trav_host / t_host, "unit": UNIT,
                     "h2d_bytes_per_step": n_pts * 12, "d2h_bytes_per_step": 80,

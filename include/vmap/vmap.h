@@ -98,6 +98,10 @@ typedef struct vmap_scan_stats {
   double resolve_ms;         /* K1b skip rule, cast-ray list, occupied marks                 */
   double walk_ms;            /* K2  DDA walk + key-set construction                          */
   double update_ms;          /* K4  log-odds update of the touched voxel blocks              */
+  /* sharded (multi-GPU) rounds only:                                                          */
+  uint64_t records_sent;     /* block records sent to other ranks                            */
+  uint64_t records_received; /* block records received from other ranks                      */
+  uint64_t blocks_applied;   /* block records applied to this shard in the round             */
 } vmap_scan_stats;
 
 typedef struct vmap vmap;
@@ -193,6 +197,54 @@ VMAP_API int vmap_debug_last_scan_keys(vmap* h, uint16_t* free_k3, size_t free_c
                                        size_t* n_occ);
 /* (float)log(p/(1-p)) constants in effect: hit, miss, clamp min, clamp max, occupancy. */
 VMAP_API int vmap_logodds_constants(const vmap* h, float out5[5]);
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU sharding (one handle = one map shard = one GPU = one process).
+ *
+ * Every 8x8x8 voxel block has one owner rank.  A scan is GENERATED on one rank (K1..K2, the
+ * key sets of octomap_world.cc:126-137 as per-block masks), the touched blocks are packed into
+ * one record stream per owner, the streams are exchanged, and every owner APPLIES the scans'
+ * records in scan order (updateOccupancy, octomap_world.cc:238-264, restricted to its blocks).
+ * vmap_dist_* does the exchange itself over NCCL (all-to-all of records over NVLink); the
+ * vmap_shard_* pair exposes the two halves so a host can use any transport.
+ * --------------------------------------------------------------------------------------------- */
+VMAP_API int vmap_set_shard(vmap* h, int rank, int world);
+/* Owner rank of the block containing key (kx,ky,kz); pure host function. */
+VMAP_API uint32_t vmap_shard_owner(uint16_t kx, uint16_t ky, uint16_t kz, int world);
+VMAP_API size_t vmap_shard_record_bytes(void);
+/* Generate one scan on this rank; counts_out[world] = records destined to each rank (may be
+ * NULL).  Nothing is applied to the map. */
+VMAP_API int vmap_shard_generate(vmap* h, const float* xyz, size_t n, size_t stride_bytes,
+                                 int is_dense, const double T_rowmajor[16], uint64_t* counts_out);
+VMAP_API int vmap_shard_generate_dev(vmap* h, const float* d_xyz, size_t n, size_t stride_bytes,
+                                     const double T_rowmajor[16], uint64_t* counts_out);
+/* Device pointer / count of the records of the last generated scan destined to rank `dest`. */
+VMAP_API int vmap_shard_records(vmap* h, int dest, const void** d_records, size_t* n_records);
+/* Apply record lists (device memory) to this shard: list i is the i-th scan of the round. */
+VMAP_API int vmap_shard_apply_dev(vmap* h, const void* const* d_record_lists,
+                                  const size_t* n_records, size_t n_lists);
+/* Partial query answers of this shard; the global answer is the element-wise MINIMUM over ranks
+ * (points: status byte, 0xFF = not mine; lines: first-hit index << 2 | status, 0xFFFFFFFF = no
+ * non-free voxel of mine on the segment -> free when that is the minimum). */
+VMAP_API int vmap_shard_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status);
+VMAP_API int vmap_shard_query_lines_dev(vmap* h, const double* d_start_end_xyz6, size_t n,
+                                        uint32_t* d_packed);
+
+/* NCCL transport.  Rank 0 obtains an id (ncclUniqueId, 128 bytes) and hands it to every rank by
+ * any means (torch.distributed broadcast in bench.py); all ranks then call vmap_dist_init. */
+VMAP_API int vmap_dist_unique_id(uint8_t out128[128]);
+VMAP_API int vmap_dist_init(vmap* h, const uint8_t id128[128], int rank, int world);
+VMAP_API int vmap_dist_shutdown(vmap* h);
+/* COLLECTIVE: every rank passes its own scan; rank r's scan is inserted as the r-th scan of the
+ * round on every shard (n may be 0 on ranks that have no scan left). */
+VMAP_API int vmap_dist_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes,
+                                         int is_dense, const double T_rowmajor[16]);
+VMAP_API int vmap_dist_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n,
+                                             size_t stride_bytes, const double T_rowmajor[16]);
+/* COLLECTIVE queries: every rank passes the same queries and receives the global statuses. */
+VMAP_API int vmap_dist_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status);
+VMAP_API int vmap_dist_query_lines_dev(vmap* h, const double* d_start_end_xyz6, size_t n,
+                                       uint8_t* d_status);
+
 /* cudaStream_t all of the handle's work is enqueued on (for CUDA-event timing by callers). */
 VMAP_API void* vmap_stream(vmap* h);
 /* Number of kernel launches issued by this handle since creation (bench.py gpu_launches). */

@@ -25,7 +25,7 @@ def test_library_is_built_in_tree():
 def test_every_declared_symbol_is_exported_and_bound():
     L = _capi.lib()
     names = header_symbols()
-    assert len(names) >= 30
+    assert len(names) >= 46
     for n in names:
         assert hasattr(L, n), n
     assert sorted(_capi.SYMBOLS) == names
@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_capi.Params) == 13 * 8
     assert C.sizeof(_capi.Config) == 8 + 4 * 8
-    assert C.sizeof(_capi.ScanStats) == 17 * 8
+    assert C.sizeof(_capi.ScanStats) == 20 * 8
     p = _capi.default_params()
     assert (p.resolution, p.probability_hit, p.probability_miss, p.threshold_min, p.threshold_max,
             p.threshold_occupancy, p.sensor_max_range, p.max_free_space,

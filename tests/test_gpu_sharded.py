@@ -1,0 +1,108 @@
+"""Sharded (multi-GPU) path on ONE GPU: G handles stand for G ranks, the test harness plays the
+exchange by handing each shard the record lists the others generated for it (device pointers,
+same GPU).  Everything else -- generate, pack, apply, the sharded queries -- is the code the
+NCCL path runs.  Bar: the UNION of the shards equals the oracle's map bit for bit."""
+import numpy as np
+import pytest
+
+import oracle
+import volumetric_mapping_b200 as vm
+from volumetric_mapping_b200 import scenes, sharded
+
+pytestmark = pytest.mark.gpu
+
+
+def leaves_packed(k, v):
+    p = oracle.pack_keys(k)
+    order = np.argsort(p, kind="stable")
+    return p[order], v.view(np.uint32)[order]
+
+
+def run_rounds(G, scans, params, capture=False):
+    shards = [vm.OctomapWorld(initial_blocks=64, **params) for _ in range(G)]
+    for r, w in enumerate(shards):
+        w.set_shard(r, G)
+    ow = oracle.OracleWorld(**params)
+    ow.set_faithful_inner_update(False)
+    n_rounds = (len(scans) + G - 1) // G
+    for k in range(n_rounds):
+        present = []
+        for r in range(G):
+            i = k * G + r
+            if i < len(scans):
+                shards[r].shard_generate(scans[i]["T"], scans[i]["points"])
+                ow.insertPointcloud(scans[i]["T"], scans[i]["points"])
+                present.append(r)
+        for d in range(G):
+            shards[d].shard_apply([shards[s].shard_records(d) for s in present])
+    return shards, ow
+
+
+@pytest.mark.parametrize("G", [2, 3])
+def test_sharded_union_equals_oracle(G):
+    rng = np.random.default_rng(21)
+    params = dict(resolution=0.1, sensor_max_range=6.0)
+    scans = []
+    for i in range(7):          # not a multiple of G: the last round is ragged
+        d = rng.normal(size=(3000, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        pts = (d * rng.uniform(0.3, 7.0, (3000, 1))).astype(np.float32)
+        scans.append({"points": pts, "T": scenes.quat_to_matrix(scenes.random_unit_quat(rng),
+                                                                 rng.uniform(-1, 1, 3))})
+    shards, ow = run_rounds(G, scans, params)
+    ks, vs = [], []
+    for r, w in enumerate(shards):
+        k, v = w.export_leaves()
+        assert np.all(sharded.owner_of_keys(k, G) == r)      # every leaf sits on its owner
+        ks.append(k); vs.append(v)
+    gk, gv = leaves_packed(np.concatenate(ks), np.concatenate(vs))
+    ok, ov = leaves_packed(*ow.export_leaves())
+    assert np.array_equal(gk, ok)
+    assert np.array_equal(gv, ov)
+    assert min(len(k) for k in ks) > 0.5 * len(ok) / G        # balanced ownership
+
+
+def test_sharded_hdl64_scans_and_queries():
+    import torch
+    G = 4
+    params = dict(resolution=0.2, sensor_max_range=50.0)
+    scans = [scenes.trajectory_scan(3 * i, resolution=0.2) for i in range(4)]
+    shards, ow = run_rounds(G, scans, params)
+    ks, vs = zip(*[w.export_leaves() for w in shards])
+    gk, gv = leaves_packed(np.concatenate(ks), np.concatenate(vs))
+    ok, ov = leaves_packed(*ow.export_leaves())
+    assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
+    # queries: element-wise minimum of the shards' partial answers
+    q = scenes.cfg5_queries(n_segments=100000, n_points=100000)
+    pts = torch.from_numpy(q["points"]).cuda()
+    seg = torch.from_numpy(q["segments"]).cuda()
+    st = torch.full((G, pts.shape[0]), 255, dtype=torch.uint8, device="cuda")
+    pk = torch.zeros((G, seg.shape[0]), dtype=torch.int64, device="cuda")
+    tmp = torch.zeros(seg.shape[0], dtype=torch.int32, device="cuda")
+    for r, w in enumerate(shards):
+        w.shard_query_points_device(pts.data_ptr(), pts.shape[0], st[r].data_ptr())
+        w.shard_query_lines_device(seg.data_ptr(), seg.shape[0], tmp.data_ptr())
+        pk[r] = tmp.to(torch.int64) & 0xFFFFFFFF
+    torch.cuda.synchronize()
+    got_p = st.min(dim=0).values.cpu().numpy()
+    m = pk.min(dim=0).values
+    got_l = torch.where(m == 0xFFFFFFFF, torch.zeros_like(m), m & 3).to(torch.uint8).cpu().numpy()
+    assert np.array_equal(got_p, ow.getCellStatusPoint(q["points"]))
+    assert np.array_equal(got_l, ow.getLineStatus(q["segments"]))
+
+
+def test_nccl_two_ranks_if_two_gpus():
+    """The real exchange: needs >= 2 GPUs (gpurun --gpus 2); skipped on a 1-GPU box."""
+    import subprocess
+    import sys
+    import os
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29531",
+           os.path.join(root, "tests", "dist_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "DIST_CHECK_OK" in out.stdout

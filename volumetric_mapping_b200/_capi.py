@@ -59,6 +59,9 @@ class ScanStats(C.Structure):
         ("resolve_ms", C.c_double),
         ("walk_ms", C.c_double),
         ("update_ms", C.c_double),
+        ("records_sent", C.c_uint64),
+        ("records_received", C.c_uint64),
+        ("blocks_applied", C.c_uint64),
     ]
 
     def as_dict(self):
@@ -75,6 +78,11 @@ SYMBOLS = [
     "vmap_leaf_count", "vmap_export_leaves", "vmap_import_leaves", "vmap_last_scan_stats",
     "vmap_set_debug_capture", "vmap_debug_last_scan_keys", "vmap_logodds_constants",
     "vmap_stream", "vmap_kernel_launches", "vmap_device_bytes",
+    "vmap_set_shard", "vmap_shard_owner", "vmap_shard_record_bytes", "vmap_shard_generate",
+    "vmap_shard_generate_dev", "vmap_shard_records", "vmap_shard_apply_dev",
+    "vmap_shard_query_points_dev", "vmap_shard_query_lines_dev", "vmap_dist_unique_id",
+    "vmap_dist_init", "vmap_dist_shutdown", "vmap_dist_insert_pointcloud",
+    "vmap_dist_insert_pointcloud_dev", "vmap_dist_query_points_dev", "vmap_dist_query_lines_dev",
 ]
 
 STATUS_NAMES = {0: "VMAP_OK", 1: "VMAP_ERR_INVALID_ARGUMENT", 2: "VMAP_ERR_CUDA",
@@ -138,6 +146,25 @@ def lib():
     L.vmap_kernel_launches.restype = C.c_uint64
     L.vmap_device_bytes.argtypes = [vp]
     L.vmap_device_bytes.restype = C.c_uint64
+    u64p = C.POINTER(C.c_uint64)
+    L.vmap_set_shard.argtypes = [vp, C.c_int, C.c_int]
+    L.vmap_shard_owner.argtypes = [C.c_uint16, C.c_uint16, C.c_uint16, C.c_int]
+    L.vmap_shard_owner.restype = C.c_uint32
+    L.vmap_shard_record_bytes.argtypes = []
+    L.vmap_shard_record_bytes.restype = sz
+    L.vmap_shard_generate.argtypes = [vp, vp, sz, sz, C.c_int, dp, u64p]
+    L.vmap_shard_generate_dev.argtypes = [vp, vp, sz, sz, dp, u64p]
+    L.vmap_shard_records.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
+    L.vmap_shard_apply_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), sz]
+    L.vmap_shard_query_points_dev.argtypes = [vp, vp, sz, vp]
+    L.vmap_shard_query_lines_dev.argtypes = [vp, vp, sz, vp]
+    L.vmap_dist_unique_id.argtypes = [vp]
+    L.vmap_dist_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.vmap_dist_shutdown.argtypes = [vp]
+    L.vmap_dist_insert_pointcloud.argtypes = [vp, vp, sz, sz, C.c_int, dp]
+    L.vmap_dist_insert_pointcloud_dev.argtypes = [vp, vp, sz, sz, dp]
+    L.vmap_dist_query_points_dev.argtypes = [vp, vp, sz, vp]
+    L.vmap_dist_query_lines_dev.argtypes = [vp, vp, sz, vp]
     _lib = L
     return L
 

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvmap_b200.so")
 SOURCES = ["vmap.cu"]
-DEPS = ["vmap.cu", "vmap_device.cuh", "vmap_kernels.cuh", "vmap_sort.cuh", "vmap_sort_host.inl",
+DEPS = ["vmap.cu", "vmap_device.cuh", "vmap_kernels.cuh", "vmap_sort.cuh", "vmap_sort_host.inl", "vmap_shard.cuh", "vmap_shard_host.inl",
         os.path.join("..", "..", "include", "vmap", "vmap.h")]
 
 NVCC_FLAGS = [
@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-shared",
 ]
+LINK_FLAGS = ["-ldl"]
 
 
 def nvcc_path():
@@ -43,7 +44,7 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + LINK_FLAGS
     if verbose:
         cmd += ["-Xptxas", "-v"]
     subprocess.check_call(cmd, cwd=HERE)

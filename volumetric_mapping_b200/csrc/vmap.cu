@@ -15,6 +15,7 @@
 #include "../../include/vmap/vmap.h"
 #include "vmap_kernels.cuh"
 #include "vmap_sort.cuh"
+#include "vmap_shard.cuh"
 
 namespace {
 
@@ -36,6 +37,7 @@ struct vmap {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evr0 = nullptr, evr1 = nullptr;  // whole sharded round (generate .. apply)
   cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // per-kernel timing marks
   bool evk_set[5] = {false, false, false, false, false};
 
@@ -57,9 +59,15 @@ struct vmap {
   DevBuf aux;                    // second staged input / output
   SortBuffers sort{};            // VMAP_DEDUPE_SORT scratch
 
-  // multi-GPU sharding (vmap_set_shard): rays r with r % world == rank are walked here; blocks
-  // are owned by owner_of(block) (vmap_device.cuh)
+  // multi-GPU sharding (vmap_shard.cuh): this handle holds the blocks with owner_of(block) ==
+  // shard_rank; scans generated here are packed into per-owner record streams
   int shard_rank = 0, shard_world = 1;
+  DevBuf pack, recv;
+  uint32_t* d_pack_counts = nullptr;          // [2 * kMaxRanks] counts + cursors
+  uint32_t h_pack_counts[kMaxRanks] = {0};
+  void* nccl_comm = nullptr;
+  uint64_t* d_count_matrix = nullptr;         // [kMaxRanks * kMaxRanks]
+  uint64_t h_count_matrix[kMaxRanks * kMaxRanks] = {0};
 
   // parity hook
   bool capture = false;
@@ -507,11 +515,14 @@ int insert_cloud_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride, i
 }  // namespace
 
 #include "vmap_sort_host.inl"
+#include "vmap_shard_host.inl"
 
 // =============================================================================================
 // C ABI
 // =============================================================================================
 extern "C" {
+
+int vmap_dist_shutdown(vmap* h);
 
 const char* vmap_version(void) { return "volumetric_mapping_b200 0.1 (sm_100a)"; }
 
@@ -602,12 +613,15 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   if (!cuda_ok(cudaEventCreate(&h->ev1), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
   for (auto& e : h->evk)
     if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
+  if (!cuda_ok(cudaEventCreate(&h->evr0), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
+  if (!cuda_ok(cudaEventCreate(&h->evr1), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
   if (!cuda_ok(cudaMallocHost((void**)&h->h_cnt, sizeof(Counters)), "cudaMallocHost")) return bail(VMAP_ERR_CUDA);
   if (!cuda_ok(cudaMallocHost((void**)&h->h_persist, sizeof(Persist)), "cudaMallocHost")) return bail(VMAP_ERR_CUDA);
   std::memset(h->h_cnt, 0, sizeof(Counters));
   std::memset(h->h_persist, 0, sizeof(Persist));
   int s = dev_alloc(h, (void**)&h->d_cnt, sizeof(Counters));
   if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_cap_n, 2 * sizeof(uint32_t));
+  if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_pack_counts, 2 * kMaxRanks * sizeof(uint32_t));
   if (s == VMAP_OK) s = init_map(h);
   if (s != VMAP_OK) return bail(s);
   *out = h;
@@ -625,6 +639,8 @@ int vmap_destroy(vmap* h) {
   cudaFree(h->in.p); cudaFree(h->out.p); cudaFree(h->aux.p);
   cudaFree(h->cap_free.p); cudaFree(h->cap_occ.p);
   cudaFree(h->d_cnt); cudaFree(h->d_cap_n);
+  vmap_dist_shutdown(h);
+  cudaFree(h->pack.p); cudaFree(h->recv.p); cudaFree(h->d_pack_counts); cudaFree(h->d_count_matrix);
   sort_free(h);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_persist) cudaFreeHost(h->h_persist);
@@ -632,6 +648,8 @@ int vmap_destroy(vmap* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto& e : h->evk)
     if (e) cudaEventDestroy(e);
+  if (h->evr0) cudaEventDestroy(h->evr0);
+  if (h->evr1) cudaEventDestroy(h->evr1);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return VMAP_OK;

@@ -82,6 +82,7 @@ struct MapView {
   uint32_t cap_mask;   // capacity - 1 (capacity is a power of two)
   uint32_t pool_cap;   // blocks
   uint32_t epoch;      // current scan epoch (1..kEpochMax)
+  uint32_t sharded;    // 1: the table also holds blocks owned by other ranks (no pool slot)
 };
 
 __device__ __forceinline__ unsigned long long block_key(uint32_t kx, uint32_t ky, uint32_t kz) {

@@ -379,7 +379,10 @@ __global__ void __launch_bounds__(256)
 k_update(DevParams P, MapView m, Counters* cnt) {
   // Abort the whole scan's update (uniformly) when a map structure must grow first.
   if (cnt->overflow_table) return;
-  if (m.persist->n_entries > m.pool_cap) {
+  // every entry owns a slot (single GPU); a sharded table also lists foreign blocks, so bound
+  // the slots by what this update can add at most
+  const uint32_t slots_bound = m.sharded ? m.persist->n_slots + cnt->n_touched : m.persist->n_entries;
+  if (slots_bound > m.pool_cap) {
     if (blockIdx.x == 0 && threadIdx.x == 0) cnt->overflow_pool = 1u;
     return;
   }
@@ -581,6 +584,15 @@ k_query_lines(DevParams P, MapView m, const double* __restrict__ ab, uint32_t n,
     return true;
   });
   status[i] = st;
+}
+
+// (first-hit index << 2 | status) -> CellStatus after the MIN-reduction over shards
+__global__ void __launch_bounds__(256)
+k_unpack_line_status(const uint32_t* __restrict__ packed, uint32_t n, uint8_t* __restrict__ status) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t v = packed[i];
+  status[i] = (v == 0xFFFFFFFFu) ? (uint8_t)0 : (uint8_t)(v & 3u);
 }
 
 }  // namespace vmapdev

@@ -1,0 +1,157 @@
+// vmap_shard.cuh -- multi-GPU sharding of the voxel-block map.
+//
+// Every 8x8x8 voxel block has exactly one owner rank (owner_of); a rank generates the key sets
+// of its own scans locally (K1..K2 into the mask columns of its own table), packs every touched
+// block into a per-destination record stream, the streams are exchanged (all-to-all over NVLink)
+// and each owner ORs the received masks into its table and runs the ordinary K4 update -- one
+// scan at a time, in scan order, so the non-commutative clamped updates stay ordered per voxel.
+#pragma once
+
+#include "vmap_kernels.cuh"
+
+namespace vmapdev {
+
+constexpr int kMaxRanks = 64;
+
+// One touched block of one scan: 8 + 64 + 64 bytes.
+struct __align__(8) BlockRecord {
+  unsigned long long block;          // 39-bit block key (vmap_device.cuh block_key)
+  uint32_t free_mask[kMaskWords];
+  uint32_t occ_mask[kMaskWords];
+};
+static_assert(sizeof(BlockRecord) == 136, "BlockRecord layout");
+
+// Owner of a block: a mix of the block key's upper hash bits (the table index uses the low
+// ones), so ownership is balanced wherever the sensor is and independent of the table size.
+__host__ __device__ __forceinline__ uint32_t owner_of(unsigned long long b, uint32_t world) {
+  b ^= b >> 30; b *= 0xbf58476d1ce4e5b9ull;
+  b ^= b >> 27; b *= 0x94d049bb133111ebull;
+  b ^= b >> 31;
+  return (uint32_t)((b >> 40) % (unsigned long long)world);
+}
+
+struct PackView {
+  BlockRecord* records;     // [capacity] bucketed by destination
+  uint32_t* counts;         // [kMaxRanks] records per destination (pass 1)
+  uint32_t* cursors;        // [kMaxRanks] running write position per destination (pass 2)
+  uint32_t capacity;
+  uint32_t world;
+};
+
+// pass 1: how many touched blocks with a non-empty mask go to each destination
+__global__ void __launch_bounds__(256) k_pack_count(MapView m, Counters* cnt, PackView pv) {
+  if (cnt->overflow_table) return;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n_touched = cnt->n_touched;
+  for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_touched; t += warps) {
+    const uint32_t h = m.touched[t];
+    const uint32_t wv = (lane < kMaskWords) ? m.free_mask[(size_t)h * kMaskWords + lane]
+                                            : m.occ_mask[(size_t)h * kMaskWords + lane - kMaskWords];
+    if (!__any_sync(0xFFFFFFFFu, wv != 0u)) continue;
+    if (lane == 0) atomicAdd(pv.counts + owner_of(m.keys[h] >> kEpochBits, pv.world), 1u);
+  }
+}
+
+// pass 2: write the records (bucket offsets = exclusive prefix of counts) and clear the masks
+__global__ void __launch_bounds__(256) k_pack_write(MapView m, Counters* cnt, PackView pv) {
+  if (cnt->overflow_table) return;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n_touched = cnt->n_touched;
+  for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_touched; t += warps) {
+    const uint32_t h = m.touched[t];
+    uint32_t* src = (lane < kMaskWords) ? m.free_mask + (size_t)h * kMaskWords + lane
+                                        : m.occ_mask + (size_t)h * kMaskWords + lane - kMaskWords;
+    const uint32_t wv = *src;
+    if (!__any_sync(0xFFFFFFFFu, wv != 0u)) continue;
+    if (wv) *src = 0u;
+    const unsigned long long b = m.keys[h] >> kEpochBits;
+    uint32_t pos = 0;
+    if (lane == 0) {
+      const uint32_t dest = owner_of(b, pv.world);
+      uint32_t base = 0;
+      for (uint32_t d = 0; d < dest; d++) base += pv.counts[d];
+      pos = base + atomicAdd(pv.cursors + dest, 1u);
+    }
+    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+    if (pos >= pv.capacity) continue;   // cannot happen: capacity >= sum(counts)
+    BlockRecord* r = pv.records + pos;
+    if (lane == 0) r->block = b;
+    if (lane < kMaskWords) r->free_mask[lane] = wv;
+    else r->occ_mask[lane - kMaskWords] = wv;
+  }
+}
+
+// Owner side: OR one scan's received records into the table's mask columns (one warp per
+// record); K4 (k_update) then applies them.
+__global__ void __launch_bounds__(256)
+k_apply_records(MapView m, Counters* cnt, const BlockRecord* __restrict__ rec, uint32_t n) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const BlockRecord* r = rec + i;
+    uint32_t h = kNotFound;
+    if (lane == 0) h = find_or_insert_touch(m, cnt, r->block);
+    h = __shfl_sync(0xFFFFFFFFu, h, 0);
+    if (h == kNotFound) continue;
+    const uint32_t wv = (lane < kMaskWords) ? r->free_mask[lane] : r->occ_mask[lane - kMaskWords];
+    if (wv) {
+      uint32_t* dst = (lane < kMaskWords) ? m.free_mask + (size_t)h * kMaskWords + lane
+                                          : m.occ_mask + (size_t)h * kMaskWords + lane - kMaskWords;
+      atomicOr(dst, wv);
+    }
+  }
+}
+
+// Sharded getLineStatus: every rank walks every segment but only probes the voxels it owns;
+// the result is (index of the first non-free owned voxel << 2) | status, 0xFFFFFFFF when none.
+// The global answer is the minimum over ranks (then status = value & 3, or free).
+__global__ void __launch_bounds__(128)
+k_query_lines_sharded(DevParams P, MapView m, const double* __restrict__ ab, uint32_t n,
+                      uint32_t* __restrict__ packed, uint32_t rank, uint32_t world) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float ax = (float)ab[6 * i], ay = (float)ab[6 * i + 1], az = (float)ab[6 * i + 2];
+  const float bx = (float)ab[6 * i + 3], by = (float)ab[6 * i + 4], bz = (float)ab[6 * i + 5];
+  uint32_t out = 0xFFFFFFFFu, idx = 0;
+  unsigned long long cached_b = kEmpty;
+  uint32_t cached_h = kNotFound;
+  bool mine = false;
+  walk_ray(P, ax, ay, az, bx, by, bz, [&](uint32_t kx, uint32_t ky, uint32_t kz) {
+    const unsigned long long b = block_key(kx, ky, kz);
+    if (b != cached_b) {
+      cached_b = b;
+      mine = owner_of(b, world) == rank;
+      cached_h = mine ? find_block(m, b) : kNotFound;
+    }
+    if (mine) {
+      const uint8_t s = voxel_status(P, m, cached_h, kx, ky, kz);
+      if (s != 0) { out = (idx << 2) | s; return false; }
+    }
+    ++idx;
+    return true;
+  });
+  packed[i] = out;
+}
+
+// Sharded getCellStatusPoint: the owner answers, everybody else writes 0xFF.
+__global__ void __launch_bounds__(256)
+k_query_points_sharded(DevParams P, MapView m, const double* __restrict__ xyz, uint32_t n,
+                       uint8_t* __restrict__ status, uint32_t rank, uint32_t world) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s0 = scaled_coord(P.res_factor, xyz[3 * i]);
+  const int s1 = scaled_coord(P.res_factor, xyz[3 * i + 1]);
+  const int s2 = scaled_coord(P.res_factor, xyz[3 * i + 2]);
+  if (!(key_in_range(s0) && key_in_range(s1) && key_in_range(s2))) {
+    // search() returns NULL on every rank: rank 0 reports it
+    status[i] = (rank == 0) ? (P.treat_unknown_as_occupied ? 1 : 2) : 0xFF;
+    return;
+  }
+  const unsigned long long b = block_key(s0, s1, s2);
+  if (owner_of(b, world) != rank) { status[i] = 0xFF; return; }
+  status[i] = voxel_status(P, m, find_block(m, b), s0, s1, s2);
+}
+
+}  // namespace vmapdev

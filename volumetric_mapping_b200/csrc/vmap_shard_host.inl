@@ -1,0 +1,439 @@
+// vmap_shard_host.inl -- host side of the multi-GPU sharding (included by vmap.cu).
+//
+//   vmap_shard_generate*   K1..K2 of one scan on this rank + packing into per-owner records
+//   vmap_shard_apply_dev   owner side: OR records of one scan after another into the table, K4
+//   vmap_dist_*            the same two steps with the exchange done here over NCCL
+//                          (libnccl.so.2 is dlopen'ed on first use; single-GPU users never need it)
+#include <dlfcn.h>
+
+namespace {
+
+// ---- minimal NCCL surface (nccl.h 2.27: types are ABI-stable since 2.x) ----------------------
+struct NcclUniqueId { char internal[128]; };
+typedef struct ncclComm* NcclComm;
+enum { kNcclUint8 = 1, kNcclUint64 = 5, kNcclUint32 = 3, kNcclMin = 3 };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string error;
+};
+NcclApi g_nccl;
+
+bool nccl_load() {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) {
+    g_nccl.error = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+    return false;
+  }
+  bool ok = true;
+  auto sym = [&](const char* s) {
+    void* p = dlsym(g_nccl.lib, s);
+    if (!p) { ok = false; g_nccl.error = std::string("missing NCCL symbol ") + s; }
+    return p;
+  };
+  g_nccl.GetUniqueId = (int (*)(NcclUniqueId*))sym("ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))sym("ncclCommInitRank");
+  g_nccl.CommDestroy = (int (*)(NcclComm))sym("ncclCommDestroy");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))sym("ncclAllGather");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclAllReduce");
+  g_nccl.Send = (int (*)(const void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclSend");
+  g_nccl.Recv = (int (*)(void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclRecv");
+  g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+  g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+  if (!ok) {
+    dlclose(g_nccl.lib);
+    g_nccl.lib = nullptr;
+  }
+  return ok;
+}
+
+#define VM_NCCL(h, expr)                                                               \
+  do {                                                                                 \
+    int r__ = (expr);                                                                  \
+    if (r__ != 0) {                                                                    \
+      (h)->err = std::string(#expr) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?"); \
+      return VMAP_ERR_DIST;                                                            \
+    }                                                                                  \
+  } while (0)
+
+PackView pack_view(vmap* h) {
+  PackView pv;
+  pv.records = (BlockRecord*)h->pack.p;
+  pv.counts = h->d_pack_counts;
+  pv.cursors = h->d_pack_counts + kMaxRanks;
+  pv.capacity = (uint32_t)std::min<size_t>(h->pack.cap / sizeof(BlockRecord), 0xFFFFFFFFu);
+  pv.world = (uint32_t)h->shard_world;
+  return pv;
+}
+
+// K1..K2 for one scan with the table-overflow retry, marks left in the table's mask columns.
+template <class Mark>
+int generate_marks(vmap* h, size_t n_points, Mark&& mark) {
+  VM_TRY(next_epoch(h));
+  uint64_t retries = 0;
+  float ms_total = 0.f;
+  for (;;) {
+    VM_TRY(begin_scan_scratch(h, n_points));
+    for (bool& b : h->evk_set) b = false;
+    VM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    VM_TRY(mark_stage(h, 0));
+    VM_TRY(mark());
+    VM_TRY(mark_stage(h, 3));
+    VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    VM_TRY(read_counters(h));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    ms_total += ms;
+    if (!h->h_cnt->overflow_table) break;
+    VM_TRY(clear_marks(h));
+    VM_TRY(grow_table(h));
+    if (++retries > 40) return fail(h, VMAP_ERR_CAPACITY, "scan could not be generated after repeated growth");
+  }
+  const Counters& c = *h->h_cnt;
+  vmap_scan_stats& s = h->stats;
+  s.points_valid = c.points_valid;
+  s.points_in_range = c.points_in_range;
+  s.rays_cast = c.rays_cast;
+  s.traversals = c.traversals;
+  s.occupied_emitted = c.occupied_emitted;
+  s.longest_ray = c.longest_ray;
+  s.blocks_touched = c.n_touched;
+  s.retries = retries;
+  s.gpu_ms = ms_total;
+  auto span = [&](int a, int b) -> double {
+    float v = 0.f;
+    if (!h->evk_set[a] || !h->evk_set[b]) return 0.0;
+    if (cudaEventElapsedTime(&v, h->evk[a], h->evk[b]) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+    return (double)v;
+  };
+  s.front_ms = span(0, 1);
+  s.resolve_ms = span(1, 2);
+  s.walk_ms = h->evk_set[2] ? span(2, 3) : span(0, 3);
+  return VMAP_OK;
+}
+
+// Pack every touched block of the generated scan into per-destination records.
+int pack_marks(vmap* h) {
+  const size_t n_touched = h->h_cnt->n_touched;
+  VM_TRY(ensure(h, &h->pack, std::max<size_t>(n_touched, 1) * sizeof(BlockRecord)));
+  VM_CUDA(h, cudaMemsetAsync(h->d_pack_counts, 0, 2 * kMaxRanks * sizeof(uint32_t), h->stream));
+  PackView pv = pack_view(h);
+  const unsigned grid = g_sm_count(h->device) * 8;
+  k_pack_count<<<grid, 256, 0, h->stream>>>(h->m, h->d_cnt, pv);
+  k_pack_write<<<grid, 256, 0, h->stream>>>(h->m, h->d_cnt, pv);
+  h->launches += 2;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaMemcpyAsync(h->h_pack_counts, h->d_pack_counts, kMaxRanks * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  // the table may now be re-hashed safely (no pending marks)
+  while ((uint64_t)h->h_persist->n_entries * 2 > h->table_cap) VM_TRY(grow_table(h));
+  return VMAP_OK;
+}
+
+int shard_generate_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_dense,
+                          const double Tm[16], uint64_t* counts_out) {
+  Transform T;
+  fill_transform_matrix(&T, Tm);
+  VM_TRY(ensure_scan(h, std::max<size_t>(n, 1)));
+  h->stats = vmap_scan_stats{};
+  h->stats.points_in = n;
+  std::memset(h->h_pack_counts, 0, kMaxRanks * sizeof(uint32_t));
+  if (n) {
+    VM_TRY(generate_marks(h, n, [&]() -> int {
+      k_front_cloud<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, d_in, (uint32_t)n,
+                                                            (uint32_t)stride, is_dense);
+      h->launches++;
+      VM_CUDA(h, cudaGetLastError());
+      return launch_resolve_and_walk(h, n, T);
+    }));
+    VM_TRY(pack_marks(h));
+  }
+  if (counts_out)
+    for (int d = 0; d < h->shard_world; d++) counts_out[d] = h->h_pack_counts[d];
+  return VMAP_OK;
+}
+
+// Owner side: apply `n_lists` scans' record lists in order (list i = the i-th scan of the round).
+int shard_apply_lists(vmap* h, const BlockRecord* const* lists, const size_t* counts, size_t n_lists) {
+  size_t total = 0;
+  for (size_t i = 0; i < n_lists; i++) total += counts[i];
+  if (total > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many block records");
+  // make room up front so that neither the table nor the pool can overflow inside the round:
+  // every record adds at most one table entry and one pool slot
+  while (((uint64_t)h->h_persist->n_entries + total) * 2 > h->table_cap) VM_TRY(grow_table(h));
+  if ((uint64_t)h->h_persist->n_slots + total > h->pool_cap) VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_slots + total));
+  VM_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
+  VM_CUDA(h, cudaEventRecord(h->evk[3], h->stream));
+  uint64_t touched = 0;
+  for (size_t i = 0; i < n_lists; i++) {
+    if (!counts[i]) continue;
+    VM_TRY(next_epoch(h));
+    VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_touched, 0, sizeof(uint32_t), h->stream));
+    const unsigned grid = (unsigned)std::min<size_t>((counts[i] + 7) / 8, (size_t)g_sm_count(h->device) * 8);
+    k_apply_records<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->m, h->d_cnt, lists[i], (uint32_t)counts[i]);
+    h->launches++;
+    VM_CUDA(h, cudaGetLastError());
+    VM_TRY(launch_capture(h));
+    VM_TRY(launch_update(h));
+    touched += counts[i];
+  }
+  VM_CUDA(h, cudaEventRecord(h->evk[4], h->stream));
+  VM_TRY(read_counters(h));
+  if (h->h_cnt->overflow_table || h->h_cnt->overflow_pool)
+    return fail(h, VMAP_ERR_CAPACITY, "internal: map overflow inside a sharded apply round");
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->evk[3], h->evk[4]);
+  h->stats.update_ms = ms;
+  h->stats.gpu_ms += ms;
+  h->stats.unique_free = h->h_cnt->unique_free;
+  h->stats.unique_occupied = h->h_cnt->unique_occupied;
+  h->stats.blocks_total = h->h_persist->n_slots;
+  h->stats.blocks_applied = touched;
+  h->captured = h->capture;
+  return VMAP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t vmap_shard_owner(uint16_t kx, uint16_t ky, uint16_t kz, int world) {
+  if (world <= 1) return 0;
+  const unsigned long long b = (unsigned long long)(kx >> 3) | ((unsigned long long)(ky >> 3) << 13) |
+                               ((unsigned long long)(kz >> 3) << 26);
+  return owner_of(b, (uint32_t)world);
+}
+
+size_t vmap_shard_record_bytes(void) { return sizeof(BlockRecord); }
+
+int vmap_set_shard(vmap* h, int rank, int world) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
+    return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bad shard rank / world");
+  h->shard_rank = rank;
+  h->shard_world = world;
+  h->m.sharded = world > 1 ? 1u : 0u;
+  return VMAP_OK;
+}
+
+int vmap_shard_generate_dev(vmap* h, const float* d_xyz, size_t n, size_t stride_bytes,
+                            const double T_rowmajor[16], uint64_t* counts_out) {
+  if (!h || (!d_xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  return shard_generate_common(h, (const uint8_t*)d_xyz, n, stride_bytes, 1, T_rowmajor, counts_out);
+}
+
+int vmap_shard_generate(vmap* h, const float* xyz, size_t n, size_t stride_bytes, int is_dense,
+                        const double T_rowmajor[16], uint64_t* counts_out) {
+  if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (n) {
+    const size_t bytes = (n - 1) * stride_bytes + 12;
+    VM_TRY(ensure(h, &h->in, bytes));
+    VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
+  }
+  return shard_generate_common(h, (const uint8_t*)h->in.p, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor, counts_out);
+}
+
+int vmap_shard_records(vmap* h, int dest, const void** d_records, size_t* n_records) {
+  if (!h || !d_records || !n_records) return VMAP_ERR_INVALID_ARGUMENT;
+  if (dest < 0 || dest >= h->shard_world) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bad destination rank");
+  size_t off = 0;
+  for (int d = 0; d < dest; d++) off += h->h_pack_counts[d];
+  *d_records = (const BlockRecord*)h->pack.p + off;
+  *n_records = h->h_pack_counts[dest];
+  return VMAP_OK;
+}
+
+int vmap_shard_apply_dev(vmap* h, const void* const* d_record_lists, const size_t* n_records, size_t n_lists) {
+  if (!h || ((!d_record_lists || !n_records) && n_lists)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  return shard_apply_lists(h, (const BlockRecord* const*)d_record_lists, n_records, n_lists);
+}
+
+// ---- NCCL-backed collective insertion --------------------------------------------------------
+int vmap_dist_unique_id(uint8_t out128[128]) {
+  if (!out128) return VMAP_ERR_INVALID_ARGUMENT;
+  if (!nccl_load()) {
+    g_create_error = g_nccl.error;
+    return VMAP_ERR_DIST;
+  }
+  NcclUniqueId id;
+  const int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) {
+    g_create_error = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r);
+    return VMAP_ERR_DIST;
+  }
+  std::memcpy(out128, id.internal, 128);
+  return VMAP_OK;
+}
+
+int vmap_dist_init(vmap* h, const uint8_t id128[128], int rank, int world) {
+  if (!h || !id128) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_TRY(vmap_set_shard(h, rank, world));
+  if (!nccl_load()) return fail(h, VMAP_ERR_DIST, g_nccl.error.c_str());
+  VM_CUDA(h, cudaSetDevice(h->device));
+  NcclUniqueId id;
+  std::memcpy(id.internal, id128, 128);
+  NcclComm comm = nullptr;
+  VM_NCCL(h, g_nccl.CommInitRank(&comm, world, id, rank));
+  h->nccl_comm = comm;
+  if (!h->d_count_matrix) VM_TRY(dev_alloc(h, (void**)&h->d_count_matrix, (size_t)kMaxRanks * kMaxRanks * sizeof(uint64_t)));
+  return VMAP_OK;
+}
+
+int vmap_dist_shutdown(vmap* h) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  if (h->nccl_comm) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    g_nccl.CommDestroy((NcclComm)h->nccl_comm);
+    h->nccl_comm = nullptr;
+  }
+  return VMAP_OK;
+}
+
+// Exchange + apply after a local generate: rank r's scan is the r-th scan of this round.
+static int dist_exchange_and_apply(vmap* h) {
+  if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
+  NcclComm comm = (NcclComm)h->nccl_comm;
+  const int G = h->shard_world, me = h->shard_rank;
+  // counts matrix: row s = records rank s sends to each destination
+  uint64_t mine[kMaxRanks];
+  for (int d = 0; d < G; d++) mine[d] = h->h_pack_counts[d];
+  VM_CUDA(h, cudaMemcpyAsync(h->d_count_matrix + (size_t)me * G, mine, G * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+  VM_NCCL(h, g_nccl.AllGather(h->d_count_matrix + (size_t)me * G, h->d_count_matrix, (size_t)G, kNcclUint64, comm, h->stream));
+  VM_CUDA(h, cudaMemcpyAsync(h->h_count_matrix, h->d_count_matrix, (size_t)G * G * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  size_t recv_counts[kMaxRanks], recv_off[kMaxRanks], total = 0;
+  for (int s = 0; s < G; s++) {
+    recv_counts[s] = (size_t)h->h_count_matrix[(size_t)s * G + me];
+    recv_off[s] = total;
+    total += recv_counts[s];
+  }
+  VM_TRY(ensure(h, &h->recv, std::max<size_t>(total, 1) * sizeof(BlockRecord)));
+  BlockRecord* recv = (BlockRecord*)h->recv.p;
+  const BlockRecord* send = (const BlockRecord*)h->pack.p;
+  size_t send_off[kMaxRanks], so = 0;
+  for (int d = 0; d < G; d++) { send_off[d] = so; so += h->h_pack_counts[d]; }
+  VM_CUDA(h, cudaEventRecord(h->evk[2], h->stream));
+  VM_NCCL(h, g_nccl.GroupStart());
+  for (int p = 0; p < G; p++) {
+    if (p == me) continue;
+    if (h->h_pack_counts[p])
+      VM_NCCL(h, g_nccl.Send(send + send_off[p], (size_t)h->h_pack_counts[p] * sizeof(BlockRecord), kNcclUint8, p, comm, h->stream));
+    if (recv_counts[p])
+      VM_NCCL(h, g_nccl.Recv(recv + recv_off[p], recv_counts[p] * sizeof(BlockRecord), kNcclUint8, p, comm, h->stream));
+  }
+  VM_NCCL(h, g_nccl.GroupEnd());
+  if (recv_counts[me])
+    VM_CUDA(h, cudaMemcpyAsync(recv + recv_off[me], send + send_off[me], recv_counts[me] * sizeof(BlockRecord),
+                               cudaMemcpyDeviceToDevice, h->stream));
+  const BlockRecord* lists[kMaxRanks];
+  for (int s = 0; s < G; s++) lists[s] = recv + recv_off[s];
+  h->stats.records_sent = so - h->h_pack_counts[me];
+  h->stats.records_received = total - recv_counts[me];
+  return shard_apply_lists(h, lists, recv_counts, (size_t)G);
+}
+
+// device time of the whole round on this rank (generate .. apply, host round trips included)
+static int finish_round_timing(vmap* h) {
+  VM_CUDA(h, cudaEventRecord(h->evr1, h->stream));
+  VM_CUDA(h, cudaEventSynchronize(h->evr1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->evr0, h->evr1);
+  h->stats.gpu_ms = ms;
+  return VMAP_OK;
+}
+
+int vmap_dist_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n, size_t stride_bytes,
+                                    const double T_rowmajor[16]) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_CUDA(h, cudaEventRecord(h->evr0, h->stream));
+  VM_TRY(vmap_shard_generate_dev(h, d_xyz, n, stride_bytes, T_rowmajor, nullptr));
+  VM_TRY(dist_exchange_and_apply(h));
+  return finish_round_timing(h);
+}
+
+int vmap_dist_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes, int is_dense,
+                                const double T_rowmajor[16]) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_CUDA(h, cudaEventRecord(h->evr0, h->stream));
+  VM_TRY(vmap_shard_generate(h, xyz, n, stride_bytes, is_dense, T_rowmajor, nullptr));
+  VM_TRY(dist_exchange_and_apply(h));
+  return finish_round_timing(h);
+}
+
+// Sharded queries: partial answers of this shard (combine = element-wise MIN over ranks).
+int vmap_shard_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status) {
+  if (!h || ((!d_xyz || !d_status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query points");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (!n) return VMAP_OK;
+  k_query_points_sharded<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->m, d_xyz, (uint32_t)n, d_status,
+                                                                 (uint32_t)h->shard_rank, (uint32_t)h->shard_world);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+int vmap_shard_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint32_t* d_packed) {
+  if (!h || ((!d_ab || !d_packed) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query segments");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (!n) return VMAP_OK;
+  k_query_lines_sharded<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->m, d_ab, (uint32_t)n, d_packed,
+                                                                (uint32_t)h->shard_rank, (uint32_t)h->shard_world);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+// Collective versions: every rank passes the same queries and receives the global answer.
+int vmap_dist_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
+  VM_TRY(vmap_shard_query_points_dev(h, d_xyz, n, d_status));
+  if (!n) return VMAP_OK;
+  VM_NCCL(h, g_nccl.AllReduce(d_status, d_status, n, kNcclUint8, kNcclMin, (NcclComm)h->nccl_comm, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+int vmap_dist_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_status) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
+  if (!n) return VMAP_OK;
+  VM_TRY(ensure(h, &h->aux, n * sizeof(uint32_t)));
+  VM_TRY(vmap_shard_query_lines_dev(h, d_ab, n, (uint32_t*)h->aux.p));
+  VM_NCCL(h, g_nccl.AllReduce(h->aux.p, h->aux.p, n, kNcclUint32, kNcclMin, (NcclComm)h->nccl_comm, h->stream));
+  k_unpack_line_status<<<grid_for(n, 256), 256, 0, h->stream>>>((const uint32_t*)h->aux.p, (uint32_t)n, d_status);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+}  // extern "C"

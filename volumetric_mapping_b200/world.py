@@ -184,6 +184,84 @@ class OctomapWorld:
         self._check(self._L.vmap_query_lines_dev(self._h, C.c_void_p(int(ab_ptr)), int(n),
                                                  C.c_void_p(int(status_ptr))))
 
+    # -- multi-GPU sharding (include/vmap/vmap.h, "Multi-GPU sharding") ------------------
+    def set_shard(self, rank, world):
+        self._check(self._L.vmap_set_shard(self._h, int(rank), int(world)))
+        self._world = int(world)
+
+    def shard_generate(self, T, xyz, is_dense=True):
+        """Generate one scan here (nothing is applied); returns records per destination rank."""
+        cloud = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        Tm = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        counts = (C.c_uint64 * max(1, getattr(self, "_world", 1)))()
+        self._check(self._L.vmap_shard_generate(self._h, cloud.ctypes.data, cloud.shape[0], 12,
+                                                int(bool(is_dense)), _dptr(Tm), counts))
+        return list(counts)
+
+    def shard_generate_device(self, T, data_ptr, n, stride_bytes=12):
+        Tm = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        counts = (C.c_uint64 * max(1, getattr(self, "_world", 1)))()
+        self._check(self._L.vmap_shard_generate_dev(self._h, C.c_void_p(int(data_ptr)), int(n),
+                                                    int(stride_bytes), _dptr(Tm), counts))
+        return list(counts)
+
+    def shard_records(self, dest):
+        ptr, n = C.c_void_p(), C.c_size_t(0)
+        self._check(self._L.vmap_shard_records(self._h, int(dest), C.byref(ptr), C.byref(n)))
+        return (ptr.value or 0), int(n.value)
+
+    def shard_apply(self, lists):
+        """lists: [(device_ptr, n_records), ...] in scan order."""
+        k = len(lists)
+        ptrs = (C.c_void_p * max(k, 1))(*[C.c_void_p(int(p)) for p, _ in lists])
+        cnts = (C.c_size_t * max(k, 1))(*[int(n) for _, n in lists])
+        self._check(self._L.vmap_shard_apply_dev(self._h, ptrs, cnts, k))
+
+    def shard_query_points_device(self, xyz_ptr, n, status_ptr):
+        self._check(self._L.vmap_shard_query_points_dev(self._h, C.c_void_p(int(xyz_ptr)), int(n),
+                                                        C.c_void_p(int(status_ptr))))
+
+    def shard_query_lines_device(self, ab_ptr, n, packed_ptr):
+        self._check(self._L.vmap_shard_query_lines_dev(self._h, C.c_void_p(int(ab_ptr)), int(n),
+                                                       C.c_void_p(int(packed_ptr))))
+
+    @staticmethod
+    def dist_unique_id():
+        buf = (C.c_uint8 * 128)()
+        L = _capi.lib()
+        st = L.vmap_dist_unique_id(buf)
+        if st != 0:
+            raise VmapError(st, (L.vmap_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    def dist_init(self, id128, rank, world):
+        buf = (C.c_uint8 * 128)(*bytes(id128))
+        self._check(self._L.vmap_dist_init(self._h, buf, int(rank), int(world)))
+        self._world = int(world)
+
+    def dist_shutdown(self):
+        self._check(self._L.vmap_dist_shutdown(self._h))
+
+    def dist_insert_pointcloud(self, T, xyz, is_dense=True):
+        """COLLECTIVE: this rank's scan becomes the rank-th scan of the round on every shard."""
+        cloud = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        Tm = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        self._check(self._L.vmap_dist_insert_pointcloud(self._h, cloud.ctypes.data, cloud.shape[0],
+                                                        12, int(bool(is_dense)), _dptr(Tm)))
+
+    def dist_insert_pointcloud_device(self, T, data_ptr, n, stride_bytes=12):
+        Tm = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        self._check(self._L.vmap_dist_insert_pointcloud_dev(self._h, C.c_void_p(int(data_ptr)),
+                                                            int(n), int(stride_bytes), _dptr(Tm)))
+
+    def dist_query_points_device(self, xyz_ptr, n, status_ptr):
+        self._check(self._L.vmap_dist_query_points_dev(self._h, C.c_void_p(int(xyz_ptr)), int(n),
+                                                       C.c_void_p(int(status_ptr))))
+
+    def dist_query_lines_device(self, ab_ptr, n, status_ptr):
+        self._check(self._L.vmap_dist_query_lines_dev(self._h, C.c_void_p(int(ab_ptr)), int(n),
+                                                      C.c_void_p(int(status_ptr))))
+
     # -- leaves / introspection ---------------------------------------------------------
     def leaf_count(self):
         n = C.c_size_t(0)
