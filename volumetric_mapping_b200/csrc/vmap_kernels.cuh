@@ -261,9 +261,13 @@ k_resolve(ScanBuffers sb, MapView m, Counters* cnt, uint32_t n, int mark_occupie
       occ = rb && cast;
     }
   }
-  if (occ && mark_occupied)
-    mark_voxel(m, cnt, m.occ_mask, (uint32_t)(key & 0xFFFFu), (uint32_t)((key >> 16) & 0xFFFFu),
-               (uint32_t)((key >> 32) & 0xFFFFu));
+  if (occ) {
+    if (mark_occupied)
+      mark_voxel(m, cnt, m.occ_mask, (uint32_t)(key & 0xFFFFu), (uint32_t)((key >> 16) & 0xFFFFu),
+                 (uint32_t)((key >> 32) & 0xFFFFu));
+    else
+      sb.flags[i] |= 8u;   // kFlagOcc (vmap_sort.cuh): emitted as a packed key by the sort mode
+  }
   // order-preserving-within-warp compaction of the cast list
   const unsigned cast_b = __ballot_sync(0xFFFFFFFFu, cast);
   const unsigned occ_b = __ballot_sync(0xFFFFFFFFu, occ);
