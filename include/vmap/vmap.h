@@ -76,6 +76,9 @@ typedef struct vmap_config {
   uint64_t max_blocks;        /* hard cap for growth; 0 = limited by device memory only      */
   uint64_t initial_scan_points;
   uint64_t initial_scan_keys; /* sort mode: packed-key buffer capacity                       */
+  uint64_t dense_window_bytes;/* budget of the per-scan dense mark window (bitmask mode): a cube
+                                 of 8^3 blocks around the sensor, 128 B per block; 0 = 6 GiB,
+                                 1 = never use the window (hash-table mask columns only)      */
 } vmap_config;
 
 /* Counters of the most recent insert call (the metric's numerators). */

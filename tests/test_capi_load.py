@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_capi.Params) == 13 * 8
-    assert C.sizeof(_capi.Config) == 8 + 4 * 8
+    assert C.sizeof(_capi.Config) == 8 + 5 * 8
     assert C.sizeof(_capi.ScanStats) == 20 * 8
     p = _capi.default_params()
     assert (p.resolution, p.probability_hit, p.probability_miss, p.threshold_min, p.threshold_max,

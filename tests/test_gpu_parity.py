@@ -15,8 +15,13 @@ pytestmark = pytest.mark.gpu
 
 I4 = np.eye(4)
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-MODES = [vm.DEDUPE_BITMASK, vm.DEDUPE_SORT]
-MODE_IDS = ["bitmask", "sort"]
+# key-set construction variants: bitmask marks in the dense window (default), bitmask marks in the
+# hash table's mask columns (window disabled), and emit + radix sort + unique
+MODES = ["dense", "table", "sort"]
+MODE_IDS = MODES
+MODE_KW = {"dense": dict(dedupe_mode=vm.DEDUPE_BITMASK),
+           "table": dict(dedupe_mode=vm.DEDUPE_BITMASK, dense_window_bytes=1),
+           "sort": dict(dedupe_mode=vm.DEDUPE_SORT)}
 
 
 def packed(k3):
@@ -52,8 +57,8 @@ def assert_same_stats(gw, ow, keys=("points_in", "points_valid", "points_in_rang
         assert g[k] == o[k], (k, g[k], o[k])
 
 
-def pair(mode=vm.DEDUPE_BITMASK, **kw):
-    gw = vm.OctomapWorld(dedupe_mode=mode, **kw)
+def pair(mode="dense", **kw):
+    gw = vm.OctomapWorld(**MODE_KW[mode], **kw)
     gw.set_debug_capture(True)
     return gw, oracle.OracleWorld(**kw)
 
@@ -89,7 +94,7 @@ def test_reproject_cfg2_full_size_vs_oracle():
 # ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
 def test_single_point_known_answer(mode):
-    gw = vm.OctomapWorld(dedupe_mode=mode, resolution=0.1, sensor_max_range=5.0)
+    gw = vm.OctomapWorld(**MODE_KW[mode], resolution=0.1, sensor_max_range=5.0)
     gw.set_debug_capture(True)
     gw.insertPointcloud(I4, [[0.55, 0.05, 0.05]])
     f, o = gw.last_scan_keys()
@@ -106,7 +111,7 @@ def test_single_point_known_answer(mode):
 
 @pytest.mark.parametrize("mode", MODES, ids=MODE_IDS)
 def test_out_of_range_clipped_free_only(mode):
-    gw = vm.OctomapWorld(dedupe_mode=mode, resolution=0.1, sensor_max_range=1.0)
+    gw = vm.OctomapWorld(**MODE_KW[mode], resolution=0.1, sensor_max_range=1.0)
     gw.set_debug_capture(True)
     gw.insertPointcloud(I4, [[2.05, 0.0, 0.0]])
     f, o = gw.last_scan_keys()
@@ -294,10 +299,11 @@ def test_hdl64_trajectory_five_scans_leaves():
     assert_same_leaves(gw, ow)
 
 
-def test_map_growth_from_tiny_initial_capacity():
-    # forces both the mid-scan table overflow path and the pool growth path
+@pytest.mark.parametrize("mode", ["dense", "table"])
+def test_map_growth_from_tiny_initial_capacity(mode):
+    # forces both the table overflow path and the pool growth path
     s = scenes.cfg1_pointcloud()
-    gw = vm.OctomapWorld(initial_blocks=1, **s["params"])
+    gw = vm.OctomapWorld(initial_blocks=1, **MODE_KW[mode], **s["params"])
     ow = oracle.OracleWorld(**s["params"])
     retries = 0
     for k in range(3):

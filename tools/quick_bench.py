@@ -7,7 +7,8 @@ from volumetric_mapping_b200 import scenes
 
 res = float(sys.argv[1]) if len(sys.argv) > 1 else 0.1
 n_scans = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-w = vm.OctomapWorld(resolution=res, sensor_max_range=50.0, initial_blocks=1 << 20)
+mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+w = vm.OctomapWorld(resolution=res, sensor_max_range=50.0, initial_blocks=1 << 20, dedupe_mode=(1 if mode == 1 else 0), dense_window_bytes=(1 if mode == 2 else 0))
 scans = [scenes.trajectory_scan(i, resolution=res) for i in range(n_scans)]
 dev = [torch.from_numpy(s["points"]).cuda() for s in scans]
 torch.cuda.synchronize()

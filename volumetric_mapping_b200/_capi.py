@@ -37,6 +37,7 @@ class Config(C.Structure):
         ("max_blocks", C.c_uint64),
         ("initial_scan_points", C.c_uint64),
         ("initial_scan_keys", C.c_uint64),
+        ("dense_window_bytes", C.c_uint64),
     ]
 
 

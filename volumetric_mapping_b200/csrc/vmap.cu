@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -68,6 +69,26 @@ struct vmap {
   void* nccl_comm = nullptr;
   uint64_t* d_count_matrix = nullptr;         // [kMaxRanks * kMaxRanks]
   uint64_t h_count_matrix[kMaxRanks * kMaxRanks] = {0};
+
+  // dense mark window (vmap_device.cuh MarkSet): the per-scan key sets of ray-generated scans
+  struct Window {
+    uint32_t* free_bits = nullptr;
+    uint32_t* occ_bits = nullptr;
+    uint32_t* touched_bits = nullptr;
+    uint32_t* list = nullptr;
+    uint32_t* locate = nullptr;
+    uint32_t n_side = 0;        // blocks per axis (cube)
+    int radius = 0;             // blocks from the sensor block to the window face
+    uint64_t n_blocks = 0;
+    uint32_t n_words = 0;       // touched bitmap words
+    uint32_t list_cap = 0;
+    bool disabled = false;      // window would exceed the budget / unlimited range
+  } win;
+  MarkSet ms{};                 // marks of the scan in flight (table or dense mode)
+  uint64_t dense_fallbacks = 0;
+  int walk_variant = 0;   // experiments (VMAP_WALK_VARIANT)
+  int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
+  size_t ckpt_want = 0;   // checkpoint capacity to allocate with the scan scratch
 
   // parity hook
   bool capture = false;
@@ -280,6 +301,12 @@ int ensure_scan(vmap* h, size_t n) {
   dev_free(h, sb.key, oc * 8);
   dev_free(h, sb.flags, oc);
   dev_free(h, sb.rays, oc * 4);
+  dev_free(h, sb.len, oc * 4);
+  dev_free(h, sb.rank, oc * 4);
+  dev_free(h, sb.len_hist, kLenBins * 4);
+  dev_free(h, sb.seg_base, (kLenBins + 1) * 4);
+  dev_free(h, sb.ray_rec, oc * sizeof(RayRec));
+  dev_free(h, sb.ckpt, (size_t)sb.ckpt_cap * sizeof(Checkpoint));
   dev_free(h, sb.first_keys, ofc * 8);
   dev_free(h, sb.first_idx, ofc * 4);
   sb = ScanBuffers{};
@@ -291,6 +318,16 @@ int ensure_scan(vmap* h, size_t n) {
   VM_TRY(dev_alloc(h, (void**)&sb.key, cap * 8));
   VM_TRY(dev_alloc(h, (void**)&sb.flags, cap));
   VM_TRY(dev_alloc(h, (void**)&sb.rays, cap * 4));
+  VM_TRY(dev_alloc(h, (void**)&sb.len, cap * 4));
+  VM_TRY(dev_alloc(h, (void**)&sb.rank, cap * 4));
+  VM_TRY(dev_alloc(h, (void**)&sb.len_hist, kLenBins * 4));
+  VM_TRY(dev_alloc(h, (void**)&sb.seg_base, (kLenBins + 1) * 4));
+  VM_TRY(dev_alloc(h, (void**)&sb.ray_rec, cap * sizeof(RayRec)));
+  {
+    const size_t cc = std::max<size_t>(cap * 8, h->ckpt_want);
+    VM_TRY(dev_alloc(h, (void**)&sb.ckpt, cc * sizeof(Checkpoint)));
+    sb.ckpt_cap = (uint32_t)std::min<size_t>(cc, 0xFFFFFFFFu);
+  }
   VM_TRY(dev_alloc(h, (void**)&sb.first_keys, fc * 8));
   VM_TRY(dev_alloc(h, (void**)&sb.first_idx, fc * 4));
   sb.first_mask = (uint32_t)(fc - 1);
@@ -307,6 +344,7 @@ int begin_scan_scratch(vmap* h, size_t n) {
   VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->min_disparity_ord, 0xFF, sizeof(uint32_t), h->stream));
   VM_CUDA(h, cudaMemsetAsync(h->sb.first_keys, 0xFF, fc * 8, h->stream));
   VM_CUDA(h, cudaMemsetAsync(h->sb.first_idx, 0xFF, fc * 4, h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->sb.len_hist, 0, kLenBins * 4, h->stream));
   return VMAP_OK;
 }
 
@@ -338,13 +376,137 @@ int g_sm_count(int device) {
   return cached[device];
 }
 
+int grow_checkpoints(vmap* h) {
+  ScanBuffers& sb = h->sb;
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  const size_t want = std::min<size_t>((size_t)sb.ckpt_cap * 2 + 1024, 0xFFFFFFFFu);
+  if (want <= sb.ckpt_cap) return fail(h, VMAP_ERR_CAPACITY, "segment checkpoint buffer limit reached");
+  dev_free(h, sb.ckpt, (size_t)sb.ckpt_cap * sizeof(Checkpoint));
+  sb.ckpt = nullptr;
+  sb.ckpt_cap = 0;
+  VM_TRY(dev_alloc(h, (void**)&sb.ckpt, want * sizeof(Checkpoint)));
+  sb.ckpt_cap = (uint32_t)want;
+  h->ckpt_want = want;
+  return VMAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mark sets
+// ---------------------------------------------------------------------------------------------
+void use_table_marks(vmap* h) {
+  MarkSet& ms = h->ms;
+  ms = MarkSet{};
+  ms.free_mask = h->m.free_mask;
+  ms.occ_mask = h->m.occ_mask;
+  ms.list = h->m.touched;
+  ms.list_cap = (uint32_t)h->table_cap;
+  ms.dense = 0;
+}
+
+void free_window(vmap* h) {
+  vmap::Window& w = h->win;
+  dev_free(h, w.free_bits, w.n_blocks * kMaskWords * 4);
+  dev_free(h, w.occ_bits, w.n_blocks * kMaskWords * 4);
+  dev_free(h, w.touched_bits, (size_t)w.n_words * 4);
+  dev_free(h, w.list, (size_t)w.list_cap * 4);
+  dev_free(h, w.locate, (size_t)w.list_cap * 4);
+  const bool dis = w.disabled;
+  w = vmap::Window{};
+  w.disabled = dis;
+}
+
+int grow_window_list(vmap* h, uint32_t want) {
+  vmap::Window& w = h->win;
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  dev_free(h, w.list, (size_t)w.list_cap * 4);
+  dev_free(h, w.locate, (size_t)w.list_cap * 4);
+  w.list = w.locate = nullptr;
+  w.list_cap = 0;
+  const uint64_t cap = std::min<uint64_t>(w.n_blocks, std::max<uint64_t>(want, 1u << 16));
+  VM_TRY(dev_alloc(h, (void**)&w.list, cap * 4));
+  VM_TRY(dev_alloc(h, (void**)&w.locate, cap * 4));
+  w.list_cap = (uint32_t)cap;
+  return VMAP_OK;
+}
+
+// A cube of 8^3 blocks centred on the sensor block that holds every voxel a ray of this scan can
+// visit: |point - origin| <= sensor_max_range after clipping (octomap_world.cc:184-185,210-212).
+// Returns false (table mode) for an unlimited range or when the cube exceeds the memory budget.
+bool setup_dense_marks(vmap* h, const float origin[3]) {
+  vmap::Window& w = h->win;
+  if (w.disabled || h->cfg.dedupe_mode != VMAP_DEDUPE_BITMASK) return false;
+  if (!(h->P.max_range >= 0.0) || !std::isfinite(h->P.max_range)) return false;
+  const double r_vox = h->P.max_range * h->P.res_factor;
+  const double r_blk = std::ceil(r_vox / 8.0) + 2.0;
+  const uint64_t budget = h->cfg.dense_window_bytes ? h->cfg.dense_window_bytes : (6ull << 30);
+  const double side = 2.0 * r_blk + 1.0;
+  const double blocks = side * side * side;
+  if (blocks * (2.0 * kMaskWords * 4 + 0.125) > (double)budget || blocks >= (double)(1u << 28)) return false;
+  const int radius = (int)r_blk;
+  if (w.radius != radius || !w.free_bits) {
+    cudaStreamSynchronize(h->stream);
+    free_window(h);
+    w.radius = radius;
+    w.n_side = (uint32_t)(2 * radius + 1);
+    w.n_blocks = (uint64_t)w.n_side * w.n_side * w.n_side;
+    w.n_words = (uint32_t)((w.n_blocks + 31) / 32);
+    bool ok = dev_alloc(h, (void**)&w.free_bits, w.n_blocks * kMaskWords * 4) == VMAP_OK &&
+              dev_alloc(h, (void**)&w.occ_bits, w.n_blocks * kMaskWords * 4) == VMAP_OK &&
+              dev_alloc(h, (void**)&w.touched_bits, (size_t)w.n_words * 4) == VMAP_OK;
+    if (ok) ok = cudaMemsetAsync(w.free_bits, 0, w.n_blocks * kMaskWords * 4, h->stream) == cudaSuccess &&
+                 cudaMemsetAsync(w.occ_bits, 0, w.n_blocks * kMaskWords * 4, h->stream) == cudaSuccess &&
+                 cudaMemsetAsync(w.touched_bits, 0, (size_t)w.n_words * 4, h->stream) == cudaSuccess;
+    if (ok) ok = grow_window_list(h, 1u << 18) == VMAP_OK;
+    if (!ok) {   // not enough device memory for the window: stay in table mode for good
+      cudaGetLastError();
+      free_window(h);
+      w.disabled = true;
+      return false;
+    }
+  }
+  int ok[3];
+  for (int i = 0; i < 3; i++) {
+    const double f = std::floor(h->P.res_factor * (double)origin[i]);
+    // sensor outside the map: its rays are never walked; park the window at the map centre
+    ok[i] = (f >= -32768.0 && f < 32768.0) ? (((int)f + 32768) >> 3) : 4096;
+  }
+  MarkSet& ms = h->ms;
+  ms = MarkSet{};
+  ms.free_mask = w.free_bits;
+  ms.occ_mask = w.occ_bits;
+  ms.touched_bits = w.touched_bits;
+  ms.list = w.list;
+  ms.locate = w.locate;
+  ms.list_cap = w.list_cap;
+  ms.x0 = ok[0] - radius; ms.y0 = ok[1] - radius; ms.z0 = ok[2] - radius;
+  ms.nx = ms.ny = ms.nz = w.n_side;
+  ms.dense = 1;
+  return true;
+}
+
+int launch_list_and_locate(vmap* h) {
+  const unsigned grid = (unsigned)std::min<uint64_t>((h->win.n_words + 255) / 256, (uint64_t)g_sm_count(h->device) * 8);
+  k_list_touched<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->ms, h->d_cnt, h->win.n_words);
+  k_locate_blocks<<<g_sm_count(h->device) * 4, 256, 0, h->stream>>>(h->ms, h->m, h->d_cnt);
+  h->launches += 2;
+  VM_CUDA(h, cudaGetLastError());
+  return VMAP_OK;
+}
+
+int clear_window_marks(vmap* h) {
+  k_clear_window<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->ms, h->win.n_words);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  return VMAP_OK;
+}
+
 // Parity hook: count the scan's key sets, size the capture buffers, then expand the masks.
 int launch_capture(vmap* h) {
   if (!h->capture) return VMAP_OK;
   for (int pass = 0; pass < 2; pass++) {
     VM_CUDA(h, cudaMemsetAsync(h->d_cap_n, 0, 2 * sizeof(uint32_t), h->stream));
     k_capture_keys<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(
-        h->m, h->d_cnt, (uint16_t*)h->cap_free.p, h->d_cap_n, pass ? (uint32_t)(h->cap_free.cap / 6) : 0u,
+        h->m, h->ms, h->d_cnt, (uint16_t*)h->cap_free.p, h->d_cap_n, pass ? (uint32_t)(h->cap_free.cap / 6) : 0u,
         (uint16_t*)h->cap_occ.p, h->d_cap_n + 1, pass ? (uint32_t)(h->cap_occ.cap / 6) : 0u);
     h->launches++;
     VM_CUDA(h, cudaGetLastError());
@@ -359,32 +521,37 @@ int launch_capture(vmap* h) {
 }
 
 int launch_update(vmap* h) {
-  k_update<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->P, h->m, h->d_cnt);
+  k_update<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->P, h->m, h->ms, h->d_cnt);
   h->launches++;
   VM_CUDA(h, cudaGetLastError());
   return VMAP_OK;
 }
 
 int clear_marks(vmap* h) {
-  k_clear_masks<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->m, h->d_cnt);
+  k_clear_masks<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->m, h->ms, h->d_cnt);
   h->launches++;
   VM_CUDA(h, cudaGetLastError());
   return VMAP_OK;
 }
 
 // Runs  mark() -> [capture] -> update  with the grow-and-retry protocol.
-//   mark() enqueues everything up to and including the kernels that set block masks.
+//   mark() enqueues everything up to and including the kernels that set block masks, into the
+//   mark set h->ms (dense window when `origin` is given and a window is available, else the
+//   table's mask columns).
 template <class Mark>
-int run_scan(vmap* h, size_t n_points, Mark&& mark) {
+int run_scan(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
   VM_TRY(next_epoch(h));
   uint64_t retries = 0;
   float ms_total = 0.f;
+  bool dense = origin && setup_dense_marks(h, origin);
+  if (!dense) use_table_marks(h);
   for (;;) {
     VM_TRY(begin_scan_scratch(h, n_points));
     for (bool& b : h->evk_set) b = false;
     VM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     VM_TRY(mark_stage(h, 0));
     VM_TRY(mark());
+    if (dense) VM_TRY(launch_list_and_locate(h));
     VM_TRY(mark_stage(h, 3));
     VM_TRY(launch_capture(h));
     if (h->capture) VM_TRY(mark_stage(h, 3));
@@ -396,10 +563,49 @@ int run_scan(vmap* h, size_t n_points, Mark&& mark) {
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     ms_total += ms;
     bool redo = false;
-    if (h->h_cnt->overflow_table) {
+    if (dense) {
+      if (h->h_cnt->overflow_ckpt) {
+        // not every segment got a checkpoint: drop the partial marks, enlarge, run the scan again
+        VM_TRY(clear_window_marks(h));
+        VM_TRY(grow_checkpoints(h));
+        redo = true;
+      } else if (h->h_cnt->overflow_window) {
+        // a voxel outside the window (cannot happen for clipped rays; kept as a safety net):
+        // drop the marks and run this scan through the table's mask columns instead
+        VM_TRY(clear_window_marks(h));
+        h->dense_fallbacks++;
+        dense = false;
+        use_table_marks(h);
+        redo = true;
+      } else {
+        // the marks are complete and still in the window: only the tail has to be repeated
+        int guard = 0;
+        while (h->h_cnt->overflow_keys || h->h_cnt->overflow_table || h->h_cnt->overflow_pool) {
+          if (++guard > 40) return fail(h, VMAP_ERR_CAPACITY, "scan could not be applied after repeated growth");
+          retries++;
+          if (h->h_cnt->overflow_keys) {
+            VM_TRY(grow_window_list(h, std::max<uint32_t>(h->h_cnt->n_touched + (h->h_cnt->n_touched >> 2), 2 * h->win.list_cap)));
+            h->ms.list = h->win.list; h->ms.locate = h->win.locate; h->ms.list_cap = h->win.list_cap;
+          } else if (h->h_cnt->overflow_table) {
+            VM_TRY(grow_table(h));
+          } else {
+            VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_entries));
+          }
+          VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_touched, 0, sizeof(uint32_t), h->stream));
+          VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->overflow_table, 0, 5 * sizeof(uint32_t), h->stream));
+          VM_TRY(launch_list_and_locate(h));
+          VM_TRY(launch_capture(h));
+          VM_TRY(launch_update(h));
+          VM_TRY(mark_stage(h, 4));
+          VM_TRY(read_counters(h));
+        }
+        VM_CUDA(h, cudaMemsetAsync(h->win.touched_bits, 0, (size_t)h->win.n_words * 4, h->stream));
+      }
+    } else if (h->h_cnt->overflow_table) {
       // the table filled up mid-scan: drop this scan's marks, double the table, run it again
       VM_TRY(clear_marks(h));
       VM_TRY(grow_table(h));  // resets every entry's epoch to 0
+      use_table_marks(h);
       redo = true;
     } else if (h->h_cnt->overflow_pool) {
       VM_TRY(clear_marks(h));
@@ -468,14 +674,26 @@ void fill_transform_quat(Transform* T, const double q[4], const double t[3]) {
 // K1b + K2 of the bitmask mode (everything after the front-end kernel).
 int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
   VM_TRY(mark_stage(h, 1));
-  k_resolve<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, h->m, h->d_cnt, (uint32_t)n, 1);
-  h->launches++;
+  k_resolve<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, h->m, h->ms, h->d_cnt, (uint32_t)n, 1);
+  k_order_rays<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, (uint32_t)n);
+  h->launches += 2;
   VM_CUDA(h, cudaGetLastError());
   VM_TRY(mark_stage(h, 2));
-  if (h->P.free_filter)
-    k_walk_mask<true><<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->m, h->d_cnt, T.origin[0], T.origin[1], T.origin[2]);
-  else
-    k_walk_mask<false><<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->m, h->d_cnt, T.origin[0], T.origin[1], T.origin[2]);
+  const float ox = T.origin[0], oy = T.origin[1], oz = T.origin[2];
+  if (h->ms.dense && !h->no_segments) {
+    // K2a + K2b: exact checkpoints, then one thread per ray segment
+    k_checkpoints<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->d_cnt, ox, oy, oz);
+    h->launches++;
+    const unsigned grid = g_sm_count(h->device) * 8;
+    if (h->P.free_filter) k_walk_segments<true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
+    else k_walk_segments<false><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
+  } else if (h->ms.dense) {
+    if (h->P.free_filter) k_walk_dense<true><<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
+    else k_walk_dense<false><<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
+  } else {
+    if (h->P.free_filter) k_walk_mask<true><<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->m, h->d_cnt, ox, oy, oz);
+    else k_walk_mask<false><<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->m, h->d_cnt, ox, oy, oz);
+  }
   h->launches++;
   VM_CUDA(h, cudaGetLastError());
   return VMAP_OK;
@@ -503,7 +721,7 @@ int insert_cloud_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride, i
     h->captured = h->capture;
     return VMAP_OK;
   }
-  return run_scan(h, n, [&]() -> int {
+  return run_scan(h, n, T.origin, [&]() -> int {
     k_front_cloud<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, d_in, (uint32_t)n,
                                                           (uint32_t)stride, is_dense);
     h->launches++;
@@ -597,6 +815,8 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   h->cfg = c;
   h->device = dev;
   derive_params(h);
+  if (const char* e = getenv("VMAP_WALK_VARIANT")) h->walk_variant = atoi(e);
+  if (const char* e = getenv("VMAP_NO_SEGMENTS")) h->no_segments = atoi(e);
   auto bail = [&](int code) {
     g_create_error = h->err;
     vmap_destroy(h);
@@ -635,6 +855,8 @@ int vmap_destroy(vmap* h) {
   free_map(h);
   ScanBuffers& sb = h->sb;
   cudaFree(sb.world); cudaFree(sb.ray_end); cudaFree(sb.key); cudaFree(sb.flags); cudaFree(sb.rays);
+  cudaFree(sb.len); cudaFree(sb.rank); cudaFree(sb.len_hist);
+  cudaFree(sb.seg_base); cudaFree(sb.ray_rec); cudaFree(sb.ckpt);
   cudaFree(sb.first_keys); cudaFree(sb.first_idx);
   cudaFree(h->in.p); cudaFree(h->out.p); cudaFree(h->aux.p);
   cudaFree(h->cap_free.p); cudaFree(h->cap_occ.p);
@@ -642,6 +864,7 @@ int vmap_destroy(vmap* h) {
   vmap_dist_shutdown(h);
   cudaFree(h->pack.p); cudaFree(h->recv.p); cudaFree(h->d_pack_counts); cudaFree(h->d_count_matrix);
   sort_free(h);
+  free_window(h);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_persist) cudaFreeHost(h->h_persist);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -750,7 +973,7 @@ static int insert_image_common(vmap* h, const uint8_t* d_img, int rows, int cols
   }
   QMat Qm;
   if (Q) std::memcpy(Qm.q, Q, sizeof(Qm.q)); else std::memset(Qm.q, 0, sizeof(Qm.q));
-  return run_scan(h, n, [&]() -> int {
+  return run_scan(h, n, T.origin, [&]() -> int {
     if (Q) {
       k_min_disparity<<<g_sm_count(h->device) * 4, 256, 0, h->stream>>>(h->d_cnt, d_img, rows, cols, pitch);
       h->launches++;
@@ -868,7 +1091,7 @@ int vmap_apply_keys(vmap* h, const uint16_t* free_k3, size_t n_free, const uint1
   VM_TRY(ensure(h, &h->aux, n_occ * 6));
   if (n_free) VM_CUDA(h, cudaMemcpyAsync(h->in.p, free_k3, n_free * 6, cudaMemcpyHostToDevice, h->stream));
   if (n_occ) VM_CUDA(h, cudaMemcpyAsync(h->aux.p, occ_k3, n_occ * 6, cudaMemcpyHostToDevice, h->stream));
-  return run_scan(h, 1, [&]() -> int {
+  return run_scan(h, 1, nullptr, [&]() -> int {
     if (n_occ) {
       k_mark_keys<<<grid_for(n_occ, 256), 256, 0, h->stream>>>(h->m, h->d_cnt, (const uint16_t*)h->aux.p, (uint32_t)n_occ, 1);
       h->launches++;

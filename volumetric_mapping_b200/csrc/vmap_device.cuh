@@ -65,6 +65,8 @@ struct Counters {           // zeroed at the start of every scan
   uint32_t overflow_table;  // probe limit hit: table must grow, scan is re-run
   uint32_t overflow_pool;   // pool too small for the new blocks: pool must grow, update re-run
   uint32_t overflow_keys;   // sort mode: key buffer too small
+  uint32_t overflow_window; // dense mode: a voxel fell outside the window
+  uint32_t overflow_ckpt;   // dense mode: segment checkpoint buffer too small
   uint32_t n_keys;          // sort mode: packed keys emitted
   uint32_t n_leaves;        // export
   uint32_t min_disparity_ord;  // ordered-int encoding of the image minimum
@@ -149,6 +151,79 @@ __device__ __forceinline__ uint32_t find_block(const MapView& m, unsigned long l
     h = (h + 1u) & m.cap_mask;
   }
   return kNotFound;
+}
+
+// Insert-or-find without touching the per-scan list (dense-window mode locates each touched
+// block once per scan, after the walk).
+__device__ __forceinline__ uint32_t find_or_insert(const MapView& m, Counters* cnt,
+                                                   unsigned long long b) {
+  uint32_t h = hash_block(b) & m.cap_mask;
+  const unsigned long long want = (b << kEpochBits) | (unsigned long long)m.epoch;
+  unsigned long long w = ld_cg_u64(m.keys + h);
+  for (int probe = 0; probe < kMaxProbe;) {
+    if (w == kEmpty) {
+      const unsigned long long old = atomicCAS(m.keys + h, kEmpty, want);
+      if (old == kEmpty) {
+        atomicAdd(&m.persist->n_entries, 1u);
+        return h;
+      }
+      w = old;
+      continue;
+    }
+    if ((w >> kEpochBits) == b) return h;
+    h = (h + 1u) & m.cap_mask;
+    ++probe;
+    w = ld_cg_u64(m.keys + h);
+  }
+  atomicExch(&cnt->overflow_table, 1u);
+  return kNotFound;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Where the marks (free / occupied voxel sets) of the scan in flight live.
+//   table mode : mask columns of the hash table, entry = table index, list = m.touched
+//   dense mode : a directly addressed window of 8^3 blocks around the sensor (x fastest), entry =
+//                window block index, list = compacted from the window's touched bitmap; `locate`
+//                holds the table index of every listed block (k_locate_blocks)
+// ---------------------------------------------------------------------------------------------
+struct MarkSet {
+  uint32_t* free_mask;       // [entries * kMaskWords]
+  uint32_t* occ_mask;        // [entries * kMaskWords]
+  uint32_t* list;            // [n_touched] entries
+  uint32_t* locate;          // dense: [n_touched] table indices
+  uint32_t* touched_bits;    // dense: 1 bit per window block
+  int x0, y0, z0;            // dense: window origin in block units
+  uint32_t nx, ny, nz;       // dense: window size in blocks
+  uint32_t list_cap;
+  uint32_t dense;
+};
+
+// window block index of the block containing key (kx,ky,kz), or kNotFound outside the window
+__device__ __forceinline__ uint32_t window_index(const MarkSet& ms, uint32_t kx, uint32_t ky, uint32_t kz) {
+  const uint32_t rx = (uint32_t)((int)(kx >> 3) - ms.x0);
+  const uint32_t ry = (uint32_t)((int)(ky >> 3) - ms.y0);
+  const uint32_t rz = (uint32_t)((int)(kz >> 3) - ms.z0);
+  if (rx >= ms.nx || ry >= ms.ny || rz >= ms.nz) return kNotFound;
+  return (rz * ms.ny + ry) * ms.nx + rx;
+}
+__device__ __forceinline__ unsigned long long window_block_key(const MarkSet& ms, uint32_t idx) {
+  const uint32_t rx = idx % ms.nx;
+  const uint32_t t = idx / ms.nx;
+  const uint32_t ry = t % ms.ny, rz = t / ms.ny;
+  return (unsigned long long)(uint32_t)((int)rx + ms.x0) | ((unsigned long long)(uint32_t)((int)ry + ms.y0) << 13) |
+         ((unsigned long long)(uint32_t)((int)rz + ms.z0) << 26);
+}
+// block key and table index of the t-th listed entry
+__device__ __forceinline__ unsigned long long listed_block(const MarkSet& ms, const MapView& m, uint32_t t,
+                                                           uint32_t* entry, uint32_t* table_h) {
+  const uint32_t e = ms.list[t];
+  *entry = e;
+  if (ms.dense) {
+    *table_h = ms.locate[t];
+    return window_block_key(ms, e);
+  }
+  *table_h = e;
+  return m.keys[e] >> kEpochBits;
 }
 
 // ---------------------------------------------------------------------------------------------

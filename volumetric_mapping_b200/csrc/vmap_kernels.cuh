@@ -14,19 +14,48 @@
 #pragma once
 
 #include "vmap_device.cuh"
+#include "vmap_seq.cuh"
 
 namespace vmapdev {
 
 constexpr uint32_t kFlagValid = 1u;   // point takes part in the scan
 constexpr uint32_t kFlagRange = 2u;   // castRay's in-range branch
 constexpr uint32_t kFlagBound = 4u;   // coordToKeyChecked(point) succeeds
+//                  kFlagOcc = 8u       (vmap_sort.cuh) the point inserts an occupied key
+constexpr uint32_t kFlagCast = 16u;   // castRay is invoked for this point (set by k_resolve)
+constexpr int kLenBins = 2048;        // cast rays are ordered by segment count: bin = min(n_seg, 2047)
+constexpr uint32_t kSegSteps = 64;    // DDA steps per ray segment (one thread walks one segment)
+
+// A ray is cut into n_seg = max(1, steps / kSegSteps) segments of equal length in the ray
+// parameter t; segment j owns the DDA steps whose crossing parameter lies in [j, j+1) * dtau.
+struct RayRec {               // per cast ray (index = position in the ordered work list)
+  double dt0, dt1, dt2;       // tDelta
+  double dlen;                // (double)length
+  double dtau;                // segment length in t
+  uint32_t e01, e2s;          // end key: e0 | e1 << 16 ; e2 | step codes << 16 (2 bits per axis: 0, 1 = +1, 2 = -1)
+  uint32_t n_seg;
+  uint32_t point;             // index of the point / pixel
+};
+struct Checkpoint {           // state of the walk at the start of a segment
+  double t0, t1, t2;          // tMax
+  uint32_t c01, c2;           // current key
+  uint32_t count;             // keys emitted by the earlier segments; 0xFFFFFFFF: nothing to walk
+  uint32_t pad;
+};
 
 struct ScanBuffers {
   float* world;             // [n*3] world-frame points (what the reference leaves in the cloud)
   float* ray_end;           // [n*3] ray end: the point, or the clipped end when out of range
   unsigned long long* key;  // [n]   unchecked endpoint key k0 | k1<<16 | k2<<32
   uint8_t* flags;           // [n]
-  uint32_t* rays;           // [n]   indices of cast rays
+  uint32_t* rays;           // [n]   indices of cast rays, longest rays first
+  uint32_t* len;            // [n]   DDA steps of the ray (key-space Manhattan distance)
+  uint32_t* rank;           // [n]   position of a cast ray inside its length bin
+  uint32_t* len_hist;       // [kLenBins] cast rays per segment-count bin
+  uint32_t* seg_base;       // [kLenBins + 1] first work slot of every segment level
+  RayRec* ray_rec;          // [n]
+  Checkpoint* ckpt;         // [ckpt_cap] one per (segment level, ray)
+  uint32_t ckpt_cap;
   unsigned long long* first_keys;  // [first_cap] per-scan table: endpoint key -> first index
   uint32_t* first_idx;             // [first_cap]
   uint32_t first_mask;
@@ -106,6 +135,16 @@ __device__ __forceinline__ void classify_point(const DevParams& P, const ScanBuf
   sb.ray_end[3 * i + 0] = ex;
   sb.ray_end[3 * i + 1] = ey;
   sb.ray_end[3 * i + 2] = ez;
+  {
+    // number of DDA steps the ray will take (exact up to rounding): orders the work list
+    const int o0 = scaled_coord(P.res_factor, (double)origin[0]), o1 = scaled_coord(P.res_factor, (double)origin[1]),
+              o2 = scaled_coord(P.res_factor, (double)origin[2]);
+    const int e0 = scaled_coord(P.res_factor, (double)ex), e1 = scaled_coord(P.res_factor, (double)ey),
+              e2 = scaled_coord(P.res_factor, (double)ez);
+    const bool walk = key_in_range(o0) && key_in_range(o1) && key_in_range(o2) && key_in_range(e0) &&
+                      key_in_range(e1) && key_in_range(e2);
+    sb.len[i] = walk ? (uint32_t)(abs(e0 - o0) + abs(e1 - o1) + abs(e2 - o2)) : 0u;
+  }
   sb.key[i] = key;
   sb.flags[i] = (uint8_t)(kFlagValid | (in_range ? kFlagRange : 0u) | (bound ? kFlagBound : 0u));
   if (in_range && bound) first_insert(sb, key, i);
@@ -233,7 +272,7 @@ k_front_disparity(DevParams P, ScanBuffers sb, Counters* cnt, Transform T, QMat 
   projected_point(P, sb, cnt, T, i, X, Y, Z);
 }
 
-// mark voxel (kx,ky,kz) in a block mask array
+// mark voxel (kx,ky,kz) in a block mask array (table mode)
 __device__ __forceinline__ void mark_voxel(const MapView& m, Counters* cnt, uint32_t* masks,
                                            uint32_t kx, uint32_t ky, uint32_t kz) {
   const uint32_t h = find_or_insert_touch(m, cnt, block_key(kx, ky, kz));
@@ -241,13 +280,29 @@ __device__ __forceinline__ void mark_voxel(const MapView& m, Counters* cnt, uint
   const uint32_t l = local_index(kx, ky, kz);
   atomicOr(masks + (size_t)h * kMaskWords + (l >> 5), 1u << (l & 31u));
 }
+// the same in the dense window (occupied endpoints)
+__device__ __forceinline__ void mark_voxel_dense(const MarkSet& ms, Counters* cnt, uint32_t* masks,
+                                                 uint32_t kx, uint32_t ky, uint32_t kz) {
+  const uint32_t idx = window_index(ms, kx, ky, kz);
+  if (idx == kNotFound) { atomicExch(&cnt->overflow_window, 1u); return; }
+  const uint32_t l = local_index(kx, ky, kz);
+  atomicOr(masks + (size_t)idx * kMaskWords + (l >> 5), 1u << (l & 31u));
+  atomicOr(ms.touched_bits + (idx >> 5), 1u << (idx & 31u));
+}
+
+__device__ __forceinline__ uint32_t ray_segments(uint32_t steps) {
+  return min(max(steps / kSegSteps, 1u), (uint32_t)(kLenBins - 1));
+}
+__device__ __forceinline__ uint32_t ray_bin(const ScanBuffers& sb, uint32_t i) {
+  return ray_segments(sb.len[i]);
+}
 
 // K1b: skip rule + work list + occupied marks.
 //   occupied_cells = { K_i : valid, in range, in bounds };  first[K] = min such i.
 //   castRay(i) is invoked  <=>  K_i not yet in occupied_cells when point i is visited
 //                           <=>  in-range&bound ? i == first[K_i] : i < first[K_i].
 __global__ void __launch_bounds__(256)
-k_resolve(ScanBuffers sb, MapView m, Counters* cnt, uint32_t n, int mark_occupied) {
+k_resolve(ScanBuffers sb, MapView m, MarkSet ms, Counters* cnt, uint32_t n, int mark_occupied) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool cast = false, occ = false;
   unsigned long long key = 0;
@@ -262,24 +317,86 @@ k_resolve(ScanBuffers sb, MapView m, Counters* cnt, uint32_t n, int mark_occupie
     }
   }
   if (occ) {
-    if (mark_occupied)
+    if (mark_occupied && ms.dense)
+      mark_voxel_dense(ms, cnt, ms.occ_mask, (uint32_t)(key & 0xFFFFu), (uint32_t)((key >> 16) & 0xFFFFu),
+                       (uint32_t)((key >> 32) & 0xFFFFu));
+    else if (mark_occupied)
       mark_voxel(m, cnt, m.occ_mask, (uint32_t)(key & 0xFFFFu), (uint32_t)((key >> 16) & 0xFFFFu),
                  (uint32_t)((key >> 32) & 0xFFFFu));
     else
       sb.flags[i] |= 8u;   // kFlagOcc (vmap_sort.cuh): emitted as a packed key by the sort mode
   }
-  // order-preserving-within-warp compaction of the cast list
+  // cast-ray work list, pass 1: position of the ray inside its length bin
+  if (cast) {
+    sb.flags[i] |= kFlagCast;
+    sb.rank[i] = atomicAdd(sb.len_hist + ray_bin(sb, i), 1u);
+  }
   const unsigned cast_b = __ballot_sync(0xFFFFFFFFu, cast);
   const unsigned occ_b = __ballot_sync(0xFFFFFFFFu, occ);
-  const uint32_t lane = threadIdx.x & 31u;
-  uint32_t base = 0;
-  if (lane == 0 && cast_b) {
-    base = atomicAdd(&cnt->n_rays, (uint32_t)__popc(cast_b));
+  if ((threadIdx.x & 31u) == 0 && cast_b) {
+    atomicAdd(&cnt->n_rays, (uint32_t)__popc(cast_b));
     atomicAdd(&cnt->rays_cast, (uint32_t)__popc(cast_b));
     if (occ_b) atomicAdd(&cnt->occupied_emitted, (uint32_t)__popc(occ_b));
   }
-  base = __shfl_sync(0xFFFFFFFFu, base, 0);
-  if (cast) sb.rays[base + __popc(cast_b & ((1u << lane) - 1u))] = i;
+}
+
+// Cast-ray work list, pass 2: longest rays first (bins in descending order), so that the 32 rays
+// of a warp take about the same number of DDA steps and the longest rays start first.
+__global__ void __launch_bounds__(256) k_order_rays(ScanBuffers sb, uint32_t n) {
+  __shared__ uint32_t off[kLenBins];
+  __shared__ uint32_t warp_sum[8];
+  constexpr int kPer = kLenBins / 256;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  // thread t owns the kPer bins starting at descending position t * kPer
+  uint32_t local[kPer], sum = 0;
+#pragma unroll
+  for (int j = 0; j < kPer; j++) {
+    local[j] = sb.len_hist[kLenBins - 1 - (threadIdx.x * kPer + j)];
+    sum += local[j];
+  }
+  uint32_t incl = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+    if (lane >= (uint32_t)o) incl += t;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  uint32_t base = incl - sum;
+  for (uint32_t w2 = 0; w2 < warp; w2++) base += warp_sum[w2];
+#pragma unroll
+  for (int j = 0; j < kPer; j++) {
+    off[kLenBins - 1 - (threadIdx.x * kPer + j)] = base;
+    base += local[j];
+  }
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (sb.flags[i] & kFlagCast))
+    sb.rays[off[ray_bin(sb, i)] + sb.rank[i]] = i;
+  if (blockIdx.x != 0) return;
+  // Work slots of the segment walker, level-major: level j holds one slot for every ray with
+  // more than j segments -- a prefix of the ordered list, off[j] rays long.
+  uint32_t lv[kPer], lsum = 0;
+#pragma unroll
+  for (int j = 0; j < kPer; j++) {
+    lv[j] = off[threadIdx.x * kPer + j];
+    lsum += lv[j];
+  }
+  uint32_t linc = lsum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, linc, o);
+    if (lane >= (uint32_t)o) linc += t;
+  }
+  __syncthreads();
+  if (lane == 31) warp_sum[warp] = linc;
+  __syncthreads();
+  uint32_t lbase = linc - lsum;
+  for (uint32_t w2 = 0; w2 < warp; w2++) lbase += warp_sum[w2];
+#pragma unroll
+  for (int j = 0; j < kPer; j++) {
+    sb.seg_base[threadIdx.x * kPer + j] = lbase;
+    lbase += lv[j];
+  }
+  if (threadIdx.x == 255) sb.seg_base[kLenBins] = lbase;
 }
 
 // K2: one thread per cast ray.  Every visited voxel is one bit of its block's 512-bit free mask
@@ -311,15 +428,16 @@ k_walk_mask(DevParams P, ScanBuffers sb, MapView m, Counters* cnt, float ox, flo
     // (B)
     if (w.live) {
       const uint32_t b0 = w.c0 >> 3, b1 = w.c1 >> 3, b2 = w.c2 >> 3;
-      uint32_t word = 0, bits = 0;
+      uint32_t word = 0xFFFFFFFFu, bits = 0, seen = 0;   // `seen`: see k_walk_dense
       for (;;) {
         ++count;
         if (!kFilter || free_filter_pass(P, ox, oy, oz, w.c0, w.c1, w.c2)) {
           const uint32_t l = local_index(w.c0, w.c1, w.c2);
           if ((l >> 5) != word) {
-            if (bits) atomicOr(mask + word, bits);
+            if (bits & ~seen) atomicOr(mask + word, bits);
             word = l >> 5;
             bits = 0;
+            seen = mask[word];
           }
           bits |= 1u << (l & 31u);
         }
@@ -327,7 +445,7 @@ k_walk_mask(DevParams P, ScanBuffers sb, MapView m, Counters* cnt, float ox, flo
         if (count >= kKeyRayMax - 1u) { w.live = false; break; }   // KeyRay capacity
         if (((w.c0 >> 3) != b0) | ((w.c1 >> 3) != b1) | ((w.c2 >> 3) != b2)) break;
       }
-      if (bits) atomicOr(mask + word, bits);
+      if (bits & ~seen) atomicOr(mask + word, bits);
     }
   }
   // statistics: traversals (sum) and longest ray (max), warp-reduced
@@ -342,6 +460,235 @@ k_walk_mask(DevParams P, ScanBuffers sb, MapView m, Counters* cnt, float ox, flo
   }
 }
 
+// K2, dense-window mode: no lookups at all.  The free mask word of every visited voxel is
+// addressed directly from its key; the bits of one 32-voxel word are collected in a register
+// and flushed with a single RED.OR when the ray moves on to another word, and the block's bit
+// in the window's touched bitmap is set when the ray enters a block.
+template <bool kFilter>
+__global__ void __launch_bounds__(128)
+k_walk_dense(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz, int variant) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  RayWalk w;
+  w.live = false;
+  if (r < cnt->n_rays) {
+    const uint32_t i = sb.rays[r];
+    w.init(P, ox, oy, oz, sb.ray_end[3 * i], sb.ray_end[3 * i + 1], sb.ray_end[3 * i + 2]);
+  }
+  uint32_t count = 0;
+  // word index (window block * 16 + word), the bits collected for it, and the word's value as
+  // read when the ray entered it.  Near the sensor every ray sets the same voxels: a RED is only
+  // issued for bits the preloaded value does not show yet (a stale value costs one redundant
+  // RED, never a missed bit), which keeps tens of thousands of same-address atomics off the L2.
+  uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0;
+  while (w.live) {
+    ++count;
+    if (!kFilter || free_filter_pass(P, ox, oy, oz, w.c0, w.c1, w.c2)) {
+      const uint32_t idx = window_index(ms, w.c0, w.c1, w.c2);
+      if (idx == kNotFound) {   // outside the window: the host re-runs the scan in table mode
+        atomicExch(&cnt->overflow_window, 1u);
+        break;
+      }
+      const uint32_t l = local_index(w.c0, w.c1, w.c2);
+      const uint32_t wi = (idx << 4) | (l >> 5);
+      if (wi != cur) {
+        if ((bits & ~seen) && variant != 1) atomicOr(ms.free_mask + cur, bits);
+        bits = 0;
+        if ((wi >> 4) != (cur >> 4)) {
+          uint32_t* tb = ms.touched_bits + (idx >> 5);
+          if (!((*tb >> (idx & 31u)) & 1u)) atomicOr(tb, 1u << (idx & 31u));
+        }
+        cur = wi;
+        seen = (variant == 0 || (variant == 3 && count < 48u)) ? ms.free_mask[wi] : 0u;
+      }
+      bits |= 1u << (l & 31u);
+    }
+    if (!w.advance()) break;
+    if (count >= kKeyRayMax - 1u) break;   // KeyRay capacity
+  }
+  if ((bits & ~seen) && variant != 1) atomicOr(ms.free_mask + cur, bits);
+  uint32_t sum = count, mx = count;
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+  }
+  if ((threadIdx.x & 31u) == 0 && sum) {
+    atomicAdd(&cnt->traversals, (unsigned long long)sum);
+    atomicMax(&cnt->longest_ray, mx);
+  }
+}
+
+// K2a: one thread per cast ray.  computeRayKeys' preamble, then the state of the walk at every
+// segment boundary by exact jump-ahead of the three tMax sequences (vmap_seq.cuh) -- no DDA
+// stepping here.  Level j's checkpoint of the ray at ordered position r goes to slot
+// seg_base[j] + r.
+__global__ void __launch_bounds__(128)
+k_checkpoints(DevParams P, ScanBuffers sb, Counters* cnt, float ox, float oy, float oz) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= cnt->n_rays) return;
+  const uint32_t i = sb.rays[r];
+  RayWalk w;
+  w.init(P, ox, oy, oz, sb.ray_end[3 * i], sb.ray_end[3 * i + 1], sb.ray_end[3 * i + 2]);
+  const uint32_t steps = sb.len[i];
+  const uint32_t n_seg = ray_segments(steps);
+  RayRec rr;
+  rr.dt0 = w.dt0; rr.dt1 = w.dt1; rr.dt2 = w.dt2;
+  rr.dlen = w.dlen;
+  rr.dtau = n_seg > 1 ? __ddiv_rn(__dmul_rn(w.dlen, (double)kSegSteps), (double)steps) : 0.0;
+  const uint32_t sc = (uint32_t)(w.s0 > 0 ? 1 : (w.s0 < 0 ? 2 : 0)) | ((uint32_t)(w.s1 > 0 ? 1 : (w.s1 < 0 ? 2 : 0)) << 2) |
+                      ((uint32_t)(w.s2 > 0 ? 1 : (w.s2 < 0 ? 2 : 0)) << 4);
+  rr.e01 = w.e0 | (w.e1 << 16);
+  rr.e2s = w.e2 | (sc << 16);
+  rr.n_seg = n_seg;
+  rr.point = i;
+  sb.ray_rec[r] = rr;
+  uint32_t n0 = 0, n1 = 0, n2 = 0;
+  double t0 = w.t0, t1 = w.t1, t2 = w.t2;
+  for (uint32_t j = 0; j < n_seg; j++) {
+    if (j > 0) {
+      const double tau = __dmul_rn((double)j, rr.dtau);
+      const unsigned long long cap = 1ull << 40;
+      if (w.s0) n0 += (uint32_t)vmapseq::seq_advance(&t0, w.dt0, tau, cap);
+      if (w.s1) n1 += (uint32_t)vmapseq::seq_advance(&t1, w.dt1, tau, cap);
+      if (w.s2) n2 += (uint32_t)vmapseq::seq_advance(&t2, w.dt2, tau, cap);
+    }
+    const uint32_t slot = sb.seg_base[j] + r;
+    if (slot >= sb.ckpt_cap) { atomicExch(&cnt->overflow_ckpt, 1u); return; }
+    Checkpoint cp;
+    cp.t0 = t0; cp.t1 = t1; cp.t2 = t2;
+    const uint32_t c0 = (w.c0 + (uint32_t)(w.s0 * (int)n0)) & 0xFFFFu;
+    const uint32_t c1 = (w.c1 + (uint32_t)(w.s1 * (int)n1)) & 0xFFFFu;
+    const uint32_t c2 = (w.c2 + (uint32_t)(w.s2 * (int)n2)) & 0xFFFFu;
+    cp.c01 = c0 | (c1 << 16);
+    cp.c2 = c2;
+    cp.count = w.live ? 1u + n0 + n1 + n2 : 0xFFFFFFFFu;
+    cp.pad = 0;
+    sb.ckpt[slot] = cp;
+  }
+}
+
+// K2b: one thread per (segment level, ray) work slot, level-major so that the lanes of a warp
+// walk neighbouring rays at the same depth.  Segment j performs the DDA steps whose crossing
+// parameter is in [j, j+1) * dtau and emits the voxels those steps enter (segment 0 also the
+// origin voxel); only the last segment can see computeRayKeys' termination tests fire.  Marks
+// go to the dense window exactly as in k_walk_dense.
+template <bool kFilter>
+__global__ void __launch_bounds__(256)
+k_walk_segments(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz,
+                int variant) {
+  __shared__ uint32_t base_s[kLenBins + 1];
+  for (int k = threadIdx.x; k <= kLenBins; k += blockDim.x) base_s[k] = sb.seg_base[k];
+  __syncthreads();
+  const uint32_t total = base_s[kLenBins];
+  uint32_t emitted = 0, longest = 0;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
+    // level of the slot: largest j with base_s[j] <= slot
+    uint32_t lo = 0, hi = kLenBins;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (base_s[mid] <= slot) lo = mid; else hi = mid;
+    }
+    const uint32_t j = lo, r = slot - base_s[lo];
+    const Checkpoint cp = sb.ckpt[slot];
+    if (cp.count == 0xFFFFFFFFu) continue;
+    const RayRec rr = sb.ray_rec[r];
+    RayWalk w;
+    w.c0 = cp.c01 & 0xFFFFu; w.c1 = cp.c01 >> 16; w.c2 = cp.c2;
+    w.e0 = rr.e01 & 0xFFFFu; w.e1 = rr.e01 >> 16; w.e2 = rr.e2s & 0xFFFFu;
+    const uint32_t sc = rr.e2s >> 16;
+    w.s0 = (sc & 3u) == 1u ? 1 : ((sc & 3u) == 2u ? -1 : 0);
+    w.s1 = ((sc >> 2) & 3u) == 1u ? 1 : (((sc >> 2) & 3u) == 2u ? -1 : 0);
+    w.s2 = ((sc >> 4) & 3u) == 1u ? 1 : (((sc >> 4) & 3u) == 2u ? -1 : 0);
+    w.t0 = cp.t0; w.t1 = cp.t1; w.t2 = cp.t2;
+    w.dt0 = rr.dt0; w.dt1 = rr.dt1; w.dt2 = rr.dt2;
+    w.dlen = rr.dlen;
+    w.live = true;
+    w.pick();
+    const bool last = (j + 1 == rr.n_seg);
+    const double tau_end = __dmul_rn((double)(j + 1), rr.dtau);
+    uint32_t count = cp.count;
+    const uint32_t count0 = count;
+    bool pending = (j == 0);            // the origin voxel belongs to segment 0
+    uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0;
+    for (;;) {
+      if (pending && (!kFilter || free_filter_pass(P, ox, oy, oz, w.c0, w.c1, w.c2))) {
+        const uint32_t idx = window_index(ms, w.c0, w.c1, w.c2);
+        if (idx == kNotFound) {   // outside the window: the host re-runs the scan in table mode
+          atomicExch(&cnt->overflow_window, 1u);
+          break;
+        }
+        const uint32_t l = local_index(w.c0, w.c1, w.c2);
+        const uint32_t wi = (idx << 4) | (l >> 5);
+        if (wi != cur) {
+          if ((bits & ~seen) && variant != 1) atomicOr(ms.free_mask + cur, bits);
+          bits = 0;
+          if ((wi >> 4) != (cur >> 4)) {
+            uint32_t* tb = ms.touched_bits + (idx >> 5);
+            if (!((*tb >> (idx & 31u)) & 1u)) atomicOr(tb, 1u << (idx & 31u));
+          }
+          cur = wi;
+          seen = (variant == 0 || (variant == 3 && count < 48u)) ? ms.free_mask[wi] : 0u;
+        }
+        bits |= 1u << (l & 31u);
+      }
+      if (!last && !(w.tmin() < tau_end)) break;   // the next step belongs to the next segment
+      if (!w.advance()) break;                     // cur == end, or min(tMax) > length
+      if (count >= kKeyRayMax - 1u) break;         // KeyRay capacity
+      ++count;
+      pending = true;
+    }
+    if ((bits & ~seen) && variant != 1) atomicOr(ms.free_mask + cur, bits);
+    emitted += count - count0 + (j == 0 ? 1u : 0u);
+    if (last) longest = max(longest, count);
+  }
+  uint32_t sum = emitted, mx = longest;
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+  }
+  if ((threadIdx.x & 31u) == 0 && sum) {
+    atomicAdd(&cnt->traversals, (unsigned long long)sum);
+    atomicMax(&cnt->longest_ray, mx);
+  }
+}
+
+// Compact the window's touched bitmap into the block list (cnt->n_touched entries).
+__global__ void __launch_bounds__(256) k_list_touched(MarkSet ms, Counters* cnt, uint32_t n_words) {
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t wbase = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; wbase < n_words;
+       wbase += gridDim.x * blockDim.x) {
+    const uint32_t wi = wbase + lane;
+    const uint32_t v = wi < n_words ? ms.touched_bits[wi] : 0u;
+    const uint32_t c = __popc(v);
+    uint32_t incl = c;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= (uint32_t)o) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (!total) continue;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&cnt->n_touched, total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    uint32_t pos = base + incl - c;
+    uint32_t rest = v;
+    while (rest) {
+      const uint32_t b = __ffs(rest) - 1;
+      rest &= rest - 1;
+      if (pos < ms.list_cap) ms.list[pos] = wi * 32u + b;
+      else atomicExch(&cnt->overflow_keys, 1u);   // list too small: the host grows it
+      ++pos;
+    }
+  }
+}
+
+// Table entry of every listed window block (inserted when new).
+__global__ void __launch_bounds__(256) k_locate_blocks(MarkSet ms, MapView m, Counters* cnt) {
+  if (cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
+  const uint32_t n = cnt->n_touched;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    ms.locate[t] = find_or_insert(m, cnt, window_block_key(ms, ms.list[t]));
+}
+
 // updateOccupancy on explicit key lists (vmap_apply_keys): mark phase.
 __global__ void __launch_bounds__(256)
 k_mark_keys(MapView m, Counters* cnt, const uint16_t* __restrict__ k3, uint32_t n, int occupied) {
@@ -352,18 +699,19 @@ k_mark_keys(MapView m, Counters* cnt, const uint16_t* __restrict__ k3, uint32_t 
 
 // Parity hook: expand this scan's masks into explicit key lists (before k_update clears them).
 __global__ void __launch_bounds__(256)
-k_capture_keys(MapView m, Counters* cnt, uint16_t* __restrict__ free_k3, uint32_t* n_free,
+k_capture_keys(MapView m, MarkSet ms, Counters* cnt, uint16_t* __restrict__ free_k3, uint32_t* n_free,
                uint32_t free_cap, uint16_t* __restrict__ occ_k3, uint32_t* n_occ, uint32_t occ_cap) {
+  if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < cnt->n_touched; t += warps) {
-    const uint32_t h = m.touched[t];
-    const unsigned long long b = m.keys[h] >> kEpochBits;
+    uint32_t e, h;
+    const unsigned long long b = listed_block(ms, m, t, &e, &h);
     const uint32_t bx = (uint32_t)(b & 0x1FFFu) << 3, by = (uint32_t)((b >> 13) & 0x1FFFu) << 3,
                    bz = (uint32_t)((b >> 26) & 0x1FFFu) << 3;
     for (int j = 0; j < kMaskWords; j++) {
-      const uint32_t o = m.occ_mask[(size_t)h * kMaskWords + j];
-      const uint32_t f = m.free_mask[(size_t)h * kMaskWords + j] & ~o;
+      const uint32_t o = ms.occ_mask[(size_t)e * kMaskWords + j];
+      const uint32_t f = ms.free_mask[(size_t)e * kMaskWords + j] & ~o;
       const uint32_t l = (uint32_t)j * 32u + lane;
       const uint32_t kx = bx + (l & 7u), ky = by + ((l >> 3) & 7u), kz = bz + (l >> 6);
       if ((o >> lane) & 1u) {
@@ -380,9 +728,9 @@ k_capture_keys(MapView m, Counters* cnt, uint16_t* __restrict__ free_k3, uint32_
 // K4: one warp per touched block.  free \ occupied, one clamped update per marked voxel
 // (occupied: +hit, free: +miss), masks cleared.  Every voxel has exactly one writer.
 __global__ void __launch_bounds__(256)
-k_update(DevParams P, MapView m, Counters* cnt) {
+k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
   // Abort the whole scan's update (uniformly) when a map structure must grow first.
-  if (cnt->overflow_table) return;
+  if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
   // every entry owns a slot (single GPU); a sharded table also lists foreign blocks, so bound
   // the slots by what this update can add at most
   const uint32_t slots_bound = m.sharded ? m.persist->n_slots + cnt->n_touched : m.persist->n_entries;
@@ -395,7 +743,18 @@ k_update(DevParams P, MapView m, Counters* cnt) {
   const uint32_t n_touched = cnt->n_touched;
   uint32_t n_free = 0, n_occ = 0;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_touched; t += warps) {
-    const uint32_t h = m.touched[t];
+    uint32_t e, h;
+    listed_block(ms, m, t, &e, &h);
+    uint32_t f = 0, o = 0;
+    if (lane < kMaskWords) {
+      uint32_t* pf = ms.free_mask + (size_t)e * kMaskWords + lane;
+      uint32_t* po = ms.occ_mask + (size_t)e * kMaskWords + lane;
+      f = *pf; o = *po;
+      if (f) *pf = 0u;
+      if (o) *po = 0u;
+      f &= ~o;  // occupied wins (octomap_world.cc:252-254)
+    }
+    if (!__any_sync(0xFFFFFFFFu, (f | o) != 0u)) continue;   // e.g. every voxel filtered out
     uint32_t slot = 0;
     if (lane == 0) {
       slot = m.slot[h];
@@ -405,15 +764,6 @@ k_update(DevParams P, MapView m, Counters* cnt) {
       }
     }
     slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
-    uint32_t f = 0, o = 0;
-    if (lane < kMaskWords) {
-      uint32_t* pf = m.free_mask + (size_t)h * kMaskWords + lane;
-      uint32_t* po = m.occ_mask + (size_t)h * kMaskWords + lane;
-      f = *pf; o = *po;
-      if (f) *pf = 0u;
-      if (o) *po = 0u;
-      f &= ~o;  // occupied wins (octomap_world.cc:252-254)
-    }
     uint32_t* vox = reinterpret_cast<uint32_t*>(m.pool) + (size_t)slot * kBlockVoxels;
 #pragma unroll
     for (int j = 0; j < kMaskWords; j++) {
@@ -434,13 +784,32 @@ k_update(DevParams P, MapView m, Counters* cnt) {
   }
 }
 
-// Drop this scan's marks (used when a scan has to be re-run on a grown table).
-__global__ void __launch_bounds__(256) k_clear_masks(MapView m, Counters* cnt) {
+// Drop this scan's marks (used when a scan has to be re-run after a grow).
+__global__ void __launch_bounds__(256) k_clear_masks(MapView m, MarkSet ms, Counters* cnt) {
   const uint32_t total = cnt->n_touched * kMaskWords;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const uint32_t h = m.touched[i / kMaskWords];
-    m.free_mask[(size_t)h * kMaskWords + (i % kMaskWords)] = 0u;
-    m.occ_mask[(size_t)h * kMaskWords + (i % kMaskWords)] = 0u;
+    const uint32_t e = ms.list[i / kMaskWords];
+    ms.free_mask[(size_t)e * kMaskWords + (i % kMaskWords)] = 0u;
+    ms.occ_mask[(size_t)e * kMaskWords + (i % kMaskWords)] = 0u;
+  }
+}
+
+// Dense window: drop every mark by walking the touched bitmap itself (the list may be
+// incomplete when this runs), then the bitmap.
+__global__ void __launch_bounds__(256) k_clear_window(MarkSet ms, uint32_t n_words) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < n_words; wi += warps) {
+    uint32_t v = ms.touched_bits[wi];
+    while (v) {
+      const uint32_t b = __ffs(v) - 1;
+      v &= v - 1;
+      const size_t e = (size_t)wi * 32u + b;
+      if (lane < kMaskWords) ms.free_mask[e * kMaskWords + lane] = 0u;
+      else ms.occ_mask[e * kMaskWords + lane - kMaskWords] = 0u;
+    }
+    __syncwarp();
+    if (lane == 0) ms.touched_bits[wi] = 0u;
   }
 }
 

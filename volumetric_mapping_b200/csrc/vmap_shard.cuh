@@ -39,34 +39,35 @@ struct PackView {
 };
 
 // pass 1: how many touched blocks with a non-empty mask go to each destination
-__global__ void __launch_bounds__(256) k_pack_count(MapView m, Counters* cnt, PackView pv) {
-  if (cnt->overflow_table) return;
+__global__ void __launch_bounds__(256) k_pack_count(MapView m, MarkSet ms, Counters* cnt, PackView pv) {
+  if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_touched = cnt->n_touched;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_touched; t += warps) {
-    const uint32_t h = m.touched[t];
-    const uint32_t wv = (lane < kMaskWords) ? m.free_mask[(size_t)h * kMaskWords + lane]
-                                            : m.occ_mask[(size_t)h * kMaskWords + lane - kMaskWords];
+    const uint32_t e = ms.list[t];
+    const uint32_t wv = (lane < kMaskWords) ? ms.free_mask[(size_t)e * kMaskWords + lane]
+                                            : ms.occ_mask[(size_t)e * kMaskWords + lane - kMaskWords];
     if (!__any_sync(0xFFFFFFFFu, wv != 0u)) continue;
-    if (lane == 0) atomicAdd(pv.counts + owner_of(m.keys[h] >> kEpochBits, pv.world), 1u);
+    const unsigned long long b = ms.dense ? window_block_key(ms, e) : (m.keys[e] >> kEpochBits);
+    if (lane == 0) atomicAdd(pv.counts + owner_of(b, pv.world), 1u);
   }
 }
 
 // pass 2: write the records (bucket offsets = exclusive prefix of counts) and clear the masks
-__global__ void __launch_bounds__(256) k_pack_write(MapView m, Counters* cnt, PackView pv) {
-  if (cnt->overflow_table) return;
+__global__ void __launch_bounds__(256) k_pack_write(MapView m, MarkSet ms, Counters* cnt, PackView pv) {
+  if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_touched = cnt->n_touched;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_touched; t += warps) {
-    const uint32_t h = m.touched[t];
-    uint32_t* src = (lane < kMaskWords) ? m.free_mask + (size_t)h * kMaskWords + lane
-                                        : m.occ_mask + (size_t)h * kMaskWords + lane - kMaskWords;
+    const uint32_t e = ms.list[t];
+    uint32_t* src = (lane < kMaskWords) ? ms.free_mask + (size_t)e * kMaskWords + lane
+                                        : ms.occ_mask + (size_t)e * kMaskWords + lane - kMaskWords;
     const uint32_t wv = *src;
     if (!__any_sync(0xFFFFFFFFu, wv != 0u)) continue;
     if (wv) *src = 0u;
-    const unsigned long long b = m.keys[h] >> kEpochBits;
+    const unsigned long long b = ms.dense ? window_block_key(ms, e) : (m.keys[e] >> kEpochBits);
     uint32_t pos = 0;
     if (lane == 0) {
       const uint32_t dest = owner_of(b, pv.world);

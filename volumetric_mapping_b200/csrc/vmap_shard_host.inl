@@ -81,27 +81,57 @@ PackView pack_view(vmap* h) {
   return pv;
 }
 
-// K1..K2 for one scan with the table-overflow retry, marks left in the table's mask columns.
+// K1..K2 for one scan with the grow-and-retry protocol; the marks are left in h->ms (dense
+// window or the table's mask columns) together with the list of touched blocks.
 template <class Mark>
-int generate_marks(vmap* h, size_t n_points, Mark&& mark) {
+int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
   VM_TRY(next_epoch(h));
   uint64_t retries = 0;
   float ms_total = 0.f;
+  bool dense = origin && setup_dense_marks(h, origin);
+  if (!dense) use_table_marks(h);
+  auto launch_list = [&]() -> int {
+    const unsigned grid = (unsigned)std::min<uint64_t>((h->win.n_words + 255) / 256, (uint64_t)g_sm_count(h->device) * 8);
+    k_list_touched<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->ms, h->d_cnt, h->win.n_words);
+    h->launches++;
+    VM_CUDA(h, cudaGetLastError());
+    return VMAP_OK;
+  };
   for (;;) {
     VM_TRY(begin_scan_scratch(h, n_points));
     for (bool& b : h->evk_set) b = false;
     VM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
     VM_TRY(mark_stage(h, 0));
     VM_TRY(mark());
+    if (dense) VM_TRY(launch_list());
     VM_TRY(mark_stage(h, 3));
     VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     VM_TRY(read_counters(h));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     ms_total += ms;
-    if (!h->h_cnt->overflow_table) break;
-    VM_TRY(clear_marks(h));
-    VM_TRY(grow_table(h));
+    if (dense) {
+      if (h->h_cnt->overflow_ckpt) {
+        VM_TRY(clear_window_marks(h));
+        VM_TRY(grow_checkpoints(h));
+      } else if (h->h_cnt->overflow_window) {
+        VM_TRY(clear_window_marks(h));
+        h->dense_fallbacks++;
+        dense = false;
+        use_table_marks(h);
+      } else if (h->h_cnt->overflow_keys) {
+        VM_TRY(grow_window_list(h, std::max<uint32_t>(h->h_cnt->n_touched + (h->h_cnt->n_touched >> 2), 2 * h->win.list_cap)));
+        h->ms.list = h->win.list; h->ms.locate = h->win.locate; h->ms.list_cap = h->win.list_cap;
+        VM_TRY(clear_window_marks(h));   // simplest: regenerate the scan with the larger list
+      } else {
+        break;
+      }
+    } else {
+      if (!h->h_cnt->overflow_table) break;
+      VM_TRY(clear_marks(h));
+      VM_TRY(grow_table(h));
+      use_table_marks(h);
+    }
     if (++retries > 40) return fail(h, VMAP_ERR_CAPACITY, "scan could not be generated after repeated growth");
   }
   const Counters& c = *h->h_cnt;
@@ -134,8 +164,9 @@ int pack_marks(vmap* h) {
   VM_CUDA(h, cudaMemsetAsync(h->d_pack_counts, 0, 2 * kMaxRanks * sizeof(uint32_t), h->stream));
   PackView pv = pack_view(h);
   const unsigned grid = g_sm_count(h->device) * 8;
-  k_pack_count<<<grid, 256, 0, h->stream>>>(h->m, h->d_cnt, pv);
-  k_pack_write<<<grid, 256, 0, h->stream>>>(h->m, h->d_cnt, pv);
+  k_pack_count<<<grid, 256, 0, h->stream>>>(h->m, h->ms, h->d_cnt, pv);
+  k_pack_write<<<grid, 256, 0, h->stream>>>(h->m, h->ms, h->d_cnt, pv);
+  if (h->ms.dense) VM_CUDA(h, cudaMemsetAsync(h->win.touched_bits, 0, (size_t)h->win.n_words * 4, h->stream));
   h->launches += 2;
   VM_CUDA(h, cudaGetLastError());
   VM_CUDA(h, cudaMemcpyAsync(h->h_pack_counts, h->d_pack_counts, kMaxRanks * sizeof(uint32_t),
@@ -155,7 +186,7 @@ int shard_generate_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride,
   h->stats.points_in = n;
   std::memset(h->h_pack_counts, 0, kMaxRanks * sizeof(uint32_t));
   if (n) {
-    VM_TRY(generate_marks(h, n, [&]() -> int {
+    VM_TRY(generate_marks(h, n, T.origin, [&]() -> int {
       k_front_cloud<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, d_in, (uint32_t)n,
                                                             (uint32_t)stride, is_dense);
       h->launches++;
@@ -178,6 +209,7 @@ int shard_apply_lists(vmap* h, const BlockRecord* const* lists, const size_t* co
   // every record adds at most one table entry and one pool slot
   while (((uint64_t)h->h_persist->n_entries + total) * 2 > h->table_cap) VM_TRY(grow_table(h));
   if ((uint64_t)h->h_persist->n_slots + total > h->pool_cap) VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_slots + total));
+  use_table_marks(h);   // received records are OR-ed into the table's mask columns
   VM_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
   VM_CUDA(h, cudaEventRecord(h->evk[3], h->stream));
   uint64_t touched = 0;

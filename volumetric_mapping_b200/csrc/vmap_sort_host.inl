@@ -52,8 +52,9 @@ int launch_resolve_and_sort(vmap* h, size_t n, const Transform& T) {
   SortBuffers& s = h->sort;
   VM_TRY(sort_ensure(h, 0, n));
   VM_TRY(mark_stage(h, 1));
-  k_resolve<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, h->m, h->d_cnt, (uint32_t)n, 0);
-  h->launches++;
+  k_resolve<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, h->m, h->ms, h->d_cnt, (uint32_t)n, 0);
+  k_order_rays<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, (uint32_t)n);
+  h->launches += 2;
   VM_CUDA(h, cudaGetLastError());
   VM_TRY(mark_stage(h, 2));
   // emit, pass 1: per-ray key counts and slots

@@ -45,14 +45,15 @@ class OctomapWorld:
     """GPU-resident OctomapWorld (insertion + point/line queries)."""
 
     def __init__(self, params=None, device=-1, dedupe_mode=DEDUPE_BITMASK, initial_blocks=0,
-                 max_blocks=0, **param_overrides):
+                 max_blocks=0, dense_window_bytes=0, **param_overrides):
         self._L = _capi.lib()
         if params is None:
             params = _capi.default_params(**param_overrides)
         elif param_overrides:
             raise TypeError("pass either params or keyword overrides")
         cfg = _capi.default_config(device=device, dedupe_mode=dedupe_mode,
-                                   initial_blocks=initial_blocks, max_blocks=max_blocks)
+                                   initial_blocks=initial_blocks, max_blocks=max_blocks,
+                                   dense_window_bytes=dense_window_bytes)
         h = C.c_void_p()
         st = self._L.vmap_create(C.byref(params), C.byref(cfg), C.byref(h))
         if st != 0:
