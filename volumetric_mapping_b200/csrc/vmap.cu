@@ -86,7 +86,7 @@ struct vmap {
   } win;
   MarkSet ms{};                 // marks of the scan in flight (table or dense mode)
   uint64_t dense_fallbacks = 0;
-  int walk_variant = 0;   // experiments (VMAP_WALK_VARIANT)
+  int walk_variant = 48;  // near-field limit of the walker's read-before-RED filter (VMAP_WALK_VARIANT)
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
   size_t ckpt_want = 0;   // checkpoint capacity to allocate with the scan scratch
 

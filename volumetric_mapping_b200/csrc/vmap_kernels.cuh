@@ -327,11 +327,18 @@ k_resolve(ScanBuffers sb, MapView m, MarkSet ms, Counters* cnt, uint32_t n, int 
       sb.flags[i] |= 8u;   // kFlagOcc (vmap_sort.cuh): emitted as a packed key by the sort mode
   }
   // cast-ray work list, pass 1: position of the ray inside its length bin
+  // (only a handful of bins are populated: one atomic per distinct bin per warp)
+  const unsigned cast_b = __ballot_sync(0xFFFFFFFFu, cast);
   if (cast) {
     sb.flags[i] |= kFlagCast;
-    sb.rank[i] = atomicAdd(sb.len_hist + ray_bin(sb, i), 1u);
+    const uint32_t bin = ray_bin(sb, i);
+    const unsigned peers = __match_any_sync(cast_b, bin);
+    const uint32_t lane_ = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane_ == (uint32_t)(__ffs(peers) - 1)) base = atomicAdd(sb.len_hist + bin, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, __ffs(peers) - 1);
+    sb.rank[i] = base + __popc(peers & ((1u << lane_) - 1u));
   }
-  const unsigned cast_b = __ballot_sync(0xFFFFFFFFu, cast);
   const unsigned occ_b = __ballot_sync(0xFFFFFFFFu, occ);
   if ((threadIdx.x & 31u) == 0 && cast_b) {
     atomicAdd(&cnt->n_rays, (uint32_t)__popc(cast_b));
@@ -607,26 +614,42 @@ k_walk_segments(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox
     const double tau_end = __dmul_rn((double)(j + 1), rr.dtau);
     uint32_t count = cp.count;
     const uint32_t count0 = count;
+    // Every voxel of the ray lies between the segment's first voxel and the ray's end voxel
+    // (each key coordinate moves monotonically; one voxel of slack for a walk that misses the
+    // end voxel): one window test per segment instead of one per step.
+    {
+      const int lo0 = (int)min(w.c0, w.e0) - 1, hi0 = (int)max(w.c0, w.e0) + 1;
+      const int lo1 = (int)min(w.c1, w.e1) - 1, hi1 = (int)max(w.c1, w.e1) + 1;
+      const int lo2 = (int)min(w.c2, w.e2) - 1, hi2 = (int)max(w.c2, w.e2) + 1;
+      const bool inside = ((lo0 >> 3) >= ms.x0) && ((hi0 >> 3) < ms.x0 + (int)ms.nx) && ((lo1 >> 3) >= ms.y0) &&
+                          ((hi1 >> 3) < ms.y0 + (int)ms.ny) && ((lo2 >> 3) >= ms.z0) && ((hi2 >> 3) < ms.z0 + (int)ms.nz);
+      if (!inside) {   // the host re-runs the scan in table mode
+        atomicExch(&cnt->overflow_window, 1u);
+        continue;
+      }
+    }
     bool pending = (j == 0);            // the origin voxel belongs to segment 0
-    uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0;
+    // cur: mask word in flight (window block * 16 + word), bits: voxels collected for it,
+    // seen: its value when the ray entered it (near the sensor, where every ray sets the same
+    // voxels: a RED is only issued for bits not visible yet), tbv: the block's word of the
+    // touched bitmap, read when the ray entered the block.  Both loads are issued on entry and
+    // consumed when the ray leaves the word, a few steps later.  Stale values cost a redundant
+    // RED, never a lost bit.
+    uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0, tbv = 0xFFFFFFFFu;
+    const uint32_t near_limit = (variant == 0) ? 0xFFFFFFFFu : (variant == 2 ? 0u : (uint32_t)variant);
     for (;;) {
       if (pending && (!kFilter || free_filter_pass(P, ox, oy, oz, w.c0, w.c1, w.c2))) {
-        const uint32_t idx = window_index(ms, w.c0, w.c1, w.c2);
-        if (idx == kNotFound) {   // outside the window: the host re-runs the scan in table mode
-          atomicExch(&cnt->overflow_window, 1u);
-          break;
-        }
+        const uint32_t idx = (((w.c2 >> 3) - (uint32_t)ms.z0) * ms.ny + ((w.c1 >> 3) - (uint32_t)ms.y0)) * ms.nx +
+                             ((w.c0 >> 3) - (uint32_t)ms.x0);
         const uint32_t l = local_index(w.c0, w.c1, w.c2);
         const uint32_t wi = (idx << 4) | (l >> 5);
         if (wi != cur) {
-          if ((bits & ~seen) && variant != 1) atomicOr(ms.free_mask + cur, bits);
+          if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
+          if (!((tbv >> ((cur >> 4) & 31u)) & 1u)) atomicOr(ms.touched_bits + (cur >> 9), 1u << ((cur >> 4) & 31u));
+          tbv = ((wi >> 4) != (cur >> 4)) ? ms.touched_bits[idx >> 5] : 0xFFFFFFFFu;
           bits = 0;
-          if ((wi >> 4) != (cur >> 4)) {
-            uint32_t* tb = ms.touched_bits + (idx >> 5);
-            if (!((*tb >> (idx & 31u)) & 1u)) atomicOr(tb, 1u << (idx & 31u));
-          }
           cur = wi;
-          seen = (variant == 0 || (variant == 3 && count < 48u)) ? ms.free_mask[wi] : 0u;
+          seen = (count < near_limit) ? ms.free_mask[wi] : 0u;
         }
         bits |= 1u << (l & 31u);
       }
@@ -636,7 +659,8 @@ k_walk_segments(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox
       ++count;
       pending = true;
     }
-    if ((bits & ~seen) && variant != 1) atomicOr(ms.free_mask + cur, bits);
+    if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
+    if (!((tbv >> ((cur >> 4) & 31u)) & 1u)) atomicOr(ms.touched_bits + (cur >> 9), 1u << ((cur >> 4) & 31u));
     emitted += count - count0 + (j == 0 ? 1u : 0u);
     if (last) longest = max(longest, count);
   }

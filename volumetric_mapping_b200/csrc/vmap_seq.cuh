@@ -83,20 +83,19 @@ VMAP_HD uint64_t seq_advance(double* t_io, double dt, double tau, uint64_t max_s
     if (e1 != e2 || e2 != e3 || e3 == 0 || e3 >= 0x7FE) continue;
     const uint64_t q = b3 - b2;                 // increment in ulps (same exponent: plain integer difference)
     if (q == 0) continue;
-    // elements b3 + j*q, j >= 1, stay in the binade while b3 + j*q <= top
+    // Elements b3 + j*q (j >= 1) stay in the binade while <= top and are below tau while
+    // <= bits(tau) - 1 (when tau lies in this binade).  Take the largest j with b3 + j*q <= lim,
+    // plus one when that lands on the first element >= tau that is still inside the binade.
     const uint64_t top = (b3 | 0x000FFFFFFFFFFFFFull);
-    uint64_t j = (top - b3) / q;
-    // ... and below tau: when tau lies in this binade (or below its top), b < bits(tau)
     const uint64_t bt = seq_bits(tau);
-    if (tau > 0 && bt <= top) {                 // tau inside this binade (tau > t3 here)
-      const uint64_t jt = (bt - 1 - b3) / q;    // largest j with b3 + j*q <= bt - 1, i.e. < tau
-      // elements 1..jt are < tau and get consumed; element jt+1 (if in the binade) is >= tau.
-      // Consume up to jt elements beyond t3 -> new current is element jt+1 only if it stays in
-      // the binade; otherwise stop at the binade edge and let the real additions finish.
-      if (jt < j) j = jt + 1 <= j ? jt + 1 : j;
-    }
-    // j = number of integer steps to take now: elements t3 .. t3+(j-1)q are consumed, current
-    // becomes t3 + j*q.  Every consumed element must be < tau: elements up to index j-1.
+    const bool tau_here = (tau > 0 && bt <= top);     // tau > t3 here, so it is in this binade
+    const uint64_t lim = tau_here ? bt - 1 : top;
+    // one division, done in double (both operands < 2^52 are exact) and corrected exactly
+    const uint64_t num = lim - b3;
+    uint64_t j = (uint64_t)((double)num / (double)q);
+    while (j * q > num) --j;
+    while ((j + 1) * q <= num) ++j;
+    if (tau_here && b3 + (j + 1) * q <= top) ++j;     // step onto the first element >= tau
     if (j == 0) continue;
     if (j > max_steps - n) j = max_steps - n;
     t = seq_from_bits(b3 + j * q);
