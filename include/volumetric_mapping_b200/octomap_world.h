@@ -1,0 +1,181 @@
+// octomap_world.h -- host-side mirror of volumetric_mapping::OctomapWorld for the scan-insertion
+// path, implemented on the C ABI of libvmap_b200.so (include/vmap/vmap.h).  Reference:
+// octomap_world/include/octomap_world/octomap_world.h:54-328 and
+// octomap_world/src/octomap_world.cc:50-264,346-360,395-418.  Header-only; link with
+// -lvmap_b200.  There is no CPU fallback: construction throws when no CUDA device is usable.
+#ifndef VOLUMETRIC_MAPPING_B200_OCTOMAP_WORLD_H_
+#define VOLUMETRIC_MAPPING_B200_OCTOMAP_WORLD_H_
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "vmap/vmap.h"
+#include "volumetric_mapping_b200/world_base.h"
+
+namespace volumetric_mapping {
+
+using compat::KeySet;
+using compat::OcTreeKey;
+
+// octomap_world.h:54-109 -- identical fields and defaults.
+struct OctomapParameters {
+  OctomapParameters()
+      : resolution(0.15), probability_hit(0.65), probability_miss(0.4), threshold_min(0.12),
+        threshold_max(0.97), threshold_occupancy(0.7), filter_speckles(true), max_free_space(0.0),
+        min_height_free_space(0.0), sensor_max_range(5.0),
+        visualize_min_z(-std::numeric_limits<double>::max()),
+        visualize_max_z(std::numeric_limits<double>::max()), treat_unknown_as_occupied(true),
+        change_detection_enabled(false) {}
+  double resolution, probability_hit, probability_miss, threshold_min, threshold_max, threshold_occupancy;
+  bool filter_speckles;
+  double max_free_space, min_height_free_space, sensor_max_range, visualize_min_z, visualize_max_z;
+  bool treat_unknown_as_occupied;
+  bool change_detection_enabled;
+};
+
+class OctomapWorld : public WorldBase {
+ public:
+  typedef std::shared_ptr<OctomapWorld> Ptr;
+
+  OctomapWorld() : handle_(nullptr) { create(OctomapParameters()); }                       // octomap_world.cc:50-51
+  explicit OctomapWorld(const OctomapParameters& params) : handle_(nullptr) { create(params); }  // :53-56
+  OctomapWorld(const OctomapWorld&) = delete;   // the reference deep-copies through a .bt stream (:59-73): use exportLeaves/importLeaves
+  OctomapWorld& operator=(const OctomapWorld&) = delete;
+  virtual ~OctomapWorld() { vmap_destroy(handle_); }
+
+  void resetMap() { check(vmap_reset(handle_)); }                                           // :75-80
+  void setOctomapParameters(const OctomapParameters& params) {                              // :84-104
+    params_ = params;
+    vmap_params p = toC(params);
+    check(vmap_set_params(handle_, &p));
+  }
+  void getOctomapParameters(OctomapParameters* params) const { *params = params_; }         // :106-108
+  void enableTreatUnknownAsOccupied() { params_.treat_unknown_as_occupied = true; setOctomapParameters(params_); }
+  void disableTreatUnknownAsOccupied() { params_.treat_unknown_as_occupied = false; setOctomapParameters(params_); }
+  virtual double getResolution() const { return params_.resolution; }
+
+  // octomap_world.cc:346-360
+  virtual CellStatus getCellStatusPoint(const Vector3d& point) const {
+    uint8_t s = 0;
+    check(vmap_query_points(handle_, point.v, 1, &s));
+    return static_cast<CellStatus>(s);
+  }
+  // octomap_world.cc:395-418
+  virtual CellStatus getLineStatus(const Vector3d& start, const Vector3d& end) const {
+    const double ab[6] = {start.x(), start.y(), start.z(), end.x(), end.y(), end.z()};
+    uint8_t s = 0;
+    check(vmap_query_lines(handle_, ab, 1, &s));
+    return static_cast<CellStatus>(s);
+  }
+  // Batched forms of the two queries (what planners call in bulk): one kernel launch.
+  void getCellStatusPoints(const std::vector<Vector3d>& points, std::vector<uint8_t>* status) const {
+    status->resize(points.size());
+    if (points.empty()) return;
+    check(vmap_query_points(handle_, points[0].v, points.size(), status->data()));
+  }
+  void getLineStatuses(const std::vector<Vector3d>& starts_ends /* start0,end0,start1,end1,... */,
+                       std::vector<uint8_t>* status) const {
+    status->resize(starts_ends.size() / 2);
+    if (status->empty()) return;
+    check(vmap_query_lines(handle_, starts_ends[0].v, status->size(), status->data()));
+  }
+
+  // updateOccupancy(KeySet*, KeySet*) (octomap_world.cc:238-264): protected in the reference but
+  // called from OctomapManager::loadOctomapCallback (octomap_manager.cc:332-341).
+  void updateOccupancy(KeySet* free_cells, KeySet* occupied_cells) {
+    if (!free_cells || !occupied_cells) throw std::invalid_argument("updateOccupancy: null key set");   // CHECK_NOTNULL :240-241
+    std::vector<uint16_t> f, o;
+    f.reserve(free_cells->size() * 3);
+    o.reserve(occupied_cells->size() * 3);
+    for (const OcTreeKey& k : *occupied_cells) {
+      o.push_back(k.k[0]); o.push_back(k.k[1]); o.push_back(k.k[2]);
+      free_cells->erase(k);                                                                              // :252-254
+    }
+    for (const OcTreeKey& k : *free_cells) { f.push_back(k.k[0]); f.push_back(k.k[1]); f.push_back(k.k[2]); }
+    check(vmap_apply_keys(handle_, f.data(), f.size() / 3, o.data(), o.size() / 3));
+  }
+
+  // On-demand export for the host-side publish / save paths (octomap_world.cc:820-856).
+  void exportLeaves(std::vector<OcTreeKey>* keys, std::vector<float>* log_odds) const {
+    size_t n = 0;
+    check(vmap_leaf_count(handle_, &n));
+    std::vector<uint16_t> k3(n * 3);
+    log_odds->resize(n);
+    if (n) check(vmap_export_leaves(handle_, k3.data(), log_odds->data(), n, &n));
+    keys->resize(n);
+    for (size_t i = 0; i < n; i++) (*keys)[i] = OcTreeKey(k3[3 * i], k3[3 * i + 1], k3[3 * i + 2]);
+  }
+  void importLeaves(const std::vector<OcTreeKey>& keys, const std::vector<float>& log_odds) {
+    std::vector<uint16_t> k3(keys.size() * 3);
+    for (size_t i = 0; i < keys.size(); i++) { k3[3 * i] = keys[i].k[0]; k3[3 * i + 1] = keys[i].k[1]; k3[3 * i + 2] = keys[i].k[2]; }
+    check(vmap_import_leaves(handle_, k3.data(), log_odds.data(), keys.size()));
+  }
+
+  vmap_scan_stats lastScanStats() const {
+    vmap_scan_stats s;
+    check(vmap_last_scan_stats(handle_, &s));
+    return s;
+  }
+  vmap* handle() const { return handle_; }
+
+ protected:
+  // octomap_world.cc:110-141.  The reference mutates the caller's cloud in place (NaN filter,
+  // world-frame transform); so does this.
+  virtual void insertPointcloudIntoMapImpl(const Transformation& T_G_sensor,
+                                           const PointCloud<PointXYZ>::Ptr& pointcloud) {
+    const Matrix4d T = T_G_sensor.getTransformationMatrix();
+    size_t n_out = pointcloud->points.size();
+    float* xyz = pointcloud->points.empty() ? nullptr : &pointcloud->points[0].x;
+    check(vmap_insert_pointcloud(handle_, xyz, pointcloud->points.size(), sizeof(PointXYZ),
+                                 pointcloud->is_dense ? 1 : 0, T.m, xyz, &n_out));
+    if (!pointcloud->is_dense) {
+      pointcloud->points.resize(n_out);
+      pointcloud->width = (uint32_t)n_out;
+      pointcloud->height = 1;
+      pointcloud->is_dense = true;
+    }
+  }
+  // octomap_world.cc:143-175
+  virtual void insertProjectedDisparityIntoMapImpl(const Transformation& sensor_to_world,
+                                                   const Mat& projected_points) {
+    const Vector3d t = sensor_to_world.getPosition();
+    check(vmap_insert_projected(handle_, projected_points.data, projected_points.rows, projected_points.cols,
+                                projected_points.step, sensor_to_world.quaternion_wxyz(), t.v));
+  }
+  // world_base.cc:51-87 fused with the above on the device.
+  virtual void insertDisparityImageImpl(const Transformation& sensor_to_world, const Mat& disparity,
+                                        const Matrix4d& Q_full, const Vector2d& full_image_size) {
+    const Vector3d t = sensor_to_world.getPosition();
+    check(vmap_insert_disparity(handle_, disparity.data, disparity.rows, disparity.cols, disparity.step,
+                                Q_full.m, full_image_size.x(), sensor_to_world.quaternion_wxyz(), t.v));
+  }
+
+  OctomapParameters params_;
+
+ private:
+  static vmap_params toC(const OctomapParameters& q) {
+    vmap_params p;
+    vmap_default_params(&p);
+    p.resolution = q.resolution; p.probability_hit = q.probability_hit; p.probability_miss = q.probability_miss;
+    p.threshold_min = q.threshold_min; p.threshold_max = q.threshold_max; p.threshold_occupancy = q.threshold_occupancy;
+    p.filter_speckles = q.filter_speckles; p.max_free_space = q.max_free_space;
+    p.min_height_free_space = q.min_height_free_space; p.sensor_max_range = q.sensor_max_range;
+    p.visualize_min_z = q.visualize_min_z; p.visualize_max_z = q.visualize_max_z;
+    p.treat_unknown_as_occupied = q.treat_unknown_as_occupied; p.change_detection_enabled = q.change_detection_enabled;
+    return p;
+  }
+  void create(const OctomapParameters& params) {
+    params_ = params;
+    vmap_params p = toC(params);
+    const int st = vmap_create(&p, nullptr, &handle_);
+    if (st != VMAP_OK) throw std::runtime_error(std::string("OctomapWorld: ") + vmap_last_error(nullptr));
+  }
+  void check(int st) const {
+    if (st != VMAP_OK) throw std::runtime_error(std::string("OctomapWorld: ") + vmap_last_error(handle_));
+  }
+  vmap* handle_;
+};
+
+}  // namespace volumetric_mapping
+#endif  // VOLUMETRIC_MAPPING_B200_OCTOMAP_WORLD_H_
