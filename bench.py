@@ -316,7 +316,7 @@ def run_b200(args):
         scan_b = float(np.mean([algorithmic_bytes(s, n_pts) for s in st]))
         scan_ms = float(np.mean([s["gpu_ms"] for s in st]))
         ach = walk_b / (walk_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_walk_mask (K2 DDA walk + key-set build)",
+        roofline = {"bound": "hbm", "kernel": "K2 = k_checkpoints + k_walk_segments (+ list/locate): DDA walk + key-set build",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": walk_b, "avg_launch_ms": walk_ms,

@@ -98,7 +98,7 @@ class VmapError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB
+    return os.environ.get("VMAP_LIB") or _build.LIB   # VMAP_LIB: A/B experiments only
 
 
 def lib():
