@@ -3,6 +3,7 @@
 // Exits non-zero when a hand-derived known answer (tests/test_oracle_insertion.py) is not met.
 #include <cstdio>
 #include <cstdlib>
+#include <sstream>
 
 #include "volumetric_mapping_b200/octomap_world.h"
 
@@ -80,6 +81,15 @@ int main() {
   std::printf("demo ok: %llu valid pixels, %llu rays, %llu traversals, %.3f ms on the device\n",
               (unsigned long long)st.points_valid, (unsigned long long)st.rays_cast,
               (unsigned long long)st.traversals, st.gpu_ms);
+  // save / load round trip through the octomap binary format
+  std::ostringstream bt;
+  EXPECT(world.writeOctomapToBinaryConst(bt));
+  EXPECT(bt.str().compare(0, 28, "# Octomap OcTree binary file") == 0);
+  EXPECT(world.writeOctomapToFile("/tmp/vmap_demo.bt"));
+  OctomapWorld other;
+  EXPECT(other.loadOctomapFromFile("/tmp/vmap_demo.bt"));
+  std::ostringstream bt2;
+  EXPECT(other.writeOctomapToBinaryConst(bt2) && bt2.str() == bt.str());
   world.resetMap();
   world.exportLeaves(&keys, &lo);
   EXPECT(keys.empty());

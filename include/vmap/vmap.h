@@ -191,6 +191,22 @@ VMAP_API int vmap_export_leaves(vmap* h, uint16_t* keys_k3, float* logodds, size
 /* Inverse (loadOctomapFromFile / setOctomapFromMsg feed): sets leaf values, no clamping. */
 VMAP_API int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds, size_t n);
 
+/* On-demand export to octomap's tree form, built on the host from the finest-level leaves:
+ * canonical pruned tree (8 equal leaf children collapse; inner value = max of children). */
+/* octree_->prune(); octree_->size().  max_likelihood != 0: after toMaxLikelihood(). */
+VMAP_API int vmap_tree_size(vmap* h, int max_likelihood, size_t* n_nodes);
+/* OctomapWorld::writeOctomapToBinaryConst (octomap_world.cc:854-856): ".bt" stream into memory
+ * (buffer == NULL: size query). */
+VMAP_API int vmap_serialize_bt(vmap* h, uint8_t* buffer, size_t capacity, size_t* n_bytes);
+/* OctomapWorld::writeOctomapToFile (octomap_world.cc:849-852).  OcTree::writeBinary(filename)
+ * thresholds the LIVE tree to the clamping values before writing; pass threshold_live_map = 1
+ * for that side effect, 0 for the const variant. */
+VMAP_API int vmap_write_bt(vmap* h, const char* path, int threshold_live_map);
+/* OctomapWorld::loadOctomapFromFile (octomap_world.cc:846-848) / setOctomapFromMsg (binary)
+ * (:833-844): replaces the map (and its resolution) with the stream's. */
+VMAP_API int vmap_load_bt(vmap* h, const char* path);
+VMAP_API int vmap_deserialize_bt(vmap* h, const uint8_t* buffer, size_t n_bytes);
+
 /* Per-scan counters of the last insert / apply call. */
 VMAP_API int vmap_last_scan_stats(const vmap* h, vmap_scan_stats* stats);
 /* Parity hook: when enabled, the next inserts keep their final free / occupied key sets. */

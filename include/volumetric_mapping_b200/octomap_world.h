@@ -6,6 +6,7 @@
 #ifndef VOLUMETRIC_MAPPING_B200_OCTOMAP_WORLD_H_
 #define VOLUMETRIC_MAPPING_B200_OCTOMAP_WORLD_H_
 
+#include <ostream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -110,6 +111,25 @@ class OctomapWorld : public WorldBase {
     std::vector<uint16_t> k3(keys.size() * 3);
     for (size_t i = 0; i < keys.size(); i++) { k3[3 * i] = keys[i].k[0]; k3[3 * i + 1] = keys[i].k[1]; k3[3 * i + 2] = keys[i].k[2]; }
     check(vmap_import_leaves(handle_, k3.data(), log_odds.data(), keys.size()));
+  }
+
+  // octomap_world.cc:846-856.  writeOctomapToFile thresholds the live map like
+  // OcTree::writeBinary(filename) does (toMaxLikelihood + prune before writing).
+  bool loadOctomapFromFile(const std::string& filename) { return vmap_load_bt(handle_, filename.c_str()) == VMAP_OK; }
+  bool writeOctomapToFile(const std::string& filename) { return vmap_write_bt(handle_, filename.c_str(), 1) == VMAP_OK; }
+  bool writeOctomapToBinaryConst(std::ostream& s) const {
+    size_t n = 0;
+    if (vmap_serialize_bt(handle_, nullptr, 0, &n) != VMAP_OK) return false;
+    std::vector<uint8_t> buf(n ? n : 1);
+    if (vmap_serialize_bt(handle_, buf.data(), buf.size(), &n) != VMAP_OK) return false;
+    s.write(reinterpret_cast<const char*>(buf.data()), (std::streamsize)n);
+    return s.good();
+  }
+  // octree_->prune(); octree_->size()
+  size_t getNumNodesPruned() const {
+    size_t n = 0;
+    check(vmap_tree_size(handle_, 0, &n));
+    return n;
   }
 
   vmap_scan_stats lastScanStats() const {

@@ -115,6 +115,9 @@ def lib():
     L.oracle_last_occupied_keys.argtypes = [vp, vp]
     L.oracle_last_scan_stats.argtypes = [vp, C.POINTER(ScanStats)]
     L.oracle_export_leaves.argtypes = [vp, vp, vp]
+    L.oracle_prune.argtypes = [vp]
+    L.oracle_write_bt.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.oracle_write_bt.restype = C.c_size_t
     _lib = L
     return L
 
@@ -280,6 +283,19 @@ class OracleWorld:
 
     def tree_node_count(self):
         return int(self._L.oracle_tree_node_count(self._h))
+
+    def prune(self):
+        self._L.oracle_prune(self._h)
+
+    def write_bt(self, live=False):
+        n = self._L.oracle_write_bt(self._h, int(bool(live)), None, 0) if not live else None
+        if live:
+            buf = (C.c_ubyte * (1 << 26))()
+            n = self._L.oracle_write_bt(self._h, 1, buf, len(buf))
+            return bytes(buf[:n])
+        buf = (C.c_ubyte * max(1, n))()
+        self._L.oracle_write_bt(self._h, 0, buf, n)
+        return bytes(buf[:n])
 
 
 def reproject(disparity, Q):

@@ -47,6 +47,7 @@
 #include <cstring>
 #include <limits>
 #include <unordered_set>
+#include <string>
 #include <vector>
 
 namespace {
@@ -328,6 +329,37 @@ class OcTree {
     if (root) leafRecurs(root, 0, Key(0, 0, 0), f);
   }
 
+  // --- prune / toMaxLikelihood / writeBinary  [octomap OcTreeBaseImpl.hxx, OccupancyOcTreeBase.hxx,
+  //     AbstractOccupancyOcTree.cpp] -- behind writeOctomapToFile / writeOctomapToBinaryConst
+  //     (octomap_world.cc:849-856)
+  void prune() {
+    if (root == NULL) return;
+    for (unsigned depth = tree_depth - 1; depth > 0; --depth) {
+      unsigned num_pruned = 0;
+      pruneRecurs(root, 0, depth, num_pruned);
+      if (num_pruned == 0) break;
+    }
+  }
+  void toMaxLikelihood() {
+    if (root) toMaxLikelihoodRecurs(root, 0, tree_depth);
+  }
+  void writeBinaryConst(std::string& out) const {
+    char buf[256];
+    out += "# Octomap OcTree binary file\n# (feel free to add / change comments, but leave the first line as it is!)\n#\n";
+    out += "id OcTree\n";
+    snprintf(buf, sizeof(buf), "size %zu\n", tree_size);
+    out += buf;
+    snprintf(buf, sizeof(buf), "res %g\n", resolution);   // std::ostream << double: 6 significant digits
+    out += buf;
+    out += "data\n";
+    if (root) writeBinaryNode(out, root);
+  }
+  void writeBinary(std::string& out) {   // non-const: thresholds and prunes the live tree first
+    toMaxLikelihood();
+    prune();
+    writeBinaryConst(out);
+  }
+
   float prob_hit_log, prob_miss_log, clamping_thres_min, clamping_thres_max, occ_prob_thres_log;
 
  private:
@@ -396,6 +428,38 @@ class OcTree {
       }
     }
     return max;
+  }
+  void pruneRecurs(Node* node, unsigned depth, unsigned max_depth, unsigned& num_pruned) {
+    if (depth < max_depth) {
+      for (unsigned i = 0; i < 8; i++)
+        if (nodeChildExists(node, i)) pruneRecurs(node->children[i], depth + 1, max_depth, num_pruned);
+    } else {
+      if (pruneNode(node)) num_pruned++;
+    }
+  }
+  void toMaxLikelihoodRecurs(Node* node, unsigned depth, unsigned max_depth) {
+    if (depth < max_depth) {
+      for (unsigned i = 0; i < 8; i++)
+        if (nodeChildExists(node, i)) toMaxLikelihoodRecurs(node->children[i], depth + 1, max_depth);
+    }
+    node->value = isNodeOccupied(node) ? clamping_thres_max : clamping_thres_min;   // nodeToMaxLikelihood
+  }
+  // two bits per child: 10 free, 01 occupied, 00 unknown, 11 has children (bit 2i first)
+  void writeBinaryNode(std::string& out, const Node* node) const {
+    unsigned char b[2] = {0, 0};
+    for (unsigned i = 0; i < 8; i++) {
+      if (!nodeChildExists(node, i)) continue;
+      const Node* child = node->children[i];
+      unsigned two;
+      if (nodeHasChildren(child)) two = 3u;
+      else if (isNodeOccupied(child)) two = 2u;     // bit[2i] = 0, bit[2i+1] = 1
+      else two = 1u;                                // bit[2i] = 1, bit[2i+1] = 0
+      b[i >> 2] |= (unsigned char)(two << (2 * (i & 3u)));
+    }
+    out.push_back((char)b[0]);
+    out.push_back((char)b[1]);
+    for (unsigned i = 0; i < 8; i++)
+      if (nodeChildExists(node, i) && nodeHasChildren(node->children[i])) writeBinaryNode(out, node->children[i]);
   }
   void updateNodeLogOdds(Node* n, float update) const {
     n->value = n->value + update;
@@ -908,5 +972,17 @@ void oracle_export_leaves(const oracle_world* w, uint16_t* out_k3, float* out_lo
   });
 }
 size_t oracle_tree_node_count(const oracle_world* w) { return w->octree->size(); }
+
+void oracle_prune(oracle_world* w) { w->octree->prune(); }
+
+// writeOctomapToFile (live != 0: OcTree::writeBinary thresholds + prunes the live tree) or
+// writeOctomapToBinaryConst (live == 0) into a caller buffer; returns the stream size.
+size_t oracle_write_bt(oracle_world* w, int live, unsigned char* buf, size_t cap) {
+  std::string out;
+  if (live) w->octree->writeBinary(out);
+  else w->octree->writeBinaryConst(out);
+  if (buf && cap >= out.size()) std::memcpy(buf, out.data(), out.size());
+  return out.size();
+}
 
 }  // extern "C"

@@ -117,6 +117,11 @@ void oracle_last_scan_stats(const oracle_world* w, oracle_scan_stats* s);
 size_t oracle_leaf_count(const oracle_world* w);
 void oracle_export_leaves(const oracle_world* w, uint16_t* out_k3, float* out_logodds);
 size_t oracle_tree_node_count(const oracle_world* w);
+/* octree_->prune() (octomap_world.cc:82). */
+void oracle_prune(oracle_world* w);
+/* writeOctomapToFile (live != 0; thresholds and prunes the live tree like OcTree::writeBinary)
+ * or writeOctomapToBinaryConst (live == 0): ".bt" stream; returns its size (buf may be NULL). */
+size_t oracle_write_bt(oracle_world* w, int live, unsigned char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

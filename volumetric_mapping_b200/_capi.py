@@ -84,6 +84,7 @@ SYMBOLS = [
     "vmap_shard_query_points_dev", "vmap_shard_query_lines_dev", "vmap_dist_unique_id",
     "vmap_dist_init", "vmap_dist_shutdown", "vmap_dist_insert_pointcloud",
     "vmap_dist_insert_pointcloud_dev", "vmap_dist_query_points_dev", "vmap_dist_query_lines_dev",
+    "vmap_tree_size", "vmap_serialize_bt", "vmap_write_bt", "vmap_load_bt", "vmap_deserialize_bt",
 ]
 
 STATUS_NAMES = {0: "VMAP_OK", 1: "VMAP_ERR_INVALID_ARGUMENT", 2: "VMAP_ERR_CUDA",
@@ -148,6 +149,11 @@ def lib():
     L.vmap_device_bytes.argtypes = [vp]
     L.vmap_device_bytes.restype = C.c_uint64
     u64p = C.POINTER(C.c_uint64)
+    L.vmap_tree_size.argtypes = [vp, C.c_int, C.POINTER(sz)]
+    L.vmap_serialize_bt.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.vmap_write_bt.argtypes = [vp, C.c_char_p, C.c_int]
+    L.vmap_load_bt.argtypes = [vp, C.c_char_p]
+    L.vmap_deserialize_bt.argtypes = [vp, vp, sz]
     L.vmap_set_shard.argtypes = [vp, C.c_int, C.c_int]
     L.vmap_shard_owner.argtypes = [C.c_uint16, C.c_uint16, C.c_uint16, C.c_int]
     L.vmap_shard_owner.restype = C.c_uint32

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvmap_b200.so")
 SOURCES = ["vmap.cu"]
-DEPS = ["vmap.cu", "vmap_device.cuh", "vmap_kernels.cuh", "vmap_sort.cuh", "vmap_sort_host.inl", "vmap_shard.cuh", "vmap_seq.cuh", "vmap_shard_host.inl",
+DEPS = ["vmap.cu", "vmap_device.cuh", "vmap_kernels.cuh", "vmap_sort.cuh", "vmap_sort_host.inl", "vmap_shard.cuh", "vmap_seq.cuh", "vmap_export_host.inl", "vmap_shard_host.inl",
         os.path.join("..", "..", "include", "vmap", "vmap.h")]
 
 NVCC_FLAGS = [

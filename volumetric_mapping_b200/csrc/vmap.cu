@@ -1271,3 +1271,5 @@ uint64_t vmap_kernel_launches(const vmap* h) { return h ? h->launches : 0; }
 uint64_t vmap_device_bytes(const vmap* h) { return h ? h->dev_bytes : 0; }
 
 }  // extern "C"
+
+#include "vmap_export_host.inl"

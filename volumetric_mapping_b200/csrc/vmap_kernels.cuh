@@ -929,6 +929,17 @@ k_export(MapView m, Counters* cnt, uint16_t* __restrict__ k3, float* __restrict_
   }
 }
 
+// OccupancyOcTreeBase::toMaxLikelihood on the leaves: occupied -> clamping max, else clamping min.
+__global__ void __launch_bounds__(256) k_to_max_likelihood(DevParams P, MapView m) {
+  const size_t total = (size_t)m.persist->n_slots * kBlockVoxels;
+  uint32_t* vox = reinterpret_cast<uint32_t*>(m.pool);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t bits = vox[i];
+    if (bits == kUnknownBits) continue;
+    vox[i] = __float_as_uint(__uint_as_float(bits) >= P.occ_thres ? P.cmax : P.cmin);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K5 queries
 // ---------------------------------------------------------------------------------------------

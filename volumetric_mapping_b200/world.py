@@ -284,6 +284,35 @@ class OctomapWorld:
         assert k.shape[0] == v.shape[0]
         self._check(self._L.vmap_import_leaves(self._h, k.ctypes.data, v.ctypes.data, k.shape[0]))
 
+    # -- on-demand export to octomap's tree form (octomap_world.cc:820-856) ----------------
+    def tree_size(self, max_likelihood=False):
+        """octree_->prune(); octree_->size()."""
+        n = C.c_size_t(0)
+        self._check(self._L.vmap_tree_size(self._h, int(bool(max_likelihood)), C.byref(n)))
+        return int(n.value)
+
+    def writeOctomapToBinaryConst(self):
+        """The .bt stream as bytes (octomap_world.cc:854-856)."""
+        n = C.c_size_t(0)
+        self._check(self._L.vmap_serialize_bt(self._h, None, 0, C.byref(n)))
+        buf = (C.c_uint8 * max(1, n.value))()
+        self._check(self._L.vmap_serialize_bt(self._h, buf, n.value, C.byref(n)))
+        return bytes(buf[: n.value])
+
+    def writeOctomapToFile(self, filename):
+        """octomap_world.cc:849-852; like OcTree::writeBinary it thresholds the live map."""
+        self._check(self._L.vmap_write_bt(self._h, str(filename).encode(), 1))
+        return True
+
+    def loadOctomapFromFile(self, filename):
+        self._check(self._L.vmap_load_bt(self._h, str(filename).encode()))
+        return True
+
+    def setOctomapFromBinaryMsg(self, data):
+        b = bytes(data)
+        buf = (C.c_uint8 * max(1, len(b))).from_buffer_copy(b or b"\0")
+        self._check(self._L.vmap_deserialize_bt(self._h, buf, len(b)))
+
     def set_debug_capture(self, enabled=True):
         self._check(self._L.vmap_set_debug_capture(self._h, int(bool(enabled))))
 
