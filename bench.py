@@ -240,6 +240,7 @@ def run_b200(args):
             sw = sharded.ShardedOctomapWorld(rank, world, local_rank, resolution=RESOLUTION,
                                              sensor_max_range=MAX_RANGE, initial_blocks=1 << 18)
             w = sw.local
+            w.set_debug_l2_flush(256 << 20)   # in-stream L2 flush before every round's apply
         else:
             w = vm.OctomapWorld(resolution=RESOLUTION, sensor_max_range=MAX_RANGE,
                                 initial_blocks=1 << 19, device=local_rank)
@@ -249,22 +250,29 @@ def run_b200(args):
         if kind == "dev" and rank == 0:
             sampler.start()          # nvidia-smi needs ~100 ms to come up: start before warm-up
             time.sleep(0.3)
+        t_region = None
         for i in range(total):
             if i == W:
+                if world > 1:
+                    w.dist_flush()
                 barrier()
                 launches0 = w.kernel_launches()
-            flush.fill_(i & 0xFF)            # evict the map from L2 between steps
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
+                t_region = time.perf_counter()
             if world > 1:
-                if i >= W:
-                    dist.barrier()          # rounds start together; wall clock is per round
-                    t0 = time.perf_counter()
+                # rounds are pipelined inside the library (exchange + apply of round k overlap the
+                # generation of round k+1): the timed region is the K rounds as a whole
                 if kind == "dev":
                     w.dist_insert_pointcloud_device(scans[i]["T"], dev_pts[i].data_ptr(), n_pts)
                 else:
                     w.dist_insert_pointcloud(scans[i]["T"], pinned[i].numpy())
-            elif kind == "dev":
+                st = w.last_scan_stats()
+                if i >= W:
+                    stats.append(st)
+                continue
+            flush.fill_(i & 0xFF)            # evict the map from L2 between steps
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if kind == "dev":
                 w.insertPointcloudDevice(scans[i]["T"], dev_pts[i].data_ptr(), n_pts)
             else:
                 w.insertPointcloudFast(scans[i]["T"], pinned[i].numpy())
@@ -274,7 +282,12 @@ def run_b200(args):
                 stats.append(st)
                 gpu_ms.append(st["gpu_ms"])
                 wall_ms.append(1e3 * dt)
+        if world > 1:
+            w.dist_flush()
         barrier()
+        if world > 1:
+            region_ms = 1e3 * (time.perf_counter() - t_region)
+            gpu_ms = wall_ms = [region_ms / K] * K
         clocks = sampler.stop() if (kind == "dev" and rank == 0) else None
         launches = w.kernel_launches() - launches0
         out = {"stats": stats, "gpu_ms": gpu_ms, "wall_ms": wall_ms, "launches": launches,
@@ -339,8 +352,11 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "resolution": RESOLUTION, "max_range": MAX_RANGE,
                        "points_per_step": n_pts,
                        "traversals_per_step": trav / K / world,
-                       "l2": "256 MiB buffer overwritten between steps (L2 flushed)",
-                       "timing": "CUDA events on the library stream around each scan's kernels",
+                       "l2": ("256 MiB buffer overwritten between steps (L2 flushed)" if world == 1 else
+                              "256 MiB buffer overwritten on the apply stream before every round"),
+                       "timing": ("CUDA events on the library stream around each scan's kernels"
+                                  if world == 1 else "wall clock over the K pipelined rounds, barrier + "
+                                  "device sync on both sides, max over ranks"),
                        "sharding": ("one map sharded by 8^3-block owner over %d ranks; step = "
                                     "round of %d scans, NCCL all-to-all of block records"
                                     % (world, world)) if world > 1 else "single GPU"},

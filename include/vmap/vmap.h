@@ -259,6 +259,12 @@ VMAP_API int vmap_dist_insert_pointcloud(vmap* h, const float* xyz, size_t n, si
                                          int is_dense, const double T_rowmajor[16]);
 VMAP_API int vmap_dist_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n,
                                              size_t stride_bytes, const double T_rowmajor[16]);
+/* The collective inserts return as soon as the round's exchange and apply are ENQUEUED: they run
+ * on a second stream while the next round is generated.  Every call that reads the map waits for
+ * the round in flight first; vmap_dist_flush does so explicitly. */
+VMAP_API int vmap_dist_flush(vmap* h);
+/* Benchmark hook: overwrite `bytes` (> L2) of scratch before every round's exchange. 0 = off. */
+VMAP_API int vmap_set_debug_l2_flush(vmap* h, size_t bytes);
 /* COLLECTIVE queries: every rank passes the same queries and receives the global statuses. */
 VMAP_API int vmap_dist_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status);
 VMAP_API int vmap_dist_query_lines_dev(vmap* h, const double* d_start_end_xyz6, size_t n,

@@ -28,6 +28,7 @@ def main():
             w.insert_round_device(s["T"], d.data_ptr(), d.shape[0])
         else:
             w.insert_round_device(None, 0, 0)
+    w.local.dist_flush()
     k, v = w.local.export_leaves()
     assert np.all(sharded.owner_of_keys(k, world) == rank)
     # collective queries

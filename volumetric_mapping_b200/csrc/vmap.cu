@@ -67,6 +67,21 @@ struct vmap {
   uint32_t* d_pack_counts = nullptr;          // [2 * kMaxRanks] counts + cursors
   uint32_t h_pack_counts[kMaxRanks] = {0};
   void* nccl_comm = nullptr;
+  double dbg_ms[4] = {0, 0, 0, 0};            // VMAP_TIMING: host wall time per phase of a round
+  uint64_t dbg_n = 0;
+  bool dbg_reset = false;
+  // overlapped rounds: exchange + apply of round k run on app_stream while round k+1 is generated
+  cudaStream_t app_stream = nullptr;
+  Counters* d_cnt_app = nullptr;
+  Counters* h_cnt_app = nullptr;              // pinned
+  Persist* h_persist_app = nullptr;           // pinned
+  DevBuf pack_inflight;                       // records being sent (generate writes into `pack`)
+  bool app_pending = false;
+  cudaEvent_t ev_app0 = nullptr, ev_app1 = nullptr;
+  DevBuf l2_flush;                            // vmap_set_debug_l2_flush
+  size_t l2_flush_bytes = 0;
+  uint64_t app_records = 0, app_sent = 0, app_received = 0;
+  bool packed = false;                        // the last generate already packed its records
   uint64_t* d_count_matrix = nullptr;         // [kMaxRanks * kMaxRanks]
   uint64_t h_count_matrix[kMaxRanks * kMaxRanks] = {0};
 
@@ -124,6 +139,8 @@ int fail(const vmap* h, int code, const char* msg) {
   h->err = msg;
   return code;
 }
+
+int flush_app(vmap* h);   // vmap_shard_host.inl: wait for an overlapped exchange/apply round
 
 int dev_alloc(vmap* h, void** p, size_t bytes) {
   *p = nullptr;
@@ -592,7 +609,7 @@ int run_scan(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
             VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_entries));
           }
           VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_touched, 0, sizeof(uint32_t), h->stream));
-          VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->overflow_table, 0, 5 * sizeof(uint32_t), h->stream));
+          VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->overflow_table, 0, 6 * sizeof(uint32_t), h->stream));
           VM_TRY(launch_list_and_locate(h));
           VM_TRY(launch_capture(h));
           VM_TRY(launch_update(h));
@@ -710,6 +727,7 @@ int launch_after_front(vmap* h, size_t n, const Transform& T) {
 
 int insert_cloud_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_dense,
                         const double Tm[16]) {
+  VM_TRY(flush_app(h));
   Transform T;
   fill_transform_matrix(&T, Tm);
   VM_TRY(ensure_scan(h, n));
@@ -862,6 +880,12 @@ int vmap_destroy(vmap* h) {
   cudaFree(h->cap_free.p); cudaFree(h->cap_occ.p);
   cudaFree(h->d_cnt); cudaFree(h->d_cap_n);
   vmap_dist_shutdown(h);
+  cudaFree(h->pack_inflight.p); cudaFree(h->l2_flush.p); cudaFree(h->d_cnt_app);
+  if (h->h_cnt_app) cudaFreeHost(h->h_cnt_app);
+  if (h->h_persist_app) cudaFreeHost(h->h_persist_app);
+  if (h->ev_app0) cudaEventDestroy(h->ev_app0);
+  if (h->ev_app1) cudaEventDestroy(h->ev_app1);
+  if (h->app_stream) cudaStreamDestroy(h->app_stream);
   cudaFree(h->pack.p); cudaFree(h->recv.p); cudaFree(h->d_pack_counts); cudaFree(h->d_count_matrix);
   sort_free(h);
   free_window(h);
@@ -881,6 +905,7 @@ int vmap_destroy(vmap* h) {
 int vmap_reset(vmap* h) {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   // octree_->clear(): keep the allocations, forget every block
   VM_CUDA(h, cudaMemsetAsync(h->m.keys, 0xFF, h->table_cap * sizeof(unsigned long long), h->stream));
@@ -960,6 +985,7 @@ int vmap_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_by
 static int insert_image_common(vmap* h, const uint8_t* d_img, int rows, int cols, size_t pitch,
                                const double* Q /* null: image is CV_32FC3 */, const double q[4],
                                const double t[3]) {
+  VM_TRY(flush_app(h));
   Transform T;
   fill_transform_quat(&T, q, t);
   const size_t n = (size_t)rows * (size_t)cols;
@@ -1084,6 +1110,7 @@ int vmap_apply_keys(vmap* h, const uint16_t* free_k3, size_t n_free, const uint1
   if (!h || (!free_k3 && n_free) || (!occ_k3 && n_occ)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n_free > 0x7FFFFFFFull || n_occ > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many keys");
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   h->stats = vmap_scan_stats{};
   if (n_free + n_occ == 0) return VMAP_OK;
   VM_TRY(ensure_scan(h, 1));
@@ -1112,6 +1139,7 @@ int vmap_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_sta
   if (!h || ((!d_xyz || !d_status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query points");
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   if (!n) return VMAP_OK;
   k_query_points<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->m, d_xyz, (uint32_t)n, d_status);
   h->launches++;
@@ -1137,6 +1165,7 @@ int vmap_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_statu
   if (!h || ((!d_ab || !d_status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query segments");
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   if (!n) return VMAP_OK;
   k_query_lines<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->m, d_ab, (uint32_t)n, d_status);
   h->launches++;
@@ -1162,6 +1191,7 @@ int vmap_query_lines(vmap* h, const double* ab, size_t n, uint8_t* status) {
 // leaves in / out
 // ---------------------------------------------------------------------------------------------
 static int count_leaves(vmap* h, uint16_t* d_k3, float* d_val, uint32_t cap, size_t* n) {
+  VM_TRY(flush_app(h));
   VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_leaves, 0, sizeof(uint32_t), h->stream));
   k_export<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->m, h->d_cnt, d_k3, d_val, cap);
   h->launches++;
@@ -1201,6 +1231,7 @@ int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in
   if (!h || ((!keys_k3 || !logodds_in) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many leaves");
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   if (!n) return VMAP_OK;
   VM_TRY(ensure(h, &h->in, n * 6));
   VM_TRY(ensure(h, &h->aux, n * 4));
@@ -1234,6 +1265,8 @@ int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in
 // ---------------------------------------------------------------------------------------------
 int vmap_last_scan_stats(const vmap* h, vmap_scan_stats* stats) {
   if (!h || !stats) return VMAP_ERR_INVALID_ARGUMENT;
+  // (an overlapped multi-GPU round still in flight: its apply-side counters arrive with
+  // vmap_dist_flush; the generation-side counters are already final)
   *stats = h->stats;
   return VMAP_OK;
 }

@@ -67,6 +67,7 @@ struct Counters {           // zeroed at the start of every scan
   uint32_t overflow_keys;   // sort mode: key buffer too small
   uint32_t overflow_window; // dense mode: a voxel fell outside the window
   uint32_t overflow_ckpt;   // dense mode: segment checkpoint buffer too small
+  uint32_t overflow_pack;   // sharded: record buffer too small (value = records needed)
   uint32_t n_keys;          // sort mode: packed keys emitted
   uint32_t n_leaves;        // export
   uint32_t min_disparity_ord;  // ordered-int encoding of the image minimum

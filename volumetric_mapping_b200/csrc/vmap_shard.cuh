@@ -57,6 +57,16 @@ __global__ void __launch_bounds__(256) k_pack_count(MapView m, MarkSet ms, Count
 // pass 2: write the records (bucket offsets = exclusive prefix of counts) and clear the masks
 __global__ void __launch_bounds__(256) k_pack_write(MapView m, MarkSet ms, Counters* cnt, PackView pv) {
   if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
+  {
+    // all-or-nothing: when the record buffer is too small nothing is written and no mask is
+    // cleared, so the host can enlarge it and launch this kernel again
+    uint32_t total = 0;
+    for (uint32_t d = 0; d < pv.world; d++) total += pv.counts[d];
+    if (total > pv.capacity) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) cnt->overflow_pack = total;
+      return;
+    }
+  }
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_touched = cnt->n_touched;
@@ -102,6 +112,57 @@ k_apply_records(MapView m, Counters* cnt, const BlockRecord* __restrict__ rec, u
                                           : m.occ_mask + (size_t)h * kMaskWords + lane - kMaskWords;
       atomicOr(dst, wv);
     }
+  }
+}
+
+// Owner side, fused: one warp per record looks the block up (inserting it and giving it a pool
+// slot when new) and applies the record's masks straight to the voxels -- occupied wins, one
+// clamped update per marked voxel, exactly K4's arithmetic.  A block appears at most once per
+// list, so every voxel still has a single writer per scan.
+__global__ void __launch_bounds__(256)
+k_apply_update(DevParams P, MapView m, Counters* cnt, const BlockRecord* __restrict__ rec, uint32_t n) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t n_free = 0, n_occ = 0;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const BlockRecord* r = rec + i;
+    uint32_t slot = kUnassigned;
+    if (lane == 0) {
+      const uint32_t h = find_or_insert(m, cnt, r->block);
+      if (h != kNotFound) {
+        slot = m.slot[h];
+        if (slot == kUnassigned) {
+          slot = atomicAdd(&m.persist->n_slots, 1u);
+          if (slot < m.pool_cap) m.slot[h] = slot;
+          else { cnt->overflow_pool = 1u; slot = kUnassigned; }
+        }
+      }
+    }
+    slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+    if (slot == kUnassigned) continue;
+    uint32_t f = 0, o = 0;
+    if (lane < kMaskWords) {
+      f = r->free_mask[lane];
+      o = r->occ_mask[lane];
+      f &= ~o;
+    }
+    uint32_t* vox = reinterpret_cast<uint32_t*>(m.pool) + (size_t)slot * kBlockVoxels;
+#pragma unroll
+    for (int j = 0; j < kMaskWords; j++) {
+      const uint32_t fw = __shfl_sync(0xFFFFFFFFu, f, j);
+      const uint32_t ow = __shfl_sync(0xFFFFFFFFu, o, j);
+      if ((fw | ow) == 0u) continue;
+      const bool is_occ = (ow >> lane) & 1u, is_free = (fw >> lane) & 1u;
+      if (is_occ || is_free) {
+        uint32_t* p = vox + j * 32 + lane;
+        *p = update_leaf(*p, is_occ ? P.hit : P.miss, P.cmin, P.cmax);
+      }
+      if (lane == 0) { n_free += __popc(fw); n_occ += __popc(ow); }
+    }
+  }
+  if (lane == 0) {
+    if (n_free) atomicAdd(&cnt->unique_free, n_free);
+    if (n_occ) atomicAdd(&cnt->unique_occupied, n_occ);
   }
 }
 

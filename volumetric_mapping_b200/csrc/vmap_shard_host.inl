@@ -6,6 +6,8 @@
 //                          (libnccl.so.2 is dlopen'ed on first use; single-GPU users never need it)
 #include <dlfcn.h>
 
+#include <chrono>
+
 namespace {
 
 // ---- minimal NCCL surface (nccl.h 2.27: types are ABI-stable since 2.x) ----------------------
@@ -81,6 +83,23 @@ PackView pack_view(vmap* h) {
   return pv;
 }
 
+PackView pack_view(vmap* h);
+
+// Enqueue the two pack kernels and the copy of the per-destination counts (no synchronisation).
+int launch_pack(vmap* h) {
+  if (!h->pack.p) VM_TRY(ensure(h, &h->pack, (size_t)(1u << 16) * sizeof(BlockRecord)));
+  VM_CUDA(h, cudaMemsetAsync(h->d_pack_counts, 0, 2 * kMaxRanks * sizeof(uint32_t), h->stream));
+  PackView pv = pack_view(h);
+  const unsigned grid = g_sm_count(h->device) * 8;
+  k_pack_count<<<grid, 256, 0, h->stream>>>(h->m, h->ms, h->d_cnt, pv);
+  k_pack_write<<<grid, 256, 0, h->stream>>>(h->m, h->ms, h->d_cnt, pv);
+  h->launches += 2;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaMemcpyAsync(h->h_pack_counts, h->d_pack_counts, kMaxRanks * sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, h->stream));
+  return VMAP_OK;
+}
+
 // K1..K2 for one scan with the grow-and-retry protocol; the marks are left in h->ms (dense
 // window or the table's mask columns) together with the list of touched blocks.
 template <class Mark>
@@ -89,7 +108,11 @@ int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
   uint64_t retries = 0;
   float ms_total = 0.f;
   bool dense = origin && setup_dense_marks(h, origin);
-  if (!dense) use_table_marks(h);
+  if (!dense) {
+    VM_TRY(flush_app(h));   // a table-mode generate touches the hash table an in-flight apply is updating
+    use_table_marks(h);
+  }
+  h->packed = false;
   auto launch_list = [&]() -> int {
     const unsigned grid = (unsigned)std::min<uint64_t>((h->win.n_words + 255) / 256, (uint64_t)g_sm_count(h->device) * 8);
     k_list_touched<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->ms, h->d_cnt, h->win.n_words);
@@ -105,6 +128,7 @@ int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
     VM_TRY(mark());
     if (dense) VM_TRY(launch_list());
     VM_TRY(mark_stage(h, 3));
+    if (dense) VM_TRY(launch_pack(h));     // same synchronisation reads the scan's and the pack's counters
     VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
     VM_TRY(read_counters(h));
     float ms = 0.f;
@@ -118,12 +142,26 @@ int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
         VM_TRY(clear_window_marks(h));
         h->dense_fallbacks++;
         dense = false;
+        VM_TRY(flush_app(h));
         use_table_marks(h);
       } else if (h->h_cnt->overflow_keys) {
         VM_TRY(grow_window_list(h, std::max<uint32_t>(h->h_cnt->n_touched + (h->h_cnt->n_touched >> 2), 2 * h->win.list_cap)));
         h->ms.list = h->win.list; h->ms.locate = h->win.locate; h->ms.list_cap = h->win.list_cap;
         VM_TRY(clear_window_marks(h));   // simplest: regenerate the scan with the larger list
       } else {
+        while (h->h_cnt->overflow_pack) {
+          // marks and counts are intact: enlarge the record buffer and write again
+          const size_t need = h->h_cnt->overflow_pack;
+          VM_TRY(ensure(h, &h->pack, (need + (need >> 2)) * sizeof(BlockRecord)));
+          VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->overflow_pack, 0, sizeof(uint32_t), h->stream));
+          VM_CUDA(h, cudaMemsetAsync(h->d_pack_counts + kMaxRanks, 0, kMaxRanks * sizeof(uint32_t), h->stream));
+          k_pack_write<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->m, h->ms, h->d_cnt, pack_view(h));
+          h->launches++;
+          VM_CUDA(h, cudaGetLastError());
+          VM_TRY(read_counters(h));
+        }
+        VM_CUDA(h, cudaMemsetAsync(h->win.touched_bits, 0, (size_t)h->win.n_words * 4, h->stream));
+        h->packed = true;
         break;
       }
     } else {
@@ -159,6 +197,10 @@ int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
 
 // Pack every touched block of the generated scan into per-destination records.
 int pack_marks(vmap* h) {
+  if (h->packed) {
+    while ((uint64_t)h->h_persist->n_entries * 2 > h->table_cap) VM_TRY(grow_table(h));
+    return VMAP_OK;
+  }
   const size_t n_touched = h->h_cnt->n_touched;
   VM_TRY(ensure(h, &h->pack, std::max<size_t>(n_touched, 1) * sizeof(BlockRecord)));
   VM_CUDA(h, cudaMemsetAsync(h->d_pack_counts, 0, 2 * kMaxRanks * sizeof(uint32_t), h->stream));
@@ -185,6 +227,7 @@ int shard_generate_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride,
   h->stats = vmap_scan_stats{};
   h->stats.points_in = n;
   std::memset(h->h_pack_counts, 0, kMaxRanks * sizeof(uint32_t));
+  h->packed = false;
   if (n) {
     VM_TRY(generate_marks(h, n, T.origin, [&]() -> int {
       k_front_cloud<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, d_in, (uint32_t)n,
@@ -202,6 +245,7 @@ int shard_generate_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride,
 
 // Owner side: apply `n_lists` scans' record lists in order (list i = the i-th scan of the round).
 int shard_apply_lists(vmap* h, const BlockRecord* const* lists, const size_t* counts, size_t n_lists) {
+  VM_TRY(flush_app(h));
   size_t total = 0;
   for (size_t i = 0; i < n_lists; i++) total += counts[i];
   if (total > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many block records");
@@ -215,14 +259,22 @@ int shard_apply_lists(vmap* h, const BlockRecord* const* lists, const size_t* co
   uint64_t touched = 0;
   for (size_t i = 0; i < n_lists; i++) {
     if (!counts[i]) continue;
-    VM_TRY(next_epoch(h));
-    VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_touched, 0, sizeof(uint32_t), h->stream));
     const unsigned grid = (unsigned)std::min<size_t>((counts[i] + 7) / 8, (size_t)g_sm_count(h->device) * 8);
-    k_apply_records<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->m, h->d_cnt, lists[i], (uint32_t)counts[i]);
-    h->launches++;
-    VM_CUDA(h, cudaGetLastError());
-    VM_TRY(launch_capture(h));
-    VM_TRY(launch_update(h));
+    if (!h->capture) {
+      // fused: records -> voxels in one launch per scan
+      k_apply_update<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->P, h->m, h->d_cnt, lists[i], (uint32_t)counts[i]);
+      h->launches++;
+      VM_CUDA(h, cudaGetLastError());
+    } else {
+      // parity hook: go through the table's mask columns so the key sets can be captured
+      VM_TRY(next_epoch(h));
+      VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_touched, 0, sizeof(uint32_t), h->stream));
+      k_apply_records<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->m, h->d_cnt, lists[i], (uint32_t)counts[i]);
+      h->launches++;
+      VM_CUDA(h, cudaGetLastError());
+      VM_TRY(launch_capture(h));
+      VM_TRY(launch_update(h));
+    }
     touched += counts[i];
   }
   VM_CUDA(h, cudaEventRecord(h->evk[4], h->stream));
@@ -334,8 +386,13 @@ int vmap_dist_init(vmap* h, const uint8_t id128[128], int rank, int world) {
 
 int vmap_dist_shutdown(vmap* h) {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  if (h->nccl_comm && getenv("VMAP_TIMING") && h->dbg_n)
+    fprintf(stderr, "[vmap rank %d] per round (host wall ms): generate+pack %.3f | count allgather + wait for previous apply %.3f | exchange/apply enqueue %.3f | (sync path) %.3f  (%llu rounds)\n",
+            h->shard_rank, h->dbg_ms[0] / h->dbg_n, h->dbg_ms[1] / h->dbg_n, h->dbg_ms[2] / h->dbg_n, h->dbg_ms[3] / h->dbg_n,
+            (unsigned long long)h->dbg_n);
   if (h->nccl_comm) {
     cudaSetDevice(h->device);
+    flush_app(h);
     cudaStreamSynchronize(h->stream);
     g_nccl.CommDestroy((NcclComm)h->nccl_comm);
     h->nccl_comm = nullptr;
@@ -344,20 +401,28 @@ int vmap_dist_shutdown(vmap* h) {
 }
 
 // Exchange + apply after a local generate: rank r's scan is the r-th scan of this round.
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 static int dist_exchange_and_apply(vmap* h) {
   if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
+  const double t_a = now_ms();
   NcclComm comm = (NcclComm)h->nccl_comm;
   const int G = h->shard_world, me = h->shard_rank;
   // counts matrix: row s = records rank s sends to each destination
-  uint64_t mine[kMaxRanks];
-  for (int d = 0; d < G; d++) mine[d] = h->h_pack_counts[d];
-  VM_CUDA(h, cudaMemcpyAsync(h->d_count_matrix + (size_t)me * G, mine, G * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
-  VM_NCCL(h, g_nccl.AllGather(h->d_count_matrix + (size_t)me * G, h->d_count_matrix, (size_t)G, kNcclUint64, comm, h->stream));
-  VM_CUDA(h, cudaMemcpyAsync(h->h_count_matrix, h->d_count_matrix, (size_t)G * G * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  // the per-destination counts are still on the device (k_pack_count): gather them from there
+  uint32_t* d_matrix = reinterpret_cast<uint32_t*>(h->d_count_matrix);
+  uint32_t* h_matrix = reinterpret_cast<uint32_t*>(h->h_count_matrix);
+  if (!h->packed)   // table-mode generate or an empty scan: counts live on the host only
+    VM_CUDA(h, cudaMemcpyAsync(h->d_pack_counts, h->h_pack_counts, kMaxRanks * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  VM_NCCL(h, g_nccl.AllGather(h->d_pack_counts, d_matrix, (size_t)kMaxRanks, kNcclUint32, comm, h->stream));
+  VM_CUDA(h, cudaMemcpyAsync(h_matrix, d_matrix, (size_t)G * kMaxRanks * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  const double t_b = now_ms();
   size_t recv_counts[kMaxRanks], recv_off[kMaxRanks], total = 0;
   for (int s = 0; s < G; s++) {
-    recv_counts[s] = (size_t)h->h_count_matrix[(size_t)s * G + me];
+    recv_counts[s] = (size_t)h_matrix[(size_t)s * kMaxRanks + me];
     recv_off[s] = total;
     total += recv_counts[s];
   }
@@ -383,16 +448,140 @@ static int dist_exchange_and_apply(vmap* h) {
   for (int s = 0; s < G; s++) lists[s] = recv + recv_off[s];
   h->stats.records_sent = so - h->h_pack_counts[me];
   h->stats.records_received = total - recv_counts[me];
-  return shard_apply_lists(h, lists, recv_counts, (size_t)G);
+  const double t_c = now_ms();
+  const int st = shard_apply_lists(h, lists, recv_counts, (size_t)G);
+  const double t_d = now_ms();
+  h->dbg_ms[1] += t_b - t_a; h->dbg_ms[2] += t_c - t_b; h->dbg_ms[3] += t_d - t_c; h->dbg_n++;
+  if (h->dbg_n == 5 && !h->dbg_reset) { h->dbg_reset = true; h->dbg_n = 0; for (double& v : h->dbg_ms) v = 0.0; }   // skip warm-up rounds
+  return st;
 }
 
-// device time of the whole round on this rank (generate .. apply, host round trips included)
-static int finish_round_timing(vmap* h) {
-  VM_CUDA(h, cudaEventRecord(h->evr1, h->stream));
-  VM_CUDA(h, cudaEventSynchronize(h->evr1));
+// Wait for the exchange + apply of the previous round (app_stream) and collect its counters.
+}  // extern "C"
+namespace {
+int flush_app(vmap* h) {
+  if (!h->app_pending) return VMAP_OK;
+  VM_CUDA(h, cudaStreamSynchronize(h->app_stream));
+  h->app_pending = false;
+  if (h->h_cnt_app->overflow_table || h->h_cnt_app->overflow_pool)
+    return fail(h, VMAP_ERR_CAPACITY, "internal: map overflow inside a sharded apply round");
+  *h->h_persist = *h->h_persist_app;
   float ms = 0.f;
-  cudaEventElapsedTime(&ms, h->evr0, h->evr1);
-  h->stats.gpu_ms = ms;
+  if (cudaEventElapsedTime(&ms, h->ev_app0, h->ev_app1) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+  h->stats.update_ms = ms;
+  h->stats.unique_free = h->h_cnt_app->unique_free;
+  h->stats.unique_occupied = h->h_cnt_app->unique_occupied;
+  h->stats.blocks_total = h->h_persist->n_slots;
+  h->stats.blocks_applied = h->app_records;
+  h->stats.records_sent = h->app_sent;
+  h->stats.records_received = h->app_received;
+  return VMAP_OK;
+}
+
+int init_app_stream(vmap* h) {
+  if (h->app_stream) return VMAP_OK;
+  VM_CUDA(h, cudaStreamCreateWithFlags(&h->app_stream, cudaStreamNonBlocking));
+  VM_CUDA(h, cudaEventCreate(&h->ev_app0));
+  VM_CUDA(h, cudaEventCreate(&h->ev_app1));
+  VM_CUDA(h, cudaMallocHost((void**)&h->h_cnt_app, sizeof(Counters)));
+  VM_CUDA(h, cudaMallocHost((void**)&h->h_persist_app, sizeof(Persist)));
+  std::memset(h->h_cnt_app, 0, sizeof(Counters));
+  VM_TRY(dev_alloc(h, (void**)&h->d_cnt_app, sizeof(Counters)));
+  return VMAP_OK;
+}
+
+// One round after the local generate + pack: count exchange, record all-to-all and the apply of
+// the round's scans, all on app_stream so that they overlap with the generation of the next
+// round on the main stream (a dense-window generate never touches the hash table or the pool).
+// Returns without waiting; flush_app() (next round, or any call that reads the map) collects it.
+int dist_round(vmap* h) {
+  if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
+  VM_TRY(init_app_stream(h));
+  NcclComm comm = (NcclComm)h->nccl_comm;
+  const int G = h->shard_world, me = h->shard_rank;
+  cudaStream_t as = h->app_stream;
+  const double t_a = now_ms();
+  // (A) counts matrix, queued behind the previous round's apply
+  uint32_t* d_matrix = reinterpret_cast<uint32_t*>(h->d_count_matrix);
+  uint32_t* h_matrix = reinterpret_cast<uint32_t*>(h->h_count_matrix);
+  if (!h->packed)   // table-mode generate or an empty scan: counts live on the host only
+    VM_CUDA(h, cudaMemcpyAsync(h->d_pack_counts, h->h_pack_counts, kMaxRanks * sizeof(uint32_t), cudaMemcpyHostToDevice, as));
+  VM_NCCL(h, g_nccl.AllGather(h->d_pack_counts, d_matrix, (size_t)kMaxRanks, kNcclUint32, comm, as));
+  VM_CUDA(h, cudaMemcpyAsync(h_matrix, d_matrix, (size_t)G * kMaxRanks * sizeof(uint32_t), cudaMemcpyDeviceToHost, as));
+  const vmap_scan_stats gen_stats = h->stats;   // this round's generation counters
+  VM_CUDA(h, cudaStreamSynchronize(as));
+  VM_TRY(flush_app(h));                         // the previous round is complete now
+  h->stats = gen_stats;
+  const double t_b = now_ms();
+  size_t recv_counts[kMaxRanks], recv_off[kMaxRanks], total = 0;
+  for (int s = 0; s < G; s++) {
+    recv_counts[s] = (size_t)h_matrix[(size_t)s * kMaxRanks + me];
+    recv_off[s] = total;
+    total += recv_counts[s];
+  }
+  if (total > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many block records");
+  // (B) both streams are idle here: buffers and map capacity can be changed safely
+  std::swap(h->pack, h->pack_inflight);         // the next generate packs into the other buffer
+  VM_TRY(ensure(h, &h->recv, std::max<size_t>(total, 1) * sizeof(BlockRecord)));
+  while (((uint64_t)h->h_persist->n_entries + total) * 2 > h->table_cap) VM_TRY(grow_table(h));
+  if ((uint64_t)h->h_persist->n_slots + total > h->pool_cap) VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_slots + total));
+  BlockRecord* recv = (BlockRecord*)h->recv.p;
+  const BlockRecord* send = (const BlockRecord*)h->pack_inflight.p;
+  size_t send_off[kMaxRanks], so = 0;
+  for (int d = 0; d < G; d++) { send_off[d] = so; so += h->h_pack_counts[d]; }
+  // (C) exchange + apply, asynchronous
+  if (h->l2_flush_bytes) VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(h->dbg_n & 0xFF), h->l2_flush_bytes, as));
+  VM_CUDA(h, cudaEventRecord(h->ev_app0, as));
+  VM_NCCL(h, g_nccl.GroupStart());
+  for (int p = 0; p < G; p++) {
+    if (p == me) continue;
+    if (h->h_pack_counts[p])
+      VM_NCCL(h, g_nccl.Send(send + send_off[p], (size_t)h->h_pack_counts[p] * sizeof(BlockRecord), kNcclUint8, p, comm, as));
+    if (recv_counts[p])
+      VM_NCCL(h, g_nccl.Recv(recv + recv_off[p], recv_counts[p] * sizeof(BlockRecord), kNcclUint8, p, comm, as));
+  }
+  VM_NCCL(h, g_nccl.GroupEnd());
+  if (recv_counts[me])
+    VM_CUDA(h, cudaMemcpyAsync(recv + recv_off[me], send + send_off[me], recv_counts[me] * sizeof(BlockRecord),
+                               cudaMemcpyDeviceToDevice, as));
+  VM_CUDA(h, cudaMemsetAsync(h->d_cnt_app, 0, sizeof(Counters), as));
+  for (int s = 0; s < G; s++) {
+    if (!recv_counts[s]) continue;
+    const unsigned grid = (unsigned)std::min<size_t>((recv_counts[s] + 7) / 8, (size_t)g_sm_count(h->device) * 8);
+    k_apply_update<<<std::max(grid, 1u), 256, 0, as>>>(h->P, h->m, h->d_cnt_app, recv + recv_off[s], (uint32_t)recv_counts[s]);
+    h->launches++;
+  }
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaEventRecord(h->ev_app1, as));
+  VM_CUDA(h, cudaMemcpyAsync(h->h_cnt_app, h->d_cnt_app, sizeof(Counters), cudaMemcpyDeviceToHost, as));
+  VM_CUDA(h, cudaMemcpyAsync(h->h_persist_app, h->m.persist, sizeof(Persist), cudaMemcpyDeviceToHost, as));
+  h->app_records = total;
+  h->app_sent = so - h->h_pack_counts[me];
+  h->app_received = total - recv_counts[me];
+  h->app_pending = true;
+  const double t_c = now_ms();
+  h->dbg_ms[1] += t_b - t_a; h->dbg_ms[2] += t_c - t_b; h->dbg_n++;
+  if (h->dbg_n == 5 && !h->dbg_reset) { h->dbg_reset = true; h->dbg_n = 0; for (double& v : h->dbg_ms) v = 0.0; }   // skip warm-up rounds
+  return VMAP_OK;
+}
+}  // namespace
+extern "C" {
+
+// Waits for the round in flight (if any); afterwards vmap_last_scan_stats reports its counters.
+int vmap_dist_flush(vmap* h) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  return flush_app(h);
+}
+
+// Test / benchmark hook: overwrite `bytes` of scratch (larger than L2) on the apply stream before
+// every round's exchange, so no round finds its map blocks in L2.  0 disables.
+int vmap_set_debug_l2_flush(vmap* h, size_t bytes) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
+  if (bytes) VM_TRY(ensure(h, &h->l2_flush, bytes));
+  h->l2_flush_bytes = bytes;
   return VMAP_OK;
 }
 
@@ -400,20 +589,28 @@ int vmap_dist_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n, size_
                                     const double T_rowmajor[16]) {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
-  VM_CUDA(h, cudaEventRecord(h->evr0, h->stream));
+  const double t0 = now_ms();
   VM_TRY(vmap_shard_generate_dev(h, d_xyz, n, stride_bytes, T_rowmajor, nullptr));
-  VM_TRY(dist_exchange_and_apply(h));
-  return finish_round_timing(h);
+  h->dbg_ms[0] += now_ms() - t0;
+  if (h->capture) {   // parity hook: synchronous round through the table's mask columns
+    VM_TRY(dist_exchange_and_apply(h));
+    return VMAP_OK;
+  }
+  return dist_round(h);
 }
 
 int vmap_dist_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes, int is_dense,
                                 const double T_rowmajor[16]) {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
-  VM_CUDA(h, cudaEventRecord(h->evr0, h->stream));
+  const double t0 = now_ms();
   VM_TRY(vmap_shard_generate(h, xyz, n, stride_bytes, is_dense, T_rowmajor, nullptr));
-  VM_TRY(dist_exchange_and_apply(h));
-  return finish_round_timing(h);
+  h->dbg_ms[0] += now_ms() - t0;
+  if (h->capture) {
+    VM_TRY(dist_exchange_and_apply(h));
+    return VMAP_OK;
+  }
+  return dist_round(h);
 }
 
 // Sharded queries: partial answers of this shard (combine = element-wise MIN over ranks).
@@ -421,6 +618,7 @@ int vmap_shard_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t*
   if (!h || ((!d_xyz || !d_status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query points");
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   if (!n) return VMAP_OK;
   k_query_points_sharded<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->m, d_xyz, (uint32_t)n, d_status,
                                                                  (uint32_t)h->shard_rank, (uint32_t)h->shard_world);
@@ -434,6 +632,7 @@ int vmap_shard_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint32_t* 
   if (!h || ((!d_ab || !d_packed) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query segments");
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   if (!n) return VMAP_OK;
   k_query_lines_sharded<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->m, d_ab, (uint32_t)n, d_packed,
                                                                 (uint32_t)h->shard_rank, (uint32_t)h->shard_world);

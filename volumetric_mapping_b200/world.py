@@ -240,6 +240,12 @@ class OctomapWorld:
         self._check(self._L.vmap_dist_init(self._h, buf, int(rank), int(world)))
         self._world = int(world)
 
+    def dist_flush(self):
+        self._check(self._L.vmap_dist_flush(self._h))
+
+    def set_debug_l2_flush(self, n_bytes):
+        self._check(self._L.vmap_set_debug_l2_flush(self._h, int(n_bytes)))
+
     def dist_shutdown(self):
         self._check(self._L.vmap_dist_shutdown(self._h))
 
