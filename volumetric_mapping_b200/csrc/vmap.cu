@@ -64,8 +64,16 @@ struct vmap {
   // shard_rank; scans generated here are packed into per-owner record streams
   int shard_rank = 0, shard_world = 1;
   DevBuf pack, recv;
-  uint32_t* d_pack_counts = nullptr;          // [2 * kMaxRanks] counts + cursors
-  uint32_t h_pack_counts[kMaxRanks] = {0};
+  uint32_t* d_pack_counts_base = nullptr;     // 2 slots x [2 * kMaxRanks] counts + cursors
+  uint32_t* d_pack_counts = nullptr;          // current slot
+  uint32_t h_pack_counts_slot[2][kMaxRanks] = {{0}, {0}};
+  uint32_t* h_pack_counts = h_pack_counts_slot[0];
+  int pack_slot = 0;
+  bool in_collective = false;                 // inside a vmap_dist_* call (may run NCCL)
+  bool round_pending = false;                 // a generated + packed round awaits its exchange
+  bool round_packed = false;                  // ... and its counts are on the device
+  int round_slot = 0;
+  vmap_scan_stats round_stats{};
   void* nccl_comm = nullptr;
   double dbg_ms[4] = {0, 0, 0, 0};            // VMAP_TIMING: host wall time per phase of a round
   uint64_t dbg_n = 0;
@@ -859,7 +867,8 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   std::memset(h->h_persist, 0, sizeof(Persist));
   int s = dev_alloc(h, (void**)&h->d_cnt, sizeof(Counters));
   if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_cap_n, 2 * sizeof(uint32_t));
-  if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_pack_counts, 2 * kMaxRanks * sizeof(uint32_t));
+  if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_pack_counts_base, 4 * kMaxRanks * sizeof(uint32_t));
+  h->d_pack_counts = h->d_pack_counts_base;
   if (s == VMAP_OK) s = init_map(h);
   if (s != VMAP_OK) return bail(s);
   *out = h;
@@ -886,7 +895,7 @@ int vmap_destroy(vmap* h) {
   if (h->ev_app0) cudaEventDestroy(h->ev_app0);
   if (h->ev_app1) cudaEventDestroy(h->ev_app1);
   if (h->app_stream) cudaStreamDestroy(h->app_stream);
-  cudaFree(h->pack.p); cudaFree(h->recv.p); cudaFree(h->d_pack_counts); cudaFree(h->d_count_matrix);
+  cudaFree(h->pack.p); cudaFree(h->recv.p); cudaFree(h->d_pack_counts_base); cudaFree(h->d_count_matrix);
   sort_free(h);
   free_window(h);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);

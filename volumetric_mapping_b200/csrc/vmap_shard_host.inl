@@ -102,14 +102,20 @@ int launch_pack(vmap* h) {
 
 // K1..K2 for one scan with the grow-and-retry protocol; the marks are left in h->ms (dense
 // window or the table's mask columns) together with the list of touched blocks.
-template <class Mark>
-int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
+// `between` runs once, after the first attempt's kernels are enqueued and before the host waits
+// for them: the multi-GPU path uses it to exchange the PREVIOUS round while this one is generated.
+template <class Mark, class Between>
+int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark, Between&& between) {
+  bool between_done = false;
   VM_TRY(next_epoch(h));
   uint64_t retries = 0;
   float ms_total = 0.f;
   bool dense = origin && setup_dense_marks(h, origin);
   if (!dense) {
-    VM_TRY(flush_app(h));   // a table-mode generate touches the hash table an in-flight apply is updating
+    // a table-mode generate touches the hash table an in-flight apply is updating: no overlap
+    between_done = true;
+    VM_TRY(between());
+    VM_TRY(flush_app(h));
     use_table_marks(h);
   }
   h->packed = false;
@@ -130,6 +136,10 @@ int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
     VM_TRY(mark_stage(h, 3));
     if (dense) VM_TRY(launch_pack(h));     // same synchronisation reads the scan's and the pack's counters
     VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+    if (!between_done) {
+      between_done = true;
+      VM_TRY(between());
+    }
     VM_TRY(read_counters(h));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, h->ev0, h->ev1);
@@ -219,8 +229,9 @@ int pack_marks(vmap* h) {
   return VMAP_OK;
 }
 
+template <class Between>
 int shard_generate_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_dense,
-                          const double Tm[16], uint64_t* counts_out) {
+                          const double Tm[16], uint64_t* counts_out, Between&& between) {
   Transform T;
   fill_transform_matrix(&T, Tm);
   VM_TRY(ensure_scan(h, std::max<size_t>(n, 1)));
@@ -228,6 +239,7 @@ int shard_generate_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride,
   h->stats.points_in = n;
   std::memset(h->h_pack_counts, 0, kMaxRanks * sizeof(uint32_t));
   h->packed = false;
+  if (!n) VM_TRY(between());
   if (n) {
     VM_TRY(generate_marks(h, n, T.origin, [&]() -> int {
       k_front_cloud<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, d_in, (uint32_t)n,
@@ -235,7 +247,7 @@ int shard_generate_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride,
       h->launches++;
       VM_CUDA(h, cudaGetLastError());
       return launch_resolve_and_walk(h, n, T);
-    }));
+    }, between));
     VM_TRY(pack_marks(h));
   }
   if (counts_out)
@@ -321,7 +333,7 @@ int vmap_shard_generate_dev(vmap* h, const float* d_xyz, size_t n, size_t stride
   if (!h || (!d_xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
-  return shard_generate_common(h, (const uint8_t*)d_xyz, n, stride_bytes, 1, T_rowmajor, counts_out);
+  return shard_generate_common(h, (const uint8_t*)d_xyz, n, stride_bytes, 1, T_rowmajor, counts_out, []() -> int { return VMAP_OK; });
 }
 
 int vmap_shard_generate(vmap* h, const float* xyz, size_t n, size_t stride_bytes, int is_dense,
@@ -334,7 +346,7 @@ int vmap_shard_generate(vmap* h, const float* xyz, size_t n, size_t stride_bytes
     VM_TRY(ensure(h, &h->in, bytes));
     VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
   }
-  return shard_generate_common(h, (const uint8_t*)h->in.p, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor, counts_out);
+  return shard_generate_common(h, (const uint8_t*)h->in.p, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor, counts_out, []() -> int { return VMAP_OK; });
 }
 
 int vmap_shard_records(vmap* h, int dest, const void** d_records, size_t* n_records) {
@@ -392,6 +404,7 @@ int vmap_dist_shutdown(vmap* h) {
             (unsigned long long)h->dbg_n);
   if (h->nccl_comm) {
     cudaSetDevice(h->device);
+    h->round_pending = false;   // (a round never exchanged is dropped: vmap_dist_flush is the collective way out)
     flush_app(h);
     cudaStreamSynchronize(h->stream);
     g_nccl.CommDestroy((NcclComm)h->nccl_comm);
@@ -460,6 +473,8 @@ static int dist_exchange_and_apply(vmap* h) {
 }  // extern "C"
 namespace {
 int flush_app(vmap* h) {
+  if (h->round_pending && !h->in_collective)
+    return fail(h, VMAP_ERR_DIST, "a sharded round awaits its exchange: call vmap_dist_flush on every rank first");
   if (!h->app_pending) return VMAP_OK;
   VM_CUDA(h, cudaStreamSynchronize(h->app_stream));
   h->app_pending = false;
@@ -475,6 +490,20 @@ int flush_app(vmap* h) {
   h->stats.blocks_applied = h->app_records;
   h->stats.records_sent = h->app_sent;
   h->stats.records_received = h->app_received;
+  return VMAP_OK;
+}
+
+// grow-only buffer used on `st` only (idle when this is called)
+int ensure_on(vmap* h, DevBuf* b, size_t bytes, cudaStream_t st) {
+  if (bytes <= b->cap) return VMAP_OK;
+  VM_CUDA(h, cudaStreamSynchronize(st));
+  dev_free(h, b->p, b->cap);
+  b->p = nullptr;
+  b->cap = 0;
+  size_t want = std::max(bytes, (size_t)4096);
+  want = (want + (want >> 1) + 255) & ~(size_t)255;
+  VM_TRY(dev_alloc(h, &b->p, want));
+  b->cap = want;
   return VMAP_OK;
 }
 
@@ -494,9 +523,13 @@ int init_app_stream(vmap* h) {
 // the round's scans, all on app_stream so that they overlap with the generation of the next
 // round on the main stream (a dense-window generate never touches the hash table or the pool).
 // Returns without waiting; flush_app() (next round, or any call that reads the map) collects it.
-int dist_round(vmap* h) {
+int complete_round(vmap* h) {
+  if (!h->round_pending) return VMAP_OK;
   if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
   VM_TRY(init_app_stream(h));
+  h->round_pending = false;
+  uint32_t* const d_counts = h->d_pack_counts_base + (size_t)h->round_slot * 2 * kMaxRanks;
+  const uint32_t* const h_counts = h->h_pack_counts_slot[h->round_slot];
   NcclComm comm = (NcclComm)h->nccl_comm;
   const int G = h->shard_world, me = h->shard_rank;
   cudaStream_t as = h->app_stream;
@@ -504,14 +537,12 @@ int dist_round(vmap* h) {
   // (A) counts matrix, queued behind the previous round's apply
   uint32_t* d_matrix = reinterpret_cast<uint32_t*>(h->d_count_matrix);
   uint32_t* h_matrix = reinterpret_cast<uint32_t*>(h->h_count_matrix);
-  if (!h->packed)   // table-mode generate or an empty scan: counts live on the host only
-    VM_CUDA(h, cudaMemcpyAsync(h->d_pack_counts, h->h_pack_counts, kMaxRanks * sizeof(uint32_t), cudaMemcpyHostToDevice, as));
-  VM_NCCL(h, g_nccl.AllGather(h->d_pack_counts, d_matrix, (size_t)kMaxRanks, kNcclUint32, comm, as));
+  if (!h->round_packed)   // table-mode generate or an empty scan: counts live on the host only
+    VM_CUDA(h, cudaMemcpyAsync(d_counts, h_counts, kMaxRanks * sizeof(uint32_t), cudaMemcpyHostToDevice, as));
+  VM_NCCL(h, g_nccl.AllGather(d_counts, d_matrix, (size_t)kMaxRanks, kNcclUint32, comm, as));
   VM_CUDA(h, cudaMemcpyAsync(h_matrix, d_matrix, (size_t)G * kMaxRanks * sizeof(uint32_t), cudaMemcpyDeviceToHost, as));
-  const vmap_scan_stats gen_stats = h->stats;   // this round's generation counters
   VM_CUDA(h, cudaStreamSynchronize(as));
-  VM_TRY(flush_app(h));                         // the previous round is complete now
-  h->stats = gen_stats;
+  VM_TRY(flush_app(h));                         // the round before this one is complete now
   const double t_b = now_ms();
   size_t recv_counts[kMaxRanks], recv_off[kMaxRanks], total = 0;
   for (int s = 0; s < G; s++) {
@@ -520,23 +551,23 @@ int dist_round(vmap* h) {
     total += recv_counts[s];
   }
   if (total > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many block records");
-  // (B) both streams are idle here: buffers and map capacity can be changed safely
-  std::swap(h->pack, h->pack_inflight);         // the next generate packs into the other buffer
-  VM_TRY(ensure(h, &h->recv, std::max<size_t>(total, 1) * sizeof(BlockRecord)));
+  // (B) the apply stream is idle here and a dense-window generate (possibly running on the main
+  // stream right now) touches neither the map nor these buffers
+  VM_TRY(ensure_on(h, &h->recv, std::max<size_t>(total, 1) * sizeof(BlockRecord), as));
   while (((uint64_t)h->h_persist->n_entries + total) * 2 > h->table_cap) VM_TRY(grow_table(h));
   if ((uint64_t)h->h_persist->n_slots + total > h->pool_cap) VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_slots + total));
   BlockRecord* recv = (BlockRecord*)h->recv.p;
   const BlockRecord* send = (const BlockRecord*)h->pack_inflight.p;
   size_t send_off[kMaxRanks], so = 0;
-  for (int d = 0; d < G; d++) { send_off[d] = so; so += h->h_pack_counts[d]; }
+  for (int d = 0; d < G; d++) { send_off[d] = so; so += h_counts[d]; }
   // (C) exchange + apply, asynchronous
   if (h->l2_flush_bytes) VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(h->dbg_n & 0xFF), h->l2_flush_bytes, as));
   VM_CUDA(h, cudaEventRecord(h->ev_app0, as));
   VM_NCCL(h, g_nccl.GroupStart());
   for (int p = 0; p < G; p++) {
     if (p == me) continue;
-    if (h->h_pack_counts[p])
-      VM_NCCL(h, g_nccl.Send(send + send_off[p], (size_t)h->h_pack_counts[p] * sizeof(BlockRecord), kNcclUint8, p, comm, as));
+    if (h_counts[p])
+      VM_NCCL(h, g_nccl.Send(send + send_off[p], (size_t)h_counts[p] * sizeof(BlockRecord), kNcclUint8, p, comm, as));
     if (recv_counts[p])
       VM_NCCL(h, g_nccl.Recv(recv + recv_off[p], recv_counts[p] * sizeof(BlockRecord), kNcclUint8, p, comm, as));
   }
@@ -556,7 +587,7 @@ int dist_round(vmap* h) {
   VM_CUDA(h, cudaMemcpyAsync(h->h_cnt_app, h->d_cnt_app, sizeof(Counters), cudaMemcpyDeviceToHost, as));
   VM_CUDA(h, cudaMemcpyAsync(h->h_persist_app, h->m.persist, sizeof(Persist), cudaMemcpyDeviceToHost, as));
   h->app_records = total;
-  h->app_sent = so - h->h_pack_counts[me];
+  h->app_sent = so - h_counts[me];
   h->app_received = total - recv_counts[me];
   h->app_pending = true;
   const double t_c = now_ms();
@@ -571,7 +602,11 @@ extern "C" {
 int vmap_dist_flush(vmap* h) {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
-  return flush_app(h);
+  h->in_collective = true;
+  int st = complete_round(h);
+  if (st == VMAP_OK) st = flush_app(h);
+  h->in_collective = false;
+  return st;
 }
 
 // Test / benchmark hook: overwrite `bytes` of scratch (larger than L2) on the apply stream before
@@ -585,32 +620,67 @@ int vmap_set_debug_l2_flush(vmap* h, size_t bytes) {
   return VMAP_OK;
 }
 
+}  // extern "C"
+namespace {
+// One collective insert: the new scan is generated on the main stream; while its kernels run, the
+// previous round (generated by the previous call) is exchanged and its apply is queued on the
+// apply stream.  The new round stays pending until the next collective call or vmap_dist_flush.
+int dist_insert(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_dense, const double Tm[16]) {
+  if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
+  VM_TRY(init_app_stream(h));
+  h->in_collective = true;
+  struct Leave { vmap* h; ~Leave() { h->in_collective = false; } } leave{h};
+  if (h->capture) {   // parity hook: synchronous round through the table's mask columns
+    VM_TRY(complete_round(h));
+    VM_TRY(flush_app(h));
+    VM_TRY(shard_generate_common(h, d_in, n, stride, is_dense, Tm, nullptr, []() -> int { return VMAP_OK; }));
+    return dist_exchange_and_apply(h);
+  }
+  // this scan packs into the buffer / count slot the pending round is not using; the send that
+  // last read that buffer was queued two calls ago -- make the main stream wait for it anyway
+  if (h->round_pending) {
+    std::swap(h->pack, h->pack_inflight);
+    h->pack_slot ^= 1;
+  }
+  h->d_pack_counts = h->d_pack_counts_base + (size_t)h->pack_slot * 2 * kMaxRanks;
+  h->h_pack_counts = h->h_pack_counts_slot[h->pack_slot];
+  static const int dbg_mode = getenv("VMAP_DIST_MODE") ? atoi(getenv("VMAP_DIST_MODE")) : 0;
+  if (h->app_pending && !(dbg_mode & 1)) VM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_app1, 0));
+  const double t0 = now_ms();
+  if (dbg_mode & 2) {   // experiment: exchange the previous round BEFORE generating (no NCCL / generate overlap)
+    VM_TRY(complete_round(h));
+    VM_TRY(shard_generate_common(h, d_in, n, stride, is_dense, Tm, nullptr, []() -> int { return VMAP_OK; }));
+  } else {
+    VM_TRY(shard_generate_common(h, d_in, n, stride, is_dense, Tm, nullptr, [&]() -> int { return complete_round(h); }));
+  }
+  h->dbg_ms[0] += now_ms() - t0;
+  h->round_pending = true;
+  h->round_packed = h->packed;
+  h->round_slot = h->pack_slot;
+  return VMAP_OK;
+}
+}  // namespace
+extern "C" {
+
 int vmap_dist_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n, size_t stride_bytes,
                                     const double T_rowmajor[16]) {
-  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  if (!h || (!d_xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
-  const double t0 = now_ms();
-  VM_TRY(vmap_shard_generate_dev(h, d_xyz, n, stride_bytes, T_rowmajor, nullptr));
-  h->dbg_ms[0] += now_ms() - t0;
-  if (h->capture) {   // parity hook: synchronous round through the table's mask columns
-    VM_TRY(dist_exchange_and_apply(h));
-    return VMAP_OK;
-  }
-  return dist_round(h);
+  return dist_insert(h, (const uint8_t*)d_xyz, n, stride_bytes, 1, T_rowmajor);
 }
 
 int vmap_dist_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes, int is_dense,
                                 const double T_rowmajor[16]) {
-  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
-  const double t0 = now_ms();
-  VM_TRY(vmap_shard_generate(h, xyz, n, stride_bytes, is_dense, T_rowmajor, nullptr));
-  h->dbg_ms[0] += now_ms() - t0;
-  if (h->capture) {
-    VM_TRY(dist_exchange_and_apply(h));
-    return VMAP_OK;
+  if (n) {
+    const size_t bytes = (n - 1) * stride_bytes + 12;
+    VM_TRY(ensure(h, &h->in, bytes));
+    VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
   }
-  return dist_round(h);
+  return dist_insert(h, (const uint8_t*)h->in.p, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor);
 }
 
 // Sharded queries: partial answers of this shard (combine = element-wise MIN over ranks).
@@ -646,6 +716,7 @@ int vmap_shard_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint32_t* 
 int vmap_dist_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status) {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
+  VM_TRY(vmap_dist_flush(h));
   VM_TRY(vmap_shard_query_points_dev(h, d_xyz, n, d_status));
   if (!n) return VMAP_OK;
   VM_NCCL(h, g_nccl.AllReduce(d_status, d_status, n, kNcclUint8, kNcclMin, (NcclComm)h->nccl_comm, h->stream));
@@ -656,6 +727,7 @@ int vmap_dist_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* 
 int vmap_dist_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_status) {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
+  VM_TRY(vmap_dist_flush(h));
   if (!n) return VMAP_OK;
   VM_TRY(ensure(h, &h->aux, n * sizeof(uint32_t)));
   VM_TRY(vmap_shard_query_lines_dev(h, d_ab, n, (uint32_t*)h->aux.p));
