@@ -153,11 +153,21 @@ def cpu_baseline_sample(budget_s=20.0):
         trav += st["traversals"]
         split[0] += st["t_keyset_s"]; split[1] += st["t_update_s"]; split[2] += st["t_inner_s"]
         scans += 1
+    # cfg5 on the CPU: a bounded sample of the same query distribution against this 4-scan map
+    q = scenes.cfg5_queries(n_segments=100000, n_points=100000,
+                            bounds=((-45.0, 45.0 + 0.5 * scans), (-45.0, 45.0), (-0.5, 4.0)))
+    t0 = time.perf_counter()
+    ow.getLineStatus(q["segments"])
+    t1 = time.perf_counter()
+    ow.getCellStatusPoint(q["points"])
+    t2 = time.perf_counter()
     return {"value": trav / t_total, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "%d full cfg3 scans of the same trajectory, %.1f s of CPU work "
                       "(keyset %.1f s / updateNode %.1f s / updateInnerOccupancy %.1f s)"
                       % (scans, t_total, split[0], split[1], split[2]),
-            "scans_per_s": scans / t_total, "host_cpus": os.cpu_count()}
+            "scans_per_s": scans / t_total, "host_cpus": os.cpu_count(),
+            "queries": {"segments_per_s": 100000 / (t1 - t0), "points_per_s": 100000 / (t2 - t1),
+                        "sample": "100k segments + 100k points vs the map of %d scans" % scans}}
 
 
 def run_reference(args):
@@ -292,11 +302,40 @@ def run_b200(args):
         launches = w.kernel_launches() - launches0
         out = {"stats": stats, "gpu_ms": gpu_ms, "wall_ms": wall_ms, "launches": launches,
                "clocks": clocks, "device_bytes": w.device_bytes()}
+        if kind == "dev" and world == 1:
+            out["queries"] = time_queries(w, total)
         if world > 1:
             sw.close()
         else:
             w.close()
         return out
+
+    def time_queries(w, n_scans):
+        """cfg5: 1M getLineStatus segments + 1M getCellStatusPoint points against the map just
+        built (device-resident queries, L2 flushed, wall clock around the C ABI call)."""
+        q = scenes.cfg5_queries(bounds=((-45.0, 45.0 + 0.5 * n_scans), (-45.0, 45.0), (-0.5, 4.0)))
+        seg = torch.from_numpy(q["segments"]).cuda()
+        pts = torch.from_numpy(q["points"]).cuda()
+        sl = torch.zeros(seg.shape[0], dtype=torch.uint8, device="cuda")
+        sp = torch.zeros(pts.shape[0], dtype=torch.uint8, device="cuda")
+        best_l, best_p = 1e9, 1e9
+        for rep in range(4):
+            flush.fill_(rep)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            w.getLineStatusDevice(seg.data_ptr(), seg.shape[0], sl.data_ptr())
+            t1 = time.perf_counter()
+            flush.fill_(rep + 7)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            w.getCellStatusPointDevice(pts.data_ptr(), pts.shape[0], sp.data_ptr())
+            t3 = time.perf_counter()
+            if rep:
+                best_l, best_p = min(best_l, t1 - t0), min(best_p, t3 - t2)
+        return {"workload": "cfg5: 1M segments (0.5-20 m) + 1M points vs the 0.1 m map of %d scans" % n_scans,
+                "segments_per_s": seg.shape[0] / best_l, "points_per_s": pts.shape[0] / best_p,
+                "line_ms": 1e3 * best_l, "point_ms": 1e3 * best_p,
+                "non_free_fraction": float((sl != 0).float().mean().item())}
 
     dev = run("dev")
     host = run("host")
@@ -370,6 +409,7 @@ def run_b200(args):
             "clocks": dev["clocks"],
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "queries": dev.get("queries"),
             "device_bytes": dev["device_bytes"],
         }
         print(json.dumps(line))

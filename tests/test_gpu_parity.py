@@ -419,3 +419,43 @@ def test_cfg5_style_queries_on_hdl64_map():
     g, o = gw.getLineStatus(q["segments"]), ow.getLineStatus(q["segments"])
     assert np.array_equal(g, o)
     assert set(g.tolist()) == {0, 1}        # treat_unknown_as_occupied folds unknown into 1
+
+
+# ---------------------------------------------------------------------------------------
+# BASELINE.json full sizes: cfg4 against the oracle (one scan), and size-independent
+# properties where the oracle would take too long
+# ---------------------------------------------------------------------------------------
+def test_cfg4_scan_full_size_0p05m():
+    s = scenes.cfg4_scan(37)                       # 0.05 m voxels, ~56 M traversals
+    gw, ow = pair("dense", **s["params"])
+    ow.set_faithful_inner_update(False)
+    gw.insertPointcloud(s["T"], s["points"])
+    ow.insertPointcloud(s["T"], s["points"])
+    assert gw.last_scan_stats()["traversals"] > 50_000_000
+    assert_same_stats(gw, ow)
+    assert_same_keys(gw, ow)
+    assert_same_leaves(gw, ow)
+
+
+def test_full_size_properties_idempotence_at_clamps_and_round_trip():
+    s = scenes.cfg3_scan()
+    gw = vm.OctomapWorld(**s["params"])
+    gw.set_debug_capture(True)
+    for _ in range(7):                             # 5 misses reach the lower clamp, 6 hits the upper
+        gw.insertPointcloudFast(s["T"], s["points"])
+    f, o = gw.last_scan_keys()
+    pf, po = oracle.pack_keys(f), oracle.pack_keys(o)
+    assert np.intersect1d(pf, po).size == 0        # free and occupied sets are disjoint
+    assert np.unique(pf).size == pf.size and np.unique(po).size == po.size
+    k7, v7 = leaves_packed(gw)
+    assert set(np.unique(v7).tolist()) == {0xbfff07f4, 0x405e7867}   # every leaf sits at a clamp
+    gw.insertPointcloudFast(s["T"], s["points"])    # ... so one more identical scan changes nothing
+    k8, v8 = leaves_packed(gw)
+    assert np.array_equal(k7, k8) and np.array_equal(v7, v8)
+    assert k7.size == pf.size + po.size             # the map is exactly the scan's key sets
+    # export -> import -> export is the identity at full size (9.8 M leaves)
+    k, v = gw.export_leaves()
+    g2 = vm.OctomapWorld(**s["params"])
+    g2.import_leaves(k, v)
+    k2, v2 = leaves_packed(g2)
+    assert np.array_equal(k2, k8) and np.array_equal(v2, v8)
