@@ -182,6 +182,18 @@ VMAP_API int vmap_query_lines(vmap* h, const double* start_end_xyz6, size_t n, u
 VMAP_API int vmap_query_lines_dev(vmap* h, const double* d_start_end_xyz6, size_t n,
                                   uint8_t* d_status);
 
+/* Query variants that are fan-outs of the two kernels above, batched:
+ * getCellTrueStatusPoint + getCellProbabilityPoint (octomap_world.cc:363-393): status with unknown
+ * kept as VMAP_CELL_UNKNOWN; probability (may be NULL) = node->getOccupancy(), -1.0 without node. */
+VMAP_API int vmap_query_points_probability(vmap* h, const double* xyz, size_t n, uint8_t* status,
+                                           double* probability);
+/* getVisibility (octomap_world.cc:420-449): n x (view point xyz, voxel to test xyz). */
+VMAP_API int vmap_query_visibility(vmap* h, const double* view_voxel_xyz6, size_t n,
+                                   int stop_at_unknown_cell, uint8_t* status);
+/* getLineStatusBoundingBox (octomap_world.cc:451-493): every segment swept with the same box. */
+VMAP_API int vmap_query_lines_bbox(vmap* h, const double* start_end_xyz6, size_t n,
+                                   const double bounding_box_size[3], uint8_t* status);
+
 /* Finest-level leaves (what octree_->begin_leafs() would visit after expanding pruned nodes):
  * used by the on-demand export to octomap::OcTree for the unchanged publish/save paths
  * (octomap_world.cc:820-856) and by the parity tests. */

@@ -69,6 +69,34 @@ class OctomapWorld : public WorldBase {
     check(vmap_query_lines(handle_, ab, 1, &s));
     return static_cast<CellStatus>(s);
   }
+  // octomap_world.cc:363-373
+  virtual CellStatus getCellTrueStatusPoint(const Vector3d& point) const {
+    uint8_t s = 0;
+    check(vmap_query_points_probability(handle_, point.v, 1, &s, nullptr));
+    return static_cast<CellStatus>(s);
+  }
+  // octomap_world.cc:375-393
+  virtual CellStatus getCellProbabilityPoint(const Vector3d& point, double* probability) const {
+    uint8_t s = 0;
+    check(vmap_query_points_probability(handle_, point.v, 1, &s, probability));
+    return static_cast<CellStatus>(s);
+  }
+  // octomap_world.cc:420-449
+  virtual CellStatus getVisibility(const Vector3d& view_point, const Vector3d& voxel_to_test,
+                                   bool stop_at_unknown_cell) const {
+    const double ab[6] = {view_point.x(), view_point.y(), view_point.z(), voxel_to_test.x(), voxel_to_test.y(), voxel_to_test.z()};
+    uint8_t s = 0;
+    check(vmap_query_visibility(handle_, ab, 1, stop_at_unknown_cell ? 1 : 0, &s));
+    return static_cast<CellStatus>(s);
+  }
+  // octomap_world.cc:451-493
+  virtual CellStatus getLineStatusBoundingBox(const Vector3d& start, const Vector3d& end,
+                                              const Vector3d& bounding_box_size) const {
+    const double ab[6] = {start.x(), start.y(), start.z(), end.x(), end.y(), end.z()};
+    uint8_t s = 0;
+    check(vmap_query_lines_bbox(handle_, ab, 1, bounding_box_size.v, &s));
+    return static_cast<CellStatus>(s);
+  }
   // Batched forms of the two queries (what planners call in bulk): one kernel launch.
   void getCellStatusPoints(const std::vector<Vector3d>& points, std::vector<uint8_t>* status) const {
     status->resize(points.size());

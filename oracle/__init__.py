@@ -96,6 +96,9 @@ def lib():
     L.oracle_apply_keys.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t]
     L.oracle_query_points.argtypes = [vp, vp, C.c_size_t, vp]
     L.oracle_query_lines.argtypes = [vp, vp, C.c_size_t, vp]
+    L.oracle_query_points_probability.argtypes = [vp, vp, C.c_size_t, vp, vp]
+    L.oracle_query_visibility.argtypes = [vp, vp, C.c_size_t, C.c_int, vp]
+    L.oracle_query_lines_bbox.argtypes = [vp, vp, C.c_size_t, dp, vp]
     L.oracle_coord_to_key_checked.argtypes = [vp, C.c_double, C.POINTER(C.c_uint16)]
     L.oracle_coord_to_key_checked.restype = C.c_int
     L.oracle_coord_to_key.argtypes = [vp, C.c_double]
@@ -229,6 +232,28 @@ class OracleWorld:
         out = np.zeros(p.shape[0], dtype=np.uint8)
         self._L.oracle_query_lines(self._h, p.ctypes.data, p.shape[0], out.ctypes.data)
         return out
+
+    def getCellProbabilityPoint(self, xyz):
+        p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        st = np.zeros(p.shape[0], dtype=np.uint8)
+        pr = np.zeros(p.shape[0], dtype=np.float64)
+        self._L.oracle_query_points_probability(self._h, p.ctypes.data, p.shape[0], st.ctypes.data,
+                                                pr.ctypes.data)
+        return st, pr
+
+    def getVisibility(self, view_voxel_xyz6, stop_at_unknown_cell):
+        p = np.ascontiguousarray(view_voxel_xyz6, dtype=np.float64).reshape(-1, 6)
+        st = np.zeros(p.shape[0], dtype=np.uint8)
+        self._L.oracle_query_visibility(self._h, p.ctypes.data, p.shape[0],
+                                        int(bool(stop_at_unknown_cell)), st.ctypes.data)
+        return st
+
+    def getLineStatusBoundingBox(self, start_end_xyz6, bounding_box_size):
+        p = np.ascontiguousarray(start_end_xyz6, dtype=np.float64).reshape(-1, 6)
+        b = np.ascontiguousarray(bounding_box_size, dtype=np.float64).reshape(3)
+        st = np.zeros(p.shape[0], dtype=np.uint8)
+        self._L.oracle_query_lines_bbox(self._h, p.ctypes.data, p.shape[0], _dptr(b), st.ctypes.data)
+        return st
 
     # -- primitives ---------------------------------------------------------------------
     def coordToKey(self, c):

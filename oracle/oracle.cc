@@ -907,6 +907,72 @@ void oracle_query_lines(const oracle_world* w, const double* ab, size_t n, uint8
   }
 }
 
+// octomap_world.cc:363-393: getCellTrueStatusPoint + getCellProbabilityPoint
+void oracle_query_points_probability(const oracle_world* w, const double* xyz, size_t n, uint8_t* status,
+                                     double* probability) {
+  for (size_t i = 0; i < n; i++) {
+    Node* node = w->octree->search(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    if (node == NULL) {
+      if (probability) probability[i] = -1.0;
+      status[i] = 2;
+    } else {
+      // OcTreeNode::getOccupancy() = probability(value) = 1. - ( 1. / (1. + exp(logodds)))
+      if (probability) probability[i] = 1. - (1. / (1. + std::exp((double)node->value)));
+      status[i] = w->octree->isNodeOccupied(node) ? 1 : 0;
+    }
+  }
+}
+
+// octomap_world.cc:420-449
+void oracle_query_visibility(const oracle_world* w, const double* ab, size_t n, int stop_at_unknown_cell,
+                             uint8_t* status) {
+  for (size_t i = 0; i < n; i++) {
+    KeyRay key_ray;
+    const Vec3f a((float)ab[6 * i], (float)ab[6 * i + 1], (float)ab[6 * i + 2]);
+    const Vec3f b((float)ab[6 * i + 3], (float)ab[6 * i + 4], (float)ab[6 * i + 5]);
+    w->octree->computeRayKeys(a, b, key_ray);
+    const Key voxel_to_test_key = w->octree->coordToKey(b);
+    uint8_t st = 0;
+    for (size_t j = 0; j < key_ray.size(); j++) {
+      const Key& key = key_ray.ray[j];
+      if (key == voxel_to_test_key) continue;
+      Node* node = w->octree->search(key);
+      if (node == NULL) {
+        if (stop_at_unknown_cell) { st = 2; break; }
+      } else if (w->octree->isNodeOccupied(node)) {
+        st = 1;
+        break;
+      }
+    }
+    status[i] = st;
+  }
+}
+
+// octomap_world.cc:451-493
+void oracle_query_lines_bbox(const oracle_world* w, const double* ab, size_t n, const double bounding_box_size[3],
+                             uint8_t* status) {
+  const double epsilon = 0.001;
+  const double resolution = w->octree->getResolution();
+  double x_disc = bounding_box_size[0] / ceil((bounding_box_size[0] + epsilon) / resolution);
+  double y_disc = bounding_box_size[1] / ceil((bounding_box_size[1] + epsilon) / resolution);
+  double z_disc = bounding_box_size[2] / ceil((bounding_box_size[2] + epsilon) / resolution);
+  if (x_disc <= 0.0) x_disc = 1.0;
+  if (y_disc <= 0.0) y_disc = 1.0;
+  if (z_disc <= 0.0) z_disc = 1.0;
+  const double hx = bounding_box_size[0] * 0.5, hy = bounding_box_size[1] * 0.5, hz = bounding_box_size[2] * 0.5;
+  for (size_t i = 0; i < n; i++) {
+    uint8_t ret = 0;
+    for (double x = -hx; x <= hx && ret == 0; x += x_disc)
+      for (double y = -hy; y <= hy && ret == 0; y += y_disc)
+        for (double z = -hz; z <= hz && ret == 0; z += z_disc) {
+          const double seg[6] = {ab[6 * i] + x,     ab[6 * i + 1] + y, ab[6 * i + 2] + z,
+                                 ab[6 * i + 3] + x, ab[6 * i + 4] + y, ab[6 * i + 5] + z};
+          oracle_query_lines(w, seg, 1, &ret);
+        }
+    status[i] = ret;
+  }
+}
+
 int oracle_coord_to_key_checked(const oracle_world* w, double c, uint16_t* key) {
   key_type k = 0;
   bool ok = w->octree->coordToKeyChecked(c, k);

@@ -95,6 +95,15 @@ void oracle_apply_keys(oracle_world* w, const uint16_t* free_k3, size_t n_free,
 void oracle_query_points(const oracle_world* w, const double* xyz, size_t n, uint8_t* status);
 void oracle_query_lines(const oracle_world* w, const double* a_b_xyz6, size_t n, uint8_t* status);
 
+/* getCellTrueStatusPoint + getCellProbabilityPoint (octomap_world.cc:363-393), getVisibility
+ * (:420-449), getLineStatusBoundingBox (:451-493). */
+void oracle_query_points_probability(const oracle_world* w, const double* xyz, size_t n,
+                                     uint8_t* status, double* probability);
+void oracle_query_visibility(const oracle_world* w, const double* view_voxel_xyz6, size_t n,
+                             int stop_at_unknown_cell, uint8_t* status);
+void oracle_query_lines_bbox(const oracle_world* w, const double* a_b_xyz6, size_t n,
+                             const double bounding_box_size[3], uint8_t* status);
+
 /* Standalone primitives (known-answer tests). */
 int oracle_coord_to_key_checked(const oracle_world* w, double c, uint16_t* key);
 uint16_t oracle_coord_to_key(const oracle_world* w, double c);

@@ -84,7 +84,8 @@ SYMBOLS = [
     "vmap_shard_query_points_dev", "vmap_shard_query_lines_dev", "vmap_dist_unique_id",
     "vmap_dist_init", "vmap_dist_shutdown", "vmap_dist_insert_pointcloud",
     "vmap_dist_insert_pointcloud_dev", "vmap_dist_query_points_dev", "vmap_dist_query_lines_dev",
-    "vmap_dist_flush", "vmap_set_debug_l2_flush", "vmap_tree_size", "vmap_serialize_bt", "vmap_write_bt", "vmap_load_bt", "vmap_deserialize_bt",
+    "vmap_dist_flush", "vmap_set_debug_l2_flush", "vmap_query_points_probability",
+    "vmap_query_visibility", "vmap_query_lines_bbox", "vmap_tree_size", "vmap_serialize_bt", "vmap_write_bt", "vmap_load_bt", "vmap_deserialize_bt",
 ]
 
 STATUS_NAMES = {0: "VMAP_OK", 1: "VMAP_ERR_INVALID_ARGUMENT", 2: "VMAP_ERR_CUDA",
@@ -150,6 +151,9 @@ def lib():
     L.vmap_device_bytes.restype = C.c_uint64
     u64p = C.POINTER(C.c_uint64)
     L.vmap_tree_size.argtypes = [vp, C.c_int, C.POINTER(sz)]
+    L.vmap_query_points_probability.argtypes = [vp, vp, sz, vp, vp]
+    L.vmap_query_visibility.argtypes = [vp, vp, sz, C.c_int, vp]
+    L.vmap_query_lines_bbox.argtypes = [vp, vp, sz, dp, vp]
     L.vmap_serialize_bt.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.vmap_write_bt.argtypes = [vp, C.c_char_p, C.c_int]
     L.vmap_load_bt.argtypes = [vp, C.c_char_p]

@@ -1150,7 +1150,7 @@ int vmap_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_sta
   VM_CUDA(h, cudaSetDevice(h->device));
   VM_TRY(flush_app(h));
   if (!n) return VMAP_OK;
-  k_query_points<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->m, d_xyz, (uint32_t)n, d_status);
+  k_query_points<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->m, d_xyz, (uint32_t)n, d_status, 0, nullptr);
   h->launches++;
   VM_CUDA(h, cudaGetLastError());
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -1191,6 +1191,102 @@ int vmap_query_lines(vmap* h, const double* ab, size_t n, uint8_t* status) {
   VM_TRY(ensure(h, &h->out, n));
   VM_CUDA(h, cudaMemcpyAsync(h->in.p, ab, n * 48, cudaMemcpyHostToDevice, h->stream));
   VM_TRY(vmap_query_lines_dev(h, (const double*)h->in.p, n, (uint8_t*)h->out.p));
+  VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+// getCellTrueStatusPoint / getCellProbabilityPoint (octomap_world.cc:363-393), batched.
+// probability (may be NULL): OcTreeNode::getOccupancy() = 1 - 1 / (1 + exp(log-odds)) evaluated on
+// the HOST in double like the reference does (libm exp), -1.0 where there is no node.
+int vmap_query_points_probability(vmap* h, const double* xyz, size_t n, uint8_t* status, double* probability) {
+  if (!h || ((!xyz || !status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query points");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
+  if (!n) return VMAP_OK;
+  VM_TRY(ensure(h, &h->in, n * 24));
+  VM_TRY(ensure(h, &h->out, n));
+  VM_TRY(ensure(h, &h->aux, n * 4));
+  VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
+  k_query_points<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->m, (const double*)h->in.p, (uint32_t)n,
+                                                         (uint8_t*)h->out.p, 1, (float*)h->aux.p);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
+  std::vector<float> lo;
+  if (probability) {
+    lo.resize(n);
+    VM_CUDA(h, cudaMemcpyAsync(lo.data(), h->aux.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  }
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (probability)
+    for (size_t i = 0; i < n; i++)
+      probability[i] = (status[i] == VMAP_CELL_UNKNOWN) ? -1.0 : 1. - (1. / (1. + std::exp((double)lo[i])));
+  return VMAP_OK;
+}
+
+// getVisibility (octomap_world.cc:420-449), batched: n x (view point xyz, voxel to test xyz).
+int vmap_query_visibility(vmap* h, const double* view_voxel_xyz6, size_t n, int stop_at_unknown_cell, uint8_t* status) {
+  if (!h || ((!view_voxel_xyz6 || !status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many queries");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
+  if (!n) return VMAP_OK;
+  VM_TRY(ensure(h, &h->in, n * 48));
+  VM_TRY(ensure(h, &h->out, n));
+  VM_CUDA(h, cudaMemcpyAsync(h->in.p, view_voxel_xyz6, n * 48, cudaMemcpyHostToDevice, h->stream));
+  k_query_visibility<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->m, (const double*)h->in.p, (uint32_t)n,
+                                                             stop_at_unknown_cell ? 1 : 0, (uint8_t*)h->out.p);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+// getLineStatusBoundingBox (octomap_world.cc:451-493), batched: every segment is swept with the
+// same box.  The offset grid is produced by the reference's own loops (accumulating doubles).
+int vmap_query_lines_bbox(vmap* h, const double* start_end_xyz6, size_t n, const double bounding_box_size[3], uint8_t* status) {
+  if (!h || ((!start_end_xyz6 || !status) && n) || !bounding_box_size) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
+  if (!n) return VMAP_OK;
+  const double epsilon = 0.001;
+  const double resolution = h->params.resolution;
+  double disc[3];
+  for (int a = 0; a < 3; a++) {
+    disc[a] = bounding_box_size[a] / std::ceil((bounding_box_size[a] + epsilon) / resolution);
+    if (disc[a] <= 0.0) disc[a] = 1.0;
+  }
+  const double half[3] = {bounding_box_size[0] * 0.5, bounding_box_size[1] * 0.5, bounding_box_size[2] * 0.5};
+  std::vector<double> off;
+  for (double x = -half[0]; x <= half[0]; x += disc[0])
+    for (double y = -half[1]; y <= half[1]; y += disc[1])
+      for (double z = -half[2]; z <= half[2]; z += disc[2]) {
+        off.push_back(x); off.push_back(y); off.push_back(z);
+        if (off.size() > 3u * (1u << 22)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bounding box too large for the resolution");
+      }
+  const size_t n_off = off.size() / 3;
+  if (n_off == 0) {   // (negative box size: the reference's loops never run -> free)
+    std::memset(status, 0, n);
+    return VMAP_OK;
+  }
+  if (n > 0x7FFFFFFFull || n_off >= (1u << 30)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many queries");
+  VM_TRY(ensure(h, &h->in, n * 48 + off.size() * 8));
+  VM_TRY(ensure(h, &h->aux, n * 4));
+  VM_TRY(ensure(h, &h->out, n));
+  double* d_ab = (double*)h->in.p;
+  double* d_off = d_ab + n * 6;
+  VM_CUDA(h, cudaMemcpyAsync(d_ab, start_end_xyz6, n * 48, cudaMemcpyHostToDevice, h->stream));
+  VM_CUDA(h, cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->aux.p, 0xFF, n * 4, h->stream));
+  const unsigned long long work = (unsigned long long)n * n_off;
+  if (work > 0x7FFFFFFFull * 128ull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many (segment, offset) pairs");
+  k_query_lines_bbox<<<(unsigned)((work + 127) / 128), 128, 0, h->stream>>>(h->P, h->m, d_ab, (uint32_t)n, d_off, (uint32_t)n_off, (uint32_t*)h->aux.p);
+  k_unpack_line_status<<<grid_for(n, 256), 256, 0, h->stream>>>((const uint32_t*)h->aux.p, (uint32_t)n, (uint8_t*)h->out.p);
+  h->launches += 2;
+  VM_CUDA(h, cudaGetLastError());
   VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;

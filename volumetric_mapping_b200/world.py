@@ -177,6 +177,37 @@ class OctomapWorld:
         self._check(self._L.vmap_query_lines(self._h, p.ctypes.data, p.shape[0], out.ctypes.data))
         return out
 
+    def getCellProbabilityPoint(self, xyz):
+        """(true status, probability) per point (octomap_world.cc:363-393)."""
+        p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        st = np.zeros(p.shape[0], dtype=np.uint8)
+        pr = np.zeros(p.shape[0], dtype=np.float64)
+        self._check(self._L.vmap_query_points_probability(self._h, p.ctypes.data, p.shape[0],
+                                                          st.ctypes.data, pr.ctypes.data))
+        return st, pr
+
+    def getCellTrueStatusPoint(self, xyz):
+        p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        st = np.zeros(p.shape[0], dtype=np.uint8)
+        self._check(self._L.vmap_query_points_probability(self._h, p.ctypes.data, p.shape[0],
+                                                          st.ctypes.data, None))
+        return st
+
+    def getVisibility(self, view_voxel_xyz6, stop_at_unknown_cell):
+        p = np.ascontiguousarray(view_voxel_xyz6, dtype=np.float64).reshape(-1, 6)
+        st = np.zeros(p.shape[0], dtype=np.uint8)
+        self._check(self._L.vmap_query_visibility(self._h, p.ctypes.data, p.shape[0],
+                                                  int(bool(stop_at_unknown_cell)), st.ctypes.data))
+        return st
+
+    def getLineStatusBoundingBox(self, start_end_xyz6, bounding_box_size):
+        p = np.ascontiguousarray(start_end_xyz6, dtype=np.float64).reshape(-1, 6)
+        b = np.ascontiguousarray(bounding_box_size, dtype=np.float64).reshape(3)
+        st = np.zeros(p.shape[0], dtype=np.uint8)
+        self._check(self._L.vmap_query_lines_bbox(self._h, p.ctypes.data, p.shape[0], _dptr(b),
+                                                  st.ctypes.data))
+        return st
+
     def getCellStatusPointDevice(self, xyz_ptr, n, status_ptr):
         self._check(self._L.vmap_query_points_dev(self._h, C.c_void_p(int(xyz_ptr)), int(n),
                                                   C.c_void_p(int(status_ptr))))
