@@ -247,8 +247,9 @@ def run_b200(args):
         """kind: 'dev' (inputs resident in HBM) or 'host' (pinned host buffers, H2D inside)."""
         if world > 1:
             from volumetric_mapping_b200 import sharded
-            sw = sharded.ShardedOctomapWorld(rank, world, local_rank, resolution=RESOLUTION,
-                                             sensor_max_range=MAX_RANGE, initial_blocks=1 << 18)
+            sw = sharded.ShardedOctomapWorld(rank, world, local_rank, batch=args.dist_batch,
+                                             resolution=RESOLUTION, sensor_max_range=MAX_RANGE,
+                                             initial_blocks=1 << 18)
             w = sw.local
             w.set_debug_l2_flush(256 << 20)   # in-stream L2 flush before every round's apply
         else:
@@ -397,8 +398,8 @@ def run_b200(args):
                                   if world == 1 else "wall clock over the K pipelined rounds, barrier + "
                                   "device sync on both sides, max over ranks"),
                        "sharding": ("one map sharded by 8^3-block owner over %d ranks; step = "
-                                    "round of %d scans, NCCL all-to-all of block records"
-                                    % (world, world)) if world > 1 else "single GPU"},
+                                    "round of %d scans, NCCL all-to-all of block records once per "
+                                    "%d rounds" % (world, world, args.dist_batch)) if world > 1 else "single GPU"},
             "scans_per_s": K * world / t_dev,
             "e2e": {"value": trav_host / t_host, "unit": UNIT,
                     "h2d_bytes_per_step": n_pts * 12, "d2h_bytes_per_step": 80,
@@ -425,6 +426,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist-batch", type=int, default=4,
+                    help="N > 1: scans per rank that share one exchange round (1..8)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

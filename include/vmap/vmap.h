@@ -275,6 +275,8 @@ VMAP_API int vmap_dist_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t
  * on a second stream while the next round is generated.  Every call that reads the map waits for
  * the round in flight first; vmap_dist_flush does so explicitly. */
 VMAP_API int vmap_dist_flush(vmap* h);
+/* Scans per rank that share one exchange round (1..8, default 1).  COLLECTIVE setting. */
+VMAP_API int vmap_dist_set_batch(vmap* h, int scans_per_rank);
 /* Benchmark hook: overwrite `bytes` (> L2) of scratch before every round's exchange. 0 = off. */
 VMAP_API int vmap_set_debug_l2_flush(vmap* h, size_t bytes);
 /* COLLECTIVE queries: every rank passes the same queries and receives the global statuses. */

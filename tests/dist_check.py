@@ -14,13 +14,16 @@ from volumetric_mapping_b200 import scenes, sharded  # noqa: E402
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(75, exit=True)   # a stuck collective must not eat the GPU budget
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     params = dict(resolution=0.2, sensor_max_range=50.0)
-    n_scans = 2 * world + 1
-    w = sharded.ShardedOctomapWorld(rank, world, local, initial_blocks=64, **params)
+    batch = int(os.environ.get("DIST_BATCH", "1"))
+    n_scans = 3 * world + 1
+    w = sharded.ShardedOctomapWorld(rank, world, local, batch=batch, initial_blocks=64, **params)
     for i in sharded.scans_of_rank(n_scans, rank, world):
         if i >= 0:
             s = scenes.trajectory_scan(2 * i, resolution=0.2)

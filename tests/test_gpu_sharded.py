@@ -91,8 +91,10 @@ def test_sharded_hdl64_scans_and_queries():
     assert np.array_equal(got_l, ow.getLineStatus(q["segments"]))
 
 
-def test_nccl_two_ranks_if_two_gpus():
-    """The real exchange: needs >= 2 GPUs (gpurun --gpus 2); skipped on a 1-GPU box."""
+@pytest.mark.parametrize("batch", [1, 2])
+def test_nccl_two_ranks_if_two_gpus(batch):
+    """The real exchange: needs >= 2 GPUs (gpurun --gpus 2); skipped on a 1-GPU box.  batch = scans
+    per rank that share one exchange round (a ragged last batch is part of the case)."""
     import subprocess
     import sys
     import os
@@ -101,8 +103,20 @@ def test_nccl_two_ranks_if_two_gpus():
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29531",
+           "--master-addr", "127.0.0.1", "--master-port", str(29531 + batch),
            os.path.join(root, "tests", "dist_check.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    import signal
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                            env=dict(os.environ, DIST_BATCH=str(batch)), start_new_session=True)
+    try:
+        stdout, stderr = proc.communicate(timeout=150)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)      # the whole process group: no stray ranks on the GPUs
+        stdout, stderr = proc.communicate()
+        raise AssertionError("dist_check timed out\n" + stdout[-3000:] + stderr[-6000:])
+    assert proc.returncode == 0, stdout[-3000:] + stderr[-6000:]
+
+    class out:   # noqa: N801
+        pass
+    out.stdout = stdout
     assert "DIST_CHECK_OK" in out.stdout

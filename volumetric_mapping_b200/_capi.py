@@ -84,7 +84,7 @@ SYMBOLS = [
     "vmap_shard_query_points_dev", "vmap_shard_query_lines_dev", "vmap_dist_unique_id",
     "vmap_dist_init", "vmap_dist_shutdown", "vmap_dist_insert_pointcloud",
     "vmap_dist_insert_pointcloud_dev", "vmap_dist_query_points_dev", "vmap_dist_query_lines_dev",
-    "vmap_dist_flush", "vmap_set_debug_l2_flush", "vmap_query_points_probability",
+    "vmap_dist_flush", "vmap_dist_set_batch", "vmap_set_debug_l2_flush", "vmap_query_points_probability",
     "vmap_query_visibility", "vmap_query_lines_bbox", "vmap_tree_size", "vmap_serialize_bt", "vmap_write_bt", "vmap_load_bt", "vmap_deserialize_bt",
 ]
 
@@ -173,6 +173,7 @@ def lib():
     L.vmap_dist_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.vmap_dist_shutdown.argtypes = [vp]
     L.vmap_dist_flush.argtypes = [vp]
+    L.vmap_dist_set_batch.argtypes = [vp, C.c_int]
     L.vmap_set_debug_l2_flush.argtypes = [vp, sz]
     L.vmap_dist_insert_pointcloud.argtypes = [vp, vp, sz, sz, C.c_int, dp]
     L.vmap_dist_insert_pointcloud_dev.argtypes = [vp, vp, sz, sz, dp]

@@ -64,11 +64,15 @@ struct vmap {
   // shard_rank; scans generated here are packed into per-owner record streams
   int shard_rank = 0, shard_world = 1;
   DevBuf pack, recv;
-  uint32_t* d_pack_counts_base = nullptr;     // 2 slots x [2 * kMaxRanks] counts + cursors
-  uint32_t* d_pack_counts = nullptr;          // current slot
-  uint32_t h_pack_counts_slot[2][kMaxRanks] = {{0}, {0}};
-  uint32_t* h_pack_counts = h_pack_counts_slot[0];
+  uint32_t* d_pack_counts_base = nullptr;     // [2 slots][kMaxBatch sub-scans][2 * kMaxRanks] counts + cursors
+  uint32_t* d_pack_counts = nullptr;          // current (slot, sub-scan)
+  uint32_t h_pack_counts_slot[2][kMaxBatch][2 * kMaxRanks] = {};
+  uint32_t* h_pack_counts = h_pack_counts_slot[0][0];
   int pack_slot = 0;
+  int pack_sub = 0;                           // sub-scans generated into the current batch
+  size_t pack_off = 0;                        // records already in `pack` (earlier sub-scans)
+  int batch_m = 1;                            // scans per rank per exchange (vmap_dist_set_batch)
+  int round_subs = 0;                         // sub-scans of the pending round
   bool in_collective = false;                 // inside a vmap_dist_* call (may run NCCL)
   bool round_pending = false;                 // a generated + packed round awaits its exchange
   bool round_packed = false;                  // ... and its counts are on the device
@@ -90,8 +94,8 @@ struct vmap {
   size_t l2_flush_bytes = 0;
   uint64_t app_records = 0, app_sent = 0, app_received = 0;
   bool packed = false;                        // the last generate already packed its records
-  uint64_t* d_count_matrix = nullptr;         // [kMaxRanks * kMaxRanks]
-  uint64_t h_count_matrix[kMaxRanks * kMaxRanks] = {0};
+  uint32_t* d_count_matrix = nullptr;         // [world][kMaxBatch][2 * kMaxRanks]
+  std::vector<uint32_t> h_count_matrix;
 
   // dense mark window (vmap_device.cuh MarkSet): the per-scan key sets of ray-generated scans
   struct Window {
@@ -854,7 +858,11 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
     return false;
   };
   if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return bail(VMAP_ERR_CUDA);
-  if (!cuda_ok(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail(VMAP_ERR_CUDA);
+  {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (!cuda_ok(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate")) return bail(VMAP_ERR_CUDA);
+  }
   if (!cuda_ok(cudaEventCreate(&h->ev0), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
   if (!cuda_ok(cudaEventCreate(&h->ev1), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
   for (auto& e : h->evk)
@@ -867,7 +875,7 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   std::memset(h->h_persist, 0, sizeof(Persist));
   int s = dev_alloc(h, (void**)&h->d_cnt, sizeof(Counters));
   if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_cap_n, 2 * sizeof(uint32_t));
-  if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_pack_counts_base, 4 * kMaxRanks * sizeof(uint32_t));
+  if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_pack_counts_base, (size_t)2 * kMaxBatch * 2 * kMaxRanks * sizeof(uint32_t));
   h->d_pack_counts = h->d_pack_counts_base;
   if (s == VMAP_OK) s = init_map(h);
   if (s != VMAP_OK) return bail(s);

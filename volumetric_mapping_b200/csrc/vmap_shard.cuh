@@ -12,6 +12,7 @@
 namespace vmapdev {
 
 constexpr int kMaxRanks = 64;
+constexpr int kMaxBatch = 8;     // scans per rank in one exchange round
 
 // One touched block of one scan: 8 + 64 + 64 bytes.
 struct __align__(8) BlockRecord {

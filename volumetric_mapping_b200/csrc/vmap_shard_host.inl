@@ -75,19 +75,34 @@ bool nccl_load() {
 
 PackView pack_view(vmap* h) {
   PackView pv;
-  pv.records = (BlockRecord*)h->pack.p;
+  pv.records = (BlockRecord*)h->pack.p + h->pack_off;   // earlier sub-scans of the batch come first
   pv.counts = h->d_pack_counts;
   pv.cursors = h->d_pack_counts + kMaxRanks;
-  pv.capacity = (uint32_t)std::min<size_t>(h->pack.cap / sizeof(BlockRecord), 0xFFFFFFFFu);
+  pv.capacity = (uint32_t)std::min<size_t>(h->pack.cap / sizeof(BlockRecord) - std::min(h->pack_off, h->pack.cap / sizeof(BlockRecord)), 0xFFFFFFFFu);
   pv.world = (uint32_t)h->shard_world;
   return pv;
 }
 
 PackView pack_view(vmap* h);
 
+// Enlarge the record buffer keeping the records of the batch's earlier sub-scans.
+int grow_pack(vmap* h, size_t want_records) {
+  const size_t have = h->pack.cap / sizeof(BlockRecord);
+  if (want_records <= have) return VMAP_OK;
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  size_t bytes = (want_records + (want_records >> 2) + 1024) * sizeof(BlockRecord);
+  void* np_ = nullptr;
+  VM_TRY(dev_alloc(h, &np_, bytes));
+  if (h->pack_off) VM_CUDA(h, cudaMemcpy(np_, h->pack.p, h->pack_off * sizeof(BlockRecord), cudaMemcpyDeviceToDevice));
+  dev_free(h, h->pack.p, h->pack.cap);
+  h->pack.p = np_;
+  h->pack.cap = bytes;
+  return VMAP_OK;
+}
+
 // Enqueue the two pack kernels and the copy of the per-destination counts (no synchronisation).
 int launch_pack(vmap* h) {
-  if (!h->pack.p) VM_TRY(ensure(h, &h->pack, (size_t)(1u << 16) * sizeof(BlockRecord)));
+  if (h->pack.cap / sizeof(BlockRecord) < h->pack_off + 1024) VM_TRY(grow_pack(h, h->pack_off + (1u << 16)));
   VM_CUDA(h, cudaMemsetAsync(h->d_pack_counts, 0, 2 * kMaxRanks * sizeof(uint32_t), h->stream));
   PackView pv = pack_view(h);
   const unsigned grid = g_sm_count(h->device) * 8;
@@ -162,7 +177,7 @@ int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark, B
         while (h->h_cnt->overflow_pack) {
           // marks and counts are intact: enlarge the record buffer and write again
           const size_t need = h->h_cnt->overflow_pack;
-          VM_TRY(ensure(h, &h->pack, (need + (need >> 2)) * sizeof(BlockRecord)));
+          VM_TRY(grow_pack(h, h->pack_off + need));
           VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->overflow_pack, 0, sizeof(uint32_t), h->stream));
           VM_CUDA(h, cudaMemsetAsync(h->d_pack_counts + kMaxRanks, 0, kMaxRanks * sizeof(uint32_t), h->stream));
           k_pack_write<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->m, h->ms, h->d_cnt, pack_view(h));
@@ -212,7 +227,7 @@ int pack_marks(vmap* h) {
     return VMAP_OK;
   }
   const size_t n_touched = h->h_cnt->n_touched;
-  VM_TRY(ensure(h, &h->pack, std::max<size_t>(n_touched, 1) * sizeof(BlockRecord)));
+  VM_TRY(grow_pack(h, h->pack_off + std::max<size_t>(n_touched, 1)));
   VM_CUDA(h, cudaMemsetAsync(h->d_pack_counts, 0, 2 * kMaxRanks * sizeof(uint32_t), h->stream));
   PackView pv = pack_view(h);
   const unsigned grid = g_sm_count(h->device) * 8;
@@ -392,7 +407,6 @@ int vmap_dist_init(vmap* h, const uint8_t id128[128], int rank, int world) {
   NcclComm comm = nullptr;
   VM_NCCL(h, g_nccl.CommInitRank(&comm, world, id, rank));
   h->nccl_comm = comm;
-  if (!h->d_count_matrix) VM_TRY(dev_alloc(h, (void**)&h->d_count_matrix, (size_t)kMaxRanks * kMaxRanks * sizeof(uint64_t)));
   return VMAP_OK;
 }
 
@@ -425,8 +439,10 @@ static int dist_exchange_and_apply(vmap* h) {
   const int G = h->shard_world, me = h->shard_rank;
   // counts matrix: row s = records rank s sends to each destination
   // the per-destination counts are still on the device (k_pack_count): gather them from there
-  uint32_t* d_matrix = reinterpret_cast<uint32_t*>(h->d_count_matrix);
-  uint32_t* h_matrix = reinterpret_cast<uint32_t*>(h->h_count_matrix);
+  if (!h->d_count_matrix) VM_TRY(dev_alloc(h, (void**)&h->d_count_matrix, (size_t)kMaxRanks * kMaxBatch * 2 * kMaxRanks * sizeof(uint32_t)));
+  h->h_count_matrix.resize((size_t)G * kMaxRanks);
+  uint32_t* d_matrix = h->d_count_matrix;
+  uint32_t* h_matrix = h->h_count_matrix.data();
   if (!h->packed)   // table-mode generate or an empty scan: counts live on the host only
     VM_CUDA(h, cudaMemcpyAsync(h->d_pack_counts, h->h_pack_counts, kMaxRanks * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
   VM_NCCL(h, g_nccl.AllGather(h->d_pack_counts, d_matrix, (size_t)kMaxRanks, kNcclUint32, comm, h->stream));
@@ -509,7 +525,11 @@ int ensure_on(vmap* h, DevBuf* b, size_t bytes, cudaStream_t st) {
 
 int init_app_stream(vmap* h) {
   if (h->app_stream) return VMAP_OK;
-  VM_CUDA(h, cudaStreamCreateWithFlags(&h->app_stream, cudaStreamNonBlocking));
+  // lower priority than the main stream: the exchange / apply of the previous round fills the
+  // gaps of the generation of the current one instead of competing with its walk kernel
+  int prio_lo = 0, prio_hi = 0;
+  VM_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  VM_CUDA(h, cudaStreamCreateWithPriority(&h->app_stream, cudaStreamNonBlocking, prio_lo));
   VM_CUDA(h, cudaEventCreate(&h->ev_app0));
   VM_CUDA(h, cudaEventCreate(&h->ev_app1));
   VM_CUDA(h, cudaMallocHost((void**)&h->h_cnt_app, sizeof(Counters)));
@@ -528,29 +548,44 @@ int complete_round(vmap* h) {
   if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
   VM_TRY(init_app_stream(h));
   h->round_pending = false;
-  uint32_t* const d_counts = h->d_pack_counts_base + (size_t)h->round_slot * 2 * kMaxRanks;
-  const uint32_t* const h_counts = h->h_pack_counts_slot[h->round_slot];
   NcclComm comm = (NcclComm)h->nccl_comm;
-  const int G = h->shard_world, me = h->shard_rank;
+  const int G = h->shard_world, me = h->shard_rank, M = h->round_subs;
+  const int slot = h->round_slot;
   cudaStream_t as = h->app_stream;
   const double t_a = now_ms();
-  // (A) counts matrix, queued behind the previous round's apply
-  uint32_t* d_matrix = reinterpret_cast<uint32_t*>(h->d_count_matrix);
-  uint32_t* h_matrix = reinterpret_cast<uint32_t*>(h->h_count_matrix);
-  if (!h->round_packed)   // table-mode generate or an empty scan: counts live on the host only
-    VM_CUDA(h, cudaMemcpyAsync(d_counts, h_counts, kMaxRanks * sizeof(uint32_t), cudaMemcpyHostToDevice, as));
-  VM_NCCL(h, g_nccl.AllGather(d_counts, d_matrix, (size_t)kMaxRanks, kNcclUint32, comm, as));
-  VM_CUDA(h, cudaMemcpyAsync(h_matrix, d_matrix, (size_t)G * kMaxRanks * sizeof(uint32_t), cudaMemcpyDeviceToHost, as));
+  // (A) count matrix [rank][sub-scan][destination], queued behind the previous round's apply
+  constexpr size_t kRow = (size_t)kMaxBatch * 2 * kMaxRanks;
+  uint32_t* const d_counts = h->d_pack_counts_base + (size_t)slot * kRow;
+  VM_CUDA(h, cudaMemcpyAsync(d_counts, h->h_pack_counts_slot[slot], kRow * sizeof(uint32_t), cudaMemcpyHostToDevice, as));
+  if (!h->d_count_matrix) VM_TRY(dev_alloc(h, (void**)&h->d_count_matrix, (size_t)kMaxRanks * kRow * sizeof(uint32_t)));
+  h->h_count_matrix.resize((size_t)G * kRow);
+  VM_NCCL(h, g_nccl.AllGather(d_counts, h->d_count_matrix, kRow, kNcclUint32, comm, as));
+  VM_CUDA(h, cudaMemcpyAsync(h->h_count_matrix.data(), h->d_count_matrix, (size_t)G * kRow * sizeof(uint32_t), cudaMemcpyDeviceToHost, as));
   VM_CUDA(h, cudaStreamSynchronize(as));
   VM_TRY(flush_app(h));                         // the round before this one is complete now
   const double t_b = now_ms();
-  size_t recv_counts[kMaxRanks], recv_off[kMaxRanks], total = 0;
-  for (int s = 0; s < G; s++) {
-    recv_counts[s] = (size_t)h_matrix[(size_t)s * kMaxRanks + me];
-    recv_off[s] = total;
-    total += recv_counts[s];
-  }
+  auto count = [&](int src, int sub, int dst) -> size_t {
+    return h->h_count_matrix[(size_t)src * kRow + (size_t)sub * 2 * kMaxRanks + dst];
+  };
+  // receive layout: scan order = sub-scan major, source rank minor
+  std::vector<size_t> recv_cnt((size_t)M * G), recv_off((size_t)M * G);
+  size_t total = 0;
+  for (int j = 0; j < M; j++)
+    for (int s = 0; s < G; s++) {
+      recv_cnt[(size_t)j * G + s] = count(s, j, me);
+      recv_off[(size_t)j * G + s] = total;
+      total += recv_cnt[(size_t)j * G + s];
+    }
   if (total > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many block records");
+  // send layout: sub-scan major, destination minor (as packed)
+  std::vector<size_t> send_off((size_t)M * G);
+  size_t so = 0, sent = 0;
+  for (int j = 0; j < M; j++)
+    for (int d = 0; d < G; d++) {
+      send_off[(size_t)j * G + d] = so;
+      so += count(me, j, d);
+      if (d != me) sent += count(me, j, d);
+    }
   // (B) the apply stream is idle here and a dense-window generate (possibly running on the main
   // stream right now) touches neither the map nor these buffers
   VM_TRY(ensure_on(h, &h->recv, std::max<size_t>(total, 1) * sizeof(BlockRecord), as));
@@ -558,28 +593,27 @@ int complete_round(vmap* h) {
   if ((uint64_t)h->h_persist->n_slots + total > h->pool_cap) VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_slots + total));
   BlockRecord* recv = (BlockRecord*)h->recv.p;
   const BlockRecord* send = (const BlockRecord*)h->pack_inflight.p;
-  size_t send_off[kMaxRanks], so = 0;
-  for (int d = 0; d < G; d++) { send_off[d] = so; so += h_counts[d]; }
   // (C) exchange + apply, asynchronous
   if (h->l2_flush_bytes) VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(h->dbg_n & 0xFF), h->l2_flush_bytes, as));
   VM_CUDA(h, cudaEventRecord(h->ev_app0, as));
   VM_NCCL(h, g_nccl.GroupStart());
-  for (int p = 0; p < G; p++) {
-    if (p == me) continue;
-    if (h_counts[p])
-      VM_NCCL(h, g_nccl.Send(send + send_off[p], (size_t)h_counts[p] * sizeof(BlockRecord), kNcclUint8, p, comm, as));
-    if (recv_counts[p])
-      VM_NCCL(h, g_nccl.Recv(recv + recv_off[p], recv_counts[p] * sizeof(BlockRecord), kNcclUint8, p, comm, as));
-  }
+  for (int j = 0; j < M; j++)
+    for (int p = 0; p < G; p++) {
+      if (p == me) continue;
+      const size_t ns = count(me, j, p), nr = recv_cnt[(size_t)j * G + p];
+      if (ns) VM_NCCL(h, g_nccl.Send(send + send_off[(size_t)j * G + p], ns * sizeof(BlockRecord), kNcclUint8, p, comm, as));
+      if (nr) VM_NCCL(h, g_nccl.Recv(recv + recv_off[(size_t)j * G + p], nr * sizeof(BlockRecord), kNcclUint8, p, comm, as));
+    }
   VM_NCCL(h, g_nccl.GroupEnd());
-  if (recv_counts[me])
-    VM_CUDA(h, cudaMemcpyAsync(recv + recv_off[me], send + send_off[me], recv_counts[me] * sizeof(BlockRecord),
-                               cudaMemcpyDeviceToDevice, as));
+  for (int j = 0; j < M; j++)
+    if (recv_cnt[(size_t)j * G + me])
+      VM_CUDA(h, cudaMemcpyAsync(recv + recv_off[(size_t)j * G + me], send + send_off[(size_t)j * G + me],
+                                 recv_cnt[(size_t)j * G + me] * sizeof(BlockRecord), cudaMemcpyDeviceToDevice, as));
   VM_CUDA(h, cudaMemsetAsync(h->d_cnt_app, 0, sizeof(Counters), as));
-  for (int s = 0; s < G; s++) {
-    if (!recv_counts[s]) continue;
-    const unsigned grid = (unsigned)std::min<size_t>((recv_counts[s] + 7) / 8, (size_t)g_sm_count(h->device) * 8);
-    k_apply_update<<<std::max(grid, 1u), 256, 0, as>>>(h->P, h->m, h->d_cnt_app, recv + recv_off[s], (uint32_t)recv_counts[s]);
+  for (size_t i = 0; i < recv_cnt.size(); i++) {
+    if (!recv_cnt[i]) continue;
+    const unsigned grid = (unsigned)std::min<size_t>((recv_cnt[i] + 7) / 8, (size_t)g_sm_count(h->device) * 8);
+    k_apply_update<<<std::max(grid, 1u), 256, 0, as>>>(h->P, h->m, h->d_cnt_app, recv + recv_off[i], (uint32_t)recv_cnt[i]);
     h->launches++;
   }
   VM_CUDA(h, cudaGetLastError());
@@ -587,13 +621,26 @@ int complete_round(vmap* h) {
   VM_CUDA(h, cudaMemcpyAsync(h->h_cnt_app, h->d_cnt_app, sizeof(Counters), cudaMemcpyDeviceToHost, as));
   VM_CUDA(h, cudaMemcpyAsync(h->h_persist_app, h->m.persist, sizeof(Persist), cudaMemcpyDeviceToHost, as));
   h->app_records = total;
-  h->app_sent = so - h_counts[me];
-  h->app_received = total - recv_counts[me];
+  h->app_sent = sent;
+  h->app_received = total;
+  for (int j = 0; j < M; j++) h->app_received -= recv_cnt[(size_t)j * G + me];
   h->app_pending = true;
   const double t_c = now_ms();
   h->dbg_ms[1] += t_b - t_a; h->dbg_ms[2] += t_c - t_b; h->dbg_n++;
   if (h->dbg_n == 5 && !h->dbg_reset) { h->dbg_reset = true; h->dbg_n = 0; for (double& v : h->dbg_ms) v = 0.0; }   // skip warm-up rounds
   return VMAP_OK;
+}
+
+// Seal the batch under construction: it becomes the pending round.
+void seal_batch(vmap* h) {
+  if (h->pack_sub == 0) return;
+  h->round_pending = true;
+  h->round_slot = h->pack_slot;
+  h->round_subs = h->pack_sub;
+  std::swap(h->pack, h->pack_inflight);   // the sealed round's records are always in pack_inflight
+  h->pack_slot ^= 1;
+  h->pack_sub = 0;
+  h->pack_off = 0;
 }
 }  // namespace
 extern "C" {
@@ -603,10 +650,25 @@ int vmap_dist_flush(vmap* h) {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   h->in_collective = true;
-  int st = complete_round(h);
+  int st = complete_round(h);          // a sealed round waiting for its exchange
+  if (st == VMAP_OK) {
+    seal_batch(h);                     // ... and a partial batch (every rank has the same one)
+    st = complete_round(h);
+  }
   if (st == VMAP_OK) st = flush_app(h);
   h->in_collective = false;
   return st;
+}
+
+// Scans per rank that share one exchange (1..8).  Larger batches amortise the exchange over more
+// scans; the map lags up to m collective calls behind (vmap_dist_flush completes it).  Collective:
+// every rank must use the same value, set between rounds.
+int vmap_dist_set_batch(vmap* h, int scans_per_rank) {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  if (scans_per_rank < 1 || scans_per_rank > kMaxBatch) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "batch must be 1..8");
+  if (h->pack_sub) return fail(h, VMAP_ERR_DIST, "a batch is under construction: call vmap_dist_flush first");
+  h->batch_m = scans_per_rank;
+  return VMAP_OK;
 }
 
 // Test / benchmark hook: overwrite `bytes` of scratch (larger than L2) on the apply stream before
@@ -631,32 +693,32 @@ int dist_insert(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_de
   h->in_collective = true;
   struct Leave { vmap* h; ~Leave() { h->in_collective = false; } } leave{h};
   if (h->capture) {   // parity hook: synchronous round through the table's mask columns
+    seal_batch(h);
     VM_TRY(complete_round(h));
     VM_TRY(flush_app(h));
+    h->pack_off = 0;
+    h->d_pack_counts = h->d_pack_counts_base;
+    h->h_pack_counts = h->h_pack_counts_slot[0][0];
     VM_TRY(shard_generate_common(h, d_in, n, stride, is_dense, Tm, nullptr, []() -> int { return VMAP_OK; }));
     return dist_exchange_and_apply(h);
   }
-  // this scan packs into the buffer / count slot the pending round is not using; the send that
-  // last read that buffer was queued two calls ago -- make the main stream wait for it anyway
-  if (h->round_pending) {
-    std::swap(h->pack, h->pack_inflight);
-    h->pack_slot ^= 1;
+  // A batch of `batch_m` scans per rank shares one exchange.  Sealing a batch moves its records
+  // to `pack_inflight` and flips the count slot (seal_batch), so this batch packs into the buffer
+  // the pending round is not using; the sends that last read it were queued a whole batch ago --
+  // the main stream waits for them anyway.
+  if (h->pack_sub == 0) {
+    h->pack_off = 0;
+    std::memset(h->h_pack_counts_slot[h->pack_slot], 0, sizeof(h->h_pack_counts_slot[h->pack_slot]));
   }
-  h->d_pack_counts = h->d_pack_counts_base + (size_t)h->pack_slot * 2 * kMaxRanks;
-  h->h_pack_counts = h->h_pack_counts_slot[h->pack_slot];
-  static const int dbg_mode = getenv("VMAP_DIST_MODE") ? atoi(getenv("VMAP_DIST_MODE")) : 0;
-  if (h->app_pending && !(dbg_mode & 1)) VM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_app1, 0));
+  h->d_pack_counts = h->d_pack_counts_base + ((size_t)h->pack_slot * kMaxBatch + h->pack_sub) * 2 * kMaxRanks;
+  h->h_pack_counts = h->h_pack_counts_slot[h->pack_slot][h->pack_sub];
+  if (h->app_pending) VM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_app1, 0));
   const double t0 = now_ms();
-  if (dbg_mode & 2) {   // experiment: exchange the previous round BEFORE generating (no NCCL / generate overlap)
-    VM_TRY(complete_round(h));
-    VM_TRY(shard_generate_common(h, d_in, n, stride, is_dense, Tm, nullptr, []() -> int { return VMAP_OK; }));
-  } else {
-    VM_TRY(shard_generate_common(h, d_in, n, stride, is_dense, Tm, nullptr, [&]() -> int { return complete_round(h); }));
-  }
+  VM_TRY(shard_generate_common(h, d_in, n, stride, is_dense, Tm, nullptr, [&]() -> int { return complete_round(h); }));
   h->dbg_ms[0] += now_ms() - t0;
-  h->round_pending = true;
-  h->round_packed = h->packed;
-  h->round_slot = h->pack_slot;
+  for (int d = 0; d < h->shard_world; d++) h->pack_off += h->h_pack_counts[d];
+  h->pack_sub++;
+  if (h->pack_sub >= h->batch_m) seal_batch(h);
   return VMAP_OK;
 }
 }  // namespace

@@ -45,7 +45,7 @@ def broadcast_id(make_id, rank, dist=None, device=None):
 class ShardedOctomapWorld:
     """OctomapWorld sharded over torch.distributed ranks (backend nccl)."""
 
-    def __init__(self, rank, world, device, **kw):
+    def __init__(self, rank, world, device, batch=1, **kw):
         import torch.distributed as dist
         self.rank, self.world = rank, world
         self.local = OctomapWorld(device=device, **kw)
@@ -53,6 +53,8 @@ class ShardedOctomapWorld:
         ident = broadcast_id(OctomapWorld.dist_unique_id, rank, dist,
                              device=torch.device("cuda", device))
         self.local.dist_init(ident, rank, world)
+        if batch != 1:
+            self.local.dist_set_batch(batch)
 
     def insert_round_device(self, T, data_ptr, n):
         """COLLECTIVE.  n == 0: this rank has no scan in the round."""

@@ -274,6 +274,9 @@ class OctomapWorld:
     def dist_flush(self):
         self._check(self._L.vmap_dist_flush(self._h))
 
+    def dist_set_batch(self, scans_per_rank):
+        self._check(self._L.vmap_dist_set_batch(self._h, int(scans_per_rank)))
+
     def set_debug_l2_flush(self, n_bytes):
         self._check(self._L.vmap_set_debug_l2_flush(self._h, int(n_bytes)))
 
