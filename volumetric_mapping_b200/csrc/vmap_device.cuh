@@ -404,6 +404,19 @@ struct RayWalk {
     pick();
   }
 
+  // One DDA step where computeRayKeys' two termination tests cannot fire (every segment of a
+  // ray but its last one, see k_walk_segments).
+  __device__ __forceinline__ void advance_inner() {
+    const bool d2 = !(d0 || d1);
+    c0 = d0 ? ((c0 + (uint32_t)s0) & 0xFFFFu) : c0;
+    c1 = d1 ? ((c1 + (uint32_t)s1) & 0xFFFFu) : c1;
+    c2 = d2 ? ((c2 + (uint32_t)s2) & 0xFFFFu) : c2;
+    t0 = d0 ? __dadd_rn(t0, dt0) : t0;
+    t1 = d1 ? __dadd_rn(t1, dt1) : t1;
+    t2 = d2 ? __dadd_rn(t2, dt2) : t2;
+    pick();
+  }
+
   // One DDA step after the current voxel has been emitted.  Returns false (and clears `live`)
   // when the walk is over, i.e. the new current voxel must NOT be emitted.
   __device__ __forceinline__ bool advance() {

@@ -628,39 +628,49 @@ k_walk_segments(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox
         continue;
       }
     }
-    bool pending = (j == 0);            // the origin voxel belongs to segment 0
     // cur: mask word in flight (window block * 16 + word), bits: voxels collected for it,
-    // seen: its value when the ray entered it (near the sensor, where every ray sets the same
-    // voxels: a RED is only issued for bits not visible yet), tbv: the block's word of the
-    // touched bitmap, read when the ray entered the block.  Both loads are issued on entry and
-    // consumed when the ray leaves the word, a few steps later.  Stale values cost a redundant
-    // RED, never a lost bit.
-    uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0, tbv = 0xFFFFFFFFu;
+    // seen: its value when the ray entered it -- near the sensor every ray sets the same voxels,
+    // so there a RED is only issued for bits not visible yet (a stale value costs a redundant
+    // RED, never a lost bit).  The block's touched bit is tested before it is set for the same
+    // reason.
+    uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0;
     const uint32_t near_limit = (variant == 0) ? 0xFFFFFFFFu : (variant == 2 ? 0u : (uint32_t)variant);
-    for (;;) {
-      if (pending && (!kFilter || free_filter_pass(P, ox, oy, oz, w.c0, w.c1, w.c2))) {
-        const uint32_t idx = (((w.c2 >> 3) - (uint32_t)ms.z0) * ms.ny + ((w.c1 >> 3) - (uint32_t)ms.y0)) * ms.nx +
-                             ((w.c0 >> 3) - (uint32_t)ms.x0);
-        const uint32_t l = local_index(w.c0, w.c1, w.c2);
-        const uint32_t wi = (idx << 4) | (l >> 5);
-        if (wi != cur) {
-          if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
-          if (!((tbv >> ((cur >> 4) & 31u)) & 1u)) atomicOr(ms.touched_bits + (cur >> 9), 1u << ((cur >> 4) & 31u));
-          tbv = ((wi >> 4) != (cur >> 4)) ? ms.touched_bits[idx >> 5] : 0xFFFFFFFFu;
-          bits = 0;
-          cur = wi;
-          seen = (count < near_limit) ? ms.free_mask[wi] : 0u;
+    auto emit = [&]() {
+      if (kFilter && !free_filter_pass(P, ox, oy, oz, w.c0, w.c1, w.c2)) return;
+      const uint32_t idx = (((w.c2 >> 3) - (uint32_t)ms.z0) * ms.ny + ((w.c1 >> 3) - (uint32_t)ms.y0)) * ms.nx +
+                           ((w.c0 >> 3) - (uint32_t)ms.x0);
+      const uint32_t l = local_index(w.c0, w.c1, w.c2);
+      const uint32_t wi = (idx << 4) | (l >> 5);
+      if (wi != cur) {
+        if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
+        if ((wi >> 4) != (cur >> 4)) {
+          uint32_t* tb = ms.touched_bits + (idx >> 5);
+          if (!((*tb >> (idx & 31u)) & 1u)) atomicOr(tb, 1u << (idx & 31u));
         }
-        bits |= 1u << (l & 31u);
+        bits = 0;
+        cur = wi;
+        seen = (count < near_limit) ? ms.free_mask[wi] : 0u;
       }
-      if (!last && !(w.tmin() < tau_end)) break;   // the next step belongs to the next segment
-      if (!w.advance()) break;                     // cur == end, or min(tMax) > length
-      if (count >= kKeyRayMax - 1u) break;         // KeyRay capacity
-      ++count;
-      pending = true;
+      bits |= 1u << (l & 31u);
+    };
+    if (j == 0) emit();                 // the origin voxel belongs to segment 0
+    if (last) {
+      for (;;) {
+        if (!w.advance()) break;                     // cur == end, or min(tMax) > length
+        if (count >= kKeyRayMax - 1u) break;         // KeyRay capacity
+        ++count;
+        emit();
+      }
+    } else {
+      // steps whose crossing parameter is below tau_end; the termination tests cannot fire here
+      while (w.tmin() < tau_end) {
+        w.advance_inner();
+        if (count >= kKeyRayMax - 1u) break;
+        ++count;
+        emit();
+      }
     }
     if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
-    if (!((tbv >> ((cur >> 4) & 31u)) & 1u)) atomicOr(ms.touched_bits + (cur >> 9), 1u << ((cur >> 4) & 31u));
     emitted += count - count0 + (j == 0 ? 1u : 0u);
     if (last) longest = max(longest, count);
   }
