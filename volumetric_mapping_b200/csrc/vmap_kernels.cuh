@@ -24,7 +24,10 @@ constexpr uint32_t kFlagBound = 4u;   // coordToKeyChecked(point) succeeds
 //                  kFlagOcc = 8u       (vmap_sort.cuh) the point inserts an occupied key
 constexpr uint32_t kFlagCast = 16u;   // castRay is invoked for this point (set by k_resolve)
 constexpr int kLenBins = 2048;        // cast rays are ordered by segment count: bin = min(n_seg, 2047)
-constexpr uint32_t kSegSteps = 64;    // DDA steps per ray segment (one thread walks one segment)
+#ifndef VMAP_SEG_STEPS
+#define VMAP_SEG_STEPS 64
+#endif
+constexpr uint32_t kSegSteps = VMAP_SEG_STEPS;    // DDA steps per ray segment (one thread walks one segment)
 
 // A ray is cut into n_seg = max(1, steps / kSegSteps) segments of equal length in the ray
 // parameter t; segment j owns the DDA steps whose crossing parameter lies in [j, j+1) * dtau.
