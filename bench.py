@@ -236,6 +236,8 @@ def run_b200(args):
     n_pts = scans[0]["points"].shape[0]
     dev_pts = [torch.from_numpy(s["points"]).cuda() for s in scans]
     pinned = [torch.from_numpy(s["points"]).pin_memory() for s in scans]
+    pinned_np = [p.numpy() for p in pinned]
+    T_c = [(C.c_double * 16)(*np.ascontiguousarray(s["T"], dtype=np.float64).reshape(16)) for s in scans]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -275,7 +277,7 @@ def run_b200(args):
                 if kind == "dev":
                     w.dist_insert_pointcloud_device(scans[i]["T"], dev_pts[i].data_ptr(), n_pts)
                 else:
-                    w.dist_insert_pointcloud(scans[i]["T"], pinned[i].numpy())
+                    w.dist_insert_pointcloud(scans[i]["T"], pinned_np[i])
                 st = w.last_scan_stats()
                 if i >= W:
                     stats.append(st)
@@ -286,7 +288,7 @@ def run_b200(args):
             if kind == "dev":
                 w.insertPointcloudDevice(scans[i]["T"], dev_pts[i].data_ptr(), n_pts)
             else:
-                w.insertPointcloudFast(scans[i]["T"], pinned[i].numpy())
+                w.insertPointcloudHostPtr(T_c[i], pinned[i].data_ptr(), n_pts)
             dt = time.perf_counter() - t0
             st = w.last_scan_stats()
             if i >= W:

@@ -114,6 +114,7 @@ struct vmap {
   MarkSet ms{};                 // marks of the scan in flight (table or dense mode)
   uint64_t dense_fallbacks = 0;
   int walk_variant = 48;  // near-field limit of the walker's read-before-RED filter (VMAP_WALK_VARIANT)
+  int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
   size_t ckpt_want = 0;   // checkpoint capacity to allocate with the scan scratch
 
@@ -332,12 +333,10 @@ int ensure_scan(vmap* h, size_t n) {
   dev_free(h, sb.rays, oc * 4);
   dev_free(h, sb.len, oc * 4);
   dev_free(h, sb.rank, oc * 4);
-  dev_free(h, sb.len_hist, kLenBins * 4);
   dev_free(h, sb.seg_base, (kLenBins + 1) * 4);
   dev_free(h, sb.ray_rec, oc * sizeof(RayRec));
   dev_free(h, sb.ckpt, (size_t)sb.ckpt_cap * sizeof(Checkpoint));
-  dev_free(h, sb.first_keys, ofc * 8);
-  dev_free(h, sb.first_idx, ofc * 4);
+  dev_free(h, sb.first_keys, ofc * 12);
   sb = ScanBuffers{};
   h->scan_cap = h->first_cap = 0;
   size_t cap = std::max<size_t>(n + (n >> 2), std::max<uint64_t>(h->cfg.initial_scan_points, 16384));
@@ -349,7 +348,7 @@ int ensure_scan(vmap* h, size_t n) {
   VM_TRY(dev_alloc(h, (void**)&sb.rays, cap * 4));
   VM_TRY(dev_alloc(h, (void**)&sb.len, cap * 4));
   VM_TRY(dev_alloc(h, (void**)&sb.rank, cap * 4));
-  VM_TRY(dev_alloc(h, (void**)&sb.len_hist, kLenBins * 4));
+  sb.len_hist = reinterpret_cast<uint32_t*>(h->d_cnt + 1);
   VM_TRY(dev_alloc(h, (void**)&sb.seg_base, (kLenBins + 1) * 4));
   VM_TRY(dev_alloc(h, (void**)&sb.ray_rec, cap * sizeof(RayRec)));
   {
@@ -357,8 +356,8 @@ int ensure_scan(vmap* h, size_t n) {
     VM_TRY(dev_alloc(h, (void**)&sb.ckpt, cc * sizeof(Checkpoint)));
     sb.ckpt_cap = (uint32_t)std::min<size_t>(cc, 0xFFFFFFFFu);
   }
-  VM_TRY(dev_alloc(h, (void**)&sb.first_keys, fc * 8));
-  VM_TRY(dev_alloc(h, (void**)&sb.first_idx, fc * 4));
+  VM_TRY(dev_alloc(h, (void**)&sb.first_keys, fc * 12));   // keys, then the indices of the table in use
+  sb.first_idx = reinterpret_cast<uint32_t*>(sb.first_keys + fc);
   sb.first_mask = (uint32_t)(fc - 1);
   h->scan_cap = cap;
   h->first_cap = fc;
@@ -369,11 +368,11 @@ int begin_scan_scratch(vmap* h, size_t n) {
   // size the first-index table to the scan (power of two >= 2n) so clearing stays proportional
   const size_t fc = std::min(h->first_cap, (size_t)next_pow2(std::max<size_t>(2 * n, 1024)));
   h->sb.first_mask = (uint32_t)(fc - 1);
-  VM_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
-  VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->min_disparity_ord, 0xFF, sizeof(uint32_t), h->stream));
-  VM_CUDA(h, cudaMemsetAsync(h->sb.first_keys, 0xFF, fc * 8, h->stream));
-  VM_CUDA(h, cudaMemsetAsync(h->sb.first_idx, 0xFF, fc * 4, h->stream));
-  VM_CUDA(h, cudaMemsetAsync(h->sb.len_hist, 0, kLenBins * 4, h->stream));
+  // two memsets per scan: counters + histogram (zero), first-index table of fc entries (0xFF:
+  // keys [0, fc) followed directly by their indices)
+  h->sb.first_idx = reinterpret_cast<uint32_t*>(h->sb.first_keys + fc);
+  VM_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters) + kLenBins * sizeof(uint32_t), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->sb.first_keys, 0xFF, fc * 12, h->stream));
   return VMAP_OK;
 }
 
@@ -550,7 +549,8 @@ int launch_capture(vmap* h) {
 }
 
 int launch_update(vmap* h) {
-  k_update<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->P, h->m, h->ms, h->d_cnt);
+  if (h->update_variant == 1) k_update<1><<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->P, h->m, h->ms, h->d_cnt);
+  else k_update<0><<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->P, h->m, h->ms, h->d_cnt);
   h->launches++;
   VM_CUDA(h, cudaGetLastError());
   return VMAP_OK;
@@ -847,6 +847,7 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   derive_params(h);
   if (const char* e = getenv("VMAP_WALK_VARIANT")) h->walk_variant = atoi(e);
   if (const char* e = getenv("VMAP_NO_SEGMENTS")) h->no_segments = atoi(e);
+  if (const char* e = getenv("VMAP_UPDATE_VARIANT")) h->update_variant = atoi(e);
   auto bail = [&](int code) {
     g_create_error = h->err;
     vmap_destroy(h);
@@ -873,7 +874,8 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   if (!cuda_ok(cudaMallocHost((void**)&h->h_persist, sizeof(Persist)), "cudaMallocHost")) return bail(VMAP_ERR_CUDA);
   std::memset(h->h_cnt, 0, sizeof(Counters));
   std::memset(h->h_persist, 0, sizeof(Persist));
-  int s = dev_alloc(h, (void**)&h->d_cnt, sizeof(Counters));
+  // per-scan counters and the segment-count histogram share one allocation (one memset per scan)
+  int s = dev_alloc(h, (void**)&h->d_cnt, sizeof(Counters) + kLenBins * sizeof(uint32_t));
   if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_cap_n, 2 * sizeof(uint32_t));
   if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_pack_counts_base, (size_t)2 * kMaxBatch * 2 * kMaxRanks * sizeof(uint32_t));
   h->d_pack_counts = h->d_pack_counts_base;
@@ -890,9 +892,9 @@ int vmap_destroy(vmap* h) {
   free_map(h);
   ScanBuffers& sb = h->sb;
   cudaFree(sb.world); cudaFree(sb.ray_end); cudaFree(sb.key); cudaFree(sb.flags); cudaFree(sb.rays);
-  cudaFree(sb.len); cudaFree(sb.rank); cudaFree(sb.len_hist);
+  cudaFree(sb.len); cudaFree(sb.rank);
   cudaFree(sb.seg_base); cudaFree(sb.ray_rec); cudaFree(sb.ckpt);
-  cudaFree(sb.first_keys); cudaFree(sb.first_idx);
+  cudaFree(sb.first_keys);
   cudaFree(h->in.p); cudaFree(h->out.p); cudaFree(h->aux.p);
   cudaFree(h->cap_free.p); cudaFree(h->cap_occ.p);
   cudaFree(h->d_cnt); cudaFree(h->d_cap_n);
@@ -1018,6 +1020,7 @@ static int insert_image_common(vmap* h, const uint8_t* d_img, int rows, int cols
   if (Q) std::memcpy(Qm.q, Q, sizeof(Qm.q)); else std::memset(Qm.q, 0, sizeof(Qm.q));
   return run_scan(h, n, T.origin, [&]() -> int {
     if (Q) {
+      VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->min_disparity_ord, 0xFF, sizeof(uint32_t), h->stream));
       k_min_disparity<<<g_sm_count(h->device) * 4, 256, 0, h->stream>>>(h->d_cnt, d_img, rows, cols, pitch);
       h->launches++;
       VM_CUDA(h, cudaGetLastError());

@@ -764,6 +764,7 @@ k_capture_keys(MapView m, MarkSet ms, Counters* cnt, uint16_t* __restrict__ free
 
 // K4: one warp per touched block.  free \ occupied, one clamped update per marked voxel
 // (occupied: +hit, free: +miss), masks cleared.  Every voxel has exactly one writer.
+template <int kVariant>
 __global__ void __launch_bounds__(256)
 k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
   // Abort the whole scan's update (uniformly) when a map structure must grow first.
@@ -802,17 +803,36 @@ k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
     }
     slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
     uint32_t* vox = reinterpret_cast<uint32_t*>(m.pool) + (size_t)slot * kBlockVoxels;
+    if (kVariant == 1) {
+      // every row's load is issued before the first update: one dependent round trip per block
+      // instead of sixteen (the kernel is latency-bound otherwise)
+      uint32_t val[kMaskWords];
 #pragma unroll
-    for (int j = 0; j < kMaskWords; j++) {
-      const uint32_t fw = __shfl_sync(0xFFFFFFFFu, f, j);
-      const uint32_t ow = __shfl_sync(0xFFFFFFFFu, o, j);
-      if ((fw | ow) == 0u) continue;
-      const bool is_occ = (ow >> lane) & 1u, is_free = (fw >> lane) & 1u;
-      if (is_occ || is_free) {
-        uint32_t* p = vox + j * 32 + lane;
-        *p = update_leaf(*p, is_occ ? P.hit : P.miss, P.cmin, P.cmax);
+      for (int j = 0; j < kMaskWords; j++) {
+        const uint32_t any = __shfl_sync(0xFFFFFFFFu, f | o, j);
+        val[j] = ((any >> lane) & 1u) ? __ldcg(vox + j * 32 + lane) : 0u;
       }
-      if (lane == 0) { n_free += __popc(fw); n_occ += __popc(ow); }
+#pragma unroll
+      for (int j = 0; j < kMaskWords; j++) {
+        const uint32_t fw = __shfl_sync(0xFFFFFFFFu, f, j);
+        const uint32_t ow = __shfl_sync(0xFFFFFFFFu, o, j);
+        const bool is_occ = (ow >> lane) & 1u, is_free = (fw >> lane) & 1u;
+        if (is_occ || is_free) vox[j * 32 + lane] = update_leaf(val[j], is_occ ? P.hit : P.miss, P.cmin, P.cmax);
+        if (lane == 0) { n_free += __popc(fw); n_occ += __popc(ow); }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kMaskWords; j++) {
+        const uint32_t fw = __shfl_sync(0xFFFFFFFFu, f, j);
+        const uint32_t ow = __shfl_sync(0xFFFFFFFFu, o, j);
+        if ((fw | ow) == 0u) continue;
+        const bool is_occ = (ow >> lane) & 1u, is_free = (fw >> lane) & 1u;
+        if (is_occ || is_free) {
+          uint32_t* p = vox + j * 32 + lane;
+          *p = update_leaf(*p, is_occ ? P.hit : P.miss, P.cmin, P.cmax);
+        }
+        if (lane == 0) { n_free += __popc(fw); n_occ += __popc(ow); }
+      }
     }
   }
   if (lane == 0) {

@@ -112,6 +112,12 @@ class OctomapWorld:
         self._check(self._L.vmap_insert_pointcloud(self._h, cloud.ctypes.data, cloud.shape[0], 12,
                                                    1, _dptr(Tm), None, None))
 
+    def insertPointcloudHostPtr(self, T_c16, host_ptr, n, stride_bytes=12):
+        """Same call with the arguments already marshalled (a (c_double*16) transform and the
+        address of n packed float32 points, e.g. pinned memory): what a C++ caller pays."""
+        self._check(self._L.vmap_insert_pointcloud(self._h, C.c_void_p(int(host_ptr)), int(n),
+                                                   int(stride_bytes), 1, T_c16, None, None))
+
     def insertPointcloudDevice(self, T, data_ptr, n, stride_bytes=12):
         """Points already in device memory (e.g. a torch tensor's data_ptr())."""
         Tm = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
