@@ -39,9 +39,14 @@ struct PackView {
   uint32_t world;
 };
 
-// pass 1: how many touched blocks with a non-empty mask go to each destination
+// pass 1: how many touched blocks with a non-empty mask go to each destination.  Counts are
+// accumulated per CTA in shared memory: one global atomic per destination per CTA, not per block
+// (tens of thousands of atomics on `world` addresses serialise in the L2).
 __global__ void __launch_bounds__(256) k_pack_count(MapView m, MarkSet ms, Counters* cnt, PackView pv) {
   if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
+  __shared__ uint32_t s_cnt[kMaxRanks];
+  if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_touched = cnt->n_touched;
@@ -51,13 +56,20 @@ __global__ void __launch_bounds__(256) k_pack_count(MapView m, MarkSet ms, Count
                                             : ms.occ_mask[(size_t)e * kMaskWords + lane - kMaskWords];
     if (!__any_sync(0xFFFFFFFFu, wv != 0u)) continue;
     const unsigned long long b = ms.dense ? window_block_key(ms, e) : (m.keys[e] >> kEpochBits);
-    if (lane == 0) atomicAdd(pv.counts + owner_of(b, pv.world), 1u);
+    if (lane == 0) atomicAdd(&s_cnt[owner_of(b, pv.world)], 1u);
   }
+  __syncthreads();
+  if (threadIdx.x < pv.world && s_cnt[threadIdx.x]) atomicAdd(pv.counts + threadIdx.x, s_cnt[threadIdx.x]);
 }
 
-// pass 2: write the records (bucket offsets = exclusive prefix of counts) and clear the masks
+// pass 2: write the records (bucket offsets = exclusive prefix of counts) and clear the masks.
+// A CTA works on rounds of 8 blocks (one per warp): the slots of a round are reserved with one
+// global atomic per destination, the position inside the reservation comes from shared memory.
 __global__ void __launch_bounds__(256) k_pack_write(MapView m, MarkSet ms, Counters* cnt, PackView pv) {
   if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
+  __shared__ uint32_t s_base[kMaxRanks];   // first record of every destination's bucket
+  __shared__ uint32_t s_cnt[kMaxRanks];    // blocks of this round per destination
+  __shared__ uint32_t s_res[kMaxRanks];    // reservation of this round inside the bucket
   {
     // all-or-nothing: when the record buffer is too small nothing is written and no mask is
     // cleared, so the host can enlarge it and launch this kernel again
@@ -68,30 +80,50 @@ __global__ void __launch_bounds__(256) k_pack_write(MapView m, MarkSet ms, Count
       return;
     }
   }
-  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  const uint32_t lane = threadIdx.x & 31u;
+  if (threadIdx.x < pv.world) {
+    uint32_t base = 0;
+    for (uint32_t d = 0; d < threadIdx.x; d++) base += pv.counts[d];
+    s_base[threadIdx.x] = base;
+  }
+  const uint32_t warps_per_cta = blockDim.x >> 5;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
   const uint32_t n_touched = cnt->n_touched;
-  for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_touched; t += warps) {
-    const uint32_t e = ms.list[t];
-    uint32_t* src = (lane < kMaskWords) ? ms.free_mask + (size_t)e * kMaskWords + lane
-                                        : ms.occ_mask + (size_t)e * kMaskWords + lane - kMaskWords;
-    const uint32_t wv = *src;
-    if (!__any_sync(0xFFFFFFFFu, wv != 0u)) continue;
-    if (wv) *src = 0u;
-    const unsigned long long b = ms.dense ? window_block_key(ms, e) : (m.keys[e] >> kEpochBits);
-    uint32_t pos = 0;
-    if (lane == 0) {
-      const uint32_t dest = owner_of(b, pv.world);
-      uint32_t base = 0;
-      for (uint32_t d = 0; d < dest; d++) base += pv.counts[d];
-      pos = base + atomicAdd(pv.cursors + dest, 1u);
+  const uint32_t stride = gridDim.x * warps_per_cta;
+  for (uint32_t t0 = blockIdx.x * warps_per_cta; t0 < n_touched; t0 += stride) {   // uniform per CTA
+    if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t t = t0 + warp;
+    uint32_t wv = 0, dest = 0, local = 0;
+    unsigned long long b = 0;
+    uint32_t* src = nullptr;
+    bool have = false;
+    if (t < n_touched) {
+      const uint32_t e = ms.list[t];
+      src = (lane < kMaskWords) ? ms.free_mask + (size_t)e * kMaskWords + lane
+                                : ms.occ_mask + (size_t)e * kMaskWords + lane - kMaskWords;
+      wv = *src;
+      have = __any_sync(0xFFFFFFFFu, wv != 0u);
+      if (have) {
+        b = ms.dense ? window_block_key(ms, e) : (m.keys[e] >> kEpochBits);
+        dest = owner_of(b, pv.world);
+        if (lane == 0) local = atomicAdd(&s_cnt[dest], 1u);
+        local = __shfl_sync(0xFFFFFFFFu, local, 0);
+      }
     }
-    pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-    if (pos >= pv.capacity) continue;   // cannot happen: capacity >= sum(counts)
-    BlockRecord* r = pv.records + pos;
-    if (lane == 0) r->block = b;
-    if (lane < kMaskWords) r->free_mask[lane] = wv;
-    else r->occ_mask[lane - kMaskWords] = wv;
+    __syncthreads();
+    if (threadIdx.x < pv.world && s_cnt[threadIdx.x]) s_res[threadIdx.x] = atomicAdd(pv.cursors + threadIdx.x, s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (have) {
+      if (wv) *src = 0u;
+      const uint32_t pos = s_base[dest] + s_res[dest] + local;
+      if (pos < pv.capacity) {   // always true: capacity >= sum(counts)
+        BlockRecord* r = pv.records + pos;
+        if (lane == 0) r->block = b;
+        if (lane < kMaskWords) r->free_mask[lane] = wv;
+        else r->occ_mask[lane - kMaskWords] = wv;
+      }
+    }
+    __syncthreads();
   }
 }
 
