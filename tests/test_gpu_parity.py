@@ -459,3 +459,22 @@ def test_full_size_properties_idempotence_at_clamps_and_round_trip():
     g2.import_leaves(k, v)
     k2, v2 = leaves_packed(g2)
     assert np.array_equal(k2, k8) and np.array_equal(v2, v8)
+
+
+def test_checkpoint_and_list_growth_fine_resolution():
+    # 20k rays of up to ~1700 DDA steps at 1 cm: far more segment checkpoints and touched blocks
+    # than the initial buffers hold -> exercises the grow-and-rerun paths of the segment walker
+    rng = np.random.default_rng(17)
+    kw = dict(resolution=0.01, sensor_max_range=10.0)
+    gw, ow = pair("dense", **kw)
+    ow.set_faithful_inner_update(False)
+    d = rng.normal(size=(20000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = (d * rng.uniform(1.0, 12.0, (20000, 1))).astype(np.float32)
+    T = scenes.quat_to_matrix(scenes.random_unit_quat(rng), [0.3, -0.2, 0.1])
+    gw.insertPointcloud(T, pts)
+    ow.insertPointcloud(T, pts)
+    assert gw.last_scan_stats()["retries"] >= 1
+    assert_same_stats(gw, ow)
+    assert_same_keys(gw, ow)
+    assert_same_leaves(gw, ow)

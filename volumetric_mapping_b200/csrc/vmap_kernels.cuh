@@ -293,6 +293,17 @@ __device__ __forceinline__ void mark_voxel_dense(const MarkSet& ms, Counters* cn
   atomicOr(ms.touched_bits + (idx >> 5), 1u << (idx & 31u));
 }
 
+// Statistics counters are bumped once per CTA, not once per warp: thousands of atomics on one
+// address serialise in the L2 and show up as a tail on short kernels.
+__device__ __forceinline__ void cta_add_u32(uint32_t* s_acc, uint32_t v) {   // s_acc: shared, zeroed
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  if ((threadIdx.x & 31u) == 0 && v) atomicAdd(s_acc, v);
+}
+__device__ __forceinline__ void cta_max_u32(uint32_t* s_acc, uint32_t v) {
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  if ((threadIdx.x & 31u) == 0 && v) atomicMax(s_acc, v);
+}
+
 __device__ __forceinline__ uint32_t ray_segments(uint32_t steps) {
   return min(max(steps / kSegSteps, 1u), (uint32_t)(kLenBins - 1));
 }
@@ -677,14 +688,16 @@ k_walk_segments(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox
     emitted += count - count0 + (j == 0 ? 1u : 0u);
     if (last) longest = max(longest, count);
   }
-  uint32_t sum = emitted, mx = longest;
-  for (int o = 16; o > 0; o >>= 1) {
-    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-    mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
-  }
-  if ((threadIdx.x & 31u) == 0 && sum) {
-    atomicAdd(&cnt->traversals, (unsigned long long)sum);
-    atomicMax(&cnt->longest_ray, mx);
+  __shared__ uint32_t s_stat[2];
+  __syncthreads();                       // (base_s is dead by now)
+  if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+  __syncthreads();
+  cta_add_u32(&s_stat[0], emitted);      // < 2^32 per CTA: <= 256 threads x a few segments x 100k keys
+  cta_max_u32(&s_stat[1], longest);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_stat[0]) {
+    atomicAdd(&cnt->traversals, (unsigned long long)s_stat[0]);
+    atomicMax(&cnt->longest_ray, s_stat[1]);
   }
 }
 
@@ -835,9 +848,17 @@ k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
       }
     }
   }
+  __shared__ uint32_t s_stat[2];
+  if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+  __syncthreads();
   if (lane == 0) {
-    if (n_free) atomicAdd(&cnt->unique_free, n_free);
-    if (n_occ) atomicAdd(&cnt->unique_occupied, n_occ);
+    if (n_free) atomicAdd(&s_stat[0], n_free);
+    if (n_occ) atomicAdd(&s_stat[1], n_occ);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_stat[0]) atomicAdd(&cnt->unique_free, s_stat[0]);
+    if (s_stat[1]) atomicAdd(&cnt->unique_occupied, s_stat[1]);
   }
 }
 
