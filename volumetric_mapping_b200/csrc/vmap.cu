@@ -211,10 +211,6 @@ void derive_params(vmap* h) {
 // ---------------------------------------------------------------------------------------------
 // map storage
 // ---------------------------------------------------------------------------------------------
-size_t table_bytes_per_entry() {
-  return sizeof(unsigned long long) + sizeof(uint32_t) * (1 + 2 * kMaskWords + 1);
-}
-
 int alloc_table(vmap* h, uint64_t cap, MapView* out) {
   MapView v = h->m;
   VM_TRY(dev_alloc(h, (void**)&v.keys, cap * sizeof(unsigned long long)));
