@@ -596,10 +596,13 @@ template <bool kFilter>
 __global__ void __launch_bounds__(256)
 k_walk_segments(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz,
                 int variant) {
+  // some checkpoints were never written (buffer too small): nothing may be walked; the host
+  // enlarges the buffer and runs the scan again
+  if (cnt->overflow_ckpt) return;
   __shared__ uint32_t base_s[kLenBins + 1];
   for (int k = threadIdx.x; k <= kLenBins; k += blockDim.x) base_s[k] = sb.seg_base[k];
   __syncthreads();
-  const uint32_t total = base_s[kLenBins];
+  const uint32_t total = min(base_s[kLenBins], sb.ckpt_cap);
   uint32_t emitted = 0, longest = 0;
   for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
     // level of the slot: largest j with base_s[j] <= slot
