@@ -709,7 +709,8 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
     // K2a + K2b: exact checkpoints, then one thread per ray segment
     k_checkpoints<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->d_cnt, ox, oy, oz);
     h->launches++;
-    const unsigned grid = g_sm_count(h->device) * 8;
+    static const int walk_ctas = getenv("VMAP_WALK_CTAS") ? atoi(getenv("VMAP_WALK_CTAS")) : 5;   // = resident CTAs per SM at 48 registers
+    const unsigned grid = g_sm_count(h->device) * walk_ctas;
     if (h->P.free_filter) k_walk_segments<true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
     else k_walk_segments<false><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
   } else if (h->ms.dense) {
