@@ -217,6 +217,12 @@ VMAP_API int vmap_write_bt(vmap* h, const char* path, int threshold_live_map);
 /* OctomapWorld::loadOctomapFromFile (octomap_world.cc:846-848) / setOctomapFromMsg (binary)
  * (:833-844): replaces the map (and its resolution) with the stream's. */
 VMAP_API int vmap_load_bt(vmap* h, const char* path);
+/* OctomapWorld::getOctomapFullMsg (octomap_world.cc:826-831) / OcTree::write: the full tree, one
+ * float log-odds per node (inner node = max of its children).  with_header = 0: the message
+ * payload (writeData); 1: a complete ".ot" stream.  vmap_deserialize_ot is the inverse
+ * (setOctomapFromMsg with a full message, :833-844). */
+VMAP_API int vmap_serialize_ot(vmap* h, int with_header, uint8_t* buffer, size_t capacity, size_t* n_bytes);
+VMAP_API int vmap_deserialize_ot(vmap* h, int with_header, const uint8_t* buffer, size_t n_bytes);
 VMAP_API int vmap_deserialize_bt(vmap* h, const uint8_t* buffer, size_t n_bytes);
 
 /* Per-scan counters of the last insert / apply call. */

@@ -121,6 +121,8 @@ def lib():
     L.oracle_prune.argtypes = [vp]
     L.oracle_write_bt.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.oracle_write_bt.restype = C.c_size_t
+    L.oracle_write_ot.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.oracle_write_ot.restype = C.c_size_t
     _lib = L
     return L
 
@@ -311,6 +313,12 @@ class OracleWorld:
 
     def prune(self):
         self._L.oracle_prune(self._h)
+
+    def write_ot(self, with_header=False):
+        n = self._L.oracle_write_ot(self._h, int(bool(with_header)), None, 0)
+        buf = (C.c_ubyte * max(1, n))()
+        self._L.oracle_write_ot(self._h, int(bool(with_header)), buf, n)
+        return bytes(buf[:n])
 
     def write_bt(self, live=False):
         n = self._L.oracle_write_bt(self._h, int(bool(live)), None, 0) if not live else None

@@ -354,6 +354,20 @@ class OcTree {
     out += "data\n";
     if (root) writeBinaryNode(out, root);
   }
+  // OcTreeBaseImpl::write / writeData (full tree: float value + child byte per node)
+  void writeFull(std::string& out, bool with_header) const {
+    if (with_header) {
+      char buf[256];
+      out += "# Octomap OcTree file\n# (feel free to add / change comments, but leave the first line as it is!)\n#\n";
+      out += "id OcTree\n";
+      snprintf(buf, sizeof(buf), "size %zu\n", tree_size);
+      out += buf;
+      snprintf(buf, sizeof(buf), "res %g\n", resolution);
+      out += buf;
+      out += "data\n";
+    }
+    if (root) writeNodesRecurs(out, root);
+  }
   void writeBinary(std::string& out) {   // non-const: thresholds and prunes the live tree first
     toMaxLikelihood();
     prune();
@@ -460,6 +474,15 @@ class OcTree {
     out.push_back((char)b[1]);
     for (unsigned i = 0; i < 8; i++)
       if (nodeChildExists(node, i) && nodeHasChildren(node->children[i])) writeBinaryNode(out, node->children[i]);
+  }
+  void writeNodesRecurs(std::string& out, const Node* node) const {
+    out.append(reinterpret_cast<const char*>(&node->value), sizeof(float));
+    unsigned char children = 0;
+    for (unsigned i = 0; i < 8; i++)
+      if (nodeChildExists(node, i)) children |= (unsigned char)(1u << i);
+    out.push_back((char)children);
+    for (unsigned i = 0; i < 8; i++)
+      if (children & (1u << i)) writeNodesRecurs(out, node->children[i]);
   }
   void updateNodeLogOdds(Node* n, float update) const {
     n->value = n->value + update;
@@ -1040,6 +1063,14 @@ void oracle_export_leaves(const oracle_world* w, uint16_t* out_k3, float* out_lo
 size_t oracle_tree_node_count(const oracle_world* w) { return w->octree->size(); }
 
 void oracle_prune(oracle_world* w) { w->octree->prune(); }
+
+// getOctomapFullMsg payload (with_header == 0) or a complete .ot stream; returns the size.
+size_t oracle_write_ot(const oracle_world* w, int with_header, unsigned char* buf, size_t cap) {
+  std::string out;
+  w->octree->writeFull(out, with_header != 0);
+  if (buf && cap >= out.size()) std::memcpy(buf, out.data(), out.size());
+  return out.size();
+}
 
 // writeOctomapToFile (live != 0: OcTree::writeBinary thresholds + prunes the live tree) or
 // writeOctomapToBinaryConst (live == 0) into a caller buffer; returns the stream size.

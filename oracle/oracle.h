@@ -131,6 +131,8 @@ void oracle_prune(oracle_world* w);
 /* writeOctomapToFile (live != 0; thresholds and prunes the live tree like OcTree::writeBinary)
  * or writeOctomapToBinaryConst (live == 0): ".bt" stream; returns its size (buf may be NULL). */
 size_t oracle_write_bt(oracle_world* w, int live, unsigned char* buf, size_t cap);
+/* OcTree::write / writeData (getOctomapFullMsg payload when with_header == 0). */
+size_t oracle_write_ot(const oracle_world* w, int with_header, unsigned char* buf, size_t cap);
 
 #ifdef __cplusplus
 }

@@ -42,6 +42,48 @@ def test_oracle_prune_after_max_likelihood_collapses_uniform_octants():
     assert live == HEADER % (16, b"0.1") + data
 
 
+def test_oracle_ot_hand_derived_stream():
+    # same 18-node tree as above: every node = float value + child byte, depth first
+    import struct
+    w = oracle.OracleWorld(resolution=0.1)
+    occ = np.array([[32768, 32768, 32768]], np.uint16)
+    free = np.array([[32769, 32768, 32768]], np.uint16)
+    w.updateOccupancy(free, occ)
+    w.updateOccupancy(np.zeros((0, 3), np.uint16), occ)
+    hit2 = struct.pack("<I", 0x3f9e795b)           # two hits (SURVEY 3.3 ladder)
+    miss = struct.pack("<I", 0xbecf991f)
+    inner = hit2                                   # inner node = max of its children
+    data = inner + bytes([0x80]) + (inner + bytes([0x01])) * 14 + inner + bytes([0x03]) + hit2 + b"\0" + miss + b"\0"
+    assert w.write_ot(with_header=False) == data
+    hdr = (b"# Octomap OcTree file\n# (feel free to add / change comments, but leave the first line as "
+           b"it is!)\n#\nid OcTree\nsize 18\nres 0.1\ndata\n")
+    assert w.write_ot(with_header=True) == hdr + data
+
+
+@pytest.mark.gpu
+def test_gpu_ot_stream_equals_oracle_stream_and_round_trips():
+    import volumetric_mapping_b200 as vm
+    rng = np.random.default_rng(13)
+    gw = vm.OctomapWorld(resolution=0.1, sensor_max_range=6.0)
+    ow = oracle.OracleWorld(resolution=0.1, sensor_max_range=6.0)
+    for k in range(3):
+        d = rng.normal(size=(5000, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        pts = (d * rng.uniform(1.0, 7.0, (5000, 1))).astype(np.float32)
+        T = scenes.quat_to_matrix([1, 0, 0, 0], [0.2 * k, 0, 0])
+        gw.insertPointcloud(T, pts)
+        ow.insertPointcloud(T, pts)
+    for hdr in (False, True):
+        assert gw.getOctomapFullMsgData(with_header=hdr) == ow.write_ot(with_header=hdr)
+    g2 = vm.OctomapWorld(resolution=0.25)
+    g2.setOctomapFromFullMsgData(gw.getOctomapFullMsgData(with_header=True), with_header=True)
+    k1, v1 = gw.export_leaves()
+    k2, v2 = g2.export_leaves()
+    a, b = np.argsort(oracle.pack_keys(k1)), np.argsort(oracle.pack_keys(k2))
+    assert np.array_equal(oracle.pack_keys(k1)[a], oracle.pack_keys(k2)[b])
+    assert np.array_equal(v1.view(np.uint32)[a], v2.view(np.uint32)[b])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("res,n_scans", [(0.15, 1), (0.1, 3)])
 def test_gpu_bt_stream_equals_oracle_stream(res, n_scans):

@@ -85,7 +85,7 @@ SYMBOLS = [
     "vmap_dist_init", "vmap_dist_shutdown", "vmap_dist_insert_pointcloud",
     "vmap_dist_insert_pointcloud_dev", "vmap_dist_query_points_dev", "vmap_dist_query_lines_dev",
     "vmap_dist_flush", "vmap_dist_set_batch", "vmap_set_debug_l2_flush", "vmap_query_points_probability",
-    "vmap_query_visibility", "vmap_query_lines_bbox", "vmap_tree_size", "vmap_serialize_bt", "vmap_write_bt", "vmap_load_bt", "vmap_deserialize_bt",
+    "vmap_query_visibility", "vmap_query_lines_bbox", "vmap_tree_size", "vmap_serialize_bt", "vmap_write_bt", "vmap_load_bt", "vmap_deserialize_bt", "vmap_serialize_ot", "vmap_deserialize_ot",
 ]
 
 STATUS_NAMES = {0: "VMAP_OK", 1: "VMAP_ERR_INVALID_ARGUMENT", 2: "VMAP_ERR_CUDA",
@@ -158,6 +158,8 @@ def lib():
     L.vmap_write_bt.argtypes = [vp, C.c_char_p, C.c_int]
     L.vmap_load_bt.argtypes = [vp, C.c_char_p]
     L.vmap_deserialize_bt.argtypes = [vp, vp, sz]
+    L.vmap_serialize_ot.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz)]
+    L.vmap_deserialize_ot.argtypes = [vp, C.c_int, vp, sz]
     L.vmap_set_shard.argtypes = [vp, C.c_int, C.c_int]
     L.vmap_shard_owner.argtypes = [C.c_uint16, C.c_uint16, C.c_uint16, C.c_int]
     L.vmap_shard_owner.restype = C.c_uint32

@@ -129,6 +129,112 @@ void write_bt_nodes(const vmap* h, const PrunedTree& t, std::string* out) {
   }
 }
 
+// OcTreeBaseImpl::writeNodesRecurs (the full ".ot" form behind getOctomapFullMsg /
+// fullMapToMsg, octomap_world.cc:826-831): per node its float value, then one byte with one bit
+// per existing child, then the children depth-first.
+void write_ot_nodes(const PrunedTree& t, std::string* out) {
+  if (t.level[0].empty()) return;
+  struct Frame { int d; size_t idx; };
+  std::vector<Frame> stack;
+  stack.push_back(Frame{0, 0});
+  while (!stack.empty()) {
+    const Frame f = stack.back();
+    stack.pop_back();
+    const TreeNode& n = t.level[f.d][f.idx];
+    out->append(reinterpret_cast<const char*>(&n.value), sizeof(float));
+    uint32_t bits = 0;
+    Frame kids[8];
+    int n_kids = 0;
+    if (n.inner) {
+      const std::vector<TreeNode>& c = t.level[f.d + 1];
+      for (size_t i = first_child(t, f.d, n.code); i < c.size() && (c[i].code >> 3) == n.code; i++) {
+        bits |= 1u << (uint32_t)(c[i].code & 7u);
+        kids[n_kids++] = Frame{f.d + 1, i};
+      }
+    }
+    out->push_back((char)bits);
+    for (int k = n_kids - 1; k >= 0; k--) stack.push_back(kids[k]);
+  }
+}
+
+std::string ot_header(const vmap* h, size_t n_nodes) {
+  std::ostringstream s;
+  s << "# Octomap OcTree file\n# (feel free to add / change comments, but leave the first line as it is!)\n#\n";
+  s << "id OcTree" << std::endl;
+  s << "size " << n_nodes << std::endl;
+  s << "res " << h->params.resolution << std::endl;
+  s << "data" << std::endl;
+  return s.str();
+}
+
+// OcTreeBaseImpl::readNodesRecurs: leaves keep their float values; pruned leaves are expanded.
+int parse_ot(vmap* h, const std::string& in, bool with_header, double* res_out, std::vector<uint16_t>* k3,
+             std::vector<float>* val) {
+  size_t pos = 0;
+  *res_out = h->params.resolution;
+  if (with_header) {
+    auto getline_ = [&](std::string* line) {
+      if (pos >= in.size()) return false;
+      const size_t e = in.find('\n', pos);
+      *line = in.substr(pos, e == std::string::npos ? std::string::npos : e - pos);
+      pos = (e == std::string::npos) ? in.size() : e + 1;
+      return true;
+    };
+    std::string line, id;
+    if (!getline_(&line) || line.compare(0, 21, "# Octomap OcTree file") != 0)
+      return fail(h, VMAP_ERR_INVALID_ARGUMENT, "not an octomap (.ot) stream");
+    double res = 0.0;
+    bool got_data = false;
+    while (getline_(&line)) {
+      if (line.empty() || line[0] == '#') continue;
+      std::istringstream ls(line);
+      std::string tok;
+      ls >> tok;
+      if (tok == "id") ls >> id;
+      else if (tok == "res") ls >> res;
+      else if (tok == "data") { got_data = true; break; }
+    }
+    if (!got_data || id != "OcTree" || !(res > 0.0)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "malformed .ot header");
+    *res_out = res;
+  }
+  k3->clear();
+  val->clear();
+  if (pos >= in.size()) return VMAP_OK;
+  struct Frame { int d; uint32_t x, y, z; };
+  std::vector<Frame> stack;
+  stack.push_back(Frame{0, 0, 0, 0});
+  while (!stack.empty()) {
+    const Frame f = stack.back();
+    stack.pop_back();
+    if (pos + 5 > in.size()) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "truncated .ot data");
+    float v;
+    std::memcpy(&v, in.data() + pos, 4);
+    const uint32_t bits = (uint8_t)in[pos + 4];
+    pos += 5;
+    if (bits == 0) {   // leaf at depth f.d
+      const uint32_t span = 1u << (16 - f.d);
+      if ((double)span * span * span > 16777216.0 || k3->size() / 3 + (size_t)span * span * span > (1ull << 31))
+        return fail(h, VMAP_ERR_CAPACITY, "pruned leaf too coarse to expand into finest-level voxels");
+      for (uint32_t z = 0; z < span; z++)
+        for (uint32_t y = 0; y < span; y++)
+          for (uint32_t x = 0; x < span; x++) {
+            k3->push_back((uint16_t)(f.x + x)); k3->push_back((uint16_t)(f.y + y)); k3->push_back((uint16_t)(f.z + z));
+            val->push_back(v);
+          }
+      continue;
+    }
+    if (f.d >= 16) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "inner node below the finest level in .ot data");
+    const uint32_t bit = 1u << (15 - f.d);
+    Frame kids[8];
+    int n_kids = 0;
+    for (uint32_t i = 0; i < 8; i++)
+      if (bits & (1u << i))
+        kids[n_kids++] = Frame{f.d + 1, f.x | ((i & 1u) ? bit : 0u), f.y | ((i & 2u) ? bit : 0u), f.z | ((i & 4u) ? bit : 0u)};
+    for (int k = n_kids - 1; k >= 0; k--) stack.push_back(kids[k]);
+  }
+  return VMAP_OK;
+}
+
 std::string bt_header(const vmap* h, size_t n_nodes) {
   std::ostringstream s;
   s << "# Octomap OcTree binary file\n# (feel free to add / change comments, but leave the first line as it is!)\n#\n";
@@ -238,6 +344,39 @@ int load_bt(vmap* h, const std::string& data) {
 }  // namespace
 
 extern "C" {
+
+// OcTree::write (full tree, float log-odds per node) into memory: getOctomapFullMsg's payload is
+// the stream without the header (with_header = 0), a ".ot" file the stream with it.
+int vmap_serialize_ot(vmap* h, int with_header, uint8_t* buffer, size_t capacity, size_t* n_bytes) {
+  if (!h || !n_bytes) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  std::vector<std::pair<uint64_t, float> > leaves;
+  VM_TRY(read_leaves_morton(h, &leaves));
+  PrunedTree t;
+  build_pruned_tree(h, leaves, false, &t);
+  std::string out = with_header ? ot_header(h, t.n_nodes) : std::string();
+  write_ot_nodes(t, &out);
+  *n_bytes = out.size();
+  if (!buffer) return VMAP_OK;
+  if (capacity < out.size()) return fail(h, VMAP_ERR_BUFFER_TOO_SMALL, "buffer too small; *n_bytes holds the stream size");
+  std::memcpy(buffer, out.data(), out.size());
+  return VMAP_OK;
+}
+
+// setOctomapFromMsg with a full message (octomap_world.cc:833-844) / OcTree::read: replaces the map.
+int vmap_deserialize_ot(vmap* h, int with_header, const uint8_t* buffer, size_t n_bytes) {
+  if (!h || (!buffer && n_bytes)) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  double res = 0.0;
+  std::vector<uint16_t> k3;
+  std::vector<float> val;
+  VM_TRY(parse_ot(h, std::string(reinterpret_cast<const char*>(buffer), n_bytes), with_header != 0, &res, &k3, &val));
+  vmap_params p = h->params;
+  p.resolution = res;
+  VM_TRY(vmap_set_params(h, &p));
+  VM_TRY(vmap_reset(h));
+  return vmap_import_leaves(h, k3.data(), val.data(), val.size());
+}
 
 // octree_->prune(); octree_->size(): node count of the canonical pruned tree.
 int vmap_tree_size(vmap* h, int max_likelihood, size_t* n_nodes) {

@@ -345,6 +345,20 @@ class OctomapWorld:
         self._check(self._L.vmap_serialize_bt(self._h, buf, n.value, C.byref(n)))
         return bytes(buf[: n.value])
 
+    def getOctomapFullMsgData(self, with_header=False):
+        """Payload of getOctomapFullMsg (octomap_world.cc:826-831): OcTree::writeData bytes; with
+        the header it is a complete .ot stream."""
+        n = C.c_size_t(0)
+        self._check(self._L.vmap_serialize_ot(self._h, int(bool(with_header)), None, 0, C.byref(n)))
+        buf = (C.c_uint8 * max(1, n.value))()
+        self._check(self._L.vmap_serialize_ot(self._h, int(bool(with_header)), buf, n.value, C.byref(n)))
+        return bytes(buf[: n.value])
+
+    def setOctomapFromFullMsgData(self, data, with_header=False):
+        b = bytes(data)
+        buf = (C.c_uint8 * max(1, len(b))).from_buffer_copy(b or b"\0")
+        self._check(self._L.vmap_deserialize_ot(self._h, int(bool(with_header)), buf, len(b)))
+
     def writeOctomapToFile(self, filename):
         """octomap_world.cc:849-852; like OcTree::writeBinary it thresholds the live map."""
         self._check(self._L.vmap_write_bt(self._h, str(filename).encode(), 1))
