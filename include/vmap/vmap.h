@@ -225,6 +225,14 @@ VMAP_API int vmap_serialize_ot(vmap* h, int with_header, uint8_t* buffer, size_t
 VMAP_API int vmap_deserialize_ot(vmap* h, int with_header, const uint8_t* buffer, size_t n_bytes);
 VMAP_API int vmap_deserialize_bt(vmap* h, const uint8_t* buffer, size_t n_bytes);
 
+/* OctomapWorld::setLogOddsBoundingBox (octomap_world.cc:781-818) behind setFree / setOccupied
+ * (:497-523): n boxes of one size; bound_handling = BoundHandling (octomap_world.h:43-52:
+ * 0 kDefault, 1 kIncludePartialBoxes, 2 kIgnorePartialBoxes).  setFree passes the clamping
+ * minimum, setOccupied the clamping maximum (vmap_logodds_constants). */
+VMAP_API int vmap_set_log_odds_bbox(vmap* h, const double* positions_xyz, size_t n_positions,
+                                    const double bounding_box_size[3], double log_odds_value,
+                                    int bound_handling);
+
 /* Per-scan counters of the last insert / apply call. */
 VMAP_API int vmap_last_scan_stats(const vmap* h, vmap_scan_stats* stats);
 /* Parity hook: when enabled, the next inserts keep their final free / occupied key sets. */

@@ -19,6 +19,9 @@ namespace volumetric_mapping {
 using compat::KeySet;
 using compat::OcTreeKey;
 
+// octomap_world.h:43-52
+enum BoundHandling { kDefault, kIncludePartialBoxes, kIgnorePartialBoxes };
+
 // octomap_world.h:54-109 -- identical fields and defaults.
 struct OctomapParameters {
   OctomapParameters()
@@ -108,6 +111,20 @@ class OctomapWorld : public WorldBase {
     status->resize(starts_ends.size() / 2);
     if (status->empty()) return;
     check(vmap_query_lines(handle_, starts_ends[0].v, status->size(), status->data()));
+  }
+
+  // octomap_world.cc:497-523: manual edits of a bounding box (setLogOddsBoundingBox :781-818)
+  virtual void setFree(const Vector3d& position, const Vector3d& bounding_box_size,
+                       const BoundHandling& insertion_method = kDefault) {
+    float c[5];
+    check(vmap_logodds_constants(handle_, c));
+    check(vmap_set_log_odds_bbox(handle_, position.v, 1, bounding_box_size.v, c[2], insertion_method));
+  }
+  virtual void setOccupied(const Vector3d& position, const Vector3d& bounding_box_size,
+                           const BoundHandling& insertion_method = kDefault) {
+    float c[5];
+    check(vmap_logodds_constants(handle_, c));
+    check(vmap_set_log_odds_bbox(handle_, position.v, 1, bounding_box_size.v, c[3], insertion_method));
   }
 
   // updateOccupancy(KeySet*, KeySet*) (octomap_world.cc:238-264): protected in the reference but

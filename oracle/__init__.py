@@ -119,6 +119,7 @@ def lib():
     L.oracle_last_scan_stats.argtypes = [vp, C.POINTER(ScanStats)]
     L.oracle_export_leaves.argtypes = [vp, vp, vp]
     L.oracle_prune.argtypes = [vp]
+    L.oracle_set_log_odds_bbox.argtypes = [vp, vp, C.c_size_t, dp, C.c_double, C.c_int]
     L.oracle_write_bt.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.oracle_write_bt.restype = C.c_size_t
     L.oracle_write_ot.argtypes = [vp, C.c_int, vp, C.c_size_t]
@@ -221,6 +222,20 @@ class OracleWorld:
         f = np.ascontiguousarray(free_k3, dtype=np.uint16).reshape(-1, 3)
         o = np.ascontiguousarray(occ_k3, dtype=np.uint16).reshape(-1, 3)
         self._L.oracle_apply_keys(self._h, f.ctypes.data, f.shape[0], o.ctypes.data, o.shape[0])
+
+    def setLogOddsBoundingBox(self, positions, bounding_box_size, log_odds_value, insertion_method=0):
+        p = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        b = np.ascontiguousarray(bounding_box_size, dtype=np.float64).reshape(3)
+        self._L.oracle_set_log_odds_bbox(self._h, p.ctypes.data, p.shape[0], _dptr(b),
+                                         float(log_odds_value), int(insertion_method))
+
+    def setFree(self, positions, bounding_box_size, insertion_method=0):
+        self.setLogOddsBoundingBox(positions, bounding_box_size, float(self.logodds_constants()[2]),
+                                   insertion_method)
+
+    def setOccupied(self, positions, bounding_box_size, insertion_method=0):
+        self.setLogOddsBoundingBox(positions, bounding_box_size, float(self.logodds_constants()[3]),
+                                   insertion_method)
 
     # -- queries ------------------------------------------------------------------------
     def getCellStatusPoint(self, xyz):

@@ -322,6 +322,34 @@ class OcTree {
   void updateInnerOccupancy() {
     if (root) updateInnerOccupancyRecurs(root, 0);
   }
+  // OccupancyOcTreeBase::setNodeValue(point3d, float log_odds, lazy_eval = true): no clamping,
+  // out-of-bounds points are ignored, inner nodes are left stale (updateInnerOccupancy follows)
+  void setNodeValueLazy(const Vec3f& p, float log_odds_value) {
+    Key key;
+    if (!coordToKeyChecked(p, key)) return;
+    bool just_created = false;
+    if (root == NULL) {
+      root = new Node();
+      tree_size++;
+      just_created = true;
+    }
+    Node* node = root;
+    for (unsigned depth = 0; depth < tree_depth; depth++) {
+      unsigned pos = computeChildIdx(key, (int)tree_depth - 1 - (int)depth);
+      bool created = false;
+      if (!nodeChildExists(node, pos)) {
+        if (!nodeHasChildren(node) && !just_created) {
+          expandNode(node);
+        } else {
+          createNodeChild(node, pos);
+          created = true;
+        }
+      }
+      node = node->children[pos];
+      just_created = created;
+    }
+    node->value = log_odds_value;
+  }
 
   // finest-level leaves, pruned nodes expanded
   template <class F>
@@ -928,6 +956,45 @@ void oracle_query_lines(const oracle_world* w, const double* ab, size_t n, uint8
     }
     status[i] = st;
   }
+}
+
+// octomap_world.cc:781-818 (setLogOddsBoundingBox) with adjustBoundingBox (:1175-1224)
+void oracle_set_log_odds_bbox(oracle_world* w, const double* positions, size_t n, const double bbox[3],
+                              double log_odds_value, int insertion_method) {
+  OcTree* t = w->octree;
+  const double resolution = t->getResolution();
+  const double epsilon = 0.001;
+  for (size_t p = 0; p < n; p++) {
+    double bbx_min[3], bbx_max[3];
+    for (int a = 0; a < 3; a++) {
+      const double position = positions[3 * p + a], size = bbox[a];
+      if (insertion_method == 0) {
+        bbx_min[a] = position - size / 2 - epsilon;
+        bbx_max[a] = position + size / 2 + epsilon;
+      } else if (insertion_method == 1) {
+        bbx_min[a] = position - size / 2 + epsilon;
+        bbx_max[a] = position + size / 2 - epsilon;
+        bbx_min[a] = (double)(float)t->keyToCoord(t->coordToKey((double)(float)bbx_min[a]));
+        bbx_max[a] = (double)(float)t->keyToCoord(t->coordToKey((double)(float)bbx_max[a]));
+        bbx_min[a] -= epsilon;
+        bbx_max[a] += epsilon;
+      } else {
+        bbx_min[a] = position - size / 2 - epsilon;
+        bbx_max[a] = position + size / 2 + epsilon;
+        bbx_min[a] = (double)(float)t->keyToCoord(t->coordToKey((double)(float)bbx_min[a]));
+        bbx_max[a] = (double)(float)t->keyToCoord(t->coordToKey((double)(float)bbx_max[a]));
+        bbx_min[a] += resolution;
+        bbx_max[a] -= resolution;
+        bbx_min[a] -= epsilon;
+        bbx_max[a] += epsilon;
+      }
+    }
+    for (double x = bbx_min[0]; x <= bbx_max[0]; x += resolution)
+      for (double y = bbx_min[1]; y <= bbx_max[1]; y += resolution)
+        for (double z = bbx_min[2]; z <= bbx_max[2]; z += resolution)
+          t->setNodeValueLazy(Vec3f((float)x, (float)y, (float)z), (float)log_odds_value);
+  }
+  t->updateInnerOccupancy();
 }
 
 // octomap_world.cc:363-393: getCellTrueStatusPoint + getCellProbabilityPoint

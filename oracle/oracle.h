@@ -104,6 +104,11 @@ void oracle_query_visibility(const oracle_world* w, const double* view_voxel_xyz
 void oracle_query_lines_bbox(const oracle_world* w, const double* a_b_xyz6, size_t n,
                              const double bounding_box_size[3], uint8_t* status);
 
+/* setLogOddsBoundingBox (octomap_world.cc:781-818; setFree / setOccupied :497-523). */
+void oracle_set_log_odds_bbox(oracle_world* w, const double* positions_xyz, size_t n,
+                              const double bounding_box_size[3], double log_odds_value,
+                              int insertion_method);
+
 /* Standalone primitives (known-answer tests). */
 int oracle_coord_to_key_checked(const oracle_world* w, double c, uint16_t* key);
 uint16_t oracle_coord_to_key(const oracle_world* w, double c);

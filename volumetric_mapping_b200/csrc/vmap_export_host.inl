@@ -378,6 +378,75 @@ int vmap_deserialize_ot(vmap* h, int with_header, const uint8_t* buffer, size_t 
   return vmap_import_leaves(h, k3.data(), val.data(), val.size());
 }
 
+// OctomapWorld::setLogOddsBoundingBox (octomap_world.cc:781-818), which is what setFree /
+// setOccupied (:497-523) call: every grid position of the adjusted box (adjustBoundingBox,
+// :1175-1224) gets its voxel set to log_odds_value (setNodeValue: no clamping; out-of-bounds
+// positions are ignored).  The loops run on the host in the reference's arithmetic (accumulating
+// doubles, float narrowing at point3d); the voxels are written on the device in one batch.
+int vmap_set_log_odds_bbox(vmap* h, const double* positions_xyz, size_t n_positions,
+                           const double bounding_box_size[3], double log_odds_value, int bound_handling) {
+  if (!h || (!positions_xyz && n_positions) || !bounding_box_size) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (bound_handling < 0 || bound_handling > 2) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bound_handling must be 0 (default), 1 (include partial) or 2 (ignore partial)");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  const double resolution = h->params.resolution;
+  const double res_factor = 1.0 / resolution;
+  const double epsilon = 0.001;
+  auto coord_to_key = [&](float c) -> uint16_t {   // OcTreeBaseImpl::coordToKey (unchecked)
+    const double f = std::floor(res_factor * (double)c);
+    const int v = (f >= -2147483648.0 && f < 2147483648.0) ? (int)f : (int)0x80000000;
+    return (uint16_t)(v + 32768);
+  };
+  auto key_to_coord = [&](uint16_t k) -> float {   // keyToCoord(OcTreeKey) narrows to float
+    return (float)((double((int)k - 32768) + 0.5) * resolution);
+  };
+  std::vector<uint16_t> k3;
+  std::vector<float> val;
+  const float value = (float)log_odds_value;   // OcTreeNode::setLogOdds(float)
+  for (size_t p = 0; p < n_positions; p++) {
+    double bmin[3], bmax[3];
+    for (int a = 0; a < 3; a++) {
+      const double pos = positions_xyz[3 * p + a], half = bounding_box_size[a] / 2;
+      if (bound_handling == 0) {
+        bmin[a] = pos - half - epsilon;
+        bmax[a] = pos + half + epsilon;
+      } else if (bound_handling == 1) {
+        bmin[a] = pos - half + epsilon;
+        bmax[a] = pos + half - epsilon;
+        bmin[a] = (double)key_to_coord(coord_to_key((float)bmin[a]));
+        bmax[a] = (double)key_to_coord(coord_to_key((float)bmax[a]));
+        bmin[a] -= epsilon;
+        bmax[a] += epsilon;
+      } else {
+        bmin[a] = pos - half - epsilon;
+        bmax[a] = pos + half + epsilon;
+        bmin[a] = (double)key_to_coord(coord_to_key((float)bmin[a]));
+        bmax[a] = (double)key_to_coord(coord_to_key((float)bmax[a]));
+        bmin[a] += resolution;
+        bmax[a] -= resolution;
+        bmin[a] -= epsilon;
+        bmax[a] += epsilon;
+      }
+    }
+    for (double x = bmin[0]; x <= bmax[0]; x += resolution)
+      for (double y = bmin[1]; y <= bmax[1]; y += resolution)
+        for (double z = bmin[2]; z <= bmax[2]; z += resolution) {
+          const float pt[3] = {(float)x, (float)y, (float)z};
+          uint16_t key[3];
+          bool ok = true;
+          for (int a = 0; a < 3; a++) {   // setNodeValue(point3d): coordToKeyChecked or nothing
+            const double f = std::floor(res_factor * (double)pt[a]);
+            if (!(f >= -32768.0 && f < 32768.0)) { ok = false; break; }
+            key[a] = (uint16_t)((int)f + 32768);
+          }
+          if (!ok) continue;
+          k3.push_back(key[0]); k3.push_back(key[1]); k3.push_back(key[2]);
+          val.push_back(value);
+          if (val.size() > (1u << 28)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bounding box too large for the resolution");
+        }
+  }
+  return vmap_import_leaves(h, k3.data(), val.data(), val.size());
+}
+
 // octree_->prune(); octree_->size(): node count of the canonical pruned tree.
 int vmap_tree_size(vmap* h, int max_likelihood, size_t* n_nodes) {
   if (!h || !n_nodes) return VMAP_ERR_INVALID_ARGUMENT;

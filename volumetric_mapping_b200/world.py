@@ -170,6 +170,21 @@ class OctomapWorld:
         self._check(self._L.vmap_apply_keys(self._h, f.ctypes.data, f.shape[0], o.ctypes.data,
                                             o.shape[0]))
 
+    # -- manual edits (octomap_world.cc:497-523, 781-818) --------------------------------
+    def setLogOddsBoundingBox(self, positions, bounding_box_size, log_odds_value, insertion_method=0):
+        p = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        b = np.ascontiguousarray(bounding_box_size, dtype=np.float64).reshape(3)
+        self._check(self._L.vmap_set_log_odds_bbox(self._h, p.ctypes.data, p.shape[0], _dptr(b),
+                                                   float(log_odds_value), int(insertion_method)))
+
+    def setFree(self, positions, bounding_box_size, insertion_method=0):
+        self.setLogOddsBoundingBox(positions, bounding_box_size, float(self.logodds_constants()[2]),
+                                   insertion_method)
+
+    def setOccupied(self, positions, bounding_box_size, insertion_method=0):
+        self.setLogOddsBoundingBox(positions, bounding_box_size, float(self.logodds_constants()[3]),
+                                   insertion_method)
+
     # -- queries ------------------------------------------------------------------------
     def getCellStatusPoint(self, xyz):
         p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
