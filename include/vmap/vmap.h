@@ -233,6 +233,12 @@ VMAP_API int vmap_set_log_odds_bbox(vmap* h, const double* positions_xyz, size_t
                                     const double bounding_box_size[3], double log_odds_value,
                                     int bound_handling);
 
+/* OctomapWorld::getChangedPoints (octomap_world.cc:1413-1440): keys collected by octomap's change
+ * detection since the last call (created leaves; leaves whose occupancy flipped) with the current
+ * occupancy of each, followed by resetChangeDetection().  Requires change_detection_enabled
+ * (vmap_params; single-GPU insertion paths). */
+VMAP_API int vmap_get_changed(vmap* h, uint16_t* keys_k3, uint8_t* occupied, size_t capacity, size_t* n);
+
 /* Per-scan counters of the last insert / apply call. */
 VMAP_API int vmap_last_scan_stats(const vmap* h, vmap_scan_stats* stats);
 /* Parity hook: when enabled, the next inserts keep their final free / occupied key sets. */

@@ -127,6 +127,29 @@ class OctomapWorld : public WorldBase {
     check(vmap_set_log_odds_bbox(handle_, position.v, 1, bounding_box_size.v, c[3], insertion_method));
   }
 
+  // octomap_world.cc:1413-1440 (needs change_detection_enabled; resets the tracking)
+  void getChangedPoints(std::vector<Vector3d>* changed_points, std::vector<bool>* changed_states) {
+    if (!changed_points) throw std::invalid_argument("getChangedPoints: null output");   // CHECK_NOTNULL
+    changed_points->clear();
+    if (changed_states) changed_states->clear();
+    size_t n = 0;
+    const int st = vmap_get_changed(handle_, nullptr, nullptr, 0, &n);
+    if (st != VMAP_OK && st != VMAP_ERR_BUFFER_TOO_SMALL) check(st);
+    if (!n) return;
+    std::vector<uint16_t> k3(n * 3);
+    std::vector<uint8_t> occ(n);
+    check(vmap_get_changed(handle_, k3.data(), occ.data(), n, &n));
+    for (size_t i = 0; i < n; i++) {
+      // pointOctomapToEigen(octree_->keyToCoord(key)): float centres widened to double
+      Vector3d c;
+      for (int a = 0; a < 3; a++) c(a) = (double)(float)((double((int)k3[3 * i + a] - 32768) + 0.5) * params_.resolution);
+      changed_points->push_back(c);
+      if (changed_states) changed_states->push_back(occ[i] != 0);
+    }
+  }
+  void enableChangeDetection() { params_.change_detection_enabled = true; setOctomapParameters(params_); }
+  void disableChangeDetection() { params_.change_detection_enabled = false; setOctomapParameters(params_); }
+
   // updateOccupancy(KeySet*, KeySet*) (octomap_world.cc:238-264): protected in the reference but
   // called from OctomapManager::loadOctomapCallback (octomap_manager.cc:332-341).
   void updateOccupancy(KeySet* free_cells, KeySet* occupied_cells) {

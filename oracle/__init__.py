@@ -119,6 +119,8 @@ def lib():
     L.oracle_last_scan_stats.argtypes = [vp, C.POINTER(ScanStats)]
     L.oracle_export_leaves.argtypes = [vp, vp, vp]
     L.oracle_prune.argtypes = [vp]
+    L.oracle_get_changed.argtypes = [vp, vp, vp, C.c_size_t]
+    L.oracle_get_changed.restype = C.c_size_t
     L.oracle_set_log_odds_bbox.argtypes = [vp, vp, C.c_size_t, dp, C.c_double, C.c_int]
     L.oracle_write_bt.argtypes = [vp, C.c_int, vp, C.c_size_t]
     L.oracle_write_bt.restype = C.c_size_t
@@ -222,6 +224,14 @@ class OracleWorld:
         f = np.ascontiguousarray(free_k3, dtype=np.uint16).reshape(-1, 3)
         o = np.ascontiguousarray(occ_k3, dtype=np.uint16).reshape(-1, 3)
         self._L.oracle_apply_keys(self._h, f.ctypes.data, f.shape[0], o.ctypes.data, o.shape[0])
+
+    def getChangedPoints(self):
+        n = self._L.oracle_get_changed(self._h, None, None, 0)
+        k = np.zeros((n, 3), dtype=np.uint16)
+        o = np.zeros(n, dtype=np.uint8)
+        if n:
+            self._L.oracle_get_changed(self._h, k.ctypes.data, o.ctypes.data, n)
+        return k, o.astype(bool)
 
     def setLogOddsBoundingBox(self, positions, bounding_box_size, log_odds_value, insertion_method=0):
         p = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)

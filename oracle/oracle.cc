@@ -46,6 +46,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <unordered_map>
 #include <unordered_set>
 #include <string>
 #include <vector>
@@ -404,6 +405,11 @@ class OcTree {
 
   float prob_hit_log, prob_miss_log, clamping_thres_min, clamping_thres_max, occ_prob_thres_log;
 
+  // change detection (OccupancyOcTreeBase::enableChangeDetection / changedKeysBegin / reset)
+  typedef std::unordered_map<Key, bool, KeyHash> KeyBoolMap;
+  bool use_change_detection = false;
+  KeyBoolMap changed_keys;
+
  private:
   Node* root;
   size_t tree_size;
@@ -542,7 +548,21 @@ class OcTree {
       }
       return retval;
     } else {
-      updateNodeLogOdds(node, log_odds_update);
+      if (use_change_detection) {
+        bool occBefore = isNodeOccupied(node);
+        updateNodeLogOdds(node, log_odds_update);
+        if (node_just_created) {  // new node
+          changed_keys.insert(std::pair<Key, bool>(key, true));
+        } else if (occBefore != isNodeOccupied(node)) {  // occupancy changed, track it
+          KeyBoolMap::iterator it = changed_keys.find(key);
+          if (it == changed_keys.end())
+            changed_keys.insert(std::pair<Key, bool>(key, false));
+          else if (it->second == false)
+            changed_keys.erase(it);
+        }
+      } else {
+        updateNodeLogOdds(node, log_odds_update);
+      }
       return node;
     }
   }
@@ -648,6 +668,7 @@ struct oracle_world {
     octree->setClampingThresMin(p.threshold_min);
     octree->setClampingThresMax(p.threshold_max);
     octree->setOccupancyThres(p.threshold_occupancy);
+    octree->use_change_detection = p.change_detection_enabled != 0;   // octomap_world.cc:99
     params = p;
   }
 
@@ -956,6 +977,21 @@ void oracle_query_lines(const oracle_world* w, const double* ab, size_t n, uint8
     }
     status[i] = st;
   }
+}
+
+// octomap_world.cc:1413-1440: getChangedPoints -- keys + current occupancy, then reset.
+size_t oracle_get_changed(oracle_world* w, uint16_t* k3, uint8_t* occupied, size_t cap) {
+  OcTree* t = w->octree;
+  const size_t n = t->changed_keys.size();
+  if (!k3 || !occupied || cap < n) return n;
+  size_t i = 0;
+  for (OcTree::KeyBoolMap::const_iterator it = t->changed_keys.begin(); it != t->changed_keys.end(); ++it, ++i) {
+    Node* node = t->search(it->first);
+    k3[3 * i] = it->first.k[0]; k3[3 * i + 1] = it->first.k[1]; k3[3 * i + 2] = it->first.k[2];
+    occupied[i] = (node != NULL && t->isNodeOccupied(node)) ? 1 : 0;
+  }
+  t->changed_keys.clear();   // resetChangeDetection()
+  return n;
 }
 
 // octomap_world.cc:781-818 (setLogOddsBoundingBox) with adjustBoundingBox (:1175-1224)

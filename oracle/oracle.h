@@ -104,6 +104,10 @@ void oracle_query_visibility(const oracle_world* w, const double* view_voxel_xyz
 void oracle_query_lines_bbox(const oracle_world* w, const double* a_b_xyz6, size_t n,
                              const double bounding_box_size[3], uint8_t* status);
 
+/* getChangedPoints (octomap_world.cc:1413-1440): returns the count; fills and resets when the
+ * buffers are large enough. */
+size_t oracle_get_changed(oracle_world* w, uint16_t* k3, uint8_t* occupied, size_t cap);
+
 /* setLogOddsBoundingBox (octomap_world.cc:781-818; setFree / setOccupied :497-523). */
 void oracle_set_log_odds_bbox(oracle_world* w, const double* positions_xyz, size_t n,
                               const double bounding_box_size[3], double log_odds_value,

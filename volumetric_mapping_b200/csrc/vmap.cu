@@ -113,6 +113,8 @@ struct vmap {
   } win;
   MarkSet ms{};                 // marks of the scan in flight (table or dense mode)
   uint64_t dense_fallbacks = 0;
+  uint32_t* chg0_store = nullptr;   // change-detection planes (MapView.chg0/1 point here while enabled)
+  uint32_t* chg1_store = nullptr;
   int walk_variant = 48;  // near-field limit of the walker's read-before-RED filter (VMAP_WALK_VARIANT)
   int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
@@ -267,10 +269,44 @@ int grow_pool(vmap* h, uint64_t need_blocks) {
   VM_CUDA(h, cudaMemcpyAsync(np_, h->m.pool, h->pool_cap * blk, cudaMemcpyDeviceToDevice, h->stream));
   VM_CUDA(h, cudaMemsetAsync((char*)np_ + h->pool_cap * blk, 0xFF, (new_cap - h->pool_cap) * blk, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->chg0_store) {   // change-detection planes grow with the pool
+    const size_t pl = (size_t)kMaskWords * sizeof(uint32_t);
+    uint32_t* n0 = nullptr;
+    uint32_t* n1 = nullptr;
+    VM_TRY(dev_alloc(h, (void**)&n0, new_cap * pl));
+    VM_TRY(dev_alloc(h, (void**)&n1, new_cap * pl));
+    VM_CUDA(h, cudaMemcpy(n0, h->chg0_store, h->pool_cap * pl, cudaMemcpyDeviceToDevice));
+    VM_CUDA(h, cudaMemcpy(n1, h->chg1_store, h->pool_cap * pl, cudaMemcpyDeviceToDevice));
+    VM_CUDA(h, cudaMemset((char*)n0 + h->pool_cap * pl, 0, (new_cap - h->pool_cap) * pl));
+    VM_CUDA(h, cudaMemset((char*)n1 + h->pool_cap * pl, 0, (new_cap - h->pool_cap) * pl));
+    dev_free(h, h->chg0_store, h->pool_cap * pl);
+    dev_free(h, h->chg1_store, h->pool_cap * pl);
+    h->chg0_store = n0;
+    h->chg1_store = n1;
+    if (h->m.chg0) {
+      h->m.chg0 = n0;
+      h->m.chg1 = n1;
+    }
+  }
   dev_free(h, h->m.pool, h->pool_cap * blk);
   h->m.pool = np_;
   h->pool_cap = new_cap;
   h->m.pool_cap = (uint32_t)new_cap;
+  return VMAP_OK;
+}
+
+// octree_->enableChangeDetection(on) (octomap_world.cc:99): the planes are allocated on first use
+// and kept (disabling only stops the tracking, like octomap keeps its changed_keys).
+int set_change_detection(vmap* h, bool on) {
+  if (on && !h->chg0_store) {
+    const size_t pl = (size_t)kMaskWords * sizeof(uint32_t);
+    VM_TRY(dev_alloc(h, (void**)&h->chg0_store, h->pool_cap * pl));
+    VM_TRY(dev_alloc(h, (void**)&h->chg1_store, h->pool_cap * pl));
+    VM_CUDA(h, cudaMemset(h->chg0_store, 0, h->pool_cap * pl));
+    VM_CUDA(h, cudaMemset(h->chg1_store, 0, h->pool_cap * pl));
+  }
+  h->m.chg0 = on ? h->chg0_store : nullptr;
+  h->m.chg1 = on ? h->chg1_store : nullptr;
   return VMAP_OK;
 }
 
@@ -877,6 +913,7 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_pack_counts_base, (size_t)2 * kMaxBatch * 2 * kMaxRanks * sizeof(uint32_t));
   h->d_pack_counts = h->d_pack_counts_base;
   if (s == VMAP_OK) s = init_map(h);
+  if (s == VMAP_OK) s = set_change_detection(h, p.change_detection_enabled != 0);
   if (s != VMAP_OK) return bail(s);
   *out = h;
   return VMAP_OK;
@@ -905,6 +942,7 @@ int vmap_destroy(vmap* h) {
   cudaFree(h->pack.p); cudaFree(h->recv.p); cudaFree(h->d_pack_counts_base); cudaFree(h->d_count_matrix);
   sort_free(h);
   free_window(h);
+  cudaFree(h->chg0_store); cudaFree(h->chg1_store);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_persist) cudaFreeHost(h->h_persist);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -930,6 +968,10 @@ int vmap_reset(vmap* h) {
   VM_CUDA(h, cudaMemsetAsync(h->m.occ_mask, 0, h->table_cap * kMaskWords * sizeof(uint32_t), h->stream));
   VM_CUDA(h, cudaMemsetAsync(h->m.pool, 0xFF, h->pool_cap * kBlockVoxels * sizeof(float), h->stream));
   VM_CUDA(h, cudaMemsetAsync(h->m.persist, 0, sizeof(Persist), h->stream));
+  if (h->chg0_store) {
+    VM_CUDA(h, cudaMemsetAsync(h->chg0_store, 0, h->pool_cap * kMaskWords * sizeof(uint32_t), h->stream));
+    VM_CUDA(h, cudaMemsetAsync(h->chg1_store, 0, h->pool_cap * kMaskWords * sizeof(uint32_t), h->stream));
+  }
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   h->epoch = 0;
   h->stats = vmap_scan_stats{};
@@ -944,6 +986,8 @@ int vmap_set_params(vmap* h, const vmap_params* params) {
   const bool new_res = params->resolution != h->params.resolution;  // octomap_world.cc:85
   h->params = *params;
   derive_params(h);
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(set_change_detection(h, params->change_detection_enabled != 0));   // octomap_world.cc:99
   if (new_res) return vmap_reset(h);
   return VMAP_OK;
 }
@@ -1371,6 +1415,39 @@ int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in
     return VMAP_OK;
   }
   return fail(h, VMAP_ERR_CAPACITY, "import could not be applied after repeated growth");
+}
+
+// OctomapWorld::getChangedPoints (octomap_world.cc:1413-1440): the keys octomap's change detection
+// collected since the last call (created leaves and leaves whose occupancy flipped), each with
+// the CURRENT occupancy of its node, then resetChangeDetection().  Needs change_detection_enabled.
+// When `capacity` is too small nothing is reset and *n holds the count.
+int vmap_get_changed(vmap* h, uint16_t* keys_k3, uint8_t* occupied, size_t capacity, size_t* n) {
+  if (!h || !n) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
+  *n = 0;
+  if (!h->m.chg0) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "change detection is not enabled (OctomapParameters::change_detection_enabled)");
+  const unsigned grid = g_sm_count(h->device) * 8;
+  VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_leaves, 0, sizeof(uint32_t), h->stream));
+  k_changed<<<grid, 256, 0, h->stream>>>(h->P, h->m, h->d_cnt, nullptr, nullptr, 0, 0);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  uint32_t total = 0;
+  VM_CUDA(h, cudaMemcpyAsync(&total, &h->d_cnt->n_leaves, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  *n = total;
+  if (total == 0) return VMAP_OK;
+  if (!keys_k3 || !occupied || capacity < total) return fail(h, VMAP_ERR_BUFFER_TOO_SMALL, "buffers too small; *n holds the number of changed keys");
+  VM_TRY(ensure(h, &h->out, (size_t)total * 6));
+  VM_TRY(ensure(h, &h->aux, total));
+  VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_leaves, 0, sizeof(uint32_t), h->stream));
+  k_changed<<<grid, 256, 0, h->stream>>>(h->P, h->m, h->d_cnt, (uint16_t*)h->out.p, (uint8_t*)h->aux.p, total, 1);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  VM_CUDA(h, cudaMemcpyAsync(keys_k3, h->out.p, (size_t)total * 6, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaMemcpyAsync(occupied, h->aux.p, total, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

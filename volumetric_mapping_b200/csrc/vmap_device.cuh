@@ -86,6 +86,11 @@ struct MapView {
   uint32_t pool_cap;   // blocks
   uint32_t epoch;      // current scan epoch (1..kEpochMax)
   uint32_t sharded;    // 1: the table also holds blocks owned by other ranks (no pool slot)
+  // octomap's change detection (changed_keys), two bit planes per pool block (16 words each):
+  // code 1 = node created since the last reset (value `true` in the KeyBoolMap), code 2 =
+  // occupancy flipped (`false`), 0 = not in the map.  NULL when change detection is off.
+  uint32_t* chg0;
+  uint32_t* chg1;
 };
 
 __device__ __forceinline__ unsigned long long block_key(uint32_t kx, uint32_t ky, uint32_t kz) {

@@ -836,6 +836,38 @@ k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
         if (is_occ || is_free) vox[j * 32 + lane] = update_leaf(val[j], is_occ ? P.hit : P.miss, P.cmin, P.cmax);
         if (lane == 0) { n_free += __popc(fw); n_occ += __popc(ow); }
       }
+    } else if (m.chg0 != nullptr) {
+      // change detection on (OccupancyOcTreeBase::updateNodeRecurs with use_change_detection):
+      // a created leaf is recorded as `true`; an occupancy flip inserts `false`, or erases an
+      // earlier `false`; a `true` entry is never changed.  Early-aborted updates record nothing.
+      uint32_t* c0 = m.chg0 + (size_t)slot * kMaskWords;
+      uint32_t* c1 = m.chg1 + (size_t)slot * kMaskWords;
+      for (int j = 0; j < kMaskWords; j++) {
+        const uint32_t fw = __shfl_sync(0xFFFFFFFFu, f, j);
+        const uint32_t ow = __shfl_sync(0xFFFFFFFFu, o, j);
+        if ((fw | ow) == 0u) continue;
+        const uint32_t o0 = c0[j], o1 = c1[j];
+        uint32_t code = ((o0 >> lane) & 1u) | (((o1 >> lane) & 1u) << 1);
+        const bool is_occ = (ow >> lane) & 1u, is_free = (fw >> lane) & 1u;
+        if (is_occ || is_free) {
+          uint32_t* p = vox + j * 32 + lane;
+          const uint32_t before = *p;
+          const uint32_t after = update_leaf(before, is_occ ? P.hit : P.miss, P.cmin, P.cmax);
+          *p = after;
+          if (before == kUnknownBits) {
+            code = 1u;
+          } else if ((__uint_as_float(before) >= P.occ_thres) != (__uint_as_float(after) >= P.occ_thres)) {
+            if (code == 0u) code = 2u;
+            else if (code == 2u) code = 0u;
+          }
+        }
+        const uint32_t n0 = __ballot_sync(0xFFFFFFFFu, code & 1u), n1 = __ballot_sync(0xFFFFFFFFu, code >> 1);
+        if (lane == 0) {
+          if (n0 != o0) c0[j] = n0;
+          if (n1 != o1) c1[j] = n1;
+          n_free += __popc(fw); n_occ += __popc(ow);
+        }
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < kMaskWords; j++) {
@@ -981,6 +1013,48 @@ k_export(MapView m, Counters* cnt, uint16_t* __restrict__ k3, float* __restrict_
           k3[3 * p + 2] = (uint16_t)(bz + (l >> 6));
           val[p] = __uint_as_float(bits);
         }
+      }
+    }
+  }
+}
+
+// getChangedPoints (octomap_world.cc:1413-1440): every key of octomap's changed_keys with the
+// CURRENT occupancy of its node; `clear` = resetChangeDetection().  Pass k3 == NULL to count.
+__global__ void __launch_bounds__(256)
+k_changed(DevParams P, MapView m, Counters* cnt, uint16_t* __restrict__ k3, uint8_t* __restrict__ state,
+          uint32_t cap, int clear) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h <= m.cap_mask; h += warps) {
+    const unsigned long long w = m.keys[h];
+    if (w == kEmpty) continue;
+    const uint32_t slot = m.slot[h];
+    if (slot == kUnassigned) continue;
+    const unsigned long long b = w >> kEpochBits;
+    const uint32_t bx = (uint32_t)(b & 0x1FFFu) << 3, by = (uint32_t)((b >> 13) & 0x1FFFu) << 3,
+                   bz = (uint32_t)((b >> 26) & 0x1FFFu) << 3;
+    for (int j = 0; j < kMaskWords; j++) {
+      const uint32_t any = m.chg0[(size_t)slot * kMaskWords + j] | m.chg1[(size_t)slot * kMaskWords + j];
+      if (!any) continue;
+      const bool mine = (any >> lane) & 1u;
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&cnt->n_leaves, (uint32_t)__popc(any));
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (mine && k3) {
+        const uint32_t p = base + __popc(any & ((1u << lane) - 1u));
+        if (p < cap) {
+          const uint32_t l = (uint32_t)j * 32u + lane;
+          k3[3 * p] = (uint16_t)(bx + (l & 7u));
+          k3[3 * p + 1] = (uint16_t)(by + ((l >> 3) & 7u));
+          k3[3 * p + 2] = (uint16_t)(bz + (l >> 6));
+          const uint32_t bits = reinterpret_cast<const uint32_t*>(m.pool)[(size_t)slot * kBlockVoxels + l];
+          state[p] = (bits != kUnknownBits && __uint_as_float(bits) >= P.occ_thres) ? 1 : 0;
+        }
+      }
+      __syncwarp();
+      if (clear && lane == 0) {
+        m.chg0[(size_t)slot * kMaskWords + j] = 0u;
+        m.chg1[(size_t)slot * kMaskWords + j] = 0u;
       }
     }
   }

@@ -170,6 +170,19 @@ class OctomapWorld:
         self._check(self._L.vmap_apply_keys(self._h, f.ctypes.data, f.shape[0], o.ctypes.data,
                                             o.shape[0]))
 
+    def getChangedPoints(self):
+        """(keys, occupied) collected by change detection since the last call; resets it
+        (octomap_world.cc:1413-1440).  Points are keyToCoord(keys)."""
+        n = C.c_size_t(0)
+        st = self._L.vmap_get_changed(self._h, None, None, 0, C.byref(n))
+        if st not in (0, 5):
+            self._check(st)
+        k = np.zeros((n.value, 3), dtype=np.uint16)
+        o = np.zeros(n.value, dtype=np.uint8)
+        if n.value:
+            self._check(self._L.vmap_get_changed(self._h, k.ctypes.data, o.ctypes.data, n.value, C.byref(n)))
+        return k, o.astype(bool)
+
     # -- manual edits (octomap_world.cc:497-523, 781-818) --------------------------------
     def setLogOddsBoundingBox(self, positions, bounding_box_size, log_odds_value, insertion_method=0):
         p = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
