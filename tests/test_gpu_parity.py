@@ -321,6 +321,13 @@ def test_max_blocks_cap_is_an_error_not_corruption():
     with pytest.raises(vm.VmapError) as e:
         gw.insertPointcloud(s["T"], s["points"])
     assert e.value.status == 3      # VMAP_ERR_CAPACITY
+    # the refused scan left nothing behind: the map is still empty and a scan that fits is exact
+    assert gw.leaf_count() == 0
+    ow = oracle.OracleWorld(**s["params"])
+    small = s["points"][:40] * np.float32(0.2)
+    gw.insertPointcloud(s["T"], small)
+    ow.insertPointcloud(s["T"], small)
+    assert_same_leaves(gw, ow)
 
 
 # ---------------------------------------------------------------------------------------

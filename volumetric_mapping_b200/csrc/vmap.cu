@@ -644,13 +644,23 @@ int run_scan(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
         while (h->h_cnt->overflow_keys || h->h_cnt->overflow_table || h->h_cnt->overflow_pool) {
           if (++guard > 40) return fail(h, VMAP_ERR_CAPACITY, "scan could not be applied after repeated growth");
           retries++;
+          int gs;
           if (h->h_cnt->overflow_keys) {
-            VM_TRY(grow_window_list(h, std::max<uint32_t>(h->h_cnt->n_touched + (h->h_cnt->n_touched >> 2), 2 * h->win.list_cap)));
+            gs = grow_window_list(h, std::max<uint32_t>(h->h_cnt->n_touched + (h->h_cnt->n_touched >> 2), 2 * h->win.list_cap));
             h->ms.list = h->win.list; h->ms.locate = h->win.locate; h->ms.list_cap = h->win.list_cap;
           } else if (h->h_cnt->overflow_table) {
-            VM_TRY(grow_table(h));
+            gs = grow_table(h);
           } else {
-            VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_entries));
+            gs = grow_pool(h, std::min<uint64_t>((uint64_t)h->h_persist->n_entries, (uint64_t)h->h_persist->n_slots + h->h_cnt->n_touched));
+          }
+          if (gs != VMAP_OK) {
+            // the scan cannot be applied (capacity): it must not leave its marks behind either,
+            // or the next scan would inherit them
+            const std::string msg = h->err;
+            clear_window_marks(h);
+            cudaStreamSynchronize(h->stream);
+            h->err = msg;
+            return gs;
           }
           VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_touched, 0, sizeof(uint32_t), h->stream));
           VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->overflow_table, 0, 6 * sizeof(uint32_t), h->stream));
@@ -669,8 +679,8 @@ int run_scan(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
       use_table_marks(h);
       redo = true;
     } else if (h->h_cnt->overflow_pool) {
-      VM_TRY(clear_marks(h));
-      VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_entries));
+      VM_TRY(clear_marks(h));   // (table mode: the marks are dropped before growing, so a failed grow leaves none)
+      VM_TRY(grow_pool(h, std::min<uint64_t>((uint64_t)h->h_persist->n_entries, (uint64_t)h->h_persist->n_slots + h->h_cnt->n_touched)));
       // epochs are still the current one: give the re-run a fresh epoch so blocks are re-listed
       VM_TRY(next_epoch(h));
       redo = true;

@@ -785,9 +785,10 @@ __global__ void __launch_bounds__(256)
 k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
   // Abort the whole scan's update (uniformly) when a map structure must grow first.
   if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
-  // every entry owns a slot (single GPU); a sharded table also lists foreign blocks, so bound
-  // the slots by what this update can add at most
-  const uint32_t slots_bound = m.sharded ? m.persist->n_slots + cnt->n_touched : m.persist->n_entries;
+  // slots after this update: at most one new slot per touched block, and (single GPU, where every
+  // entry ends up owning a slot) never more than there are entries
+  const uint32_t by_touch = m.persist->n_slots + cnt->n_touched;
+  const uint32_t slots_bound = m.sharded ? by_touch : min(by_touch, m.persist->n_entries);
   if (slots_bound > m.pool_cap) {
     if (blockIdx.x == 0 && threadIdx.x == 0) cnt->overflow_pool = 1u;
     return;
