@@ -225,6 +225,15 @@ VMAP_API int vmap_serialize_ot(vmap* h, int with_header, uint8_t* buffer, size_t
 VMAP_API int vmap_deserialize_ot(vmap* h, int with_header, const uint8_t* buffer, size_t n_bytes);
 VMAP_API int vmap_deserialize_bt(vmap* h, const uint8_t* buffer, size_t n_bytes);
 
+/* The same tree fold and stream writers / readers on caller-supplied leaves, WITHOUT a device
+ * (pure host functions; kind 0 = ".bt", 1 = full-tree data, 2 = ".ot" with header). */
+VMAP_API int vmap_host_tree_stream(const vmap_params* params, const uint16_t* keys_k3,
+                                   const float* logodds, size_t n, int kind, uint8_t* buffer,
+                                   size_t capacity, size_t* n_bytes, size_t* n_nodes);
+VMAP_API int vmap_host_parse_stream(const vmap_params* params, int kind, const uint8_t* buffer,
+                                    size_t n_bytes, uint16_t* keys_k3, float* logodds,
+                                    size_t capacity, size_t* n_leaves, double* resolution);
+
 /* OctomapWorld::setLogOddsBoundingBox (octomap_world.cc:781-818) behind setFree / setOccupied
  * (:497-523): n boxes of one size; bound_handling = BoundHandling (octomap_world.h:43-52:
  * 0 kDefault, 1 kIncludePartialBoxes, 2 kIgnorePartialBoxes).  setFree passes the clamping

@@ -13,6 +13,7 @@
 // not available here, so the byte layout is restated from the upstream sources [UPSTREAM-recalled]
 // and pinned by a hand-derived stream and by the oracle's independent pointer-tree writer.
 #include <fstream>
+#include <memory>
 #include <sstream>
 
 namespace {
@@ -445,6 +446,67 @@ int vmap_set_log_odds_bbox(vmap* h, const double* positions_xyz, size_t n_positi
         }
   }
   return vmap_import_leaves(h, k3.data(), val.data(), val.size());
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same tree fold / stream code on caller-supplied leaves, without a device: used by hosts that
+// already hold the leaves (and by the CPU test-suite, which checks these writers and readers
+// against the oracle's pointer-tree implementation on maps the oracle built).
+//   kind 0: ".bt" (max-likelihood, OcTree::writeBinaryConst)   1: full-tree data (writeData)
+//   kind 2: ".ot" stream with header (OcTree::write)
+// ---------------------------------------------------------------------------------------------
+int vmap_host_tree_stream(const vmap_params* params, const uint16_t* keys_k3, const float* logodds_in, size_t n,
+                          int kind, uint8_t* buffer, size_t capacity, size_t* n_bytes, size_t* n_nodes) {
+  if (!params || ((!keys_k3 || !logodds_in) && n) || !n_bytes || kind < 0 || kind > 2) return VMAP_ERR_INVALID_ARGUMENT;
+  std::unique_ptr<vmap> tmp(new vmap());
+  tmp->params = *params;
+  derive_params(tmp.get());
+  std::vector<std::pair<uint64_t, float> > leaves(n);
+  for (size_t i = 0; i < n; i++)
+    leaves[i] = std::make_pair(host_spread3(keys_k3[3 * i]) | (host_spread3(keys_k3[3 * i + 1]) << 1) | (host_spread3(keys_k3[3 * i + 2]) << 2), logodds_in[i]);
+  std::sort(leaves.begin(), leaves.end(), [](const std::pair<uint64_t, float>& a, const std::pair<uint64_t, float>& b) { return a.first < b.first; });
+  PrunedTree t;
+  build_pruned_tree(tmp.get(), leaves, kind == 0, &t);
+  std::string out;
+  if (kind == 0) {
+    out = bt_header(tmp.get(), t.n_nodes);
+    write_bt_nodes(tmp.get(), t, &out);
+  } else {
+    if (kind == 2) out = ot_header(tmp.get(), t.n_nodes);
+    write_ot_nodes(t, &out);
+  }
+  *n_bytes = out.size();
+  if (n_nodes) *n_nodes = t.n_nodes;
+  if (!buffer) return VMAP_OK;
+  if (capacity < out.size()) return VMAP_ERR_BUFFER_TOO_SMALL;
+  std::memcpy(buffer, out.data(), out.size());
+  return VMAP_OK;
+}
+
+// Inverse: finest-level leaves of a stream (pruned leaves expanded).  *n_leaves always receives
+// the leaf count; the arrays are filled when `capacity` suffices.
+int vmap_host_parse_stream(const vmap_params* params, int kind, const uint8_t* buffer, size_t n_bytes,
+                           uint16_t* keys_k3, float* logodds_out, size_t capacity, size_t* n_leaves,
+                           double* resolution) {
+  if (!params || (!buffer && n_bytes) || !n_leaves || kind < 0 || kind > 2) return VMAP_ERR_INVALID_ARGUMENT;
+  std::unique_ptr<vmap> tmp(new vmap());
+  tmp->params = *params;
+  derive_params(tmp.get());
+  std::vector<uint16_t> k3;
+  std::vector<float> val;
+  double res = params->resolution;
+  const std::string in(reinterpret_cast<const char*>(buffer), n_bytes);
+  const int st = (kind == 0) ? parse_bt(tmp.get(), in, &res, &k3, &val) : parse_ot(tmp.get(), in, kind == 2, &res, &k3, &val);
+  if (st != VMAP_OK) {
+    g_create_error = tmp->err;
+    return st;
+  }
+  *n_leaves = val.size();
+  if (resolution) *resolution = res;
+  if (!keys_k3 || !logodds_out || capacity < val.size()) return val.empty() ? VMAP_OK : VMAP_ERR_BUFFER_TOO_SMALL;
+  std::memcpy(keys_k3, k3.data(), k3.size() * sizeof(uint16_t));
+  std::memcpy(logodds_out, val.data(), val.size() * sizeof(float));
+  return VMAP_OK;
 }
 
 // octree_->prune(); octree_->size(): node count of the canonical pruned tree.
