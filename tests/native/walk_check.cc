@@ -1,0 +1,124 @@
+// Host build of the product's per-thread walker code (vmap_device.cuh / vmap_walk.cuh) for the CPU
+// test-suite, driven by tests/test_walk_host_emulation.py.  The checker below marks one scan's
+// free voxels three ways and the Python side compares them:
+//   walk_plain        walk_ray (the straightforward DDA)      -> marks through window_index()
+//   walk_segmented    ray_checkpoints + walk_slot_dilated     -> marks through dilated addresses
+// and hands individual rays' keys to Python for comparison with the oracle's computeRayKeys.
+#include "../../volumetric_mapping_b200/csrc/vmap_walk.cuh"
+
+#include <vector>
+
+using namespace vmapdev;
+
+namespace {
+DevParams make_params(double res, double max_free_space, double min_height_free_space) {
+  DevParams P;
+  memset(&P, 0, sizeof(P));
+  P.res = res;
+  P.res_factor = 1.0 / res;
+  P.max_range = -1.0;
+  P.max_free_space = max_free_space;
+  P.min_height_free_space = min_height_free_space;
+  P.free_filter = max_free_space != 0.0;
+  return P;
+}
+MarkSet make_window(const int32_t origin_block[3], const uint32_t dims[3], uint32_t* free_mask, uint32_t* touched) {
+  MarkSet ms;
+  memset(&ms, 0, sizeof(ms));
+  ms.free_mask = free_mask;
+  ms.touched_bits = touched;
+  ms.x0 = origin_block[0]; ms.y0 = origin_block[1]; ms.z0 = origin_block[2];
+  ms.nx = dims[0]; ms.ny = dims[1]; ms.nz = dims[2];
+  ms.dense = 1;
+  return ms;
+}
+}  // namespace
+
+extern "C" {
+
+// keys of one ray by the plain DDA (k3 out, up to cap keys); returns the key count
+uint32_t wc_ray_keys(double res, const float* origin, const float* end, uint16_t* k3, uint32_t cap) {
+  const DevParams P = make_params(res, 0.0, 0.0);
+  uint32_t n = 0;
+  return walk_ray(P, origin[0], origin[1], origin[2], end[0], end[1], end[2], [&](uint32_t a, uint32_t b, uint32_t c) {
+    if (n < cap) { k3[3 * n] = (uint16_t)a; k3[3 * n + 1] = (uint16_t)b; k3[3 * n + 2] = (uint16_t)c; }
+    n++;
+    return true;
+  });
+}
+
+// number of DDA steps the front-end predicts for a ray (classify_point's `len`)
+static uint32_t predicted_steps(const DevParams& P, const float* o, const float* e) {
+  const int o0 = scaled_coord(P.res_factor, (double)o[0]), o1 = scaled_coord(P.res_factor, (double)o[1]),
+            o2 = scaled_coord(P.res_factor, (double)o[2]);
+  const int e0 = scaled_coord(P.res_factor, (double)e[0]), e1 = scaled_coord(P.res_factor, (double)e[1]),
+            e2 = scaled_coord(P.res_factor, (double)e[2]);
+  const bool walk = key_in_range(o0) && key_in_range(o1) && key_in_range(o2) && key_in_range(e0) && key_in_range(e1) &&
+                    key_in_range(e2);
+  return walk ? (uint32_t)(abs(e0 - o0) + abs(e1 - o1) + abs(e2 - o2)) : 0u;
+}
+
+// Plain marks.  stats: [traversals, longest, overflow_window]
+int wc_walk_plain(double res, double max_free_space, double min_height, const float* origin, const float* ends,
+                  uint32_t n_rays, const int32_t* origin_block, const uint32_t* dims, uint32_t* free_mask,
+                  uint32_t* touched, uint64_t* stats) {
+  const DevParams P = make_params(res, max_free_space, min_height);
+  const MarkSet ms = make_window(origin_block, dims, free_mask, touched);
+  uint64_t trav = 0, longest = 0, ovf = 0;
+  for (uint32_t r = 0; r < n_rays; r++) {
+    const float* e = ends + 3 * r;
+    const uint32_t n = walk_ray(P, origin[0], origin[1], origin[2], e[0], e[1], e[2], [&](uint32_t a, uint32_t b, uint32_t c) {
+      if (P.free_filter && !free_filter_pass(P, origin[0], origin[1], origin[2], a, b, c)) return true;
+      const uint32_t idx = window_index(ms, a, b, c);
+      if (idx == kNotFound) { ovf = 1; return true; }
+      const uint32_t l = local_index(a, b, c);
+      ms.free_mask[(size_t)idx * kMaskWords + (l >> 5)] |= 1u << (l & 31u);
+      ms.touched_bits[idx >> 5] |= 1u << (idx & 31u);
+      return true;
+    });
+    trav += n;
+    longest = std::max<uint64_t>(longest, n);
+  }
+  stats[0] = trav; stats[1] = longest; stats[2] = ovf;
+  return 0;
+}
+
+// Segmented marks: checkpoints for every ray, then every (level, ray) slot on its own, levels
+// outermost (the order the kernel's level-major slots are walked in is irrelevant for the marks,
+// but this one is the least like the plain walk).  stats: [traversals, longest, overflow_window, slots]
+int wc_walk_segmented(double res, double max_free_space, double min_height, const float* origin, const float* ends,
+                      uint32_t n_rays, const int32_t* origin_block, const uint32_t* dims, uint32_t* free_mask,
+                      uint32_t* touched, uint32_t near_limit, uint64_t* stats) {
+  const DevParams P = make_params(res, max_free_space, min_height);
+  const MarkSet ms = make_window(origin_block, dims, free_mask, touched);
+  if (!dilated_window_fits(ms.nx, ms.ny, ms.nz)) return 1;
+  const DilatedWindow dw = dilated_window(ms);
+  Counters cnt;
+  memset(&cnt, 0, sizeof(cnt));
+  std::vector<RayRec> recs(n_rays);
+  std::vector<std::vector<Checkpoint> > cps(n_rays);
+  uint32_t max_seg = 0;
+  for (uint32_t r = 0; r < n_rays; r++) {
+    const float* e = ends + 3 * r;
+    ray_checkpoints(P, origin[0], origin[1], origin[2], e[0], e[1], e[2], predicted_steps(P, origin, e), r, &recs[r],
+                    [&](uint32_t, const Checkpoint& cp) { cps[r].push_back(cp); return true; });
+    max_seg = std::max(max_seg, (uint32_t)cps[r].size());
+  }
+  uint32_t emitted = 0, longest = 0;
+  uint64_t trav = 0, slots = 0;
+  for (uint32_t jj = max_seg; jj-- > 0;) {       // deepest level first
+    for (uint32_t r = 0; r < n_rays; r++) {
+      if (jj >= cps[r].size()) continue;
+      emitted = 0;
+      if (P.free_filter)
+        walk_slot_dilated<true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest);
+      else
+        walk_slot_dilated<false>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest);
+      trav += emitted;
+      slots++;
+    }
+  }
+  stats[0] = trav; stats[1] = longest; stats[2] = cnt.overflow_window; stats[3] = slots;
+  return 0;
+}
+}

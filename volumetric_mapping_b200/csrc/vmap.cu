@@ -105,6 +105,7 @@ struct vmap {
     uint32_t* list = nullptr;
     uint32_t* locate = nullptr;
     uint32_t n_side = 0;        // blocks per axis (cube)
+    uint32_t stride = 0;        // x / y extent as allocated: n_side, or the next power of two (dilated addressing)
     int radius = 0;             // blocks from the sensor block to the window face
     uint64_t n_blocks = 0;
     uint32_t n_words = 0;       // touched bitmap words
@@ -116,6 +117,7 @@ struct vmap {
   uint32_t* chg0_store = nullptr;   // change-detection planes (MapView.chg0/1 point here while enabled)
   uint32_t* chg1_store = nullptr;
   int walk_variant = 48;  // near-field limit of the walker's read-before-RED filter (VMAP_WALK_VARIANT)
+  int walk_addr = 0;      // 1: dilated window addressing in the segment walker (VMAP_WALK_ADDR, experimental)
   int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
   size_t ckpt_want = 0;   // checkpoint capacity to allocate with the scan scratch
@@ -500,15 +502,24 @@ bool setup_dense_marks(vmap* h, const float origin[3]) {
   const double r_blk = std::ceil(r_vox / 8.0) + 2.0;
   const uint64_t budget = h->cfg.dense_window_bytes ? h->cfg.dense_window_bytes : (6ull << 30);
   const double side = 2.0 * r_blk + 1.0;
-  const double blocks = side * side * side;
+  // dilated addressing wants power-of-two x / y extents; fall back to the cube when that does
+  // not fit a 32-bit bit address
+  uint32_t stride = (uint32_t)side;
+  if (h->walk_addr == 1 && side < 65536.0) {
+    uint32_t p2 = 1;
+    while (p2 < (uint32_t)side) p2 <<= 1;
+    if (dilated_window_fits(p2, p2, (uint32_t)side)) stride = p2;
+  }
+  const double blocks = (double)stride * (double)stride * side;
   if (blocks * (2.0 * kMaskWords * 4 + 0.125) > (double)budget || blocks >= (double)(1u << 28)) return false;
   const int radius = (int)r_blk;
-  if (w.radius != radius || !w.free_bits) {
+  if (w.radius != radius || w.stride != stride || !w.free_bits) {
     cudaStreamSynchronize(h->stream);
     free_window(h);
     w.radius = radius;
     w.n_side = (uint32_t)(2 * radius + 1);
-    w.n_blocks = (uint64_t)w.n_side * w.n_side * w.n_side;
+    w.stride = stride;
+    w.n_blocks = (uint64_t)w.stride * w.stride * w.n_side;
     w.n_words = (uint32_t)((w.n_blocks + 31) / 32);
     bool ok = dev_alloc(h, (void**)&w.free_bits, w.n_blocks * kMaskWords * 4) == VMAP_OK &&
               dev_alloc(h, (void**)&w.occ_bits, w.n_blocks * kMaskWords * 4) == VMAP_OK &&
@@ -539,7 +550,8 @@ bool setup_dense_marks(vmap* h, const float origin[3]) {
   ms.locate = w.locate;
   ms.list_cap = w.list_cap;
   ms.x0 = ok[0] - radius; ms.y0 = ok[1] - radius; ms.z0 = ok[2] - radius;
-  ms.nx = ms.ny = ms.nz = w.n_side;
+  ms.nx = ms.ny = w.stride;
+  ms.nz = w.n_side;
   ms.dense = 1;
   return true;
 }
@@ -757,7 +769,10 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
     h->launches++;
     static const int walk_ctas = getenv("VMAP_WALK_CTAS") ? atoi(getenv("VMAP_WALK_CTAS")) : 5;   // = resident CTAs per SM at 48 registers
     const unsigned grid = g_sm_count(h->device) * walk_ctas;
-    if (h->P.free_filter) k_walk_segments<true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
+    const bool dilated = h->walk_addr == 1 && dilated_window_fits(h->ms.nx, h->ms.ny, h->ms.nz);
+    if (dilated && h->P.free_filter) k_walk_segments_dilated<true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
+    else if (dilated) k_walk_segments_dilated<false><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
+    else if (h->P.free_filter) k_walk_segments<true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
     else k_walk_segments<false><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
   } else if (h->ms.dense) {
     if (h->P.free_filter) k_walk_dense<true><<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
@@ -889,6 +904,7 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   h->device = dev;
   derive_params(h);
   if (const char* e = getenv("VMAP_WALK_VARIANT")) h->walk_variant = atoi(e);
+  if (const char* e = getenv("VMAP_WALK_ADDR")) h->walk_addr = atoi(e);
   if (const char* e = getenv("VMAP_NO_SEGMENTS")) h->no_segments = atoi(e);
   if (const char* e = getenv("VMAP_UPDATE_VARIANT")) h->update_variant = atoi(e);
   auto bail = [&](int code) {

@@ -6,7 +6,9 @@
 // the reference (octomap / PCL / Eigen compiled without FMA) irrespective of nvcc's -fmad flag.
 #pragma once
 
+#if !defined(VMAP_HOST_EMULATION)   // (tests/native/cuda_host_shim.h stands in for the CUDA headers)
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace vmapdev {

@@ -15,6 +15,7 @@
 
 #include "vmap_device.cuh"
 #include "vmap_seq.cuh"
+#include "vmap_walk.cuh"
 
 namespace vmapdev {
 
@@ -23,29 +24,6 @@ constexpr uint32_t kFlagRange = 2u;   // castRay's in-range branch
 constexpr uint32_t kFlagBound = 4u;   // coordToKeyChecked(point) succeeds
 //                  kFlagOcc = 8u       (vmap_sort.cuh) the point inserts an occupied key
 constexpr uint32_t kFlagCast = 16u;   // castRay is invoked for this point (set by k_resolve)
-constexpr int kLenBins = 2048;        // cast rays are ordered by segment count: bin = min(n_seg, 2047)
-#ifndef VMAP_SEG_STEPS
-#define VMAP_SEG_STEPS 64
-#endif
-constexpr uint32_t kSegSteps = VMAP_SEG_STEPS;    // DDA steps per ray segment (one thread walks one segment)
-
-// A ray is cut into n_seg = max(1, steps / kSegSteps) segments of equal length in the ray
-// parameter t; segment j owns the DDA steps whose crossing parameter lies in [j, j+1) * dtau.
-struct RayRec {               // per cast ray (index = position in the ordered work list)
-  double dt0, dt1, dt2;       // tDelta
-  double dlen;                // (double)length
-  double dtau;                // segment length in t
-  uint32_t e01, e2s;          // end key: e0 | e1 << 16 ; e2 | step codes << 16 (2 bits per axis: 0, 1 = +1, 2 = -1)
-  uint32_t n_seg;
-  uint32_t point;             // index of the point / pixel
-};
-struct Checkpoint {           // state of the walk at the start of a segment
-  double t0, t1, t2;          // tMax
-  uint32_t c01, c2;           // current key
-  uint32_t count;             // keys emitted by the earlier segments; 0xFFFFFFFF: nothing to walk
-  uint32_t pad;
-};
-
 struct ScanBuffers {
   float* world;             // [n*3] world-frame points (what the reference leaves in the cloud)
   float* ray_end;           // [n*3] ray end: the point, or the clipped end when out of range
@@ -304,9 +282,6 @@ __device__ __forceinline__ void cta_max_u32(uint32_t* s_acc, uint32_t v) {
   if ((threadIdx.x & 31u) == 0 && v) atomicMax(s_acc, v);
 }
 
-__device__ __forceinline__ uint32_t ray_segments(uint32_t steps) {
-  return min(max(steps / kSegSteps, 1u), (uint32_t)(kLenBins - 1));
-}
 __device__ __forceinline__ uint32_t ray_bin(const ScanBuffers& sb, uint32_t i) {
   return ray_segments(sb.len[i]);
 }
@@ -547,44 +522,16 @@ k_checkpoints(DevParams P, ScanBuffers sb, Counters* cnt, float ox, float oy, fl
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= cnt->n_rays) return;
   const uint32_t i = sb.rays[r];
-  RayWalk w;
-  w.init(P, ox, oy, oz, sb.ray_end[3 * i], sb.ray_end[3 * i + 1], sb.ray_end[3 * i + 2]);
-  const uint32_t steps = sb.len[i];
-  const uint32_t n_seg = ray_segments(steps);
-  RayRec rr;
-  rr.dt0 = w.dt0; rr.dt1 = w.dt1; rr.dt2 = w.dt2;
-  rr.dlen = w.dlen;
-  rr.dtau = n_seg > 1 ? __ddiv_rn(__dmul_rn(w.dlen, (double)kSegSteps), (double)steps) : 0.0;
-  const uint32_t sc = (uint32_t)(w.s0 > 0 ? 1 : (w.s0 < 0 ? 2 : 0)) | ((uint32_t)(w.s1 > 0 ? 1 : (w.s1 < 0 ? 2 : 0)) << 2) |
-                      ((uint32_t)(w.s2 > 0 ? 1 : (w.s2 < 0 ? 2 : 0)) << 4);
-  rr.e01 = w.e0 | (w.e1 << 16);
-  rr.e2s = w.e2 | (sc << 16);
-  rr.n_seg = n_seg;
-  rr.point = i;
-  sb.ray_rec[r] = rr;
-  uint32_t n0 = 0, n1 = 0, n2 = 0;
-  double t0 = w.t0, t1 = w.t1, t2 = w.t2;
-  for (uint32_t j = 0; j < n_seg; j++) {
-    if (j > 0) {
-      const double tau = __dmul_rn((double)j, rr.dtau);
-      const unsigned long long cap = 1ull << 40;
-      if (w.s0) n0 += (uint32_t)vmapseq::seq_advance(&t0, w.dt0, tau, cap);
-      if (w.s1) n1 += (uint32_t)vmapseq::seq_advance(&t1, w.dt1, tau, cap);
-      if (w.s2) n2 += (uint32_t)vmapseq::seq_advance(&t2, w.dt2, tau, cap);
-    }
-    const uint32_t slot = sb.seg_base[j] + r;
-    if (slot >= sb.ckpt_cap) { atomicExch(&cnt->overflow_ckpt, 1u); return; }
-    Checkpoint cp;
-    cp.t0 = t0; cp.t1 = t1; cp.t2 = t2;
-    const uint32_t c0 = (w.c0 + (uint32_t)(w.s0 * (int)n0)) & 0xFFFFu;
-    const uint32_t c1 = (w.c1 + (uint32_t)(w.s1 * (int)n1)) & 0xFFFFu;
-    const uint32_t c2 = (w.c2 + (uint32_t)(w.s2 * (int)n2)) & 0xFFFFu;
-    cp.c01 = c0 | (c1 << 16);
-    cp.c2 = c2;
-    cp.count = w.live ? 1u + n0 + n1 + n2 : 0xFFFFFFFFu;
-    cp.pad = 0;
-    sb.ckpt[slot] = cp;
-  }
+  ray_checkpoints(P, ox, oy, oz, sb.ray_end[3 * i], sb.ray_end[3 * i + 1], sb.ray_end[3 * i + 2], sb.len[i], i,
+                  &sb.ray_rec[r], [&](uint32_t j, const Checkpoint& cp) {
+                    const uint32_t slot = sb.seg_base[j] + r;
+                    if (slot >= sb.ckpt_cap) {
+                      atomicExch(&cnt->overflow_ckpt, 1u);
+                      return false;
+                    }
+                    sb.ckpt[slot] = cp;
+                    return true;
+                  });
 }
 
 // K2b: one thread per (segment level, ray) work slot, level-major so that the lanes of a warp
@@ -696,6 +643,44 @@ k_walk_segments(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox
   if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
   __syncthreads();
   cta_add_u32(&s_stat[0], emitted);      // < 2^32 per CTA: <= 256 threads x a few segments x 100k keys
+  cta_max_u32(&s_stat[1], longest);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_stat[0]) {
+    atomicAdd(&cnt->traversals, (unsigned long long)s_stat[0]);
+    atomicMax(&cnt->longest_ray, s_stat[1]);
+  }
+}
+
+// K2b with dilated window addressing (vmap_walk.cuh: walk_slot_dilated); same slots, same marks.
+// Only launched for windows whose x / y extents are powers of two (VMAP_WALK_ADDR=1).
+template <bool kFilter>
+__global__ void __launch_bounds__(256)
+k_walk_segments_dilated(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz,
+                        int variant) {
+  if (cnt->overflow_ckpt) return;
+  __shared__ uint32_t base_s[kLenBins + 1];
+  for (int k = threadIdx.x; k <= kLenBins; k += blockDim.x) base_s[k] = sb.seg_base[k];
+  __syncthreads();
+  const uint32_t total = min(base_s[kLenBins], sb.ckpt_cap);
+  const DilatedWindow dw = dilated_window(ms);
+  const uint32_t near_limit = (variant == 0) ? 0xFFFFFFFFu : (variant == 2 ? 0u : (uint32_t)variant);
+  uint32_t emitted = 0, longest = 0;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
+    uint32_t lo = 0, hi = kLenBins;
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (base_s[mid] <= slot) lo = mid; else hi = mid;
+    }
+    const Checkpoint cp = sb.ckpt[slot];
+    if (cp.count == 0xFFFFFFFFu) continue;
+    walk_slot_dilated<kFilter>(P, ms, dw, cnt, cp, sb.ray_rec[slot - base_s[lo]], lo, ox, oy, oz, near_limit, &emitted,
+                               &longest);
+  }
+  __shared__ uint32_t s_stat[2];
+  __syncthreads();
+  if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+  __syncthreads();
+  cta_add_u32(&s_stat[0], emitted);
   cta_max_u32(&s_stat[1], longest);
   __syncthreads();
   if (threadIdx.x == 0 && s_stat[0]) {

@@ -1,0 +1,271 @@
+// vmap_walk.cuh -- per-thread bodies of the segmented ray walker (K2a / K2b), kept free of
+// block- and warp-level primitives so that the same code also builds for the host: the CPU
+// test-suite (tests/native/walk_check.cc) runs it slot by slot against the plain DDA.
+//
+//   ray_checkpoints      state of one ray's walk at every segment boundary (exact jump-ahead)
+//   walk_slot            one (segment level, ray) work slot -> marks in the dense window
+//   walk_slot_dilated    the same walk, carrying the window address of the current voxel as three
+//                        per-axis bit fields instead of recomputing it from the key at every step
+#pragma once
+
+#include "vmap_device.cuh"
+#include "vmap_seq.cuh"
+
+namespace vmapdev {
+
+constexpr int kLenBins = 2048;        // cast rays are ordered by segment count: bin = min(n_seg, 2047)
+#ifndef VMAP_SEG_STEPS
+#define VMAP_SEG_STEPS 64
+#endif
+constexpr uint32_t kSegSteps = VMAP_SEG_STEPS;    // DDA steps per ray segment (one thread walks one segment)
+
+// A ray is cut into n_seg = max(1, steps / kSegSteps) segments of equal length in the ray
+// parameter t; segment j owns the DDA steps whose crossing parameter lies in [j, j+1) * dtau.
+struct RayRec {               // per cast ray (index = position in the ordered work list)
+  double dt0, dt1, dt2;       // tDelta
+  double dlen;                // (double)length
+  double dtau;                // segment length in t
+  uint32_t e01, e2s;          // end key: e0 | e1 << 16 ; e2 | step codes << 16 (2 bits per axis: 0, 1 = +1, 2 = -1)
+  uint32_t n_seg;
+  uint32_t point;             // index of the point / pixel
+};
+struct Checkpoint {           // state of the walk at the start of a segment
+  double t0, t1, t2;          // tMax
+  uint32_t c01, c2;           // current key
+  uint32_t count;             // keys emitted by the earlier segments; 0xFFFFFFFF: nothing to walk
+  uint32_t pad;
+};
+
+__device__ __forceinline__ uint32_t ray_segments(uint32_t steps) {
+  return min(max(steps / kSegSteps, 1u), (uint32_t)(kLenBins - 1));
+}
+
+// K2a body.  computeRayKeys' preamble, then the state of the walk at every segment boundary by
+// exact jump-ahead of the three tMax sequences (vmap_seq.cuh) -- no DDA stepping here.
+// `put(j, cp)` stores the checkpoint of level j and returns false when it has no room.
+template <class Put>
+__device__ __forceinline__ void ray_checkpoints(const DevParams& P, float ox, float oy, float oz, float ex, float ey,
+                                                float ez, uint32_t steps, uint32_t point, RayRec* rec, Put&& put) {
+  RayWalk w;
+  w.init(P, ox, oy, oz, ex, ey, ez);
+  const uint32_t n_seg = ray_segments(steps);
+  RayRec rr;
+  rr.dt0 = w.dt0; rr.dt1 = w.dt1; rr.dt2 = w.dt2;
+  rr.dlen = w.dlen;
+  rr.dtau = n_seg > 1 ? __ddiv_rn(__dmul_rn(w.dlen, (double)kSegSteps), (double)steps) : 0.0;
+  const uint32_t sc = (uint32_t)(w.s0 > 0 ? 1 : (w.s0 < 0 ? 2 : 0)) | ((uint32_t)(w.s1 > 0 ? 1 : (w.s1 < 0 ? 2 : 0)) << 2) |
+                      ((uint32_t)(w.s2 > 0 ? 1 : (w.s2 < 0 ? 2 : 0)) << 4);
+  rr.e01 = w.e0 | (w.e1 << 16);
+  rr.e2s = w.e2 | (sc << 16);
+  rr.n_seg = n_seg;
+  rr.point = point;
+  *rec = rr;
+  uint32_t n0 = 0, n1 = 0, n2 = 0;
+  double t0 = w.t0, t1 = w.t1, t2 = w.t2;
+  for (uint32_t j = 0; j < n_seg; j++) {
+    if (j > 0) {
+      const double tau = __dmul_rn((double)j, rr.dtau);
+      const unsigned long long cap = 1ull << 40;
+      if (w.s0) n0 += (uint32_t)vmapseq::seq_advance(&t0, w.dt0, tau, cap);
+      if (w.s1) n1 += (uint32_t)vmapseq::seq_advance(&t1, w.dt1, tau, cap);
+      if (w.s2) n2 += (uint32_t)vmapseq::seq_advance(&t2, w.dt2, tau, cap);
+    }
+    Checkpoint cp;
+    cp.t0 = t0; cp.t1 = t1; cp.t2 = t2;
+    const uint32_t c0 = (w.c0 + (uint32_t)(w.s0 * (int)n0)) & 0xFFFFu;
+    const uint32_t c1 = (w.c1 + (uint32_t)(w.s1 * (int)n1)) & 0xFFFFu;
+    const uint32_t c2 = (w.c2 + (uint32_t)(w.s2 * (int)n2)) & 0xFFFFu;
+    cp.c01 = c0 | (c1 << 16);
+    cp.c2 = c2;
+    cp.count = w.live ? 1u + n0 + n1 + n2 : 0xFFFFFFFFu;
+    cp.pad = 0;
+    if (!put(j, cp)) return;
+  }
+}
+
+// Every voxel of a ray lies between the segment's first voxel and the ray's end voxel (each key
+// coordinate moves monotonically; one voxel of slack for a walk that misses the end voxel): one
+// window test per segment instead of one per step.
+__device__ __forceinline__ bool segment_inside_window(const MarkSet& ms, uint32_t c0, uint32_t c1, uint32_t c2,
+                                                      uint32_t e0, uint32_t e1, uint32_t e2) {
+  const int lo0 = (int)min(c0, e0) - 1, hi0 = (int)max(c0, e0) + 1;
+  const int lo1 = (int)min(c1, e1) - 1, hi1 = (int)max(c1, e1) + 1;
+  const int lo2 = (int)min(c2, e2) - 1, hi2 = (int)max(c2, e2) + 1;
+  return ((lo0 >> 3) >= ms.x0) && ((hi0 >> 3) < ms.x0 + (int)ms.nx) && ((lo1 >> 3) >= ms.y0) &&
+         ((hi1 >> 3) < ms.y0 + (int)ms.ny) && ((lo2 >> 3) >= ms.z0) && ((hi2 >> 3) < ms.z0 + (int)ms.nz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b body, dilated addressing.  Needs a window whose x and y extents (in blocks) are powers of
+// two: the bit address of a voxel in the window's free-mask array is then the concatenation
+//      [ rz | ry : py | rx : px | lz : 3 | ly : 3 | lx : 3 ]         (r* = block, l* = voxel in block)
+// and splits into one word per axis (A0 holds rx and lx, A1 ry and ly, A2 rz and lz) with the
+// other axes' bits zero.  A step of +-1 voxel along an axis is   A = (A + K) & M   with M the
+// axis' bit mask and K = -M (carry runs through the gaps) or -1 (borrow runs through them), so
+// the DDA never touches the 16-bit keys again: address = A0 | A1 | A2, mask word = address >> 5,
+// bit = address & 31, block = address >> 9, and "reached the end voxel" is one compare of
+// addresses.  Marks are identical to walk_slot's.
+// ---------------------------------------------------------------------------------------------
+template <bool B> struct BoolTag { static constexpr bool value = B; };
+
+struct DilatedWindow {
+  uint32_t m0, m1, m2;   // bit masks of the three axes
+  uint32_t sh1, sh2;     // position of the ry / rz fields
+};
+__host__ __device__ inline bool dilated_window_fits(uint32_t nx, uint32_t ny, uint32_t nz) {
+  if (!nx || !ny || !nz || (nx & (nx - 1u)) || (ny & (ny - 1u))) return false;
+  uint32_t px = 0, py = 0, pz = 0;
+  while ((1u << px) < nx) px++;
+  while ((1u << py) < ny) py++;
+  while ((1u << pz) < nz) pz++;
+  return 9u + px + py + pz <= 31u;
+}
+__device__ __forceinline__ DilatedWindow dilated_window(const MarkSet& ms) {
+  uint32_t px = 0, py = 0;
+  while ((1u << px) < ms.nx) px++;
+  while ((1u << py) < ms.ny) py++;
+  DilatedWindow d;
+  d.sh1 = 9u + px;
+  d.sh2 = 9u + px + py;
+  d.m0 = ((ms.nx - 1u) << 9) | 0x007u;
+  d.m1 = ((ms.ny - 1u) << d.sh1) | 0x038u;
+  d.m2 = (0xFFFFFFFFu << d.sh2) | 0x1C0u;
+  return d;
+}
+// rel = voxel coordinate relative to the window's first voxel
+__device__ __forceinline__ uint32_t dilate_axis(uint32_t rel, uint32_t local_shift, uint32_t block_shift) {
+  return ((rel & 7u) << local_shift) | ((rel >> 3) << block_shift);
+}
+
+// (t0 < tau) || (t1 < tau) || (t2 < tau)  ==  min(tMax) < tau, as three chained compares: the
+// compiler would otherwise build fmin(t0, t1, t2) with its NaN fix-ups (some 18 instructions).
+__device__ __forceinline__ bool any_below(double t0, double t1, double t2, double tau) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.lt.f64 p, %1, %4;\n\t"
+      "setp.lt.or.f64 p, %2, %4, p;\n\t"
+      "setp.lt.or.f64 p, %3, %4, p;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r) : "d"(t0), "d"(t1), "d"(t2), "d"(tau));
+  return r != 0u;
+#else
+  return (t0 < tau) || (t1 < tau) || (t2 < tau);
+#endif
+}
+// (t0 > len) && (t1 > len) && (t2 > len)  ==  min(tMax) > len
+__device__ __forceinline__ bool all_above(double t0, double t1, double t2, double len) {
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  asm("{\n\t.reg .pred p;\n\t"
+      "setp.gt.f64 p, %1, %4;\n\t"
+      "setp.gt.and.f64 p, %2, %4, p;\n\t"
+      "setp.gt.and.f64 p, %3, %4, p;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(r) : "d"(t0), "d"(t1), "d"(t2), "d"(len));
+  return r != 0u;
+#else
+  return (t0 > len) && (t1 > len) && (t2 > len);
+#endif
+}
+
+template <bool kFilter>
+__device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const MarkSet& ms, const DilatedWindow& dw,
+                                                  Counters* cnt, const Checkpoint& cp, const RayRec& rr, uint32_t j,
+                                                  float ox, float oy, float oz, uint32_t near_limit,
+                                                  uint32_t* emitted, uint32_t* longest) {
+  if (cp.count == 0xFFFFFFFFu) return;
+  uint32_t c0 = cp.c01 & 0xFFFFu, c1 = cp.c01 >> 16, c2 = cp.c2;
+  const uint32_t e0 = rr.e01 & 0xFFFFu, e1 = rr.e01 >> 16, e2 = rr.e2s & 0xFFFFu;
+  if (!segment_inside_window(ms, c0, c1, c2, e0, e1, e2)) {   // the host re-runs the scan in table mode
+    atomicExch(&cnt->overflow_window, 1u);
+    return;
+  }
+  const uint32_t sc = rr.e2s >> 16;
+  // step codes: 0 = the ray does not move along the axis (its tMax is DBL_MAX), 1 = +1, 2 = -1
+  const uint32_t sc0 = sc & 3u, sc1 = (sc >> 2) & 3u, sc2 = (sc >> 4) & 3u;
+  const uint32_t k0 = sc0 == 1u ? (0u - dw.m0) : (sc0 == 2u ? 0xFFFFFFFFu : 0u);
+  const uint32_t k1 = sc1 == 1u ? (0u - dw.m1) : (sc1 == 2u ? 0xFFFFFFFFu : 0u);
+  const uint32_t k2 = sc2 == 1u ? (0u - dw.m2) : (sc2 == 2u ? 0xFFFFFFFFu : 0u);
+  const uint32_t wx = (uint32_t)ms.x0 << 3, wy = (uint32_t)ms.y0 << 3, wz = (uint32_t)ms.z0 << 3;
+  uint32_t a0 = dilate_axis(c0 - wx, 0u, 9u), a1 = dilate_axis(c1 - wy, 3u, dw.sh1), a2 = dilate_axis(c2 - wz, 6u, dw.sh2);
+  const uint32_t a_end = dilate_axis(e0 - wx, 0u, 9u) | dilate_axis(e1 - wy, 3u, dw.sh1) | dilate_axis(e2 - wz, 6u, dw.sh2);
+  // key steps (only the free-space filter still needs the keys)
+  const int s0 = sc0 == 1u ? 1 : (sc0 == 2u ? -1 : 0), s1 = sc1 == 1u ? 1 : (sc1 == 2u ? -1 : 0),
+            s2 = sc2 == 1u ? 1 : (sc2 == 2u ? -1 : 0);
+  double t0 = cp.t0, t1 = cp.t1, t2 = cp.t2;
+  const double dt0 = rr.dt0, dt1 = rr.dt1, dt2 = rr.dt2;
+  const bool last = (j + 1 == rr.n_seg);
+  uint32_t count = cp.count;
+  const uint32_t count0 = count;
+  // cur / bits / seen: as in walk_slot
+  uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0;
+  auto emit = [&]() {
+    if (kFilter && !free_filter_pass(P, ox, oy, oz, c0, c1, c2)) return;
+    const uint32_t a = a0 | a1 | a2;
+    const uint32_t wi = a >> 5;
+    if (wi != cur) {
+      if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
+      if ((wi ^ cur) >= 16u) {                       // another block
+        uint32_t* tb = ms.touched_bits + (a >> 14);
+        const uint32_t bit = 1u << ((a >> 9) & 31u);
+        if (!(*tb & bit)) atomicOr(tb, bit);
+      }
+      bits = 0;
+      cur = wi;
+      seen = (count < near_limit) ? ms.free_mask[wi] : 0u;
+    }
+    bits |= 1u << (a & 31u);
+  };
+  // one DDA step: strict '<' comparisons, ties go to the later axis (computeRayKeys)
+  auto step = [&]() {
+    const bool a01 = t0 < t1, a02 = t0 < t2, a12 = t1 < t2;
+    const bool d0 = a01 && a02, d1 = !a01 && a12;
+    if (d0) {
+      a0 = (a0 + k0) & dw.m0;
+      t0 = __dadd_rn(t0, dt0);
+      if (kFilter) c0 = (c0 + (uint32_t)s0) & 0xFFFFu;
+    } else if (d1) {
+      a1 = (a1 + k1) & dw.m1;
+      t1 = __dadd_rn(t1, dt1);
+      if (kFilter) c1 = (c1 + (uint32_t)s1) & 0xFFFFu;
+    } else {
+      a2 = (a2 + k2) & dw.m2;
+      t2 = __dadd_rn(t2, dt2);
+      if (kFilter) c2 = (c2 + (uint32_t)s2) & 0xFFFFu;
+    }
+  };
+  if (j == 0) emit();                 // the origin voxel belongs to segment 0
+  const double dlen = rr.dlen;
+  const double tau_end = __dmul_rn((double)(j + 1), rr.dtau);
+  auto run = [&](auto capped) {
+    if (last) {
+      for (;;) {
+        step();
+        if ((a0 | a1 | a2) == a_end) break;                            // cur == end
+        if (all_above(t0, t1, t2, dlen)) break;                        // min(tMax) > length
+        if (decltype(capped)::value && count >= kKeyRayMax - 1u) break;   // KeyRay capacity
+        ++count;
+        emit();
+      }
+    } else {
+      // steps whose crossing parameter is below tau_end; the termination tests cannot fire here
+      while (any_below(t0, t1, t2, tau_end)) {
+        step();
+        if (decltype(capped)::value && count >= kKeyRayMax - 1u) break;
+        ++count;
+        emit();
+      }
+    }
+  };
+  // Only rays that could reach KeyRay's capacity carry the per-step test: a walk takes at most
+  // (Manhattan distance of the keys) + 3 steps, and n_seg = steps / kSegSteps (saturating at
+  // kLenBins - 1, which is far above the capacity).
+  if ((rr.n_seg + 1u) * kSegSteps + 4u >= kKeyRayMax - 1u) run(BoolTag<true>());
+  else run(BoolTag<false>());
+  if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
+  *emitted += count - count0 + (j == 0 ? 1u : 0u);
+  if (last) *longest = max(*longest, count);
+}
+
+}  // namespace vmapdev
