@@ -88,7 +88,7 @@ int wc_walk_plain(double res, double max_free_space, double min_height, const fl
 // but this one is the least like the plain walk).  stats: [traversals, longest, overflow_window, slots]
 int wc_walk_segmented(double res, double max_free_space, double min_height, const float* origin, const float* ends,
                       uint32_t n_rays, const int32_t* origin_block, const uint32_t* dims, uint32_t* free_mask,
-                      uint32_t* touched, uint32_t near_limit, uint64_t* stats) {
+                      uint32_t* touched, uint32_t near_limit, int mode, uint64_t* stats) {
   const DevParams P = make_params(res, max_free_space, min_height);
   const MarkSet ms = make_window(origin_block, dims, free_mask, touched);
   if (!dilated_window_fits(ms.nx, ms.ny, ms.nz)) return 1;
@@ -110,10 +110,10 @@ int wc_walk_segmented(double res, double max_free_space, double min_height, cons
     for (uint32_t r = 0; r < n_rays; r++) {
       if (jj >= cps[r].size()) continue;
       emitted = 0;
-      if (P.free_filter)
-        walk_slot_dilated<true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest);
-      else
-        walk_slot_dilated<false>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest);
+#define WC_SLOT(F, M) walk_slot_dilated<F, M>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest)
+      if (P.free_filter) { if (mode == 1) WC_SLOT(true, 1); else WC_SLOT(true, 0); }
+      else { if (mode == 1) WC_SLOT(false, 1); else WC_SLOT(false, 0); }
+#undef WC_SLOT
       trav += emitted;
       slots++;
     }

@@ -42,7 +42,7 @@ def lib():
     L.wc_ray_keys.restype = C.c_uint32
     L.wc_walk_plain.argtypes = [C.c_double, C.c_double, C.c_double, vp, vp, C.c_uint32, vp, vp, vp, vp, vp]
     L.wc_walk_segmented.argtypes = [C.c_double, C.c_double, C.c_double, vp, vp, C.c_uint32, vp, vp, vp, vp,
-                                    C.c_uint32, vp]
+                                    C.c_uint32, C.c_int, vp]
     return L
 
 
@@ -63,7 +63,7 @@ def run_both(L, res, origin, ends, max_free=0.0, min_height=0.0, near_limit=48):
     ob, dims = window_for(res, origin, ends)
     n_blocks = int(dims[0]) * int(dims[1]) * int(dims[2])
     out = []
-    for which in ("plain", "seg"):
+    for which in ("plain", "seg0", "seg1"):      # seg<mode>: walk_slot_dilated<., mode>
         fm = np.zeros(n_blocks * 16, np.uint32)
         tb = np.zeros((n_blocks + 31) // 32, np.uint32)
         stats = np.zeros(4, np.uint64)
@@ -73,16 +73,17 @@ def run_both(L, res, origin, ends, max_free=0.0, min_height=0.0, near_limit=48):
         else:
             assert L.wc_walk_segmented(res, max_free, min_height, origin.ctypes.data, ends.ctypes.data, len(ends),
                                        ob.ctypes.data, dims.ctypes.data, fm.ctypes.data, tb.ctypes.data, near_limit,
-                                       stats.ctypes.data) == 0
+                                       int(which[-1]), stats.ctypes.data) == 0
         out.append((fm, tb, stats))
-    (fa, ta, sa), (fb, tb_, sb) = out
-    assert sa[2] == 0 and sb[2] == 0, "window overflow"
-    assert int(sa[0]) == int(sb[0]), ("traversals", sa, sb)
-    assert int(sa[1]) == int(sb[1]), ("longest ray", sa, sb)
-    bad = np.flatnonzero(fa != fb)
-    assert bad.size == 0, (bad[:5], fa[bad[:5]], fb[bad[:5]])
-    assert np.array_equal(ta, tb_)
-    return sa, sb
+    fa, ta, sa = out[0]
+    for fb, tb_, sb in out[1:]:
+        assert sa[2] == 0 and sb[2] == 0, "window overflow"
+        assert int(sa[0]) == int(sb[0]), ("traversals", sa, sb)
+        assert int(sa[1]) == int(sb[1]), ("longest ray", sa, sb)
+        bad = np.flatnonzero(fa != fb)
+        assert bad.size == 0, (bad[:5], fa[bad[:5]], fb[bad[:5]])
+        assert np.array_equal(ta, tb_)
+    return sa, out[1][2]
 
 
 def lidar_rays(n_elev, n_azim, seed, yaw):

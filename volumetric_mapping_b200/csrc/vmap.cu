@@ -104,8 +104,9 @@ struct vmap {
     uint32_t* touched_bits = nullptr;
     uint32_t* list = nullptr;
     uint32_t* locate = nullptr;
-    uint32_t n_side = 0;        // blocks per axis (cube)
+    uint32_t n_side = 0;        // blocks per axis needed (cube)
     uint32_t stride = 0;        // x / y extent as allocated: n_side, or the next power of two (dilated addressing)
+    int reach_vox = -1;         // >= 0: dilated layout, the window starts at block (sensor voxel - reach_vox) >> 3
     int radius = 0;             // blocks from the sensor block to the window face
     uint64_t n_blocks = 0;
     uint32_t n_words = 0;       // touched bitmap words
@@ -114,9 +115,11 @@ struct vmap {
   } win;
   MarkSet ms{};                 // marks of the scan in flight (table or dense mode)
   uint64_t dense_fallbacks = 0;
+  bool traced = false;        // VMAP_TRACE: the walker selection has been printed
   uint32_t* chg0_store = nullptr;   // change-detection planes (MapView.chg0/1 point here while enabled)
   uint32_t* chg1_store = nullptr;
   int walk_variant = 48;  // near-field limit of the walker's read-before-RED filter (VMAP_WALK_VARIANT)
+  int walk_ctas = 5;      // CTAs per SM of the segment walker's grid = resident CTAs at 48 registers (VMAP_WALK_CTAS)
   int walk_addr = 0;      // 1: dilated window addressing in the segment walker (VMAP_WALK_ADDR, experimental)
   int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
@@ -501,24 +504,33 @@ bool setup_dense_marks(vmap* h, const float origin[3]) {
   const double r_vox = h->P.max_range * h->P.res_factor;
   const double r_blk = std::ceil(r_vox / 8.0) + 2.0;
   const uint64_t budget = h->cfg.dense_window_bytes ? h->cfg.dense_window_bytes : (6ull << 30);
-  const double side = 2.0 * r_blk + 1.0;
-  // dilated addressing wants power-of-two x / y extents; fall back to the cube when that does
-  // not fit a 32-bit bit address
-  uint32_t stride = (uint32_t)side;
-  if (h->walk_addr == 1 && side < 65536.0) {
+  double side = 2.0 * r_blk + 1.0;
+  uint32_t stride = (uint32_t)std::min(side, 4294967295.0);
+  int reach_vox = -1;
+  if (h->walk_addr >= 1 && r_vox < 262144.0) {
+    // Dilated addressing wants power-of-two x / y extents and a 31-bit bit address.  Placing the
+    // window by the sensor's VOXEL (not its block) needs only floor(2 * reach / 8) + 2 blocks per
+    // axis, reach = the farthest voxel a clipped ray can visit + the walker's slack.
+    const int reach = (int)std::ceil(r_vox) + 3;
+    const uint32_t need = (uint32_t)(2 * reach) / 8u + 2u;
     uint32_t p2 = 1;
-    while (p2 < (uint32_t)side) p2 <<= 1;
-    if (dilated_window_fits(p2, p2, (uint32_t)side)) stride = p2;
+    while (p2 < need) p2 <<= 1;
+    if (dilated_window_fits(p2, p2, need)) {
+      reach_vox = reach;
+      side = (double)need;
+      stride = p2;
+    }
   }
   const double blocks = (double)stride * (double)stride * side;
   if (blocks * (2.0 * kMaskWords * 4 + 0.125) > (double)budget || blocks >= (double)(1u << 28)) return false;
   const int radius = (int)r_blk;
-  if (w.radius != radius || w.stride != stride || !w.free_bits) {
+  if (w.radius != radius || w.stride != stride || w.reach_vox != reach_vox || !w.free_bits) {
     cudaStreamSynchronize(h->stream);
     free_window(h);
     w.radius = radius;
-    w.n_side = (uint32_t)(2 * radius + 1);
+    w.n_side = (uint32_t)side;
     w.stride = stride;
+    w.reach_vox = reach_vox;
     w.n_blocks = (uint64_t)w.stride * w.stride * w.n_side;
     w.n_words = (uint32_t)((w.n_blocks + 31) / 32);
     bool ok = dev_alloc(h, (void**)&w.free_bits, w.n_blocks * kMaskWords * 4) == VMAP_OK &&
@@ -550,6 +562,14 @@ bool setup_dense_marks(vmap* h, const float origin[3]) {
   ms.locate = w.locate;
   ms.list_cap = w.list_cap;
   ms.x0 = ok[0] - radius; ms.y0 = ok[1] - radius; ms.z0 = ok[2] - radius;
+  if (w.reach_vox >= 0) {
+    int first[3];
+    for (int i = 0; i < 3; i++) {
+      const double f = std::floor(h->P.res_factor * (double)origin[i]);
+      first[i] = (f >= -32768.0 && f < 32768.0) ? (((int)f + 32768 - w.reach_vox) >> 3) : 4096;
+    }
+    ms.x0 = first[0]; ms.y0 = first[1]; ms.z0 = first[2];
+  }
   ms.nx = ms.ny = w.stride;
   ms.nz = w.n_side;
   ms.dense = 1;
@@ -767,11 +787,26 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
     // K2a + K2b: exact checkpoints, then one thread per ray segment
     k_checkpoints<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->d_cnt, ox, oy, oz);
     h->launches++;
-    static const int walk_ctas = getenv("VMAP_WALK_CTAS") ? atoi(getenv("VMAP_WALK_CTAS")) : 5;   // = resident CTAs per SM at 48 registers
-    const unsigned grid = g_sm_count(h->device) * walk_ctas;
-    const bool dilated = h->walk_addr == 1 && dilated_window_fits(h->ms.nx, h->ms.ny, h->ms.nz);
-    if (dilated && h->P.free_filter) k_walk_segments_dilated<true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
-    else if (dilated) k_walk_segments_dilated<false><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
+    const unsigned grid = g_sm_count(h->device) * (unsigned)h->walk_ctas;
+    // VMAP_WALK_ADDR (experimental): 1 dilated addressing, 2 + deferred touched test, 3 dilated at 6 CTAs / SM,
+    // 4 deferred at 6 CTAs / SM
+    const bool dilated = h->walk_addr >= 1 && dilated_window_fits(h->ms.nx, h->ms.ny, h->ms.nz);
+    if (!h->traced && getenv("VMAP_TRACE")) {
+      h->traced = true;
+      fprintf(stderr, "[vmap] segment walker: %s addressing (mode %d), window %u x %u x %u blocks at (%d, %d, %d), fallbacks so far %llu\n",
+              dilated ? "dilated" : "block", h->walk_addr, h->ms.nx, h->ms.ny, h->ms.nz, h->ms.x0, h->ms.y0, h->ms.z0,
+              (unsigned long long)h->dense_fallbacks);
+    }
+#define VMAP_WALK_DIL(F, M, C) k_walk_segments_dilated<F, M, C><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant)
+    // (with the free-space filter the keys are needed at every step anyway and the block-addressed
+    // kernel measured faster: profiles/r01_ab_walk_dilated.json)
+    if (dilated && !h->P.free_filter) {
+      if (h->walk_addr == 2) VMAP_WALK_DIL(false, 1, 5);
+      else if (h->walk_addr == 3) VMAP_WALK_DIL(false, 0, 6);
+      else if (h->walk_addr == 4) VMAP_WALK_DIL(false, 1, 6);
+      else VMAP_WALK_DIL(false, 0, 5);
+    }
+#undef VMAP_WALK_DIL
     else if (h->P.free_filter) k_walk_segments<true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
     else k_walk_segments<false><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
   } else if (h->ms.dense) {
@@ -905,6 +940,7 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   derive_params(h);
   if (const char* e = getenv("VMAP_WALK_VARIANT")) h->walk_variant = atoi(e);
   if (const char* e = getenv("VMAP_WALK_ADDR")) h->walk_addr = atoi(e);
+  if (const char* e = getenv("VMAP_WALK_CTAS")) h->walk_ctas = std::max(1, atoi(e));
   if (const char* e = getenv("VMAP_NO_SEGMENTS")) h->no_segments = atoi(e);
   if (const char* e = getenv("VMAP_UPDATE_VARIANT")) h->update_variant = atoi(e);
   auto bail = [&](int code) {

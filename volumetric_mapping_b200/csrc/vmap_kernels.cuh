@@ -653,8 +653,8 @@ k_walk_segments(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox
 
 // K2b with dilated window addressing (vmap_walk.cuh: walk_slot_dilated); same slots, same marks.
 // Only launched for windows whose x / y extents are powers of two (VMAP_WALK_ADDR=1).
-template <bool kFilter>
-__global__ void __launch_bounds__(256)
+template <bool kFilter, int kMode, int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas)
 k_walk_segments_dilated(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz,
                         int variant) {
   if (cnt->overflow_ckpt) return;
@@ -673,7 +673,7 @@ k_walk_segments_dilated(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, 
     }
     const Checkpoint cp = sb.ckpt[slot];
     if (cp.count == 0xFFFFFFFFu) continue;
-    walk_slot_dilated<kFilter>(P, ms, dw, cnt, cp, sb.ray_rec[slot - base_s[lo]], lo, ox, oy, oz, near_limit, &emitted,
+    walk_slot_dilated<kFilter, kMode>(P, ms, dw, cnt, cp, sb.ray_rec[slot - base_s[lo]], lo, ox, oy, oz, near_limit, &emitted,
                                &longest);
   }
   __shared__ uint32_t s_stat[2];

@@ -169,7 +169,10 @@ __device__ __forceinline__ bool all_above(double t0, double t1, double t2, doubl
 #endif
 }
 
-template <bool kFilter>
+// kMode 0: the block's touched bit is tested when the ray enters the block.
+// kMode 1: the touched word is only LOADED at block entry and tested when the ray leaves the
+//          block (or ends), so that the walk never waits for that load.
+template <bool kFilter, int kMode = 0>
 __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const MarkSet& ms, const DilatedWindow& dw,
                                                   Counters* cnt, const Checkpoint& cp, const RayRec& rr, uint32_t j,
                                                   float ox, float oy, float oz, uint32_t near_limit,
@@ -200,6 +203,8 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
   const uint32_t count0 = count;
   // cur / bits / seen: as in walk_slot
   uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0;
+  // kMode 1: touched word of the block in flight as loaded at entry (all ones: nothing pending)
+  uint32_t tb_val = 0xFFFFFFFFu, tb_blk = 0;
   auto emit = [&]() {
     if (kFilter && !free_filter_pass(P, ox, oy, oz, c0, c1, c2)) return;
     const uint32_t a = a0 | a1 | a2;
@@ -207,9 +212,15 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
     if (wi != cur) {
       if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
       if ((wi ^ cur) >= 16u) {                       // another block
-        uint32_t* tb = ms.touched_bits + (a >> 14);
-        const uint32_t bit = 1u << ((a >> 9) & 31u);
-        if (!(*tb & bit)) atomicOr(tb, bit);
+        if (kMode == 0) {
+          uint32_t* tb = ms.touched_bits + (a >> 14);
+          const uint32_t bit = 1u << ((a >> 9) & 31u);
+          if (!(*tb & bit)) atomicOr(tb, bit);
+        } else {
+          if (!((tb_val >> (tb_blk & 31u)) & 1u)) atomicOr(ms.touched_bits + (tb_blk >> 5), 1u << (tb_blk & 31u));
+          tb_blk = a >> 9;
+          tb_val = ms.touched_bits[tb_blk >> 5];
+        }
       }
       bits = 0;
       cur = wi;
@@ -264,6 +275,7 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
   if ((rr.n_seg + 1u) * kSegSteps + 4u >= kKeyRayMax - 1u) run(BoolTag<true>());
   else run(BoolTag<false>());
   if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
+  if (kMode == 1 && !((tb_val >> (tb_blk & 31u)) & 1u)) atomicOr(ms.touched_bits + (tb_blk >> 5), 1u << (tb_blk & 31u));
   *emitted += count - count0 + (j == 0 ? 1u : 0u);
   if (last) *longest = max(*longest, count);
 }
