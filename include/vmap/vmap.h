@@ -194,6 +194,21 @@ VMAP_API int vmap_query_visibility(vmap* h, const double* view_voxel_xyz6, size_
 VMAP_API int vmap_query_lines_bbox(vmap* h, const double* start_end_xyz6, size_t n,
                                    const double bounding_box_size[3], uint8_t* status);
 
+/* getCellStatusBoundingBox (octomap_world.cc:274-344): status of a box of `bounding_box_size`
+ * centred on each point -- the centre's own status when it is not free, else occupied if any
+ * occupied leaf lies in the box, else unknown (occupied when treat_unknown_as_occupied) if
+ * octomap's getUnknownLeafCenters finds a hole, else free.  Single-device maps only. */
+VMAP_API int vmap_query_bbox_status(vmap* h, const double* xyz, size_t n,
+                                    const double bounding_box_size[3], uint8_t* status);
+VMAP_API int vmap_query_bbox_status_dev(vmap* h, const double* d_xyz, size_t n,
+                                        const double bounding_box_size[3], uint8_t* d_status);
+/* checkPathForCollisionsWithRobot (octomap_world.cc:1384-1400; checkSinglePoseCollision
+ * :1402-1412): *collides = 1 and *collision_index (may be NULL) = earliest pose whose robot box
+ * is not free (treat_unknown_as_occupied) / is occupied (otherwise). */
+VMAP_API int vmap_check_path_collisions(vmap* h, const double* xyz, size_t n,
+                                        const double robot_size[3], int* collides,
+                                        size_t* collision_index);
+
 /* Finest-level leaves (what octree_->begin_leafs() would visit after expanding pruned nodes):
  * used by the on-demand export to octomap::OcTree for the unchanged publish/save paths
  * (octomap_world.cc:820-856) and by the parity tests. */

@@ -7,6 +7,7 @@
 #define VOLUMETRIC_MAPPING_B200_OCTOMAP_WORLD_H_
 
 #include <ostream>
+#include <iostream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -42,9 +43,20 @@ class OctomapWorld : public WorldBase {
  public:
   typedef std::shared_ptr<OctomapWorld> Ptr;
 
-  OctomapWorld() : handle_(nullptr) { create(OctomapParameters()); }                       // octomap_world.cc:50-51
-  explicit OctomapWorld(const OctomapParameters& params) : handle_(nullptr) { create(params); }  // :53-56
-  OctomapWorld(const OctomapWorld&) = delete;   // the reference deep-copies through a .bt stream (:59-73): use exportLeaves/importLeaves
+  OctomapWorld() : handle_(nullptr), robot_size_(1.0, 1.0, 1.0) { create(OctomapParameters()); }   // octomap_world.cc:50-51
+  explicit OctomapWorld(const OctomapParameters& params)                                    // :53-56
+      : handle_(nullptr), robot_size_(1.0, 1.0, 1.0) { create(params); }
+  // Deep copy (octomap_world.cc:59-73).  Like the reference it goes through the BINARY stream
+  // (writeOctomapToBinaryConst -> readBinary -> prune), so the copy holds the max-likelihood map:
+  // every leaf at the clamping minimum or maximum.
+  OctomapWorld(const OctomapWorld& rhs) : handle_(nullptr), robot_size_(rhs.robot_size_) {
+    create(rhs.params_);
+    size_t n = 0;
+    check(vmap_serialize_bt(rhs.handle_, nullptr, 0, &n));
+    std::vector<uint8_t> buf(n ? n : 1);
+    check(vmap_serialize_bt(rhs.handle_, buf.data(), buf.size(), &n));
+    if (vmap_deserialize_bt(handle_, buf.data(), n) != VMAP_OK) std::cerr << "Could not copy octree!\n";
+  }
   OctomapWorld& operator=(const OctomapWorld&) = delete;
   virtual ~OctomapWorld() { vmap_destroy(handle_); }
 
@@ -99,6 +111,34 @@ class OctomapWorld : public WorldBase {
     uint8_t s = 0;
     check(vmap_query_lines_bbox(handle_, ab, 1, bounding_box_size.v, &s));
     return static_cast<CellStatus>(s);
+  }
+  // octomap_world.cc:274-344
+  virtual CellStatus getCellStatusBoundingBox(const Vector3d& point, const Vector3d& bounding_box_size) const {
+    const double p[3] = {point.x(), point.y(), point.z()};
+    const double b[3] = {bounding_box_size.x(), bounding_box_size.y(), bounding_box_size.z()};
+    uint8_t s = 0;
+    check(vmap_query_bbox_status(handle_, p, 1, b, &s));
+    return static_cast<CellStatus>(s);
+  }
+  // octomap_world.cc:1372-1412: collision checks of the robot's bounding box
+  virtual void setRobotSize(const Vector3d& robot_size) { robot_size_ = robot_size; }
+  virtual Vector3d getRobotSize() const { return robot_size_; }
+  virtual bool checkCollisionWithRobot(const Vector3d& robot_position) {
+    std::vector<Vector3d> one(1, robot_position);
+    return checkPathForCollisionsWithRobot(one, nullptr);
+  }
+  virtual bool checkPathForCollisionsWithRobot(const std::vector<Vector3d>& robot_positions, size_t* collision_index) {
+    if (robot_positions.empty()) return false;
+    std::vector<double> xyz(3 * robot_positions.size());
+    for (size_t i = 0; i < robot_positions.size(); i++) {
+      xyz[3 * i] = robot_positions[i].x(); xyz[3 * i + 1] = robot_positions[i].y(); xyz[3 * i + 2] = robot_positions[i].z();
+    }
+    const double b[3] = {robot_size_.x(), robot_size_.y(), robot_size_.z()};
+    int collides = 0;
+    size_t index = 0;
+    check(vmap_check_path_collisions(handle_, xyz.data(), robot_positions.size(), b, &collides, &index));
+    if (collides && collision_index != nullptr) *collision_index = index;
+    return collides != 0;
   }
   // Batched forms of the two queries (what planners call in bulk): one kernel launch.
   void getCellStatusPoints(const std::vector<Vector3d>& points, std::vector<uint8_t>* status) const {
@@ -263,6 +303,7 @@ class OctomapWorld : public WorldBase {
     if (st != VMAP_OK) throw std::runtime_error(std::string("OctomapWorld: ") + vmap_last_error(handle_));
   }
   vmap* handle_;
+  Vector3d robot_size_;   // Eigen::Vector3d::Ones() by default (octomap_world.cc:54)
 };
 
 }  // namespace volumetric_mapping

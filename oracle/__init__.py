@@ -99,6 +99,9 @@ def lib():
     L.oracle_query_points_probability.argtypes = [vp, vp, C.c_size_t, vp, vp]
     L.oracle_query_visibility.argtypes = [vp, vp, C.c_size_t, C.c_int, vp]
     L.oracle_query_lines_bbox.argtypes = [vp, vp, C.c_size_t, dp, vp]
+    L.oracle_query_bbox_status.argtypes = [vp, vp, C.c_size_t, dp, vp]
+    L.oracle_check_path_collisions.argtypes = [vp, vp, C.c_size_t, dp, C.POINTER(C.c_size_t)]
+    L.oracle_check_path_collisions.restype = C.c_int
     L.oracle_coord_to_key_checked.argtypes = [vp, C.c_double, C.POINTER(C.c_uint16)]
     L.oracle_coord_to_key_checked.restype = C.c_int
     L.oracle_coord_to_key.argtypes = [vp, C.c_double]
@@ -281,6 +284,21 @@ class OracleWorld:
         st = np.zeros(p.shape[0], dtype=np.uint8)
         self._L.oracle_query_lines_bbox(self._h, p.ctypes.data, p.shape[0], _dptr(b), st.ctypes.data)
         return st
+
+    def getCellStatusBoundingBox(self, xyz, bounding_box_size):
+        p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        b = np.ascontiguousarray(bounding_box_size, dtype=np.float64).reshape(3)
+        st = np.zeros(p.shape[0], dtype=np.uint8)
+        self._L.oracle_query_bbox_status(self._h, p.ctypes.data, p.shape[0], _dptr(b), st.ctypes.data)
+        return st
+
+    def checkPathForCollisionsWithRobot(self, xyz, robot_size):
+        """(collides, index of the earliest colliding pose or None)"""
+        p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        b = np.ascontiguousarray(robot_size, dtype=np.float64).reshape(3)
+        idx = C.c_size_t(0)
+        hit = self._L.oracle_check_path_collisions(self._h, p.ctypes.data, p.shape[0], _dptr(b), C.byref(idx))
+        return bool(hit), (int(idx.value) if hit else None)
 
     # -- primitives ---------------------------------------------------------------------
     def coordToKey(self, c):

@@ -297,6 +297,87 @@ class OcTree {
   }
   bool isNodeOccupied(const Node* n) const { return n->value >= occ_prob_thres_log; }
 
+  // --- node geometry at a depth  [octomap OcTreeBaseImpl.h keyToCoord(key, depth), getNodeSize] ----
+  double getNodeSize(unsigned depth) const { return resolution * double(1 << (tree_depth - depth)); }
+  double keyToCoord(key_type key, unsigned depth) const {
+    if (depth == 0) return 0.0;
+    if (depth == tree_depth) return keyToCoord(key);
+    return (std::floor((double(key) - double(tree_max_val)) / double(1 << (tree_depth - depth))) + 0.5) *
+           getNodeSize(depth);
+  }
+  Node* search(const Vec3f& p) const {           // search(const point3d&): checked key, NULL outside
+    Key key;
+    if (!coordToKeyChecked(p, key)) return NULL;
+    return search(key);
+  }
+
+  // --- leaf_bbx_iterator  [octomap OcTreeIterator.hxx] ---------------------------------------
+  // Visits, depth first in child order, every leaf (a node without children, or a node at the
+  // finest depth) whose key cube passes the iterator's overlap test against [minKey, maxKey].
+  // The test is made when a child is pushed and is conservative by one key on the upper side:
+  //   minKey <= key + (tree_max_val >> depth)  &&  maxKey >= key - (tree_max_val >> depth).
+  // `f(node, key, depth)` returns false to stop the iteration; the function then returns false.
+  static void computeChildKey(unsigned pos, key_type center_offset_key, const Key& parent_key, Key& child_key) {
+    for (unsigned a = 0; a < 3; a++) {
+      if (pos & (1u << a)) child_key.k[a] = (key_type)(parent_key.k[a] + center_offset_key);
+      else child_key.k[a] = (key_type)(parent_key.k[a] - center_offset_key - (center_offset_key ? 0 : 1));
+    }
+  }
+  template <class F>
+  bool leafsBBXRecurs(const Node* node, const Key& key, unsigned depth, const Key& minKey, const Key& maxKey,
+                      F& f) const {
+    if (depth == tree_depth || !nodeHasChildren(node)) return f(node, key, depth);
+    const key_type center_offset_key = (key_type)(tree_max_val >> (depth + 1));
+    for (unsigned i = 0; i < 8; i++) {
+      if (!nodeChildExists(node, i)) continue;
+      Key ck;
+      computeChildKey(i, center_offset_key, key, ck);
+      bool overlap = true;
+      for (unsigned a = 0; a < 3; a++)
+        overlap = overlap && ((int)minKey.k[a] <= (int)ck.k[a] + (int)center_offset_key) &&
+                  ((int)maxKey.k[a] >= (int)ck.k[a] - (int)center_offset_key);
+      if (overlap && !leafsBBXRecurs(node->children[i], ck, depth + 1, minKey, maxKey, f)) return false;
+    }
+    return true;
+  }
+  template <class F>
+  bool forEachLeafBBX(const Vec3f& min, const Vec3f& max, F f) const {
+    if (root == NULL) return true;
+    Key minKey, maxKey;
+    if (!coordToKeyChecked(min, minKey) || !coordToKeyChecked(max, maxKey)) return true;   // end iterator
+    return leafsBBXRecurs(root, Key(tree_max_val, tree_max_val, tree_max_val), 0, minKey, maxKey, f);
+  }
+
+  // --- getUnknownLeafCenters(pmin, pmax, depth = 0)  [octomap OcTreeBaseImpl.hxx] ----------------
+  // Only "is there any" is needed by the caller.  The upstream loop adds the step BEFORE each
+  // query, in float: the layer of pmin's voxel is never tested, the layer `steps` voxels above is.
+  bool anyUnknownLeafCenter(const Vec3f& pmin, const Vec3f& pmax) const {
+    const Vec3f pmin_clamped = keyToCoord(coordToKey(pmin));
+    const Vec3f pmax_clamped = keyToCoord(coordToKey(pmax));
+    float diff[3];
+    unsigned steps[3];
+    const float step_size = (float)(resolution * std::pow(2.0, 0.0));
+    for (int i = 0; i < 3; ++i) {
+      diff[i] = pmax_clamped(i) - pmin_clamped(i);
+      const float q = std::floor(diff[i] / step_size);
+      steps[i] = q > 0.0f ? (unsigned)q : 0u;   // (negative: the box is inverted, nothing to scan)
+    }
+    Vec3f p = pmin_clamped;
+    for (unsigned x = 0; x < steps[0]; ++x) {
+      p.d[0] += step_size;
+      for (unsigned y = 0; y < steps[1]; ++y) {
+        p.d[1] += step_size;
+        for (unsigned z = 0; z < steps[2]; ++z) {
+          p.d[2] += step_size;
+          if (search(p) == NULL) return true;
+        }
+        p.d[2] = pmin_clamped(2);
+      }
+      p.d[1] = pmin_clamped(1);
+    }
+    return false;
+  }
+
   // --- updateNode ----------------------------------------------------------------------
   Node* updateNode(const Key& key, bool occupied) {
     float logOdds = prob_miss_log;
@@ -1047,6 +1128,74 @@ void oracle_query_points_probability(const oracle_world* w, const double* xyz, s
       status[i] = w->octree->isNodeOccupied(node) ? 1 : 0;
     }
   }
+}
+
+// octomap_world.cc:858-880.  As written upstream the loop searches `key` itself (not
+// `current_key`) 26 times, so an occupied node always "finds a neighbour" and is never a speckle;
+// restated as is.
+static bool is_speckle_node(const OcTree* t, const Key& key) {
+  for (int n = 0; n < 26; n++) {
+    Node* node = t->search(key);
+    if (node && t->isNodeOccupied(node)) return false;
+  }
+  return true;
+}
+
+// octomap_world.cc:274-344 getCellStatusBoundingBox
+static uint8_t bbox_status(const oracle_world* w, const double point[3], const double size[3]) {
+  const OcTree* t = w->octree;
+  const uint8_t unknown_as = w->params.treat_unknown_as_occupied ? 1 : 2;
+  // center point unknown or occupied: quit
+  Node* cn = t->search(point[0], point[1], point[2]);
+  const uint8_t center_status = cn == NULL ? unknown_as : (t->isNodeOccupied(cn) ? 1 : 0);
+  if (center_status != 0) return center_status;
+  Key key;
+  if (!t->coordToKeyChecked(Vec3f((float)point[0], (float)point[1], (float)point[2]), key)) return unknown_as;
+  double mn[3], mx[3];
+  for (int a = 0; a < 3; a++) {
+    mn[a] = point[a] - size[a] / 2;
+    mx[a] = point[a] + size[a] / 2;
+  }
+  const Vec3f bbx_min((float)mn[0], (float)mn[1], (float)mn[2]), bbx_max((float)mx[0], (float)mx[1], (float)mx[2]);
+  bool occupied = false;
+  t->forEachLeafBBX(bbx_min, bbx_max, [&](const Node* node, const Key& k, unsigned depth) {
+    const double cube_size = t->getNodeSize(depth);
+    // "Check if it is really inside bounding box, since leaf_bbx_iterator begins too early"
+    for (int a = 0; a < 3; a++) {
+      const double c = t->keyToCoord(k.k[a], depth);
+      const double lower = c - (cube_size / 2) * 1.0, upper = c + (cube_size / 2) * 1.0;
+      if (upper < (double)bbx_min(a) || lower > (double)bbx_max(a)) return true;   // continue
+    }
+    if (t->isNodeOccupied(node)) {
+      if (w->params.filter_speckles && is_speckle_node(t, k)) return true;
+      occupied = true;
+      return false;
+    }
+    return true;
+  });
+  if (occupied) return 1;
+  if (t->anyUnknownLeafCenter(bbx_min, bbx_max)) return unknown_as;
+  return 0;
+}
+
+void oracle_query_bbox_status(const oracle_world* w, const double* xyz, size_t n, const double bounding_box_size[3],
+                              uint8_t* status) {
+  for (size_t i = 0; i < n; i++) status[i] = bbox_status(w, xyz + 3 * i, bounding_box_size);
+}
+
+// octomap_world.cc:1384-1412 checkPathForCollisionsWithRobot / checkSinglePoseCollision: returns
+// 1 and the index of the earliest colliding pose, or 0.
+int oracle_check_path_collisions(const oracle_world* w, const double* xyz, size_t n, const double robot_size[3],
+                                 size_t* collision_index) {
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t st = bbox_status(w, xyz + 3 * i, robot_size);
+    const bool hit = w->params.treat_unknown_as_occupied ? (st != 0) : (st == 1);
+    if (hit) {
+      if (collision_index) *collision_index = i;
+      return 1;
+    }
+  }
+  return 0;
 }
 
 // octomap_world.cc:420-449

@@ -104,6 +104,13 @@ void oracle_query_visibility(const oracle_world* w, const double* view_voxel_xyz
 void oracle_query_lines_bbox(const oracle_world* w, const double* a_b_xyz6, size_t n,
                              const double bounding_box_size[3], uint8_t* status);
 
+/* getCellStatusBoundingBox (octomap_world.cc:274-344; octomap's leaf_bbx_iterator and
+ * getUnknownLeafCenters restated) and checkPathForCollisionsWithRobot (:1384-1412). */
+void oracle_query_bbox_status(const oracle_world* w, const double* xyz, size_t n,
+                              const double bounding_box_size[3], uint8_t* status);
+int oracle_check_path_collisions(const oracle_world* w, const double* xyz, size_t n,
+                                 const double robot_size[3], size_t* collision_index);
+
 /* getChangedPoints (octomap_world.cc:1413-1440): returns the count; fills and resets when the
  * buffers are large enough. */
 size_t oracle_get_changed(oracle_world* w, uint16_t* k3, uint8_t* occupied, size_t cap);

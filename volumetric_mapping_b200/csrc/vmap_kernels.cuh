@@ -16,6 +16,7 @@
 #include "vmap_device.cuh"
 #include "vmap_seq.cuh"
 #include "vmap_walk.cuh"
+#include "vmap_query.cuh"
 
 namespace vmapdev {
 
@@ -1180,6 +1181,20 @@ k_query_lines_bbox(DevParams P, MapView m, const double* __restrict__ ab, uint32
                                 (float)__dadd_rn(ab[6 * i + 2], oz), (float)__dadd_rn(ab[6 * i + 3], ox),
                                 (float)__dadd_rn(ab[6 * i + 4], oy), (float)__dadd_rn(ab[6 * i + 5], oz));
   if (s != 0) atomicMin(packed + i, (j << 2) | s);
+}
+
+// getCellStatusBoundingBox (octomap_world.cc:274-344), batched: one warp per box, the lanes share
+// the box's voxels (vmap_query.cuh).
+__global__ void __launch_bounds__(256)
+k_query_bbox(DevParams P, MapView m, const double* __restrict__ xyz, uint32_t n, BoxQuery q,
+             uint8_t* __restrict__ status) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const BoxScan r = bbox_scan(P, m, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], q, lane, 32u);
+    const bool occ = __any_sync(0xFFFFFFFFu, r.occupied), unk = __any_sync(0xFFFFFFFFu, r.unknown);
+    if (lane == 0) status[i] = bbox_combine(P, r.decided, occ, unk);
+  }
 }
 
 // (first-hit index << 2 | status) -> CellStatus after the MIN-reduction over shards

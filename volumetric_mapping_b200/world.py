@@ -242,6 +242,32 @@ class OctomapWorld:
                                                   st.ctypes.data))
         return st
 
+    def getCellStatusBoundingBox(self, xyz, bounding_box_size):
+        """octomap_world.cc:274-344, batched: one box size, many centres."""
+        p = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        b = np.ascontiguousarray(bounding_box_size, dtype=np.float64).reshape(3)
+        st = np.zeros(p.shape[0], dtype=np.uint8)
+        self._check(self._L.vmap_query_bbox_status(self._h, p.ctypes.data, p.shape[0], _dptr(b), st.ctypes.data))
+        return st
+
+    def setRobotSize(self, robot_size):
+        self._robot_size = np.ascontiguousarray(robot_size, dtype=np.float64).reshape(3).copy()
+
+    def getRobotSize(self):
+        return getattr(self, "_robot_size", np.ones(3)).copy()
+
+    def checkCollisionWithRobot(self, robot_position):
+        return self.checkPathForCollisionsWithRobot(np.asarray(robot_position, np.float64).reshape(1, 3))[0]
+
+    def checkPathForCollisionsWithRobot(self, robot_positions):
+        """octomap_world.cc:1384-1400: (collides, index of the earliest colliding pose or None)."""
+        p = np.ascontiguousarray(robot_positions, dtype=np.float64).reshape(-1, 3)
+        b = self.getRobotSize()
+        hit, idx = C.c_int(0), C.c_size_t(0)
+        self._check(self._L.vmap_check_path_collisions(self._h, p.ctypes.data, p.shape[0], _dptr(b), C.byref(hit),
+                                                       C.byref(idx)))
+        return bool(hit.value), (int(idx.value) if hit.value else None)
+
     def getCellStatusPointDevice(self, xyz_ptr, n, status_ptr):
         self._check(self._L.vmap_query_points_dev(self._h, C.c_void_p(int(xyz_ptr)), int(n),
                                                   C.c_void_p(int(status_ptr))))
