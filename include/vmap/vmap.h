@@ -249,6 +249,14 @@ VMAP_API int vmap_host_parse_stream(const vmap_params* params, int kind, const u
                                     size_t n_bytes, uint16_t* keys_k3, float* logodds,
                                     size_t capacity, size_t* n_leaves, double* resolution);
 
+/* OctomapManager::loadOctomapCallback's point-cloud branch (octomap_manager.cc:313-344): every
+ * point of a .pcd / .ply file whose key lies inside the map becomes an occupied key; the free set
+ * stays empty; updateOccupancy applies them.  vmap_insert_occupied_points is the same for points
+ * already in memory; vmap_host_read_pointcloud_file only parses the file (no device needed). */
+VMAP_API int vmap_load_occupied_pointcloud_file(vmap* h, const char* path, size_t* n_points);
+VMAP_API int vmap_insert_occupied_points(vmap* h, const float* xyz, size_t n, size_t stride_bytes);
+VMAP_API int vmap_host_read_pointcloud_file(const char* path, float* xyz, size_t capacity, size_t* n);
+
 /* OctomapWorld::setLogOddsBoundingBox (octomap_world.cc:781-818) behind setFree / setOccupied
  * (:497-523): n boxes of one size; bound_handling = BoundHandling (octomap_world.h:43-52:
  * 0 kDefault, 1 kIncludePartialBoxes, 2 kIgnorePartialBoxes).  setFree passes the clamping

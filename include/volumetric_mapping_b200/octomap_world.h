@@ -225,6 +225,11 @@ class OctomapWorld : public WorldBase {
   // OcTree::writeBinary(filename) does (toMaxLikelihood + prune before writing).
   bool loadOctomapFromFile(const std::string& filename) { return vmap_load_bt(handle_, filename.c_str()) == VMAP_OK; }
   bool writeOctomapToFile(const std::string& filename) { return vmap_write_bt(handle_, filename.c_str(), 1) == VMAP_OK; }
+  // OctomapManager::loadOctomapCallback's .pcd / .ply branch (octomap_manager.cc:313-344): the
+  // file's points become occupied keys, the free set stays empty.
+  bool loadOccupiedPointcloudFile(const std::string& filename) {
+    return vmap_load_occupied_pointcloud_file(handle_, filename.c_str(), nullptr) == VMAP_OK;
+  }
   bool writeOctomapToBinaryConst(std::ostream& s) const {
     size_t n = 0;
     if (vmap_serialize_bt(handle_, nullptr, 0, &n) != VMAP_OK) return false;

@@ -1,5 +1,5 @@
 """Stand-alone GPU check of getCellStatusBoundingBox / checkPathForCollisionsWithRobot against the
-oracle (run in its own process by tests/test_gpu_zz_bbox_status.py, so that a device fault in this
+oracle (run in its own process by tests/test_gpu_zz_first_hardware_run.py, so that a device fault in this
 not-yet-hardware-proven kernel cannot disturb the rest of the GPU suite)."""
 import os
 import sys

@@ -1619,3 +1619,4 @@ uint64_t vmap_device_bytes(const vmap* h) { return h ? h->dev_bytes : 0; }
 }  // extern "C"
 
 #include "vmap_export_host.inl"
+#include "vmap_cloud_io_host.inl"

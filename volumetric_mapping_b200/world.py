@@ -8,6 +8,7 @@ pcl::PointCloud / cv::Mat / Eigen types, a (q_wxyz, t) pair or a 4x4 matrix for
 kindr::minimal::QuatTransformation.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -241,6 +242,16 @@ class OctomapWorld:
         self._check(self._L.vmap_query_lines_bbox(self._h, p.ctypes.data, p.shape[0], _dptr(b),
                                                   st.ctypes.data))
         return st
+
+    def loadOccupiedPointcloudFile(self, filename):
+        """loadOctomapCallback's .pcd / .ply branch (octomap_manager.cc:313-344); returns the point count."""
+        n = C.c_size_t(0)
+        self._check(self._L.vmap_load_occupied_pointcloud_file(self._h, os.fsencode(filename), C.byref(n)))
+        return int(n.value)
+
+    def insertOccupiedPoints(self, xyz):
+        p = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        self._check(self._L.vmap_insert_occupied_points(self._h, p.ctypes.data, p.shape[0], 12))
 
     def getCellStatusBoundingBox(self, xyz, bounding_box_size):
         """octomap_world.cc:274-344, batched: one box size, many centres."""
