@@ -94,3 +94,17 @@ def test_empty_and_malformed_streams():
     cut = good[:-3]
     buf = (C.c_uint8 * len(cut)).from_buffer_copy(cut)
     assert L.vmap_host_parse_stream(C.byref(params), 0, buf, len(cut), None, None, 0, C.byref(n), C.byref(res)) == 1
+
+
+def test_cpp_exceptions_do_not_cross_the_c_abi():
+    """An impossible allocation inside an entry point comes back as an error code and a message."""
+    L = _capi.lib()
+    params = _capi.default_params(resolution=0.1)
+    k = np.zeros((1, 3), np.uint16); v = np.zeros(1, np.float32)
+    n = C.c_size_t(0)
+    st = L.vmap_host_tree_stream(C.byref(params), k.ctypes.data, v.ctypes.data, C.c_size_t(1 << 60), 0, None, 0,
+                                 C.byref(n), None)
+    assert st in (1, 3)
+    L.vmap_last_error.restype = C.c_char_p
+    msg = L.vmap_last_error(None)
+    assert msg and (b"allocation" in msg or b"exception" in msg)

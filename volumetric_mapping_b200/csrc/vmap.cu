@@ -155,6 +155,27 @@ namespace {
     if (s__ != VMAP_OK) return s__;  \
   } while (0)
 
+// No C++ exception may cross the C ABI: every entry point is a function-try-block that ends here.
+static int vmap_on_exception(vmap* h) noexcept {
+  int code = VMAP_ERR_INVALID_ARGUMENT;
+  try {
+    std::string what = "unknown C++ exception";
+    try {
+      throw;
+    } catch (const std::bad_alloc&) {
+      what = "host memory allocation failed";
+      code = VMAP_ERR_CAPACITY;
+    } catch (const std::exception& e) {
+      what = std::string("C++ exception: ") + e.what();
+    } catch (...) {
+    }
+    if (h) h->err = what;
+    else g_create_error = what;
+  } catch (...) {
+  }
+  return code;
+}
+
 int fail(const vmap* h, int code, const char* msg) {
   h->err = msg;
   return code;
@@ -895,7 +916,7 @@ void vmap_default_config(vmap_config* c) {
 
 const char* vmap_last_error(const vmap* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out) {
+int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out) try {
   if (!out) {
     g_create_error = "vmap_create: out is NULL";
     return VMAP_ERR_INVALID_ARGUMENT;
@@ -979,9 +1000,9 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   if (s != VMAP_OK) return bail(s);
   *out = h;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(nullptr); }
 
-int vmap_destroy(vmap* h) {
+int vmap_destroy(vmap* h) try {
   if (!h) return VMAP_OK;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
@@ -1016,9 +1037,9 @@ int vmap_destroy(vmap* h) {
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_reset(vmap* h) {
+int vmap_reset(vmap* h) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   VM_TRY(flush_app(h));
@@ -1039,9 +1060,9 @@ int vmap_reset(vmap* h) {
   h->stats = vmap_scan_stats{};
   h->captured = false;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_set_params(vmap* h, const vmap_params* params) {
+int vmap_set_params(vmap* h, const vmap_params* params) try {
   if (!h || !params) return VMAP_ERR_INVALID_ARGUMENT;
   if (!(params->resolution > 0.0) || !std::isfinite(params->resolution))
     return fail(h, VMAP_ERR_INVALID_ARGUMENT, "resolution must be positive");
@@ -1052,27 +1073,27 @@ int vmap_set_params(vmap* h, const vmap_params* params) {
   VM_TRY(set_change_detection(h, params->change_detection_enabled != 0));   // octomap_world.cc:99
   if (new_res) return vmap_reset(h);
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_get_params(const vmap* h, vmap_params* params) {
+int vmap_get_params(const vmap* h, vmap_params* params) try {
   if (!h || !params) return VMAP_ERR_INVALID_ARGUMENT;
   *params = h->params;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(const_cast<vmap*>(h)); }
 
 // ---------------------------------------------------------------------------------------------
 // insertion
 // ---------------------------------------------------------------------------------------------
 int vmap_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n, size_t stride_bytes,
-                               const double T_rowmajor[16]) {
+                               const double T_rowmajor[16]) try {
   if (!h || (!d_xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
   return insert_cloud_common(h, reinterpret_cast<const uint8_t*>(d_xyz), n, stride_bytes, 1, T_rowmajor);
-}
+} catch (...) { return vmap_on_exception(h); }
 
 int vmap_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes, int is_dense,
-                           const double T_rowmajor[16], float* xyz_world_out, size_t* n_out) {
+                           const double T_rowmajor[16], float* xyz_world_out, size_t* n_out) try {
   if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1102,7 +1123,7 @@ int vmap_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_by
     if (n_out) *n_out = j;
   }
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 static int insert_image_common(vmap* h, const uint8_t* d_img, int rows, int cols, size_t pitch,
                                const double* Q /* null: image is CV_32FC3 */, const double q[4],
@@ -1147,7 +1168,7 @@ static int check_image_args(vmap* h, const void* img, int rows, int cols, size_t
 }
 
 int vmap_insert_projected(vmap* h, const float* xyz_hw3, int rows, int cols, size_t row_pitch_bytes,
-                          const double q_wxyz[4], const double t[3]) {
+                          const double q_wxyz[4], const double t[3]) try {
   VM_TRY(check_image_args(h, xyz_hw3, rows, cols, row_pitch_bytes, 12, q_wxyz, t));
   VM_CUDA(h, cudaSetDevice(h->device));
   const size_t bytes = (size_t)rows * row_pitch_bytes;
@@ -1156,7 +1177,7 @@ int vmap_insert_projected(vmap* h, const float* xyz_hw3, int rows, int cols, siz
     VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz_hw3, bytes, cudaMemcpyHostToDevice, h->stream));
   }
   return insert_image_common(h, (const uint8_t*)h->in.p, rows, cols, row_pitch_bytes, nullptr, q_wxyz, t);
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // world_base.cc:55-69
 static void fixup_q(const double Q_full[16], double full_image_width, int cols, double Q[16]) {
@@ -1176,18 +1197,18 @@ static void fixup_q(const double Q_full[16], double full_image_width, int cols, 
 
 int vmap_insert_disparity_dev(vmap* h, const float* d_disparity, int rows, int cols,
                               size_t row_pitch_bytes, const double Q_full_rowmajor[16],
-                              double full_image_width, const double q_wxyz[4], const double t[3]) {
+                              double full_image_width, const double q_wxyz[4], const double t[3]) try {
   VM_TRY(check_image_args(h, d_disparity, rows, cols, row_pitch_bytes, 4, q_wxyz, t));
   if (!Q_full_rowmajor) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "null Q");
   VM_CUDA(h, cudaSetDevice(h->device));
   double Q[16];
   fixup_q(Q_full_rowmajor, full_image_width, cols > 0 ? cols : 1, Q);
   return insert_image_common(h, (const uint8_t*)d_disparity, rows, cols, row_pitch_bytes, Q, q_wxyz, t);
-}
+} catch (...) { return vmap_on_exception(h); }
 
 int vmap_insert_disparity(vmap* h, const float* disparity, int rows, int cols, size_t row_pitch_bytes,
                           const double Q_full_rowmajor[16], double full_image_width,
-                          const double q_wxyz[4], const double t[3]) {
+                          const double q_wxyz[4], const double t[3]) try {
   VM_TRY(check_image_args(h, disparity, rows, cols, row_pitch_bytes, 4, q_wxyz, t));
   if (!Q_full_rowmajor) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "null Q");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1199,10 +1220,10 @@ int vmap_insert_disparity(vmap* h, const float* disparity, int rows, int cols, s
   double Q[16];
   fixup_q(Q_full_rowmajor, full_image_width, cols > 0 ? cols : 1, Q);
   return insert_image_common(h, (const uint8_t*)h->in.p, rows, cols, row_pitch_bytes, Q, q_wxyz, t);
-}
+} catch (...) { return vmap_on_exception(h); }
 
 int vmap_reproject(vmap* h, const float* disparity, int rows, int cols, size_t row_pitch_bytes,
-                   const double Q_rowmajor[16], float* xyz_hw3_out) {
+                   const double Q_rowmajor[16], float* xyz_hw3_out) try {
   const double qi[4] = {1, 0, 0, 0}, ti[3] = {0, 0, 0};
   VM_TRY(check_image_args(h, disparity, rows, cols, row_pitch_bytes, 4, qi, ti));
   if (!Q_rowmajor || !xyz_hw3_out) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument");
@@ -1227,9 +1248,9 @@ int vmap_reproject(vmap* h, const float* disparity, int rows, int cols, size_t r
   VM_CUDA(h, cudaMemcpyAsync(xyz_hw3_out, h->out.p, n * 12, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_apply_keys(vmap* h, const uint16_t* free_k3, size_t n_free, const uint16_t* occ_k3, size_t n_occ) {
+int vmap_apply_keys(vmap* h, const uint16_t* free_k3, size_t n_free, const uint16_t* occ_k3, size_t n_occ) try {
   if (!h || (!free_k3 && n_free) || (!occ_k3 && n_occ)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n_free > 0x7FFFFFFFull || n_occ > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many keys");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1253,12 +1274,12 @@ int vmap_apply_keys(vmap* h, const uint16_t* free_k3, size_t n_free, const uint1
     VM_CUDA(h, cudaGetLastError());
     return VMAP_OK;
   });
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // ---------------------------------------------------------------------------------------------
 // queries
 // ---------------------------------------------------------------------------------------------
-int vmap_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status) {
+int vmap_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status) try {
   if (!h || ((!d_xyz || !d_status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query points");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1269,9 +1290,9 @@ int vmap_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_sta
   VM_CUDA(h, cudaGetLastError());
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_query_points(vmap* h, const double* xyz, size_t n, uint8_t* status) {
+int vmap_query_points(vmap* h, const double* xyz, size_t n, uint8_t* status) try {
   if (!h || ((!xyz || !status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   if (!n) return VMAP_OK;
@@ -1282,9 +1303,9 @@ int vmap_query_points(vmap* h, const double* xyz, size_t n, uint8_t* status) {
   VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_status) {
+int vmap_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_status) try {
   if (!h || ((!d_ab || !d_status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query segments");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1295,9 +1316,9 @@ int vmap_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_statu
   VM_CUDA(h, cudaGetLastError());
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_query_lines(vmap* h, const double* ab, size_t n, uint8_t* status) {
+int vmap_query_lines(vmap* h, const double* ab, size_t n, uint8_t* status) try {
   if (!h || ((!ab || !status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   if (!n) return VMAP_OK;
@@ -1308,12 +1329,12 @@ int vmap_query_lines(vmap* h, const double* ab, size_t n, uint8_t* status) {
   VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // getCellTrueStatusPoint / getCellProbabilityPoint (octomap_world.cc:363-393), batched.
 // probability (may be NULL): OcTreeNode::getOccupancy() = 1 - 1 / (1 + exp(log-odds)) evaluated on
 // the HOST in double like the reference does (libm exp), -1.0 where there is no node.
-int vmap_query_points_probability(vmap* h, const double* xyz, size_t n, uint8_t* status, double* probability) {
+int vmap_query_points_probability(vmap* h, const double* xyz, size_t n, uint8_t* status, double* probability) try {
   if (!h || ((!xyz || !status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query points");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1338,10 +1359,10 @@ int vmap_query_points_probability(vmap* h, const double* xyz, size_t n, uint8_t*
     for (size_t i = 0; i < n; i++)
       probability[i] = (status[i] == VMAP_CELL_UNKNOWN) ? -1.0 : 1. - (1. / (1. + std::exp((double)lo[i])));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // getVisibility (octomap_world.cc:420-449), batched: n x (view point xyz, voxel to test xyz).
-int vmap_query_visibility(vmap* h, const double* view_voxel_xyz6, size_t n, int stop_at_unknown_cell, uint8_t* status) {
+int vmap_query_visibility(vmap* h, const double* view_voxel_xyz6, size_t n, int stop_at_unknown_cell, uint8_t* status) try {
   if (!h || ((!view_voxel_xyz6 || !status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many queries");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1357,7 +1378,7 @@ int vmap_query_visibility(vmap* h, const double* view_voxel_xyz6, size_t n, int 
   VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // getCellStatusBoundingBox (octomap_world.cc:274-344), batched: every point with the same box.
 static int query_bbox_device(vmap* h, const double* d_xyz, size_t n, const double bounding_box_size[3], uint8_t* d_status) {
@@ -1374,7 +1395,7 @@ static int query_bbox_device(vmap* h, const double* d_xyz, size_t n, const doubl
   return VMAP_OK;
 }
 
-int vmap_query_bbox_status_dev(vmap* h, const double* d_xyz, size_t n, const double bounding_box_size[3], uint8_t* d_status) {
+int vmap_query_bbox_status_dev(vmap* h, const double* d_xyz, size_t n, const double bounding_box_size[3], uint8_t* d_status) try {
   if (!h || ((!d_xyz || !d_status) && n) || !bounding_box_size) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many queries");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1383,9 +1404,9 @@ int vmap_query_bbox_status_dev(vmap* h, const double* d_xyz, size_t n, const dou
   VM_TRY(query_bbox_device(h, d_xyz, n, bounding_box_size, d_status));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_query_bbox_status(vmap* h, const double* xyz, size_t n, const double bounding_box_size[3], uint8_t* status) {
+int vmap_query_bbox_status(vmap* h, const double* xyz, size_t n, const double bounding_box_size[3], uint8_t* status) try {
   if (!h || ((!xyz || !status) && n) || !bounding_box_size) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many queries");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1398,12 +1419,12 @@ int vmap_query_bbox_status(vmap* h, const double* xyz, size_t n, const double bo
   VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // checkPathForCollisionsWithRobot / checkSinglePoseCollision (octomap_world.cc:1384-1412): every
 // pose is tested in one launch; the earliest colliding index is picked on the host.
 int vmap_check_path_collisions(vmap* h, const double* xyz, size_t n, const double robot_size[3], int* collides,
-                               size_t* collision_index) {
+                               size_t* collision_index) try {
   if (!h || (!xyz && n) || !robot_size || !collides) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   *collides = 0;
   if (!n) return VMAP_OK;
@@ -1418,11 +1439,11 @@ int vmap_check_path_collisions(vmap* h, const double* xyz, size_t n, const doubl
     }
   }
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // getLineStatusBoundingBox (octomap_world.cc:451-493), batched: every segment is swept with the
 // same box.  The offset grid is produced by the reference's own loops (accumulating doubles).
-int vmap_query_lines_bbox(vmap* h, const double* start_end_xyz6, size_t n, const double bounding_box_size[3], uint8_t* status) {
+int vmap_query_lines_bbox(vmap* h, const double* start_end_xyz6, size_t n, const double bounding_box_size[3], uint8_t* status) try {
   if (!h || ((!start_end_xyz6 || !status) && n) || !bounding_box_size) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   VM_TRY(flush_app(h));
@@ -1465,7 +1486,7 @@ int vmap_query_lines_bbox(vmap* h, const double* start_end_xyz6, size_t n, const
   VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // ---------------------------------------------------------------------------------------------
 // leaves in / out
@@ -1483,13 +1504,13 @@ static int count_leaves(vmap* h, uint16_t* d_k3, float* d_val, uint32_t cap, siz
   return VMAP_OK;
 }
 
-int vmap_leaf_count(vmap* h, size_t* n) {
+int vmap_leaf_count(vmap* h, size_t* n) try {
   if (!h || !n) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   return count_leaves(h, nullptr, nullptr, 0, n);
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_export_leaves(vmap* h, uint16_t* keys_k3, float* logodds_out, size_t capacity, size_t* n) {
+int vmap_export_leaves(vmap* h, uint16_t* keys_k3, float* logodds_out, size_t capacity, size_t* n) try {
   if (!h || !n) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   size_t total = 0;
@@ -1505,9 +1526,9 @@ int vmap_export_leaves(vmap* h, uint16_t* keys_k3, float* logodds_out, size_t ca
   VM_CUDA(h, cudaMemcpyAsync(logodds_out, h->aux.p, total * 4, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in, size_t n) {
+int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in, size_t n) try {
   if (!h || ((!keys_k3 || !logodds_in) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many leaves");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1538,13 +1559,13 @@ int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in
     return VMAP_OK;
   }
   return fail(h, VMAP_ERR_CAPACITY, "import could not be applied after repeated growth");
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // OctomapWorld::getChangedPoints (octomap_world.cc:1413-1440): the keys octomap's change detection
 // collected since the last call (created leaves and leaves whose occupancy flipped), each with
 // the CURRENT occupancy of its node, then resetChangeDetection().  Needs change_detection_enabled.
 // When `capacity` is too small nothing is reset and *n holds the count.
-int vmap_get_changed(vmap* h, uint16_t* keys_k3, uint8_t* occupied, size_t capacity, size_t* n) {
+int vmap_get_changed(vmap* h, uint16_t* keys_k3, uint8_t* occupied, size_t capacity, size_t* n) try {
   if (!h || !n) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   VM_TRY(flush_app(h));
@@ -1571,28 +1592,28 @@ int vmap_get_changed(vmap* h, uint16_t* keys_k3, uint8_t* occupied, size_t capac
   VM_CUDA(h, cudaMemcpyAsync(occupied, h->aux.p, total, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // ---------------------------------------------------------------------------------------------
 // introspection
 // ---------------------------------------------------------------------------------------------
-int vmap_last_scan_stats(const vmap* h, vmap_scan_stats* stats) {
+int vmap_last_scan_stats(const vmap* h, vmap_scan_stats* stats) try {
   if (!h || !stats) return VMAP_ERR_INVALID_ARGUMENT;
   // (an overlapped multi-GPU round still in flight: its apply-side counters arrive with
   // vmap_dist_flush; the generation-side counters are already final)
   *stats = h->stats;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(const_cast<vmap*>(h)); }
 
-int vmap_set_debug_capture(vmap* h, int enabled) {
+int vmap_set_debug_capture(vmap* h, int enabled) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   h->capture = enabled != 0;
   if (!h->capture) h->captured = false;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 int vmap_debug_last_scan_keys(vmap* h, uint16_t* free_k3, size_t free_capacity, size_t* n_free,
-                              uint16_t* occ_k3, size_t occ_capacity, size_t* n_occ) {
+                              uint16_t* occ_k3, size_t occ_capacity, size_t* n_occ) try {
   if (!h || !n_free || !n_occ) return VMAP_ERR_INVALID_ARGUMENT;
   if (!h->captured) return fail(h, VMAP_ERR_NOT_CAPTURED, "debug capture was not enabled for the last scan");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -1604,13 +1625,13 @@ int vmap_debug_last_scan_keys(vmap* h, uint16_t* free_k3, size_t free_capacity, 
   if (*n_occ) VM_CUDA(h, cudaMemcpyAsync(occ_k3, h->cap_occ.p, *n_occ * 6, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_logodds_constants(const vmap* h, float out5[5]) {
+int vmap_logodds_constants(const vmap* h, float out5[5]) try {
   if (!h || !out5) return VMAP_ERR_INVALID_ARGUMENT;
   out5[0] = h->P.hit; out5[1] = h->P.miss; out5[2] = h->P.cmin; out5[3] = h->P.cmax; out5[4] = h->P.occ_thres;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(const_cast<vmap*>(h)); }
 
 void* vmap_stream(vmap* h) { return h ? (void*)h->stream : nullptr; }
 uint64_t vmap_kernel_launches(const vmap* h) { return h ? h->launches : 0; }

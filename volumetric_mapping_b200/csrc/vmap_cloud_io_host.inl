@@ -223,7 +223,7 @@ inline int read_cloud_file(const char* path, std::vector<float>* xyz, std::strin
 extern "C" {
 
 // xyz of a .pcd / .ply file (pure host; *n always receives the point count).
-int vmap_host_read_pointcloud_file(const char* path, float* xyz, size_t capacity, size_t* n) {
+int vmap_host_read_pointcloud_file(const char* path, float* xyz, size_t capacity, size_t* n) try {
   if (!path || !n) return VMAP_ERR_INVALID_ARGUMENT;
   std::vector<float> pts;
   std::string err;
@@ -236,12 +236,12 @@ int vmap_host_read_pointcloud_file(const char* path, float* xyz, size_t capacity
   if (!xyz || capacity < *n) return *n ? VMAP_ERR_BUFFER_TOO_SMALL : VMAP_OK;
   std::memcpy(xyz, pts.data(), pts.size() * sizeof(float));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(nullptr); }
 
 // The occupied-only insertion of loadOctomapCallback (octomap_manager.cc:330-341): every point
 // with coordToKeyChecked(point) inside the map becomes an occupied key (a KeySet: duplicates
 // collapse), the free set stays empty, updateOccupancy applies them.
-int vmap_insert_occupied_points(vmap* h, const float* xyz, size_t n, size_t stride_bytes) {
+int vmap_insert_occupied_points(vmap* h, const float* xyz, size_t n, size_t stride_bytes) try {
   if (!h || (!xyz && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   std::vector<uint16_t> occ;
@@ -262,10 +262,10 @@ int vmap_insert_occupied_points(vmap* h, const float* xyz, size_t n, size_t stri
     occ.push_back((uint16_t)s[0]); occ.push_back((uint16_t)s[1]); occ.push_back((uint16_t)s[2]);
   }
   return vmap_apply_keys(h, nullptr, 0, occ.data(), occ.size() / 3);
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // loadOctomapCallback's non-.bt branch.
-int vmap_load_occupied_pointcloud_file(vmap* h, const char* path, size_t* n_points) {
+int vmap_load_occupied_pointcloud_file(vmap* h, const char* path, size_t* n_points) try {
   if (!h || !path) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   std::vector<float> pts;
   std::string err;
@@ -273,6 +273,6 @@ int vmap_load_occupied_pointcloud_file(vmap* h, const char* path, size_t* n_poin
   if (st != VMAP_OK) return fail(h, st, err.c_str());
   if (n_points) *n_points = pts.size() / 3;
   return vmap_insert_occupied_points(h, pts.data(), pts.size() / 3, 12);
-}
+} catch (...) { return vmap_on_exception(h); }
 
 }  // extern "C"

@@ -348,7 +348,7 @@ extern "C" {
 
 // OcTree::write (full tree, float log-odds per node) into memory: getOctomapFullMsg's payload is
 // the stream without the header (with_header = 0), a ".ot" file the stream with it.
-int vmap_serialize_ot(vmap* h, int with_header, uint8_t* buffer, size_t capacity, size_t* n_bytes) {
+int vmap_serialize_ot(vmap* h, int with_header, uint8_t* buffer, size_t capacity, size_t* n_bytes) try {
   if (!h || !n_bytes) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   std::vector<std::pair<uint64_t, float> > leaves;
@@ -362,10 +362,10 @@ int vmap_serialize_ot(vmap* h, int with_header, uint8_t* buffer, size_t capacity
   if (capacity < out.size()) return fail(h, VMAP_ERR_BUFFER_TOO_SMALL, "buffer too small; *n_bytes holds the stream size");
   std::memcpy(buffer, out.data(), out.size());
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // setOctomapFromMsg with a full message (octomap_world.cc:833-844) / OcTree::read: replaces the map.
-int vmap_deserialize_ot(vmap* h, int with_header, const uint8_t* buffer, size_t n_bytes) {
+int vmap_deserialize_ot(vmap* h, int with_header, const uint8_t* buffer, size_t n_bytes) try {
   if (!h || (!buffer && n_bytes)) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   double res = 0.0;
@@ -377,7 +377,7 @@ int vmap_deserialize_ot(vmap* h, int with_header, const uint8_t* buffer, size_t 
   VM_TRY(vmap_set_params(h, &p));
   VM_TRY(vmap_reset(h));
   return vmap_import_leaves(h, k3.data(), val.data(), val.size());
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // OctomapWorld::setLogOddsBoundingBox (octomap_world.cc:781-818), which is what setFree /
 // setOccupied (:497-523) call: every grid position of the adjusted box (adjustBoundingBox,
@@ -385,7 +385,7 @@ int vmap_deserialize_ot(vmap* h, int with_header, const uint8_t* buffer, size_t 
 // positions are ignored).  The loops run on the host in the reference's arithmetic (accumulating
 // doubles, float narrowing at point3d); the voxels are written on the device in one batch.
 int vmap_set_log_odds_bbox(vmap* h, const double* positions_xyz, size_t n_positions,
-                           const double bounding_box_size[3], double log_odds_value, int bound_handling) {
+                           const double bounding_box_size[3], double log_odds_value, int bound_handling) try {
   if (!h || (!positions_xyz && n_positions) || !bounding_box_size) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (bound_handling < 0 || bound_handling > 2) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bound_handling must be 0 (default), 1 (include partial) or 2 (ignore partial)");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -446,7 +446,7 @@ int vmap_set_log_odds_bbox(vmap* h, const double* positions_xyz, size_t n_positi
         }
   }
   return vmap_import_leaves(h, k3.data(), val.data(), val.size());
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // ---------------------------------------------------------------------------------------------
 // The same tree fold / stream code on caller-supplied leaves, without a device: used by hosts that
@@ -456,7 +456,7 @@ int vmap_set_log_odds_bbox(vmap* h, const double* positions_xyz, size_t n_positi
 //   kind 2: ".ot" stream with header (OcTree::write)
 // ---------------------------------------------------------------------------------------------
 int vmap_host_tree_stream(const vmap_params* params, const uint16_t* keys_k3, const float* logodds_in, size_t n,
-                          int kind, uint8_t* buffer, size_t capacity, size_t* n_bytes, size_t* n_nodes) {
+                          int kind, uint8_t* buffer, size_t capacity, size_t* n_bytes, size_t* n_nodes) try {
   if (!params || ((!keys_k3 || !logodds_in) && n) || !n_bytes || kind < 0 || kind > 2) return VMAP_ERR_INVALID_ARGUMENT;
   std::unique_ptr<vmap> tmp(new vmap());
   tmp->params = *params;
@@ -481,13 +481,13 @@ int vmap_host_tree_stream(const vmap_params* params, const uint16_t* keys_k3, co
   if (capacity < out.size()) return VMAP_ERR_BUFFER_TOO_SMALL;
   std::memcpy(buffer, out.data(), out.size());
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(nullptr); }
 
 // Inverse: finest-level leaves of a stream (pruned leaves expanded).  *n_leaves always receives
 // the leaf count; the arrays are filled when `capacity` suffices.
 int vmap_host_parse_stream(const vmap_params* params, int kind, const uint8_t* buffer, size_t n_bytes,
                            uint16_t* keys_k3, float* logodds_out, size_t capacity, size_t* n_leaves,
-                           double* resolution) {
+                           double* resolution) try {
   if (!params || (!buffer && n_bytes) || !n_leaves || kind < 0 || kind > 2) return VMAP_ERR_INVALID_ARGUMENT;
   std::unique_ptr<vmap> tmp(new vmap());
   tmp->params = *params;
@@ -507,10 +507,10 @@ int vmap_host_parse_stream(const vmap_params* params, int kind, const uint8_t* b
   std::memcpy(keys_k3, k3.data(), k3.size() * sizeof(uint16_t));
   std::memcpy(logodds_out, val.data(), val.size() * sizeof(float));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(nullptr); }
 
 // octree_->prune(); octree_->size(): node count of the canonical pruned tree.
-int vmap_tree_size(vmap* h, int max_likelihood, size_t* n_nodes) {
+int vmap_tree_size(vmap* h, int max_likelihood, size_t* n_nodes) try {
   if (!h || !n_nodes) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   std::vector<std::pair<uint64_t, float> > leaves;
@@ -519,10 +519,10 @@ int vmap_tree_size(vmap* h, int max_likelihood, size_t* n_nodes) {
   build_pruned_tree(h, leaves, max_likelihood != 0, &t);
   *n_nodes = t.n_nodes;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // OctomapWorld::writeOctomapToBinaryConst (octomap_world.cc:854-856) into memory.
-int vmap_serialize_bt(vmap* h, uint8_t* buffer, size_t capacity, size_t* n_bytes) {
+int vmap_serialize_bt(vmap* h, uint8_t* buffer, size_t capacity, size_t* n_bytes) try {
   if (!h || !n_bytes) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   std::string out;
@@ -532,12 +532,12 @@ int vmap_serialize_bt(vmap* h, uint8_t* buffer, size_t capacity, size_t* n_bytes
   if (capacity < out.size()) return fail(h, VMAP_ERR_BUFFER_TOO_SMALL, "buffer too small; *n_bytes holds the stream size");
   std::memcpy(buffer, out.data(), out.size());
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // OctomapWorld::writeOctomapToFile (octomap_world.cc:849-852) -> OcTree::writeBinary(filename),
 // which thresholds the LIVE tree to the clamping values (toMaxLikelihood) and prunes it before
 // writing; threshold_live_map != 0 reproduces that side effect on the device map.
-int vmap_write_bt(vmap* h, const char* path, int threshold_live_map) {
+int vmap_write_bt(vmap* h, const char* path, int threshold_live_map) try {
   if (!h || !path) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   if (threshold_live_map) {
@@ -551,10 +551,10 @@ int vmap_write_bt(vmap* h, const char* path, int threshold_live_map) {
   if (!f) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "cannot open output file");
   f.write(out.data(), (std::streamsize)out.size());
   return f.good() ? VMAP_OK : fail(h, VMAP_ERR_INVALID_ARGUMENT, "write failed");
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // OctomapWorld::loadOctomapFromFile (octomap_world.cc:846-848) -> readBinary: replaces the map.
-int vmap_load_bt(vmap* h, const char* path) {
+int vmap_load_bt(vmap* h, const char* path) try {
   if (!h || !path) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   std::ifstream f(path, std::ios::binary);
@@ -562,13 +562,13 @@ int vmap_load_bt(vmap* h, const char* path) {
   std::stringstream ss;
   ss << f.rdbuf();
   return load_bt(h, ss.str());
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // setOctomapFromMsg with a binary message (octomap_world.cc:833-844): same stream from memory.
-int vmap_deserialize_bt(vmap* h, const uint8_t* buffer, size_t n_bytes) {
+int vmap_deserialize_bt(vmap* h, const uint8_t* buffer, size_t n_bytes) try {
   if (!h || (!buffer && n_bytes)) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   return load_bt(h, std::string(reinterpret_cast<const char*>(buffer), n_bytes));
-}
+} catch (...) { return vmap_on_exception(h); }
 
 }  // extern "C"

@@ -333,7 +333,7 @@ uint32_t vmap_shard_owner(uint16_t kx, uint16_t ky, uint16_t kz, int world) {
 
 size_t vmap_shard_record_bytes(void) { return sizeof(BlockRecord); }
 
-int vmap_set_shard(vmap* h, int rank, int world) {
+int vmap_set_shard(vmap* h, int rank, int world) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
     return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bad shard rank / world");
@@ -341,18 +341,18 @@ int vmap_set_shard(vmap* h, int rank, int world) {
   h->shard_world = world;
   h->m.sharded = world > 1 ? 1u : 0u;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 int vmap_shard_generate_dev(vmap* h, const float* d_xyz, size_t n, size_t stride_bytes,
-                            const double T_rowmajor[16], uint64_t* counts_out) {
+                            const double T_rowmajor[16], uint64_t* counts_out) try {
   if (!h || (!d_xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
   return shard_generate_common(h, (const uint8_t*)d_xyz, n, stride_bytes, 1, T_rowmajor, counts_out, []() -> int { return VMAP_OK; });
-}
+} catch (...) { return vmap_on_exception(h); }
 
 int vmap_shard_generate(vmap* h, const float* xyz, size_t n, size_t stride_bytes, int is_dense,
-                        const double T_rowmajor[16], uint64_t* counts_out) {
+                        const double T_rowmajor[16], uint64_t* counts_out) try {
   if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -362,9 +362,9 @@ int vmap_shard_generate(vmap* h, const float* xyz, size_t n, size_t stride_bytes
     VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
   }
   return shard_generate_common(h, (const uint8_t*)h->in.p, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor, counts_out, []() -> int { return VMAP_OK; });
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_shard_records(vmap* h, int dest, const void** d_records, size_t* n_records) {
+int vmap_shard_records(vmap* h, int dest, const void** d_records, size_t* n_records) try {
   if (!h || !d_records || !n_records) return VMAP_ERR_INVALID_ARGUMENT;
   if (dest < 0 || dest >= h->shard_world) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "bad destination rank");
   size_t off = 0;
@@ -372,16 +372,16 @@ int vmap_shard_records(vmap* h, int dest, const void** d_records, size_t* n_reco
   *d_records = (const BlockRecord*)h->pack.p + off;
   *n_records = h->h_pack_counts[dest];
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_shard_apply_dev(vmap* h, const void* const* d_record_lists, const size_t* n_records, size_t n_lists) {
+int vmap_shard_apply_dev(vmap* h, const void* const* d_record_lists, const size_t* n_records, size_t n_lists) try {
   if (!h || ((!d_record_lists || !n_records) && n_lists)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   return shard_apply_lists(h, (const BlockRecord* const*)d_record_lists, n_records, n_lists);
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // ---- NCCL-backed collective insertion --------------------------------------------------------
-int vmap_dist_unique_id(uint8_t out128[128]) {
+int vmap_dist_unique_id(uint8_t out128[128]) try {
   if (!out128) return VMAP_ERR_INVALID_ARGUMENT;
   if (!nccl_load()) {
     g_create_error = g_nccl.error;
@@ -395,9 +395,9 @@ int vmap_dist_unique_id(uint8_t out128[128]) {
   }
   std::memcpy(out128, id.internal, 128);
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(nullptr); }
 
-int vmap_dist_init(vmap* h, const uint8_t id128[128], int rank, int world) {
+int vmap_dist_init(vmap* h, const uint8_t id128[128], int rank, int world) try {
   if (!h || !id128) return VMAP_ERR_INVALID_ARGUMENT;
   VM_TRY(vmap_set_shard(h, rank, world));
   if (!nccl_load()) return fail(h, VMAP_ERR_DIST, g_nccl.error.c_str());
@@ -408,9 +408,9 @@ int vmap_dist_init(vmap* h, const uint8_t id128[128], int rank, int world) {
   VM_NCCL(h, g_nccl.CommInitRank(&comm, world, id, rank));
   h->nccl_comm = comm;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_dist_shutdown(vmap* h) {
+int vmap_dist_shutdown(vmap* h) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   if (h->nccl_comm && getenv("VMAP_TIMING") && h->dbg_n)
     fprintf(stderr, "[vmap rank %d] per round (host wall ms): generate+pack %.3f | count allgather + wait for previous apply %.3f | exchange/apply enqueue %.3f | (sync path) %.3f  (%llu rounds)\n",
@@ -425,7 +425,7 @@ int vmap_dist_shutdown(vmap* h) {
     h->nccl_comm = nullptr;
   }
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // Exchange + apply after a local generate: rank r's scan is the r-th scan of this round.
 static double now_ms() {
@@ -646,7 +646,7 @@ void seal_batch(vmap* h) {
 extern "C" {
 
 // Waits for the round in flight (if any); afterwards vmap_last_scan_stats reports its counters.
-int vmap_dist_flush(vmap* h) {
+int vmap_dist_flush(vmap* h) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   h->in_collective = true;
@@ -658,29 +658,29 @@ int vmap_dist_flush(vmap* h) {
   if (st == VMAP_OK) st = flush_app(h);
   h->in_collective = false;
   return st;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // Scans per rank that share one exchange (1..8).  Larger batches amortise the exchange over more
 // scans; the map lags up to m collective calls behind (vmap_dist_flush completes it).  Collective:
 // every rank must use the same value, set between rounds.
-int vmap_dist_set_batch(vmap* h, int scans_per_rank) {
+int vmap_dist_set_batch(vmap* h, int scans_per_rank) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   if (scans_per_rank < 1 || scans_per_rank > kMaxBatch) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "batch must be 1..8");
   if (h->pack_sub) return fail(h, VMAP_ERR_DIST, "a batch is under construction: call vmap_dist_flush first");
   h->batch_m = scans_per_rank;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // Test / benchmark hook: overwrite `bytes` of scratch (larger than L2) on the apply stream before
 // every round's exchange, so no round finds its map blocks in L2.  0 disables.
-int vmap_set_debug_l2_flush(vmap* h, size_t bytes) {
+int vmap_set_debug_l2_flush(vmap* h, size_t bytes) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
   VM_TRY(flush_app(h));
   if (bytes) VM_TRY(ensure(h, &h->l2_flush, bytes));
   h->l2_flush_bytes = bytes;
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 }  // extern "C"
 namespace {
@@ -725,15 +725,15 @@ int dist_insert(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_de
 extern "C" {
 
 int vmap_dist_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n, size_t stride_bytes,
-                                    const double T_rowmajor[16]) {
+                                    const double T_rowmajor[16]) try {
   if (!h || (!d_xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
   return dist_insert(h, (const uint8_t*)d_xyz, n, stride_bytes, 1, T_rowmajor);
-}
+} catch (...) { return vmap_on_exception(h); }
 
 int vmap_dist_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes, int is_dense,
-                                const double T_rowmajor[16]) {
+                                const double T_rowmajor[16]) try {
   if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -743,10 +743,10 @@ int vmap_dist_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stri
     VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
   }
   return dist_insert(h, (const uint8_t*)h->in.p, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor);
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // Sharded queries: partial answers of this shard (combine = element-wise MIN over ranks).
-int vmap_shard_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status) {
+int vmap_shard_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status) try {
   if (!h || ((!d_xyz || !d_status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query points");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -758,9 +758,9 @@ int vmap_shard_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t*
   VM_CUDA(h, cudaGetLastError());
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_shard_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint32_t* d_packed) {
+int vmap_shard_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint32_t* d_packed) try {
   if (!h || ((!d_ab || !d_packed) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query segments");
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -772,10 +772,10 @@ int vmap_shard_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint32_t* 
   VM_CUDA(h, cudaGetLastError());
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 // Collective versions: every rank passes the same queries and receives the global answer.
-int vmap_dist_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status) {
+int vmap_dist_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_status) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
   VM_TRY(vmap_dist_flush(h));
@@ -784,9 +784,9 @@ int vmap_dist_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* 
   VM_NCCL(h, g_nccl.AllReduce(d_status, d_status, n, kNcclUint8, kNcclMin, (NcclComm)h->nccl_comm, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
-int vmap_dist_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_status) {
+int vmap_dist_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_status) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   if (!h->nccl_comm) return fail(h, VMAP_ERR_DIST, "vmap_dist_init has not been called");
   VM_TRY(vmap_dist_flush(h));
@@ -799,6 +799,6 @@ int vmap_dist_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_
   VM_CUDA(h, cudaGetLastError());
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   return VMAP_OK;
-}
+} catch (...) { return vmap_on_exception(h); }
 
 }  // extern "C"
