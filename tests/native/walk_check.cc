@@ -6,6 +6,7 @@
 // and hands individual rays' keys to Python for comparison with the oracle's computeRayKeys.
 #include "../../volumetric_mapping_b200/csrc/vmap_walk.cuh"
 
+#include <algorithm>
 #include <vector>
 
 using namespace vmapdev;
@@ -85,7 +86,7 @@ int wc_walk_plain(double res, double max_free_space, double min_height, const fl
 
 // Segmented marks: checkpoints for every ray, then every (level, ray) slot on its own, levels
 // outermost (the order the kernel's level-major slots are walked in is irrelevant for the marks,
-// but this one is the least like the plain walk).  stats: [traversals, longest, overflow_window, slots]
+// but this one is the least like the plain walk).  stats: [traversals, longest, overflow_window, slots, near chunks]
 int wc_walk_segmented(double res, double max_free_space, double min_height, const float* origin, const float* ends,
                       uint32_t n_rays, const int32_t* origin_block, const uint32_t* dims, uint32_t* free_mask,
                       uint32_t* touched, uint32_t near_limit, int mode, uint64_t* stats) {
@@ -106,6 +107,46 @@ int wc_walk_segmented(double res, double max_free_space, double min_height, cons
   }
   uint32_t emitted = 0, longest = 0;
   uint64_t trav = 0, slots = 0;
+  if (mode == 2) {
+    // The near-field kernel's schedule: rays ordered by segment count (descending), slots
+    // level-major, chunks of 256 slots; a chunk made of first-segment slots only collects the
+    // marks around the sensor in its own bit grid and flushes it when the chunk is done.
+    std::vector<uint32_t> order(n_rays);
+    for (uint32_t r = 0; r < n_rays; r++) order[r] = r;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cps[a].size() > cps[b].size(); });
+    std::vector<std::pair<uint32_t, uint32_t> > slot_list;   // (level, ray)
+    for (uint32_t jj = 0; jj < max_seg; jj++)
+      for (uint32_t r : order)
+        if (jj < cps[r].size()) slot_list.push_back(std::make_pair(jj, r));
+    size_t level0 = 0;
+    while (level0 < slot_list.size() && slot_list[level0].first == 0) level0++;
+    std::vector<uint32_t> grid(kNearWords, 0u);
+    NearGrid near;
+    near.words = grid.data();
+    const int s0 = scaled_coord(P.res_factor, (double)origin[0]), s1 = scaled_coord(P.res_factor, (double)origin[1]),
+              s2 = scaled_coord(P.res_factor, (double)origin[2]);
+    const bool near_ok = key_in_range(s0) && key_in_range(s1) && key_in_range(s2) &&
+                         near_grid_place(ms, (uint32_t)s0, (uint32_t)s1, (uint32_t)s2, &near);
+    uint64_t near_chunks = 0;
+    for (size_t c0 = 0; c0 < slot_list.size(); c0 += 256) {
+      const bool first_level = near_ok && c0 + 256 <= level0;
+      for (size_t t = c0; t < std::min(c0 + 256, slot_list.size()); t++) {
+        const uint32_t jj = slot_list[t].first, r = slot_list[t].second;
+        emitted = 0;
+        if (first_level)
+          walk_slot_dilated<false, 0, true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, near);
+        else
+          walk_slot_dilated<false, 0, false>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest);
+        trav += emitted;
+        slots++;
+      }
+      if (first_level) {
+        for (uint32_t k = 0; k < kNearWords; k++) near_flush_word(ms, near, k);
+        near_chunks++;
+      }
+    }
+    stats[4] = near_chunks;
+  } else
   for (uint32_t jj = max_seg; jj-- > 0;) {       // deepest level first
     for (uint32_t r = 0; r < n_rays; r++) {
       if (jj >= cps[r].size()) continue;

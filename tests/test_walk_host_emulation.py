@@ -50,8 +50,9 @@ def window_for(res, origin, ends):
     """A power-of-two window (in 8^3 blocks) around every voxel the rays can visit."""
     pts = np.vstack([np.asarray(origin, np.float64)[None], np.asarray(ends, np.float64)])
     k = np.floor(pts / res).astype(np.int64) + 32768
-    lo = (k.min(0) - 2) >> 3
-    hi = (k.max(0) + 2) >> 3
+    # (like the product's window, at least five blocks on every side of the sensor's block)
+    lo = np.minimum((k.min(0) - 2) >> 3, (k[0] >> 3) - 5)
+    hi = np.maximum((k.max(0) + 2) >> 3, (k[0] >> 3) + 5)
     ext = hi - lo + 1
     dims = np.array([1 << int(np.ceil(np.log2(ext[0]))), 1 << int(np.ceil(np.log2(ext[1]))), ext[2]], np.uint32)
     return lo.astype(np.int32), dims
@@ -63,10 +64,11 @@ def run_both(L, res, origin, ends, max_free=0.0, min_height=0.0, near_limit=48):
     ob, dims = window_for(res, origin, ends)
     n_blocks = int(dims[0]) * int(dims[1]) * int(dims[2])
     out = []
-    for which in ("plain", "seg0", "seg1"):      # seg<mode>: walk_slot_dilated<., mode>
+    modes = ("plain", "seg0", "seg1") if max_free else ("plain", "seg0", "seg1", "seg2")
+    for which in modes:      # seg0 / seg1: walk_slot_dilated<., mode>; seg2: near-field combining schedule
         fm = np.zeros(n_blocks * 16, np.uint32)
         tb = np.zeros((n_blocks + 31) // 32, np.uint32)
-        stats = np.zeros(4, np.uint64)
+        stats = np.zeros(5, np.uint64)
         if which == "plain":
             L.wc_walk_plain(res, max_free, min_height, origin.ctypes.data, ends.ctypes.data, len(ends),
                             ob.ctypes.data, dims.ctypes.data, fm.ctypes.data, tb.ctypes.data, stats.ctypes.data)
@@ -83,7 +85,7 @@ def run_both(L, res, origin, ends, max_free=0.0, min_height=0.0, near_limit=48):
         bad = np.flatnonzero(fa != fb)
         assert bad.size == 0, (bad[:5], fa[bad[:5]], fb[bad[:5]])
         assert np.array_equal(ta, tb_)
-    return sa, out[1][2]
+    return sa, out[-1][2] if len(out) == 4 else out[1][2]
 
 
 def lidar_rays(n_elev, n_azim, seed, yaw):
@@ -115,6 +117,7 @@ def test_segmented_dilated_walk_equals_plain_walk_on_a_lidar_scan(lib, res):
     origin, world = lidar_rays(32, 360, seed=3, yaw=0.3)
     sa, sb = run_both(lib, res, origin, world)
     assert int(sb[3]) > len(world)            # rays really were cut into several segments
+    assert int(sb[4]) >= 10                   # and whole first-segment chunks went through the near grid
 
 
 def test_with_free_space_filter(lib):

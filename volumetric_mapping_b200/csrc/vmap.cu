@@ -120,6 +120,7 @@ struct vmap {
   uint32_t* chg1_store = nullptr;
   int walk_variant = 48;  // near-field limit of the walker's read-before-RED filter (VMAP_WALK_VARIANT)
   int walk_ctas = 5;      // CTAs per SM of the segment walker's grid = resident CTAs at 48 registers (VMAP_WALK_CTAS)
+  int walk_order = 0;     // 1: golden-ratio chunk order in the dilated segment walker (VMAP_WALK_ORDER, experimental)
   int walk_addr = 0;      // 1: dilated window addressing in the segment walker (VMAP_WALK_ADDR, experimental)
   int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
@@ -810,7 +811,7 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
     h->launches++;
     const unsigned grid = g_sm_count(h->device) * (unsigned)h->walk_ctas;
     // VMAP_WALK_ADDR (experimental): 1 dilated addressing, 2 + deferred touched test, 3 dilated at 6 CTAs / SM,
-    // 4 deferred at 6 CTAs / SM
+    // 4 deferred at 6 CTAs / SM, 5 dilated + near-field combining in shared memory
     const bool dilated = h->walk_addr >= 1 && dilated_window_fits(h->ms.nx, h->ms.ny, h->ms.nz);
     if (!h->traced && getenv("VMAP_TRACE")) {
       h->traced = true;
@@ -818,11 +819,12 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
               dilated ? "dilated" : "block", h->walk_addr, h->ms.nx, h->ms.ny, h->ms.nz, h->ms.x0, h->ms.y0, h->ms.z0,
               (unsigned long long)h->dense_fallbacks);
     }
-#define VMAP_WALK_DIL(F, M, C) k_walk_segments_dilated<F, M, C><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant)
+#define VMAP_WALK_DIL(F, M, C) k_walk_segments_dilated<F, M, C><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, h->walk_order)
     // (with the free-space filter the keys are needed at every step anyway and the block-addressed
     // kernel measured faster: profiles/r01_ab_walk_dilated.json)
     if (dilated && !h->P.free_filter) {
-      if (h->walk_addr == 2) VMAP_WALK_DIL(false, 1, 5);
+      if (h->walk_addr == 5) k_walk_segments_near<<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, h->walk_order);
+      else if (h->walk_addr == 2) VMAP_WALK_DIL(false, 1, 5);
       else if (h->walk_addr == 3) VMAP_WALK_DIL(false, 0, 6);
       else if (h->walk_addr == 4) VMAP_WALK_DIL(false, 1, 6);
       else VMAP_WALK_DIL(false, 0, 5);
@@ -962,6 +964,7 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   if (const char* e = getenv("VMAP_WALK_VARIANT")) h->walk_variant = atoi(e);
   if (const char* e = getenv("VMAP_WALK_ADDR")) h->walk_addr = atoi(e);
   if (const char* e = getenv("VMAP_WALK_CTAS")) h->walk_ctas = std::max(1, atoi(e));
+  if (const char* e = getenv("VMAP_WALK_ORDER")) h->walk_order = atoi(e);
   if (const char* e = getenv("VMAP_NO_SEGMENTS")) h->no_segments = atoi(e);
   if (const char* e = getenv("VMAP_UPDATE_VARIANT")) h->update_variant = atoi(e);
   auto bail = [&](int code) {

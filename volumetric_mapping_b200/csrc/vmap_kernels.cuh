@@ -653,11 +653,15 @@ k_walk_segments(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox
 }
 
 // K2b with dilated window addressing (vmap_walk.cuh: walk_slot_dilated); same slots, same marks.
-// Only launched for windows whose x / y extents are powers of two (VMAP_WALK_ADDR=1).
+// Only launched for windows whose x / y extents are powers of two (VMAP_WALK_ADDR >= 1).
+// order == 1 (VMAP_WALK_ORDER, experimental): the 256-slot chunks are visited in golden-ratio
+// stride order instead of level-major order, so that the first-segment slots -- which all mark the
+// same words around the sensor -- are spread over the kernel's run time instead of filling its
+// first wave (marks do not depend on the order).
 template <bool kFilter, int kMode, int kMinCtas>
 __global__ void __launch_bounds__(256, kMinCtas)
 k_walk_segments_dilated(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz,
-                        int variant) {
+                        int variant, int order) {
   if (cnt->overflow_ckpt) return;
   __shared__ uint32_t base_s[kLenBins + 1];
   for (int k = threadIdx.x; k <= kLenBins; k += blockDim.x) base_s[k] = sb.seg_base[k];
@@ -665,8 +669,22 @@ k_walk_segments_dilated(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, 
   const uint32_t total = min(base_s[kLenBins], sb.ckpt_cap);
   const DilatedWindow dw = dilated_window(ms);
   const uint32_t near_limit = (variant == 0) ? 0xFFFFFFFFu : (variant == 2 ? 0u : (uint32_t)variant);
+  const uint32_t n_chunks = (total + 255u) >> 8;
+  uint32_t stride = 1;
+  if (order == 1 && n_chunks > 2u) {
+    stride = (uint32_t)((double)n_chunks * 0.6180339887498949);
+    if (stride < 1u) stride = 1u;
+    for (;; stride++) {           // a stride coprime to n_chunks visits every chunk exactly once
+      uint32_t a = stride, b = n_chunks;
+      while (b) { const uint32_t t = a % b; a = b; b = t; }
+      if (a == 1u) break;
+    }
+  }
   uint32_t emitted = 0, longest = 0;
-  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
+  for (uint32_t q = blockIdx.x; q < n_chunks; q += gridDim.x) {
+    const uint32_t chunk = (uint32_t)(((unsigned long long)q * stride) % n_chunks);
+    const uint32_t slot = chunk * 256u + threadIdx.x;
+    if (slot >= total) continue;
     uint32_t lo = 0, hi = kLenBins;
     while (hi - lo > 1) {
       const uint32_t mid = (lo + hi) >> 1;
@@ -675,7 +693,84 @@ k_walk_segments_dilated(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, 
     const Checkpoint cp = sb.ckpt[slot];
     if (cp.count == 0xFFFFFFFFu) continue;
     walk_slot_dilated<kFilter, kMode>(P, ms, dw, cnt, cp, sb.ray_rec[slot - base_s[lo]], lo, ox, oy, oz, near_limit, &emitted,
-                               &longest);
+                                      &longest);
+  }
+  __shared__ uint32_t s_stat[2];
+  __syncthreads();
+  if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+  __syncthreads();
+  cta_add_u32(&s_stat[0], emitted);
+  cta_max_u32(&s_stat[1], longest);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_stat[0]) {
+    atomicAdd(&cnt->traversals, (unsigned long long)s_stat[0]);
+    atomicMax(&cnt->longest_ray, s_stat[1]);
+  }
+}
+
+// K2b, dilated addressing + near-field combining (vmap_walk.cuh: NearGrid).  Chunks that consist
+// of first-segment slots only collect the marks around the sensor in a 32 KiB shared bit grid and
+// flush it once per chunk; every other chunk runs exactly like k_walk_segments_dilated.
+__global__ void __launch_bounds__(256, 4)
+k_walk_segments_near(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz,
+                     int variant, int order) {
+  if (cnt->overflow_ckpt) return;
+  __shared__ uint32_t base_s[kLenBins + 1];
+  __shared__ uint32_t near_s[kNearWords];
+  for (int k = threadIdx.x; k <= kLenBins; k += blockDim.x) base_s[k] = sb.seg_base[k];
+  for (uint32_t k = threadIdx.x; k < kNearWords; k += blockDim.x) near_s[k] = 0u;
+  __syncthreads();
+  const uint32_t total = min(base_s[kLenBins], sb.ckpt_cap);
+  const DilatedWindow dw = dilated_window(ms);
+  const uint32_t near_limit = (variant == 0) ? 0xFFFFFFFFu : (variant == 2 ? 0u : (uint32_t)variant);
+  NearGrid near;
+  near.words = near_s;
+  bool near_ok = false;
+  {
+    // every ray starts in the sensor's voxel (coordToKeyChecked(origin), as in RayWalk::init)
+    const int s0 = scaled_coord(P.res_factor, (double)ox), s1 = scaled_coord(P.res_factor, (double)oy),
+              s2 = scaled_coord(P.res_factor, (double)oz);
+    if (key_in_range(s0) && key_in_range(s1) && key_in_range(s2))
+      near_ok = near_grid_place(ms, (uint32_t)s0, (uint32_t)s1, (uint32_t)s2, &near);
+  }
+  const uint32_t n_chunks = (total + 255u) >> 8;
+  uint32_t stride = 1;
+  if (order == 1 && n_chunks > 2u) {
+    stride = (uint32_t)((double)n_chunks * 0.6180339887498949);
+    if (stride < 1u) stride = 1u;
+    for (;; stride++) {
+      uint32_t a = stride, b = n_chunks;
+      while (b) { const uint32_t t = a % b; a = b; b = t; }
+      if (a == 1u) break;
+    }
+  }
+  uint32_t emitted = 0, longest = 0;
+  for (uint32_t q = blockIdx.x; q < n_chunks; q += gridDim.x) {
+    const uint32_t chunk = (uint32_t)(((unsigned long long)q * stride) % n_chunks);
+    const uint32_t slot = chunk * 256u + threadIdx.x;
+    // (uniform over the CTA) the whole chunk lies in level 0
+    const bool first_level = near_ok && (chunk * 256u + 256u <= base_s[1]);
+    if (slot < total) {
+      uint32_t lo = 0, hi = kLenBins;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (base_s[mid] <= slot) lo = mid; else hi = mid;
+      }
+      const Checkpoint cp = sb.ckpt[slot];
+      if (cp.count != 0xFFFFFFFFu) {
+        if (first_level)
+          walk_slot_dilated<false, 0, true>(P, ms, dw, cnt, cp, sb.ray_rec[slot - base_s[lo]], lo, ox, oy, oz, near_limit,
+                                            &emitted, &longest, near);
+        else
+          walk_slot_dilated<false, 0, false>(P, ms, dw, cnt, cp, sb.ray_rec[slot - base_s[lo]], lo, ox, oy, oz, near_limit,
+                                             &emitted, &longest);
+      }
+    }
+    if (first_level) {
+      __syncthreads();
+      for (uint32_t k = threadIdx.x; k < kNearWords; k += blockDim.x) near_flush_word(ms, near, k);
+      __syncthreads();
+    }
   }
   __shared__ uint32_t s_stat[2];
   __syncthreads();

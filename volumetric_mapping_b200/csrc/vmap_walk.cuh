@@ -169,14 +169,51 @@ __device__ __forceinline__ bool all_above(double t0, double t1, double t2, doubl
 #endif
 }
 
+// Near-field combining (experimental, VMAP_WALK_ADDR=5): the first segments of all rays cross the
+// same few thousand mask words around the sensor, and the same-address RED.OR traffic on them is
+// what the walker waits for (profiles/README.md).  A CTA that works on a chunk of first-segment
+// slots therefore collects the marks that fall into a cube of 8^3 blocks around the sensor's block
+// in a bit grid of its own (shared memory on the device) and writes each non-zero word to the
+// window once per chunk, after testing it against what is already set.
+constexpr uint32_t kNearBlocks = 8;                                        // blocks per side of the cube
+constexpr uint32_t kNearWords = kNearBlocks * kNearBlocks * kNearBlocks * kMaskWords;   // 8192 words = 32 KiB
+struct NearGrid {
+  uint32_t* words;            // [kNearWords], zero between chunks
+  uint32_t bx0, by0, bz0;     // first block of the cube, window-relative block coordinates
+};
+// cube of blocks centred on the block of voxel (c0, c1, c2); false when it leaves the window
+__device__ __forceinline__ bool near_grid_place(const MarkSet& ms, uint32_t c0, uint32_t c1, uint32_t c2, NearGrid* g) {
+  const int bx = (int)(c0 >> 3) - ms.x0 - (int)(kNearBlocks / 2), by = (int)(c1 >> 3) - ms.y0 - (int)(kNearBlocks / 2),
+            bz = (int)(c2 >> 3) - ms.z0 - (int)(kNearBlocks / 2);
+  if (bx < 0 || by < 0 || bz < 0 || bx + (int)kNearBlocks > (int)ms.nx || by + (int)kNearBlocks > (int)ms.ny ||
+      bz + (int)kNearBlocks > (int)ms.nz)
+    return false;
+  g->bx0 = (uint32_t)bx; g->by0 = (uint32_t)by; g->bz0 = (uint32_t)bz;
+  return true;
+}
+// word i of the grid -> window (one caller per word, after every slot of the chunk is done)
+__device__ __forceinline__ void near_flush_word(const MarkSet& ms, const NearGrid& g, uint32_t i) {
+  const uint32_t bits = g.words[i];
+  if (!bits) return;
+  g.words[i] = 0u;
+  const uint32_t b = i >> 4;
+  const uint32_t idx = ((g.bz0 + (b >> 6)) * ms.ny + (g.by0 + ((b >> 3) & 7u))) * ms.nx + (g.bx0 + (b & 7u));
+  uint32_t* w = ms.free_mask + ((size_t)idx * kMaskWords + (i & 15u));
+  if (bits & ~*w) atomicOr(w, bits);
+  uint32_t* tb = ms.touched_bits + (idx >> 5);
+  const uint32_t bit = 1u << (idx & 31u);
+  if (!(*tb & bit)) atomicOr(tb, bit);
+}
+
 // kMode 0: the block's touched bit is tested when the ray enters the block.
 // kMode 1: the touched word is only LOADED at block entry and tested when the ray leaves the
 //          block (or ends), so that the walk never waits for that load.
-template <bool kFilter, int kMode = 0>
+// kNear: marks inside `near`'s cube go to the CTA's own bit grid (see NearGrid) instead of the window.
+template <bool kFilter, int kMode = 0, bool kNear = false>
 __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const MarkSet& ms, const DilatedWindow& dw,
                                                   Counters* cnt, const Checkpoint& cp, const RayRec& rr, uint32_t j,
                                                   float ox, float oy, float oz, uint32_t near_limit,
-                                                  uint32_t* emitted, uint32_t* longest) {
+                                                  uint32_t* emitted, uint32_t* longest, const NearGrid& near = NearGrid()) {
   if (cp.count == 0xFFFFFFFFu) return;
   uint32_t c0 = cp.c01 & 0xFFFFu, c1 = cp.c01 >> 16, c2 = cp.c2;
   const uint32_t e0 = rr.e01 & 0xFFFFu, e1 = rr.e01 >> 16, e2 = rr.e2s & 0xFFFFu;
@@ -205,14 +242,30 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
   uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0;
   // kMode 1: touched word of the block in flight as loaded at entry (all ones: nothing pending)
   uint32_t tb_val = 0xFFFFFFFFu, tb_blk = 0;
+  // kNear: base word of the current block in the near grid, or kNotFound outside the cube
+  uint32_t near_base = kNotFound;
+  auto flush = [&]() {
+    if (kNear && near_base != kNotFound) {
+      if (bits) atomicOr(near.words + (near_base | (cur & 15u)), bits);
+    } else if (bits & ~seen) {
+      atomicOr(ms.free_mask + cur, bits);
+    }
+  };
   auto emit = [&]() {
     if (kFilter && !free_filter_pass(P, ox, oy, oz, c0, c1, c2)) return;
     const uint32_t a = a0 | a1 | a2;
     const uint32_t wi = a >> 5;
     if (wi != cur) {
-      if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
+      flush();
       if ((wi ^ cur) >= 16u) {                       // another block
-        if (kMode == 0) {
+        if (kNear) {
+          const uint32_t dx = (a0 >> 9) - near.bx0, dy = (a1 >> dw.sh1) - near.by0, dz = (a2 >> dw.sh2) - near.bz0;
+          near_base = (dx < kNearBlocks && dy < kNearBlocks && dz < kNearBlocks)
+                          ? ((((dz * kNearBlocks) + dy) * kNearBlocks + dx) << 4) : kNotFound;
+        }
+        if (kNear && near_base != kNotFound) {
+          // touched bit: set when the grid is flushed
+        } else if (kMode == 0) {
           uint32_t* tb = ms.touched_bits + (a >> 14);
           const uint32_t bit = 1u << ((a >> 9) & 31u);
           if (!(*tb & bit)) atomicOr(tb, bit);
@@ -224,7 +277,7 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
       }
       bits = 0;
       cur = wi;
-      seen = (count < near_limit) ? ms.free_mask[wi] : 0u;
+      seen = (!(kNear && near_base != kNotFound) && count < near_limit) ? ms.free_mask[wi] : 0u;
     }
     bits |= 1u << (a & 31u);
   };
@@ -274,7 +327,7 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
   // kLenBins - 1, which is far above the capacity).
   if ((rr.n_seg + 1u) * kSegSteps + 4u >= kKeyRayMax - 1u) run(BoolTag<true>());
   else run(BoolTag<false>());
-  if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
+  flush();
   if (kMode == 1 && !((tb_val >> (tb_blk & 31u)) & 1u)) atomicOr(ms.touched_bits + (tb_blk >> 5), 1u << (tb_blk & 31u));
   *emitted += count - count0 + (j == 0 ? 1u : 0u);
   if (last) *longest = max(*longest, count);
