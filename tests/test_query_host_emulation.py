@@ -132,6 +132,38 @@ def test_pruned_leaf_below_the_box_is_visited_like_upstream(lib):
     hm.close()
 
 
+@pytest.mark.parametrize("res,lo", [(0.25, 16), (0.1, 64)])
+def test_large_pruned_leaves_spanning_several_blocks(lib, res, lo):
+    """A 16^3-voxel cube of identical occupied voxels collapses into one depth-12 leaf (two 8^3
+    blocks per side): the leaf reconstruction has to look beyond the voxel's own block.  At 0.1 m
+    the cube's upper x / y faces sit at 8.0 m -- exactly representable, so boxes that start there
+    meet the leaf's face computed at the LEAF's depth, where the last ulp depends on the depth."""
+    ow = oracle.OracleWorld(params=oracle.default_params(resolution=res, treat_unknown_as_occupied=0))
+    B = 32768
+    r16 = np.arange(16)
+    occ = np.stack(np.meshgrid(B + lo + r16, B + lo + r16, B + r16, indexing="ij"), -1).reshape(-1, 3).astype(np.uint16)
+    rr = np.arange(lo - 8, lo + 32)
+    shell = np.stack(np.meshgrid(B + rr, B + rr, B + np.arange(-8, 24), indexing="ij"), -1).reshape(-1, 3)
+    inside = np.all((shell >= [B + lo, B + lo, B]) & (shell < [B + lo + 16, B + lo + 16, B + 16]), axis=1)
+    free = shell[~inside].astype(np.uint16)
+    for _ in range(3):
+        ow.updateOccupancy(free, occ)
+    assert ow.tree_node_count() < 3 * len(free)          # the occupied cube is one node, not 4096
+    hm = HostMap(lib, ow)
+    # boxes whose min faces touch the cube's max faces, boxes that overlap it, boxes one voxel away
+    g = np.arange(lo + 12, lo + 24)
+    gx, gy, gz = np.meshgrid(g, g, np.arange(12, 22), indexing="ij")
+    for off in (0.0, 0.5):
+        pts = np.stack([(gx.ravel() + off) * res, (gy.ravel() + off) * res, (gz.ravel() + off) * res], 1)
+        for size in ([2 * res] * 3, [res] * 3, [4 * res, 2 * res, 6 * res]):
+            want = ow.getCellStatusBoundingBox(pts, size)
+            got = hm.bbox(pts, size, 32)
+            bad = np.flatnonzero(got != want)
+            assert bad.size == 0, (off, size, bad[:5], pts[bad[:5]], got[bad[:5]], want[bad[:5]])
+            assert {0, 1} <= set(np.unique(want).tolist())
+    hm.close()
+
+
 @pytest.mark.parametrize("res", [0.25, 0.125])
 def test_face_aligned_boxes_at_binary_resolutions(lib, res):
     """Box faces exactly on voxel faces (exactly representable coordinates), solid occupied boxes
