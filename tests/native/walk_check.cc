@@ -2,7 +2,8 @@
 // test-suite, driven by tests/test_walk_host_emulation.py.  The checker below marks one scan's
 // free voxels three ways and the Python side compares them:
 //   walk_plain        walk_ray (the straightforward DDA)      -> marks through window_index()
-//   walk_segmented    ray_checkpoints + walk_slot_dilated     -> marks through dilated addresses
+//   walk_segmented    ray_checkpoints + walk_slot (the default walker) or walk_slot_dilated
+//                     (experimental walkers)                 -> marks through block / dilated addresses
 // and hands individual rays' keys to Python for comparison with the oracle's computeRayKeys.
 #include "../../volumetric_mapping_b200/csrc/vmap_walk.cuh"
 
@@ -152,7 +153,12 @@ int wc_walk_segmented(double res, double max_free_space, double min_height, cons
       if (jj >= cps[r].size()) continue;
       emitted = 0;
 #define WC_SLOT(F, M) walk_slot_dilated<F, M>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest)
-      if (P.free_filter) { if (mode == 1) WC_SLOT(true, 1); else WC_SLOT(true, 0); }
+      // mode 3: the default walker (block addressing); its `variant` argument encodes the near limit
+      const int variant = near_limit == 0xFFFFFFFFu ? 0 : (near_limit == 0u ? 2 : (int)near_limit);
+      if (mode == 3) {
+        if (P.free_filter) walk_slot<true>(P, ms, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], variant, &emitted, &longest);
+        else walk_slot<false>(P, ms, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], variant, &emitted, &longest);
+      } else if (P.free_filter) { if (mode == 1) WC_SLOT(true, 1); else WC_SLOT(true, 0); }
       else { if (mode == 1) WC_SLOT(false, 1); else WC_SLOT(false, 0); }
 #undef WC_SLOT
       trav += emitted;

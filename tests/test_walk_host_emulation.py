@@ -3,8 +3,9 @@ cuda_host_shim.h) and run one "thread" at a time on the CPU:
 
 * walk_ray (vmap_device.cuh, the DDA every query / emit kernel uses) against the oracle's
   computeRayKeys, key by key;
-* ray_checkpoints + walk_slot_dilated (vmap_walk.cuh: exact ray segmentation with the dilated
-  window addressing) against walk_ray's marks for whole scans -- identical free-mask words,
+* ray_checkpoints + walk_slot (vmap_walk.cuh: exact ray segmentation, the walker that ships) and
+  + walk_slot_dilated (the experimental addressing / near-field variants) against walk_ray's marks
+  for whole scans -- identical free-mask words,
   touched bitmap, traversal count and longest ray, with and without the free-space filter,
   including rays that end inside the origin voxel's block, axis-parallel rays, ties and rays
   longer than KeyRay's capacity.
@@ -64,8 +65,8 @@ def run_both(L, res, origin, ends, max_free=0.0, min_height=0.0, near_limit=48):
     ob, dims = window_for(res, origin, ends)
     n_blocks = int(dims[0]) * int(dims[1]) * int(dims[2])
     out = []
-    modes = ("plain", "seg0", "seg1") if max_free else ("plain", "seg0", "seg1", "seg2")
-    for which in modes:      # seg0 / seg1: walk_slot_dilated<., mode>; seg2: near-field combining schedule
+    modes = ("plain", "seg3", "seg0", "seg1") if max_free else ("plain", "seg3", "seg0", "seg1", "seg2")
+    for which in modes:      # seg3: walk_slot (the default walker); seg0 / seg1: walk_slot_dilated<., mode>; seg2: near-field combining schedule
         fm = np.zeros(n_blocks * 16, np.uint32)
         tb = np.zeros((n_blocks + 31) // 32, np.uint32)
         stats = np.zeros(5, np.uint64)
@@ -85,7 +86,7 @@ def run_both(L, res, origin, ends, max_free=0.0, min_height=0.0, near_limit=48):
         bad = np.flatnonzero(fa != fb)
         assert bad.size == 0, (bad[:5], fa[bad[:5]], fb[bad[:5]])
         assert np.array_equal(ta, tb_)
-    return sa, out[-1][2] if len(out) == 4 else out[1][2]
+    return sa, out[-1][2] if len(out) == 5 else out[1][2]
 
 
 def lidar_rays(n_elev, n_azim, seed, yaw):

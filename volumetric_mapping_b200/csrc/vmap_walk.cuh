@@ -95,6 +95,94 @@ __device__ __forceinline__ bool segment_inside_window(const MarkSet& ms, uint32_
          ((hi1 >> 3) < ms.y0 + (int)ms.ny) && ((lo2 >> 3) >= ms.z0) && ((hi2 >> 3) < ms.z0 + (int)ms.nz);
 }
 
+// K2b body, block addressing (the default walker).  One (segment level j, ray) work slot: performs
+// the DDA steps whose crossing parameter is in [j, j+1) * dtau and emits the voxels those steps
+// enter (segment 0 also the origin voxel); only the last segment can see computeRayKeys'
+// termination tests fire.  Marks go to the dense window.
+template <bool kFilter>
+__device__ __forceinline__ void walk_slot(const DevParams& P, const MarkSet& ms, Counters* cnt, const Checkpoint& cp,
+                                          const RayRec& rr, uint32_t j, float ox, float oy, float oz, int variant,
+                                          uint32_t* emitted_io, uint32_t* longest_io) {
+  uint32_t emitted = *emitted_io, longest = *longest_io;
+  RayWalk w;
+  w.c0 = cp.c01 & 0xFFFFu; w.c1 = cp.c01 >> 16; w.c2 = cp.c2;
+  w.e0 = rr.e01 & 0xFFFFu; w.e1 = rr.e01 >> 16; w.e2 = rr.e2s & 0xFFFFu;
+  const uint32_t sc = rr.e2s >> 16;
+  w.s0 = (sc & 3u) == 1u ? 1 : ((sc & 3u) == 2u ? -1 : 0);
+  w.s1 = ((sc >> 2) & 3u) == 1u ? 1 : (((sc >> 2) & 3u) == 2u ? -1 : 0);
+  w.s2 = ((sc >> 4) & 3u) == 1u ? 1 : (((sc >> 4) & 3u) == 2u ? -1 : 0);
+  w.t0 = cp.t0; w.t1 = cp.t1; w.t2 = cp.t2;
+  w.dt0 = rr.dt0; w.dt1 = rr.dt1; w.dt2 = rr.dt2;
+  w.dlen = rr.dlen;
+  w.live = true;
+  w.pick();
+  const bool last = (j + 1 == rr.n_seg);
+  const double tau_end = __dmul_rn((double)(j + 1), rr.dtau);
+  uint32_t count = cp.count;
+  const uint32_t count0 = count;
+  // Every voxel of the ray lies between the segment's first voxel and the ray's end voxel
+  // (each key coordinate moves monotonically; one voxel of slack for a walk that misses the
+  // end voxel): one window test per segment instead of one per step.
+  {
+    const int lo0 = (int)min(w.c0, w.e0) - 1, hi0 = (int)max(w.c0, w.e0) + 1;
+    const int lo1 = (int)min(w.c1, w.e1) - 1, hi1 = (int)max(w.c1, w.e1) + 1;
+    const int lo2 = (int)min(w.c2, w.e2) - 1, hi2 = (int)max(w.c2, w.e2) + 1;
+    const bool inside = ((lo0 >> 3) >= ms.x0) && ((hi0 >> 3) < ms.x0 + (int)ms.nx) && ((lo1 >> 3) >= ms.y0) &&
+                        ((hi1 >> 3) < ms.y0 + (int)ms.ny) && ((lo2 >> 3) >= ms.z0) && ((hi2 >> 3) < ms.z0 + (int)ms.nz);
+    if (!inside) {   // the host re-runs the scan in table mode
+      atomicExch(&cnt->overflow_window, 1u);
+      return;
+    }
+  }
+  // cur: mask word in flight (window block * 16 + word), bits: voxels collected for it,
+  // seen: its value when the ray entered it -- near the sensor every ray sets the same voxels,
+  // so there a RED is only issued for bits not visible yet (a stale value costs a redundant
+  // RED, never a lost bit).  The block's touched bit is tested before it is set for the same
+  // reason.
+  uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0;
+  const uint32_t near_limit = (variant == 0) ? 0xFFFFFFFFu : (variant == 2 ? 0u : (uint32_t)variant);
+  auto emit = [&]() {
+    if (kFilter && !free_filter_pass(P, ox, oy, oz, w.c0, w.c1, w.c2)) return;
+    const uint32_t idx = (((w.c2 >> 3) - (uint32_t)ms.z0) * ms.ny + ((w.c1 >> 3) - (uint32_t)ms.y0)) * ms.nx +
+                         ((w.c0 >> 3) - (uint32_t)ms.x0);
+    const uint32_t l = local_index(w.c0, w.c1, w.c2);
+    const uint32_t wi = (idx << 4) | (l >> 5);
+    if (wi != cur) {
+      if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
+      if ((wi >> 4) != (cur >> 4)) {
+        uint32_t* tb = ms.touched_bits + (idx >> 5);
+        if (!((*tb >> (idx & 31u)) & 1u)) atomicOr(tb, 1u << (idx & 31u));
+      }
+      bits = 0;
+      cur = wi;
+      seen = (count < near_limit) ? ms.free_mask[wi] : 0u;
+    }
+    bits |= 1u << (l & 31u);
+  };
+  if (j == 0) emit();                 // the origin voxel belongs to segment 0
+  if (last) {
+    for (;;) {
+      if (!w.advance()) break;                     // cur == end, or min(tMax) > length
+      if (count >= kKeyRayMax - 1u) break;         // KeyRay capacity
+      ++count;
+      emit();
+    }
+  } else {
+    // steps whose crossing parameter is below tau_end; the termination tests cannot fire here
+    while (w.tmin() < tau_end) {
+      w.advance_inner();
+      if (count >= kKeyRayMax - 1u) break;
+      ++count;
+      emit();
+    }
+  }
+  if (bits & ~seen) atomicOr(ms.free_mask + cur, bits);
+  emitted += count - count0 + (j == 0 ? 1u : 0u);
+  if (last) longest = max(longest, count);
+  *emitted_io = emitted;
+  *longest_io = longest;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2b body, dilated addressing.  Needs a window whose x and y extents (in blocks) are powers of
 // two: the bit address of a voxel in the window's free-mask array is then the concatenation
