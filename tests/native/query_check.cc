@@ -80,4 +80,45 @@ void qc_bbox_status(void* p, double res, float occ_thres, int treat_unknown_as_o
     status[i] = bbox_combine(P, decided, occ, unk);
   }
 }
+
+static DevParams qc_params(double res, float occ_thres, int treat_unknown_as_occupied) {
+  DevParams P;
+  memset(&P, 0, sizeof(P));
+  P.res = res;
+  P.res_factor = 1.0 / res;
+  P.occ_thres = occ_thres;
+  P.treat_unknown_as_occupied = treat_unknown_as_occupied;
+  return P;
+}
+
+// getCellStatusPoint (true_status 0) / getCellTrueStatusPoint (1); logodds may be NULL
+void qc_point_status(void* p, double res, float occ_thres, int unk, const double* xyz, size_t n, int true_status,
+                     uint8_t* status, float* logodds) {
+  HostMap* hm = static_cast<HostMap*>(p);
+  const DevParams P = qc_params(res, occ_thres, unk);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t bits;
+    status[i] = point_status(P, hm->view, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], true_status, &bits);
+    if (logodds) logodds[i] = __uint_as_float(bits == kUnknownBits ? 0x7FC00000u : bits);
+  }
+}
+
+// getLineStatus
+void qc_line_status(void* p, double res, float occ_thres, int unk, const double* ab, size_t n, uint8_t* status) {
+  HostMap* hm = static_cast<HostMap*>(p);
+  const DevParams P = qc_params(res, occ_thres, unk);
+  for (size_t i = 0; i < n; i++)
+    status[i] = line_status(P, hm->view, (float)ab[6 * i], (float)ab[6 * i + 1], (float)ab[6 * i + 2], (float)ab[6 * i + 3],
+                            (float)ab[6 * i + 4], (float)ab[6 * i + 5]);
+}
+
+// getVisibility
+void qc_visibility(void* p, double res, float occ_thres, int unk, const double* ab, size_t n, int stop_at_unknown,
+                   uint8_t* status) {
+  HostMap* hm = static_cast<HostMap*>(p);
+  const DevParams P = qc_params(res, occ_thres, unk);
+  for (size_t i = 0; i < n; i++)
+    status[i] = visibility_status(P, hm->view, (float)ab[6 * i], (float)ab[6 * i + 1], (float)ab[6 * i + 2],
+                                  (float)ab[6 * i + 3], (float)ab[6 * i + 4], (float)ab[6 * i + 5], stop_at_unknown);
+}
 }

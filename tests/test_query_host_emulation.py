@@ -33,6 +33,9 @@ def lib():
     L.qc_map_create.restype = vp
     L.qc_map_destroy.argtypes = [vp]
     L.qc_bbox_status.argtypes = [vp, C.c_double, C.c_float, C.c_int, vp, C.c_size_t, vp, C.c_uint32, vp]
+    L.qc_point_status.argtypes = [vp, C.c_double, C.c_float, C.c_int, vp, C.c_size_t, C.c_int, vp, vp]
+    L.qc_line_status.argtypes = [vp, C.c_double, C.c_float, C.c_int, vp, C.c_size_t, vp]
+    L.qc_visibility.argtypes = [vp, C.c_double, C.c_float, C.c_int, vp, C.c_size_t, C.c_int, vp]
     return L
 
 
@@ -54,6 +57,27 @@ class HostMap:
         st = np.zeros(len(xyz), np.uint8)
         self.L.qc_bbox_status(self.h, self.res, self.occ, self.unk, xyz.ctypes.data, len(xyz), size.ctypes.data,
                               lanes, st.ctypes.data)
+        return st
+
+    def points(self, xyz, true_status=0):
+        xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+        st = np.zeros(len(xyz), np.uint8)
+        lo = np.zeros(len(xyz), np.float32)
+        self.L.qc_point_status(self.h, self.res, self.occ, self.unk, xyz.ctypes.data, len(xyz), true_status,
+                               st.ctypes.data, lo.ctypes.data)
+        return st, lo
+
+    def lines(self, ab):
+        ab = np.ascontiguousarray(ab, np.float64).reshape(-1, 6)
+        st = np.zeros(len(ab), np.uint8)
+        self.L.qc_line_status(self.h, self.res, self.occ, self.unk, ab.ctypes.data, len(ab), st.ctypes.data)
+        return st
+
+    def visibility(self, ab, stop_at_unknown):
+        ab = np.ascontiguousarray(ab, np.float64).reshape(-1, 6)
+        st = np.zeros(len(ab), np.uint8)
+        self.L.qc_visibility(self.h, self.res, self.occ, self.unk, ab.ctypes.data, len(ab), int(stop_at_unknown),
+                             st.ctypes.data)
         return st
 
     def close(self):
@@ -213,4 +237,36 @@ def test_path_collision_index(lib):
     first = np.flatnonzero(st == 1)          # unknown is not a collision when it is not treated as occupied
     assert hit == (first.size > 0)
     assert hit and idx == int(first[0]) and 0 < idx < 90
+    hm.close()
+
+
+@pytest.mark.parametrize("res,unk", [(0.1, True), (0.15, False)])
+def test_point_line_and_visibility_queries_match_oracle(lib, res, unk):
+    """The per-thread bodies of k_query_points / k_query_lines / k_query_visibility (the kernels
+    the GPU suite checks end to end) on the CPU."""
+    ow = build_world(res, unk)
+    hm = HostMap(lib, ow)
+    rng = np.random.default_rng(11)
+    pts = rng.uniform([-8, -7, -1.0], [9, 8, 3.5], size=(20000, 3))
+    pts[:5] = [[4000.0, 0, 0], [0, 0, -3300.0], [np.nan, 0, 0], [0.05, 0.05, 1.25], [1e12, -1e12, 0]]
+    st, lo = hm.points(pts)
+    assert np.array_equal(st, ow.getCellStatusPoint(pts))
+    want_st, want_p = ow.getCellProbabilityPoint(pts)
+    st_true, lo = hm.points(pts, true_status=1)
+    assert np.array_equal(st_true, want_st)
+    known = want_st != 2
+    p = 1.0 - 1.0 / (1.0 + np.exp(lo[known].astype(np.float64)))      # OcTreeNode::getOccupancy()
+    assert np.array_equal(p, want_p[known]) and np.all(np.isnan(lo[~known]))
+    a = rng.uniform([-7, -6, 0.0], [8, 7, 3.0], size=(6000, 3))
+    d = rng.normal(size=(6000, 3))
+    b = a + d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.05, 9.0, (6000, 1))
+    ab = np.hstack([a, b])
+    ab[0] = [0.05, 0.05, 1.2, 0.05, 0.05, 1.2]               # same voxel: empty ray -> free
+    ab[1] = [0.05, 0.05, 1.2, 5000.0, 0.0, 1.2]              # end outside the map: no keys -> free
+    want = ow.getLineStatus(ab)
+    got = hm.lines(ab)
+    assert np.array_equal(got, want)
+    assert set(np.unique(want).tolist()) >= ({0, 1} if unk else {0, 1, 2})
+    for stop in (0, 1):
+        assert np.array_equal(hm.visibility(ab, stop), ow.getVisibility(ab, stop))
     hm.close()

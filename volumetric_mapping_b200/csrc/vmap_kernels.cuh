@@ -1081,18 +1081,6 @@ __global__ void __launch_bounds__(256) k_to_max_likelihood(DevParams P, MapView 
 // ---------------------------------------------------------------------------------------------
 // K5 queries
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint8_t voxel_status(const DevParams& P, const MapView& m, uint32_t h,
-                                                uint32_t kx, uint32_t ky, uint32_t kz) {
-  uint32_t bits = kUnknownBits;
-  if (h != kNotFound) {
-    const uint32_t slot = m.slot[h];
-    if (slot != kUnassigned)
-      bits = reinterpret_cast<const uint32_t*>(m.pool)[(size_t)slot * kBlockVoxels + local_index(kx, ky, kz)];
-  }
-  if (bits == kUnknownBits) return P.treat_unknown_as_occupied ? 1 : 2;
-  return (__uint_as_float(bits) >= P.occ_thres) ? 1 : 0;   // isNodeOccupied
-}
-
 // getCellStatusPoint: octree_->search(x,y,z) quantises the DOUBLE coordinates.
 //   true_status == 0 : getCellStatusPoint      (octomap_world.cc:346-360; unknown -> occupied when configured)
 //   true_status == 1 : getCellTrueStatusPoint  (:363-373; unknown stays unknown)
@@ -1102,40 +1090,10 @@ k_query_points(DevParams P, MapView m, const double* __restrict__ xyz, uint32_t 
                uint8_t* __restrict__ status, int true_status, float* __restrict__ logodds) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int s0 = scaled_coord(P.res_factor, xyz[3 * i]);
-  const int s1 = scaled_coord(P.res_factor, xyz[3 * i + 1]);
-  const int s2 = scaled_coord(P.res_factor, xyz[3 * i + 2]);
-  uint32_t bits = kUnknownBits;
-  if (key_in_range(s0) && key_in_range(s1) && key_in_range(s2)) {   // else search() returns NULL
-    const uint32_t h = find_block(m, block_key(s0, s1, s2));
-    if (h != kNotFound) {
-      const uint32_t slot = m.slot[h];
-      if (slot != kUnassigned)
-        bits = reinterpret_cast<const uint32_t*>(m.pool)[(size_t)slot * kBlockVoxels + local_index(s0, s1, s2)];
-    }
-  }
-  uint8_t st;
-  if (bits == kUnknownBits) st = (P.treat_unknown_as_occupied && !true_status) ? 1 : 2;
-  else st = (__uint_as_float(bits) >= P.occ_thres) ? 1 : 0;
+  uint32_t bits;
+  const uint8_t st = point_status(P, m, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], true_status, &bits);
   status[i] = st;
   if (logodds) logodds[i] = __uint_as_float(bits == kUnknownBits ? 0x7FC00000u : bits);
-}
-
-// getLineStatus on float end points: status of the first non-free voxel in DDA order, end voxel
-// excluded (octomap_world.cc:395-418).
-__device__ __forceinline__ uint8_t line_status(const DevParams& P, const MapView& m, float ax, float ay,
-                                               float az, float bx, float by, float bz) {
-  uint8_t st = 0;
-  unsigned long long cached_b = kEmpty;
-  uint32_t cached_h = kNotFound;
-  walk_ray(P, ax, ay, az, bx, by, bz, [&](uint32_t kx, uint32_t ky, uint32_t kz) {
-    const unsigned long long b = block_key(kx, ky, kz);
-    if (b != cached_b) { cached_b = b; cached_h = find_block(m, b); }
-    const uint8_t s = voxel_status(P, m, cached_h, kx, ky, kz);
-    if (s != 0) { st = s; return false; }
-    return true;
-  });
-  return st;
 }
 
 __global__ void __launch_bounds__(128)
@@ -1156,34 +1114,8 @@ k_query_visibility(DevParams P, MapView m, const double* __restrict__ ab, uint32
                    uint8_t* __restrict__ status) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float ax = (float)ab[6 * i], ay = (float)ab[6 * i + 1], az = (float)ab[6 * i + 2];
-  const float bx = (float)ab[6 * i + 3], by = (float)ab[6 * i + 4], bz = (float)ab[6 * i + 5];
-  // coordToKey (unchecked, wraps) of the voxel under test
-  const uint32_t t0 = (uint32_t)scaled_coord(P.res_factor, (double)bx) & 0xFFFFu;
-  const uint32_t t1 = (uint32_t)scaled_coord(P.res_factor, (double)by) & 0xFFFFu;
-  const uint32_t t2 = (uint32_t)scaled_coord(P.res_factor, (double)bz) & 0xFFFFu;
-  uint8_t st = 0;
-  unsigned long long cached_b = kEmpty;
-  uint32_t cached_h = kNotFound;
-  walk_ray(P, ax, ay, az, bx, by, bz, [&](uint32_t kx, uint32_t ky, uint32_t kz) {
-    if (kx == t0 && ky == t1 && kz == t2) return true;
-    const unsigned long long b = block_key(kx, ky, kz);
-    if (b != cached_b) { cached_b = b; cached_h = find_block(m, b); }
-    uint32_t bits = kUnknownBits;
-    if (cached_h != kNotFound) {
-      const uint32_t slot = m.slot[cached_h];
-      if (slot != kUnassigned)
-        bits = reinterpret_cast<const uint32_t*>(m.pool)[(size_t)slot * kBlockVoxels + local_index(kx, ky, kz)];
-    }
-    if (bits == kUnknownBits) {
-      if (stop_at_unknown) { st = 2; return false; }
-    } else if (__uint_as_float(bits) >= P.occ_thres) {
-      st = 1;
-      return false;
-    }
-    return true;
-  });
-  status[i] = st;
+  status[i] = visibility_status(P, m, (float)ab[6 * i], (float)ab[6 * i + 1], (float)ab[6 * i + 2], (float)ab[6 * i + 3],
+                                (float)ab[6 * i + 4], (float)ab[6 * i + 5], stop_at_unknown);
 }
 
 // getLineStatusBoundingBox (octomap_world.cc:451-493): the reference shifts the segment by every
