@@ -17,6 +17,7 @@
 #include "vmap_seq.cuh"
 #include "vmap_walk.cuh"
 #include "vmap_query.cuh"
+#include "vmap_front.cuh"
 
 namespace vmapdev {
 
@@ -41,13 +42,6 @@ struct ScanBuffers {
   unsigned long long* first_keys;  // [first_cap] per-scan table: endpoint key -> first index
   uint32_t* first_idx;             // [first_cap]
   uint32_t first_mask;
-};
-
-struct Transform {
-  double m[12];   // row-major 3x4 of getTransformationMatrix()
-  double q[4];    // w x y z
-  double t[3];
-  float origin[3];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -91,42 +85,13 @@ __device__ __forceinline__ void classify_point(const DevParams& P, const ScanBuf
   sb.world[3 * i + 0] = px;
   sb.world[3 * i + 1] = py;
   sb.world[3 * i + 2] = pz;
-  const int s0 = scaled_coord(P.res_factor, (double)px);
-  const int s1 = scaled_coord(P.res_factor, (double)py);
-  const int s2 = scaled_coord(P.res_factor, (double)pz);
-  const unsigned long long key = (unsigned long long)((uint32_t)s0 & 0xFFFFu) |
-                                 ((unsigned long long)((uint32_t)s1 & 0xFFFFu) << 16) |
-                                 ((unsigned long long)((uint32_t)s2 & 0xFFFFu) << 32);
-  const bool bound = key_in_range(s0) && key_in_range(s1) && key_in_range(s2);
-  // castRay: (point - sensor_origin).norm() <= sensor_max_range, norm() in double on a float sum
-  float dx = __fsub_rn(px, origin[0]), dy = __fsub_rn(py, origin[1]), dz = __fsub_rn(pz, origin[2]);
-  const double len = __dsqrt_rn((double)norm_sq_f(dx, dy, dz));
-  const bool in_range = (P.max_range < 0.0) || (len <= P.max_range);
-  float ex = px, ey = py, ez = pz;
-  if (!in_range) {
-    // new_end = origin + (point - origin).normalized() * sensor_max_range   (all float)
-    if (len > 0) {
-      const float fl = (float)len;
-      dx = __fdiv_rn(dx, fl); dy = __fdiv_rn(dy, fl); dz = __fdiv_rn(dz, fl);
-    }
-    const float mr = (float)P.max_range;
-    ex = __fadd_rn(origin[0], __fmul_rn(dx, mr));
-    ey = __fadd_rn(origin[1], __fmul_rn(dy, mr));
-    ez = __fadd_rn(origin[2], __fmul_rn(dz, mr));
-  }
-  sb.ray_end[3 * i + 0] = ex;
-  sb.ray_end[3 * i + 1] = ey;
-  sb.ray_end[3 * i + 2] = ez;
-  {
-    // number of DDA steps the ray will take (exact up to rounding): orders the work list
-    const int o0 = scaled_coord(P.res_factor, (double)origin[0]), o1 = scaled_coord(P.res_factor, (double)origin[1]),
-              o2 = scaled_coord(P.res_factor, (double)origin[2]);
-    const int e0 = scaled_coord(P.res_factor, (double)ex), e1 = scaled_coord(P.res_factor, (double)ey),
-              e2 = scaled_coord(P.res_factor, (double)ez);
-    const bool walk = key_in_range(o0) && key_in_range(o1) && key_in_range(o2) && key_in_range(e0) &&
-                      key_in_range(e1) && key_in_range(e2);
-    sb.len[i] = walk ? (uint32_t)(abs(e0 - o0) + abs(e1 - o1) + abs(e2 - o2)) : 0u;
-  }
+  const PointClass c = classify_math(P, origin, px, py, pz);
+  const unsigned long long key = c.key;
+  const bool bound = c.bound, in_range = c.in_range;
+  sb.ray_end[3 * i + 0] = c.ex;
+  sb.ray_end[3 * i + 1] = c.ey;
+  sb.ray_end[3 * i + 2] = c.ez;
+  sb.len[i] = c.len;
   sb.key[i] = key;
   sb.flags[i] = (uint8_t)(kFlagValid | (in_range ? kFlagRange : 0u) | (bound ? kFlagBound : 0u));
   if (in_range && bound) first_insert(sb, key, i);
@@ -152,35 +117,16 @@ k_front_cloud(DevParams P, ScanBuffers sb, Counters* cnt, Transform T, const uin
     sb.world[3 * i] = fx; sb.world[3 * i + 1] = fy; sb.world[3 * i + 2] = fz;
     return;
   }
-  const double x = fx, y = fy, z = fz;
-  // static_cast<float>(m(r,0)*x + m(r,1)*y + m(r,2)*z + m(r,3)), left to right, double
-  const float wx = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.m[0], x), __dmul_rn(T.m[1], y)), __dmul_rn(T.m[2], z)), T.m[3]);
-  const float wy = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.m[4], x), __dmul_rn(T.m[5], y)), __dmul_rn(T.m[6], z)), T.m[7]);
-  const float wz = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T.m[8], x), __dmul_rn(T.m[9], y)), __dmul_rn(T.m[10], z)), T.m[11]);
+  float wx, wy, wz;
+  matrix_transform(T, fx, fy, fz, &wx, &wy, &wz);
   classify_point(P, sb, cnt, T.origin, i, wx, wy, wz);
-}
-
-// Eigen::Quaterniond::_transformVector(v) + t  (kindr QuatTransformation::operator*)
-__device__ __forceinline__ void quat_transform(const Transform& T, double vx, double vy, double vz,
-                                               double* ox, double* oy, double* oz) {
-  const double w = T.q[0], x = T.q[1], y = T.q[2], z = T.q[3];
-  double u0 = __dsub_rn(__dmul_rn(y, vz), __dmul_rn(z, vy));
-  double u1 = __dsub_rn(__dmul_rn(z, vx), __dmul_rn(x, vz));
-  double u2 = __dsub_rn(__dmul_rn(x, vy), __dmul_rn(y, vx));
-  u0 = __dadd_rn(u0, u0); u1 = __dadd_rn(u1, u1); u2 = __dadd_rn(u2, u2);
-  const double c0 = __dsub_rn(__dmul_rn(y, u2), __dmul_rn(z, u1));
-  const double c1 = __dsub_rn(__dmul_rn(z, u0), __dmul_rn(x, u2));
-  const double c2 = __dsub_rn(__dmul_rn(x, u1), __dmul_rn(y, u0));
-  *ox = __dadd_rn(__dadd_rn(__dadd_rn(vx, __dmul_rn(w, u0)), c0), T.t[0]);
-  *oy = __dadd_rn(__dadd_rn(__dadd_rn(vy, __dmul_rn(w, u1)), c1), T.t[1]);
-  *oz = __dadd_rn(__dadd_rn(__dadd_rn(vz, __dmul_rn(w, u2)), c2), T.t[2]);
 }
 
 __device__ __forceinline__ void projected_point(const DevParams& P, const ScanBuffers& sb,
                                                 Counters* cnt, const Transform& T, uint32_t i,
                                                 float sx, float sy, float sz) {
   // isValidPoint(pt) && !(pt.z < 0)   (octomap_world.cc:156, 232-236)
-  const bool valid = (sz != 10000.0f) && !isinf(sz) && !(sz < 0.0f);
+  const bool valid = projected_valid(sz);
   if (!valid) {
     sb.flags[i] = 0;
     return;
@@ -214,25 +160,6 @@ k_min_disparity(Counters* cnt, const uint8_t* __restrict__ img, int rows, int co
   for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, o));
   if ((threadIdx.x & 31) == 0 && best != 0xFFFFFFFFu) atomicMin(&cnt->min_disparity_ord, best);
 }
-
-// cv::reprojectImageTo3D, OpenCV 4.13 arithmetic: one pixel.
-__device__ __forceinline__ void reproject_pixel(const double* Q, double min_disp, uint32_t u,
-                                                uint32_t v, float disp, float* X, float* Y, float* Z) {
-  const double x = (double)u, y = (double)v, d = (double)disp;
-  double h[4];
-#pragma unroll
-  for (int r = 0; r < 4; r++)
-    h[r] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(Q[4 * r], x), __dmul_rn(Q[4 * r + 1], y)),
-                               __dmul_rn(Q[4 * r + 2], d)),
-                     __dmul_rn(Q[4 * r + 3], 1.0));
-  const double iw = __ddiv_rn(1.0, h[3]);
-  *X = (float)__dmul_rn((double)(float)h[0], iw);
-  *Y = (float)__dmul_rn((double)(float)h[1], iw);
-  *Z = (float)__dmul_rn((double)(float)h[2], iw);
-  if (fabs(__dsub_rn(d, min_disp)) <= 1.1920928955078125e-07) *Z = 10000.0f;
-}
-
-struct QMat { double q[16]; };
 
 // K1 (disparity): projection fused with validity test, quaternion transform and classification.
 __global__ void __launch_bounds__(256)
