@@ -58,3 +58,15 @@ void fc_classify(double res, double max_range, const float* origin, const float*
   }
 }
 }
+
+// updateNode's leaf arithmetic: apply a sequence of hits (1) / misses (0) to one voxel, starting
+// from "no node"; returns the final value bits
+extern "C" uint32_t fc_update_sequence(const uint8_t* hits, size_t n, float hit, float miss, float cmin, float cmax,
+                                       uint32_t* trace) {
+  uint32_t bits = kUnknownBits;
+  for (size_t i = 0; i < n; i++) {
+    bits = update_leaf(bits, hits[i] ? hit : miss, cmin, cmax);
+    if (trace) trace[i] = bits;
+  }
+  return bits;
+}

@@ -136,3 +136,24 @@ def test_classify_math_is_castray_arithmetic(lib, res, max_range):
     assert np.array_equal(ln.astype(np.int64), want_len)
     if max_range > 0:
         assert 0.05 < in_range.mean() < 0.95
+
+
+def test_update_leaf_ladders_match_oracle(lib):
+    """updateNode / updateNodeLogOdds on one voxel (early abort at the clamps, new node = 0,
+    clamp order): the product's update_leaf against the oracle's tree, step by step."""
+    lib.fc_update_sequence.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    lib.fc_update_sequence.restype = C.c_uint32
+    rng = np.random.default_rng(3)
+    for params in ({}, {"probability_hit": 0.9, "probability_miss": 0.2, "threshold_min": 0.3, "threshold_max": 0.8}):
+        for trial in range(6):
+            ow = oracle.OracleWorld(resolution=0.1, **params)
+            hit, miss, cmin, cmax, _ = (np.float32(v) for v in ow.logodds_constants())
+            seq = (rng.random(60) < (0.2 + 0.12 * trial)).astype(np.uint8)
+            trace = np.zeros(len(seq), np.uint32)
+            lib.fc_update_sequence(seq.ctypes.data, len(seq), hit, miss, cmin, cmax, trace.ctypes.data)
+            key = np.array([[32768 + 3, 32768 - 4, 32768 + 5]], np.uint16)
+            none = np.zeros((0, 3), np.uint16)
+            for i, h in enumerate(seq):
+                ow.updateOccupancy(none if h else key, key if h else none)
+                _, v = ow.export_leaves()
+                assert len(v) == 1 and np.float32(v[0]).view(np.uint32) == trace[i], (params, trial, i)
