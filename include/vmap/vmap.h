@@ -249,6 +249,14 @@ VMAP_API int vmap_host_parse_stream(const vmap_params* params, int kind, const u
                                     size_t n_bytes, uint16_t* keys_k3, float* logodds,
                                     size_t capacity, size_t* n_leaves, double* resolution);
 
+/* Pipelined vmap_insert_pointcloud for scans streamed from host memory: vmap_stage_pointcloud
+ * starts an asynchronous host->device copy of a scan (the host buffer, ideally pinned, must stay
+ * untouched until the matching vmap_insert_staged returns); vmap_insert_staged inserts the oldest
+ * staged scan exactly like vmap_insert_pointcloud_dev.  Staging scan k+1 before inserting scan k
+ * overlaps its copy with scan k's kernels.  At most two scans can be staged. */
+VMAP_API int vmap_stage_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes);
+VMAP_API int vmap_insert_staged(vmap* h, int is_dense, const double T_rowmajor[16]);
+
 /* OctomapManager::loadOctomapCallback's point-cloud branch (octomap_manager.cc:313-344): every
  * point of a .pcd / .ply file whose key lies inside the map becomes an occupied key; the free set
  * stays empty; updateOccupancy applies them.  vmap_insert_occupied_points is the same for points

@@ -87,6 +87,7 @@ SYMBOLS = [
     "vmap_dist_flush", "vmap_dist_set_batch", "vmap_set_debug_l2_flush", "vmap_query_points_probability",
     "vmap_query_visibility", "vmap_query_lines_bbox", "vmap_tree_size", "vmap_serialize_bt", "vmap_write_bt", "vmap_load_bt", "vmap_deserialize_bt", "vmap_serialize_ot", "vmap_deserialize_ot", "vmap_set_log_odds_bbox", "vmap_get_changed", "vmap_host_tree_stream", "vmap_host_parse_stream",
     "vmap_query_bbox_status", "vmap_query_bbox_status_dev", "vmap_check_path_collisions",
+    "vmap_stage_pointcloud", "vmap_insert_staged",
     "vmap_load_occupied_pointcloud_file", "vmap_insert_occupied_points", "vmap_host_read_pointcloud_file",
 ]
 
@@ -154,6 +155,8 @@ def lib():
     u64p = C.POINTER(C.c_uint64)
     L.vmap_tree_size.argtypes = [vp, C.c_int, C.POINTER(sz)]
     L.vmap_query_bbox_status.argtypes = [vp, vp, sz, dp, vp]
+    L.vmap_stage_pointcloud.argtypes = [vp, vp, sz, sz]
+    L.vmap_insert_staged.argtypes = [vp, C.c_int, dp]
     L.vmap_load_occupied_pointcloud_file.argtypes = [vp, C.c_char_p, C.POINTER(sz)]
     L.vmap_insert_occupied_points.argtypes = [vp, vp, sz, sz]
     L.vmap_host_read_pointcloud_file.argtypes = [C.c_char_p, vp, sz, C.POINTER(sz)]

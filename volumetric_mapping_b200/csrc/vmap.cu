@@ -120,6 +120,13 @@ struct vmap {
   uint32_t* chg1_store = nullptr;
   int walk_variant = 48;  // near-field limit of the walker's read-before-RED filter (VMAP_WALK_VARIANT)
   int walk_ctas = 5;      // CTAs per SM of the segment walker's grid = resident CTAs at 48 registers (VMAP_WALK_CTAS)
+  // vmap_stage_pointcloud / vmap_insert_staged: two device staging buffers filled on their own stream
+  DevBuf stage[2];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  size_t stage_n[2] = {0, 0}, stage_stride[2] = {0, 0};
+  bool staged[2] = {false, false};
+  int stage_next = 0;         // slot the next vmap_stage_pointcloud fills
   int walk_order = 0;     // 1: golden-ratio chunk order in the dilated segment walker (VMAP_WALK_ORDER, experimental)
   int walk_addr = 0;      // 1: dilated window addressing in the segment walker (VMAP_WALK_ADDR, experimental)
   int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
@@ -1029,6 +1036,10 @@ int vmap_destroy(vmap* h) try {
   sort_free(h);
   free_window(h);
   cudaFree(h->chg0_store); cudaFree(h->chg1_store);
+  cudaFree(h->stage[0].p); cudaFree(h->stage[1].p);
+  for (auto& e : h->ev_stage)
+    if (e) cudaEventDestroy(e);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_persist) cudaFreeHost(h->h_persist);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1169,6 +1180,49 @@ static int check_image_args(vmap* h, const void* img, int rows, int cols, size_t
   if (pitch < (size_t)cols * px_bytes || (pitch & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "row pitch too small or not a multiple of 4");
   return VMAP_OK;
 }
+
+// Pipelined form of vmap_insert_pointcloud for callers that stream scans from host memory: stage
+// scan k+1 (asynchronous host->device copy on a stream of its own; the host buffer -- ideally
+// pinned -- must stay untouched until the matching vmap_insert_staged returns) while scan k is
+// being inserted.  Scans are inserted in the order they were staged; at most two may be staged.
+int vmap_stage_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes) try {
+  if (!h || (!xyz && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many points");
+  const int k = h->stage_next;
+  if (h->staged[k]) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "two scans are already staged: call vmap_insert_staged first");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (!h->copy_stream) {
+    VM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev_stage) VM_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const size_t bytes = n ? (n - 1) * stride_bytes + 12 : 0;
+  if (bytes > h->stage[k].cap) {
+    // (the slot is free: nothing in flight reads it; ensure() also drains the main stream)
+    VM_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    VM_TRY(ensure(h, &h->stage[k], bytes));
+  }
+  if (bytes) VM_CUDA(h, cudaMemcpyAsync(h->stage[k].p, xyz, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+  VM_CUDA(h, cudaEventRecord(h->ev_stage[k], h->copy_stream));
+  h->stage_n[k] = n;
+  h->stage_stride[k] = stride_bytes;
+  h->staged[k] = true;
+  h->stage_next = k ^ 1;
+  return VMAP_OK;
+} catch (...) { return vmap_on_exception(h); }
+
+int vmap_insert_staged(vmap* h, int is_dense, const double T_rowmajor[16]) try {
+  if (!h || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  // oldest staged slot: the one the next stage call would NOT fill, if it is staged; else the other
+  int k = h->stage_next;
+  if (!h->staged[k]) k ^= 1;
+  if (!h->staged[k]) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "no staged scan");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_stage[k], 0));
+  const int st = insert_cloud_common(h, (const uint8_t*)h->stage[k].p, h->stage_n[k], h->stage_stride[k], is_dense ? 1 : 0, T_rowmajor);
+  h->staged[k] = false;
+  return st;
+} catch (...) { return vmap_on_exception(h); }
 
 int vmap_insert_projected(vmap* h, const float* xyz_hw3, int rows, int cols, size_t row_pitch_bytes,
                           const double q_wxyz[4], const double t[3]) try {

@@ -243,6 +243,14 @@ class OctomapWorld:
                                                   st.ctypes.data))
         return st
 
+    def stagePointcloudHostPtr(self, host_ptr, n, stride_bytes=12):
+        """Start the asynchronous host->device copy of a scan (see vmap_stage_pointcloud)."""
+        self._check(self._L.vmap_stage_pointcloud(self._h, C.c_void_p(int(host_ptr)), int(n), int(stride_bytes)))
+
+    def insertStaged(self, T, is_dense=True):
+        Tm = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        self._check(self._L.vmap_insert_staged(self._h, int(bool(is_dense)), _dptr(Tm)))
+
     def loadOccupiedPointcloudFile(self, filename):
         """loadOctomapCallback's .pcd / .ply branch (octomap_manager.cc:313-344); returns the point count."""
         n = C.c_size_t(0)
