@@ -33,3 +33,13 @@ def test_occupied_pointcloud_loader_matches_oracle():
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0 and "CLOUD_LOAD_OK" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="first hardware run pending (pipelined host-memory insertion)")
+def test_staged_insertion_builds_the_same_map():
+    r = subprocess.run([sys.executable, os.path.join(HERE, "staged_check.py")], capture_output=True, text=True,
+                       timeout=240)
+    sys.stdout.write(r.stdout[-4000:])
+    sys.stderr.write(r.stderr[-4000:])
+    assert r.returncode == 0 and "STAGED_OK" in r.stdout
