@@ -404,11 +404,14 @@ class OcTree {
   void updateInnerOccupancy() {
     if (root) updateInnerOccupancyRecurs(root, 0);
   }
-  // OccupancyOcTreeBase::setNodeValue(point3d, float log_odds, lazy_eval = true): no clamping,
-  // out-of-bounds points are ignored, inner nodes are left stale (updateInnerOccupancy follows)
+  // OccupancyOcTreeBase::setNodeValue(point3d, float log_odds, lazy_eval = true): out-of-bounds
+  // points are ignored; the value is clamped to [clamping_thres_min, clamping_thres_max] ("clamp
+  // log odds within range" at the top of setNodeValue(key, ...)); inner nodes are left stale
+  // (updateInnerOccupancy follows)
   void setNodeValueLazy(const Vec3f& p, float log_odds_value) {
     Key key;
     if (!coordToKeyChecked(p, key)) return;
+    log_odds_value = std::min(std::max(log_odds_value, clamping_thres_min), clamping_thres_max);
     bool just_created = false;
     if (root == NULL) {
       root = new Node();

@@ -1,11 +1,10 @@
 """GPU parity of getCellStatusBoundingBox / checkPathForCollisionsWithRobot and of the
 occupied-only .pcd / .ply loader (8 f3).
 
-The per-lane body of this query (vmap_query.cuh) is checked against the oracle on the CPU by
-tests/test_query_host_emulation.py.  The kernel around it was written after the round's GPU budget
-was spent, so its first hardware run happens in the driver's round-end suite: the check runs in
-its own process and is marked xfail(strict=False) until it has passed on a B200 once (an XPASS in
-the report is that proof; remove the marker then)."""
+The per-lane body of this query (vmap_query.cuh) is also checked against the oracle on the CPU by
+tests/test_query_host_emulation.py.  Each check runs in its own process.  (All three passed on a
+B200 in the round-1 driver suite and again in round 2 -- gpurun_out r02_suite_baseline.log -- so the
+xfail markers they carried for their first hardware run are gone.)"""
 import os
 import subprocess
 import sys
@@ -16,7 +15,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first hardware run pending; CPU emulation of the same source passes")
 def test_bbox_status_and_path_collisions_match_oracle():
     r = subprocess.run([sys.executable, os.path.join(HERE, "bbox_check.py")], capture_output=True, text=True,
                        timeout=240)
@@ -26,7 +24,6 @@ def test_bbox_status_and_path_collisions_match_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first hardware run pending; the file readers are CPU-tested and the device side is vmap_apply_keys")
 def test_occupied_pointcloud_loader_matches_oracle():
     r = subprocess.run([sys.executable, os.path.join(HERE, "cloud_load_check.py")], capture_output=True, text=True,
                        timeout=240)
@@ -36,7 +33,6 @@ def test_occupied_pointcloud_loader_matches_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first hardware run pending (pipelined host-memory insertion)")
 def test_staged_insertion_builds_the_same_map():
     r = subprocess.run([sys.executable, os.path.join(HERE, "staged_check.py")], capture_output=True, text=True,
                        timeout=240)

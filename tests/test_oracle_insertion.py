@@ -217,3 +217,15 @@ def test_cfg1_counts_match_survey_sizing_probe():
     st = w.last_scan_stats()
     assert (st["points_in_range"], st["rays_cast"], st["traversals"], st["unique_free"],
             st["unique_occupied"]) == (5915, 9638, 362225, 93443, 5553)
+
+
+def test_set_log_odds_bounding_box_clamps_like_setNodeValue():
+    """octomap's setNodeValue(key, log_odds, lazy) starts with "clamp log odds within range": a box
+    edit with a value beyond the clamping thresholds stores the threshold itself."""
+    ow = oracle.OracleWorld(resolution=0.2, sensor_max_range=5.0)
+    ow.setLogOddsBoundingBox([[1.0, 1.0, 1.0]], [0.4, 0.4, 0.4], 9.0, 0)
+    ow.setLogOddsBoundingBox([[-1.0, -1.0, 1.0]], [0.4, 0.4, 0.4], -9.0, 0)
+    ow.setLogOddsBoundingBox([[3.0, 0.0, 0.0]], [0.1, 0.1, 0.1], 0.5, 0)
+    _, v = ow.export_leaves()
+    c = ow.logodds_constants()
+    assert set(np.asarray(v, np.float32).tolist()) == {float(c[2]), float(c[3]), 0.5}

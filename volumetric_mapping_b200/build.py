@@ -8,8 +8,18 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvmap_b200.so")
 SOURCES = ["vmap.cu"]
-DEPS = ["vmap.cu", "vmap_device.cuh", "vmap_kernels.cuh", "vmap_sort.cuh", "vmap_sort_host.inl", "vmap_shard.cuh", "vmap_seq.cuh", "vmap_export_host.inl", "vmap_shard_host.inl",
-        os.path.join("..", "..", "include", "vmap", "vmap.h")]
+
+
+def deps():
+    """Every file the library is compiled from: all of csrc/ plus the public header."""
+    import glob
+    out = []
+    for pat in ("*.cu", "*.cuh", "*.inl", "*.h"):
+        out += glob.glob(os.path.join(CSRC, pat))
+    out.append(os.path.join(HERE, "..", "include", "vmap", "vmap.h"))
+    out.append(os.path.abspath(__file__))
+    return out
+
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
@@ -38,7 +48,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in deps())
 
 
 def build(force=False, verbose=False):

@@ -128,7 +128,7 @@ struct vmap {
   bool staged[2] = {false, false};
   int stage_next = 0;         // slot the next vmap_stage_pointcloud fills
   int walk_order = 0;     // 1: golden-ratio chunk order in the dilated segment walker (VMAP_WALK_ORDER, experimental)
-  int walk_addr = 0;      // 1: dilated window addressing in the segment walker (VMAP_WALK_ADDR, experimental)
+  int walk_addr = 1;      // segment walker: 1 dilated window addressing (default), 0 block addressing, 2..5 experiments (VMAP_WALK_ADDR)
   int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
   size_t ckpt_want = 0;   // checkpoint capacity to allocate with the scan scratch
@@ -1217,11 +1217,11 @@ int vmap_insert_staged(vmap* h, int is_dense, const double T_rowmajor[16]) try {
   int k = h->stage_next;
   if (!h->staged[k]) k ^= 1;
   if (!h->staged[k]) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "no staged scan");
+  // (the slot is released on every exit path: a failed call must not leave it staged for good)
+  struct Release { vmap* h; int k; ~Release() { h->staged[k] = false; } } release{h, k};
   VM_CUDA(h, cudaSetDevice(h->device));
   VM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_stage[k], 0));
-  const int st = insert_cloud_common(h, (const uint8_t*)h->stage[k].p, h->stage_n[k], h->stage_stride[k], is_dense ? 1 : 0, T_rowmajor);
-  h->staged[k] = false;
-  return st;
+  return insert_cloud_common(h, (const uint8_t*)h->stage[k].p, h->stage_n[k], h->stage_stride[k], is_dense ? 1 : 0, T_rowmajor);
 } catch (...) { return vmap_on_exception(h); }
 
 int vmap_insert_projected(vmap* h, const float* xyz_hw3, int rows, int cols, size_t row_pitch_bytes,

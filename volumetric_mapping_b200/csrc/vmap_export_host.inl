@@ -381,8 +381,8 @@ int vmap_deserialize_ot(vmap* h, int with_header, const uint8_t* buffer, size_t 
 
 // OctomapWorld::setLogOddsBoundingBox (octomap_world.cc:781-818), which is what setFree /
 // setOccupied (:497-523) call: every grid position of the adjusted box (adjustBoundingBox,
-// :1175-1224) gets its voxel set to log_odds_value (setNodeValue: no clamping; out-of-bounds
-// positions are ignored).  The loops run on the host in the reference's arithmetic (accumulating
+// :1175-1224) gets its voxel set to log_odds_value (OccupancyOcTreeBase::setNodeValue clamps the
+// value to [clamping_thres_min, clamping_thres_max] first; out-of-bounds positions are ignored).  The loops run on the host in the reference's arithmetic (accumulating
 // doubles, float narrowing at point3d); the voxels are written on the device in one batch.
 int vmap_set_log_odds_bbox(vmap* h, const double* positions_xyz, size_t n_positions,
                            const double bounding_box_size[3], double log_odds_value, int bound_handling) try {
@@ -402,7 +402,9 @@ int vmap_set_log_odds_bbox(vmap* h, const double* positions_xyz, size_t n_positi
   };
   std::vector<uint16_t> k3;
   std::vector<float> val;
-  const float value = (float)log_odds_value;   // OcTreeNode::setLogOdds(float)
+  // setNodeValue(point3d, float log_odds_value, lazy): the double is narrowed to float at the call,
+  // then clamped: std::min(std::max(v, clamping_thres_min), clamping_thres_max)
+  const float value = std::min(std::max((float)log_odds_value, h->P.cmin), h->P.cmax);
   for (size_t p = 0; p < n_positions; p++) {
     double bmin[3], bmax[3];
     for (int a = 0; a < 3; a++) {
@@ -540,6 +542,7 @@ int vmap_serialize_bt(vmap* h, uint8_t* buffer, size_t capacity, size_t* n_bytes
 int vmap_write_bt(vmap* h, const char* path, int threshold_live_map) try {
   if (!h || !path) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));   // the thresholding pass must not race an apply round still in flight
   if (threshold_live_map) {
     k_to_max_likelihood<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->P, h->m);
     h->launches++;
