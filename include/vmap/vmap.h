@@ -143,6 +143,30 @@ VMAP_API int vmap_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t 
 VMAP_API int vmap_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n,
                                         size_t stride_bytes, const double T_rowmajor[16]);
 
+/* ---- the scan pipeline ------------------------------------------------------------------------
+ * vmap_insert_pointcloud[_dev] is PIPELINED: the call stages the scan on the device, enqueues all
+ * of its kernels and returns as soon as the caller's buffer has been consumed (and, when
+ * xyz_world_out is given, rewritten); up to `depth` scans stay in flight, overlapping on the
+ * device, while their updates of the map are applied strictly in insertion order.  Every other
+ * entry point that reads or edits the map drains the pipeline first, so the reference's
+ * observable behaviour (octomap_world.cc:110-141 is synchronous) is unchanged; what changes is
+ * WHEN a failure is reported: a scan that cannot be applied (VMAP_ERR_CAPACITY) is dropped without
+ * leaving marks behind and the error is returned by the call that retires it -- a later insert,
+ * vmap_flush, or the next reading call.  depth 0 restores fully synchronous inserts.
+ * Key capture (vmap_set_debug_capture), VMAP_DEDUPE_SORT, unlimited sensor range, windows over
+ * vmap_config.dense_window_bytes and sharded handles always insert synchronously. */
+VMAP_API int vmap_flush(vmap* h);
+VMAP_API int vmap_set_pipeline_depth(vmap* h, int depth /* 0, 1 or 2 (default) */);
+/* Sums of the per-scan counters over every scan inserted since creation / vmap_reset (drains the
+ * pipeline first); *n_scans scans, *n_replayed of them had their update refused on the device for
+ * lack of room and were replayed after the map had grown (both may be NULL). */
+VMAP_API int vmap_totals(vmap* h, vmap_scan_stats* sums, uint64_t* n_scans, uint64_t* n_replayed);
+/* Device-timed region around any number of calls: begin drains everything on the handle and
+ * records a CUDA event, end drains again, records a second event and returns the milliseconds
+ * between the two. */
+VMAP_API int vmap_region_begin(vmap* h);
+VMAP_API int vmap_region_end(vmap* h, double* ms);
+
 /* OctomapWorld::insertProjectedDisparityIntoMapImpl (octomap_world.cc:143-175): CV_32FC3 image
  * of sensor-frame points, rows x cols, row_pitch_bytes between rows; sensor_to_world given as
  * unit quaternion (w,x,y,z) + translation, the form the reference evaluates (:162). */
@@ -182,6 +206,12 @@ VMAP_API int vmap_query_lines(vmap* h, const double* start_end_xyz6, size_t n, u
 VMAP_API int vmap_query_lines_dev(vmap* h, const double* d_start_end_xyz6, size_t n,
                                   uint8_t* d_status);
 
+/* Measurement twin of vmap_query_lines_dev: also returns how many voxels the reference's loop
+ * (octomap_world.cc:405-415: one octree_->search per key until the first non-free one) probes in
+ * total -- the `probes` of the query's algorithmic-byte figure. */
+VMAP_API int vmap_query_lines_probes_dev(vmap* h, const double* d_start_end_xyz6, size_t n,
+                                         uint8_t* d_status, uint64_t* probes);
+
 /* Query variants that are fan-outs of the two kernels above, batched:
  * getCellTrueStatusPoint + getCellProbabilityPoint (octomap_world.cc:363-393): status with unknown
  * kept as VMAP_CELL_UNKNOWN; probability (may be NULL) = node->getOccupancy(), -1.0 without node. */
@@ -215,6 +245,10 @@ VMAP_API int vmap_check_path_collisions(vmap* h, const double* xyz, size_t n,
 VMAP_API int vmap_leaf_count(vmap* h, size_t* n);
 VMAP_API int vmap_export_leaves(vmap* h, uint16_t* keys_k3, float* logodds, size_t capacity,
                                 size_t* n);
+/* Order-independent 64-bit digest of (key, log-odds bit pattern) over all leaves, and their count:
+ * two maps (or a sharded map's shards summed together, the sum wraps modulo 2^64) hold bit-identical
+ * leaves iff both numbers agree.  volumetric_mapping_b200.sharded.leaf_digest is the host mirror. */
+VMAP_API int vmap_leaf_digest(vmap* h, uint64_t* n_leaves, uint64_t* digest);
 /* Inverse (loadOctomapFromFile / setOctomapFromMsg feed): sets leaf values, no clamping. */
 VMAP_API int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds, size_t n);
 

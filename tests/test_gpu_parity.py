@@ -320,6 +320,7 @@ def test_max_blocks_cap_is_an_error_not_corruption():
     gw = vm.OctomapWorld(initial_blocks=64, max_blocks=64, **s["params"])
     with pytest.raises(vm.VmapError) as e:
         gw.insertPointcloud(s["T"], s["points"])
+        gw.flush()                  # (pipelined insertion: the failure is reported when the scan is retired)
     assert e.value.status == 3      # VMAP_ERR_CAPACITY
     # the refused scan left nothing behind: the map is still empty and a scan that fits is exact
     assert gw.leaf_count() == 0

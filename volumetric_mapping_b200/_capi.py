@@ -89,6 +89,8 @@ SYMBOLS = [
     "vmap_query_bbox_status", "vmap_query_bbox_status_dev", "vmap_check_path_collisions",
     "vmap_stage_pointcloud", "vmap_insert_staged",
     "vmap_load_occupied_pointcloud_file", "vmap_insert_occupied_points", "vmap_host_read_pointcloud_file",
+    "vmap_leaf_digest", "vmap_query_lines_probes_dev",
+    "vmap_flush", "vmap_set_pipeline_depth", "vmap_totals", "vmap_region_begin", "vmap_region_end",
 ]
 
 STATUS_NAMES = {0: "VMAP_OK", 1: "VMAP_ERR_INVALID_ARGUMENT", 2: "VMAP_ERR_CUDA",
@@ -154,6 +156,13 @@ def lib():
     L.vmap_device_bytes.restype = C.c_uint64
     u64p = C.POINTER(C.c_uint64)
     L.vmap_tree_size.argtypes = [vp, C.c_int, C.POINTER(sz)]
+    L.vmap_leaf_digest.argtypes = [vp, u64p, u64p]
+    L.vmap_flush.argtypes = [vp]
+    L.vmap_set_pipeline_depth.argtypes = [vp, C.c_int]
+    L.vmap_totals.argtypes = [vp, C.POINTER(ScanStats), u64p, u64p]
+    L.vmap_region_begin.argtypes = [vp]
+    L.vmap_region_end.argtypes = [vp, dp]
+    L.vmap_query_lines_probes_dev.argtypes = [vp, vp, sz, vp, u64p]
     L.vmap_query_bbox_status.argtypes = [vp, vp, sz, dp, vp]
     L.vmap_stage_pointcloud.argtypes = [vp, vp, sz, sz]
     L.vmap_insert_staged.argtypes = [vp, C.c_int, dp]

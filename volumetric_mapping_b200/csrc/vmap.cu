@@ -29,18 +29,80 @@ struct DevBuf {  // grow-only device buffer
   size_t cap = 0;
 };
 
+// dense mark window (vmap_device.cuh MarkSet): the per-scan key sets of ray-generated scans
+struct Window {
+  uint32_t* free_bits = nullptr;
+  uint32_t* occ_bits = nullptr;
+  uint32_t* touched_bits = nullptr;
+  uint32_t* list = nullptr;
+  uint32_t* locate = nullptr;
+  uint32_t n_side = 0;        // blocks per axis needed (cube)
+  uint32_t stride = 0;        // x / y extent as allocated: n_side, or the next power of two (dilated addressing)
+  int reach_vox = -1;         // >= 0: dilated layout, the window starts at block (sensor voxel - reach_vox) >> 3
+  int radius = 0;             // blocks from the sensor block to the window face
+  uint64_t n_blocks = 0;
+  uint32_t n_words = 0;       // touched bitmap words
+  uint32_t list_cap = 0;
+  bool disabled = false;      // window would exceed the budget / unlimited range
+};
+
+// What a pipelined scan needs to be run again from its staged input (recovery after a refusal).
+struct ScanMeta {
+  size_t n = 0, stride = 0;
+  int is_dense = 1;
+  double Tm[16] = {0};
+};
+
+// Everything ONE scan in flight owns: its stream, scratch, counters, staged input and mark window.
+// `vmap` derives from it (the members below are "the current scan context" everywhere in this
+// file) and keeps a second one in `alt`; pipelined insertion alternates between the two by swapping
+// them, so consecutive scans overlap on the device while the map itself is updated in scan order.
+struct ScanCtx {
+  int ctx_id = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // per-kernel timing marks
+  bool evk_set[5] = {false, false, false, false, false};
+  ScanBuffers sb{};
+  size_t scan_cap = 0;
+  size_t first_cap = 0;
+  size_t ckpt_want = 0;       // checkpoint capacity to allocate with the scan scratch
+  Counters* d_cnt = nullptr;
+  Counters* h_cnt = nullptr;          // pinned
+  Persist* h_persist_snap = nullptr;  // pinned: Persist as this context's last pipelined scan left it
+  DevBuf in;                          // staged input (points / image / keys / query coordinates)
+  Window win;
+  MarkSet ms{};                       // marks of the scan in flight (table or dense mode)
+  // pipelined insertion
+  cudaEvent_t ev_done = nullptr;      // the scan in flight is complete, counters read back
+  cudaEvent_t ev_h2d = nullptr;       // its input has left the caller's buffer
+  bool in_flight = false;
+  uint64_t seq = 0;                   // number of the scan in flight (order of insertion)
+  ScanMeta meta;
+};
+
 }  // namespace
 
-struct vmap {
+struct vmap : ScanCtx {
   vmap_params params;
   vmap_config cfg;
   DevParams P;
   int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t evr0 = nullptr, evr1 = nullptr;  // whole sharded round (generate .. apply)
-  cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // per-kernel timing marks
-  bool evk_set[5] = {false, false, false, false, false};
+  cudaEvent_t evr0 = nullptr, evr1 = nullptr;  // timed region (vmap_region_begin / _end)
+  ScanCtx alt;                   // the other scan context (created on the first pipelined insert)
+  bool alt_ready = false;
+  int pipe_depth = 2;            // scans that may stay in flight when an insert call returns (0 = synchronous)
+  int pipe_n = 0;                // scans in flight
+  uint64_t pipe_seq = 0;
+  bool pipe_grow = false;        // grow the map at the next quiescent point (headroom is getting thin)
+  uint32_t pipe_touch_max = 0;   // most blocks one scan has touched so far
+  uint64_t pipe_stalls = 0;      // scans whose update was refused on the device and replayed
+  vmap_scan_stats totals{};      // sums over every scan inserted since creation / reset
+  uint64_t total_scans = 0;
+  cudaEvent_t ev_wb = nullptr;   // front-end kernel done (write-back of the world-frame cloud)
+  DevBuf wb;                     // write-back image for strides != 12
+  uint8_t* wb_host = nullptr;    // pinned staging for the NaN-compacting write-back
+  size_t wb_host_cap = 0;
 
   // voxel-block map
   MapView m{};
@@ -49,13 +111,7 @@ struct vmap {
   uint32_t epoch = 0;
 
   // per-scan scratch
-  ScanBuffers sb{};
-  size_t scan_cap = 0;
-  size_t first_cap = 0;
-  Counters* d_cnt = nullptr;
-  Counters* h_cnt = nullptr;     // pinned
   Persist* h_persist = nullptr;  // pinned
-  DevBuf in;                     // staged input (points / image / keys / query coordinates)
   DevBuf out;                    // staged output (statuses, exported leaves)
   DevBuf aux;                    // second staged input / output
   SortBuffers sort{};            // VMAP_DEDUPE_SORT scratch
@@ -97,23 +153,6 @@ struct vmap {
   uint32_t* d_count_matrix = nullptr;         // [world][kMaxBatch][2 * kMaxRanks]
   std::vector<uint32_t> h_count_matrix;
 
-  // dense mark window (vmap_device.cuh MarkSet): the per-scan key sets of ray-generated scans
-  struct Window {
-    uint32_t* free_bits = nullptr;
-    uint32_t* occ_bits = nullptr;
-    uint32_t* touched_bits = nullptr;
-    uint32_t* list = nullptr;
-    uint32_t* locate = nullptr;
-    uint32_t n_side = 0;        // blocks per axis needed (cube)
-    uint32_t stride = 0;        // x / y extent as allocated: n_side, or the next power of two (dilated addressing)
-    int reach_vox = -1;         // >= 0: dilated layout, the window starts at block (sensor voxel - reach_vox) >> 3
-    int radius = 0;             // blocks from the sensor block to the window face
-    uint64_t n_blocks = 0;
-    uint32_t n_words = 0;       // touched bitmap words
-    uint32_t list_cap = 0;
-    bool disabled = false;      // window would exceed the budget / unlimited range
-  } win;
-  MarkSet ms{};                 // marks of the scan in flight (table or dense mode)
   uint64_t dense_fallbacks = 0;
   bool traced = false;        // VMAP_TRACE: the walker selection has been printed
   uint32_t* chg0_store = nullptr;   // change-detection planes (MapView.chg0/1 point here while enabled)
@@ -131,7 +170,6 @@ struct vmap {
   int walk_addr = 1;      // segment walker: 1 dilated window addressing (default), 0 block addressing, 2..5 experiments (VMAP_WALK_ADDR)
   int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
-  size_t ckpt_want = 0;   // checkpoint capacity to allocate with the scan scratch
 
   // parity hook
   bool capture = false;
@@ -189,7 +227,15 @@ int fail(const vmap* h, int code, const char* msg) {
   return code;
 }
 
-int flush_app(vmap* h);   // vmap_shard_host.inl: wait for an overlapped exchange/apply round
+int flush_rounds(vmap* h); // vmap_shard_host.inl: wait for an overlapped exchange/apply round
+int pipe_flush(vmap* h);   // below: drain the pipelined scans
+// Every entry point that reads or edits the map outside the scan pipeline starts here: nothing is
+// in flight on the handle afterwards.  Deferred failures of pipelined scans surface here.
+int flush_app(vmap* h) {
+  const int st = pipe_flush(h);
+  const int st2 = flush_rounds(h);
+  return st != VMAP_OK ? st : st2;
+}
 
 int dev_alloc(vmap* h, void** p, size_t bytes) {
   *p = nullptr;
@@ -498,19 +544,19 @@ void use_table_marks(vmap* h) {
 }
 
 void free_window(vmap* h) {
-  vmap::Window& w = h->win;
+  Window& w = h->win;
   dev_free(h, w.free_bits, w.n_blocks * kMaskWords * 4);
   dev_free(h, w.occ_bits, w.n_blocks * kMaskWords * 4);
   dev_free(h, w.touched_bits, (size_t)w.n_words * 4);
   dev_free(h, w.list, (size_t)w.list_cap * 4);
   dev_free(h, w.locate, (size_t)w.list_cap * 4);
   const bool dis = w.disabled;
-  w = vmap::Window{};
+  w = Window{};
   w.disabled = dis;
 }
 
 int grow_window_list(vmap* h, uint32_t want) {
-  vmap::Window& w = h->win;
+  Window& w = h->win;
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   dev_free(h, w.list, (size_t)w.list_cap * 4);
   dev_free(h, w.locate, (size_t)w.list_cap * 4);
@@ -527,7 +573,7 @@ int grow_window_list(vmap* h, uint32_t want) {
 // visit: |point - origin| <= sensor_max_range after clipping (octomap_world.cc:184-185,210-212).
 // Returns false (table mode) for an unlimited range or when the cube exceeds the memory budget.
 bool setup_dense_marks(vmap* h, const float origin[3]) {
-  vmap::Window& w = h->win;
+  Window& w = h->win;
   if (w.disabled || h->cfg.dedupe_mode != VMAP_DEDUPE_BITMASK) return false;
   if (!(h->P.max_range >= 0.0) || !std::isfinite(h->P.max_range)) return false;
   const double r_vox = h->P.max_range * h->P.res_factor;
@@ -605,11 +651,10 @@ bool setup_dense_marks(vmap* h, const float origin[3]) {
   return true;
 }
 
-int launch_list_and_locate(vmap* h) {
+int launch_list(vmap* h) {
   const unsigned grid = (unsigned)std::min<uint64_t>((h->win.n_words + 255) / 256, (uint64_t)g_sm_count(h->device) * 8);
   k_list_touched<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->ms, h->d_cnt, h->win.n_words);
-  k_locate_blocks<<<g_sm_count(h->device) * 4, 256, 0, h->stream>>>(h->ms, h->m, h->d_cnt);
-  h->launches += 2;
+  h->launches++;
   VM_CUDA(h, cudaGetLastError());
   return VMAP_OK;
 }
@@ -649,6 +694,29 @@ int launch_update(vmap* h) {
   return VMAP_OK;
 }
 
+// The ordered half of a scan ("tail"): everything that touches the MAP.  Dense mode: admission
+// (one thread), table entries of the listed window blocks (+ the pool verdict by the last CTA),
+// update.  Table mode: the pool verdict (one thread), update.  A refused tail leaves the scan's
+// marks, list and touched bitmap as they are, so it can be run again after the map has grown.
+// poison != 0 (pipelined insertion): a refusal also stalls every later tail (Persist::stalled).
+int launch_tail(vmap* h, int poison) {
+  if (h->ms.dense) {
+    k_admit<<<1, 32, 0, h->stream>>>(h->ms, h->m, h->d_cnt, poison);
+    k_locate_blocks<<<g_sm_count(h->device) * 4, 256, 0, h->stream>>>(h->ms, h->m, h->d_cnt, poison);
+    h->launches += 2;
+  } else {
+    k_admit_pool<<<1, 32, 0, h->stream>>>(h->m, h->d_cnt);
+    h->launches++;
+  }
+  VM_CUDA(h, cudaGetLastError());
+  VM_TRY(mark_stage(h, 3));
+  VM_TRY(launch_capture(h));
+  if (h->capture) VM_TRY(mark_stage(h, 3));
+  VM_TRY(launch_update(h));
+  VM_TRY(mark_stage(h, 4));
+  return VMAP_OK;
+}
+
 int clear_marks(vmap* h) {
   k_clear_masks<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->m, h->ms, h->d_cnt);
   h->launches++;
@@ -656,101 +724,39 @@ int clear_marks(vmap* h) {
   return VMAP_OK;
 }
 
-// Runs  mark() -> [capture] -> update  with the grow-and-retry protocol.
-//   mark() enqueues everything up to and including the kernels that set block masks, into the
-//   mark set h->ms (dense window when `origin` is given and a window is available, else the
-//   table's mask columns).
-template <class Mark>
-int run_scan(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
-  VM_TRY(next_epoch(h));
-  uint64_t retries = 0;
-  float ms_total = 0.f;
-  bool dense = origin && setup_dense_marks(h, origin);
-  if (!dense) use_table_marks(h);
-  for (;;) {
-    VM_TRY(begin_scan_scratch(h, n_points));
-    for (bool& b : h->evk_set) b = false;
-    VM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-    VM_TRY(mark_stage(h, 0));
-    VM_TRY(mark());
-    if (dense) VM_TRY(launch_list_and_locate(h));
-    VM_TRY(mark_stage(h, 3));
-    VM_TRY(launch_capture(h));
-    if (h->capture) VM_TRY(mark_stage(h, 3));
-    VM_TRY(launch_update(h));
-    VM_TRY(mark_stage(h, 4));
-    VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-    VM_TRY(read_counters(h));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-    ms_total += ms;
-    bool redo = false;
-    if (dense) {
-      if (h->h_cnt->overflow_ckpt) {
-        // not every segment got a checkpoint: drop the partial marks, enlarge, run the scan again
-        VM_TRY(clear_window_marks(h));
-        VM_TRY(grow_checkpoints(h));
-        redo = true;
-      } else if (h->h_cnt->overflow_window) {
-        // a voxel outside the window (cannot happen for clipped rays; kept as a safety net):
-        // drop the marks and run this scan through the table's mask columns instead
-        VM_TRY(clear_window_marks(h));
-        h->dense_fallbacks++;
-        dense = false;
-        use_table_marks(h);
-        redo = true;
-      } else {
-        // the marks are complete and still in the window: only the tail has to be repeated
-        int guard = 0;
-        while (h->h_cnt->overflow_keys || h->h_cnt->overflow_table || h->h_cnt->overflow_pool) {
-          if (++guard > 40) return fail(h, VMAP_ERR_CAPACITY, "scan could not be applied after repeated growth");
-          retries++;
-          int gs;
-          if (h->h_cnt->overflow_keys) {
-            gs = grow_window_list(h, std::max<uint32_t>(h->h_cnt->n_touched + (h->h_cnt->n_touched >> 2), 2 * h->win.list_cap));
-            h->ms.list = h->win.list; h->ms.locate = h->win.locate; h->ms.list_cap = h->win.list_cap;
-          } else if (h->h_cnt->overflow_table) {
-            gs = grow_table(h);
-          } else {
-            gs = grow_pool(h, std::min<uint64_t>((uint64_t)h->h_persist->n_entries, (uint64_t)h->h_persist->n_slots + h->h_cnt->n_touched));
-          }
-          if (gs != VMAP_OK) {
-            // the scan cannot be applied (capacity): it must not leave its marks behind either,
-            // or the next scan would inherit them
-            const std::string msg = h->err;
-            clear_window_marks(h);
-            cudaStreamSynchronize(h->stream);
-            h->err = msg;
-            return gs;
-          }
-          VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_touched, 0, sizeof(uint32_t), h->stream));
-          VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->overflow_table, 0, 6 * sizeof(uint32_t), h->stream));
-          VM_TRY(launch_list_and_locate(h));
-          VM_TRY(launch_capture(h));
-          VM_TRY(launch_update(h));
-          VM_TRY(mark_stage(h, 4));
-          VM_TRY(read_counters(h));
-        }
-        VM_CUDA(h, cudaMemsetAsync(h->win.touched_bits, 0, (size_t)h->win.n_words * 4, h->stream));
-      }
-    } else if (h->h_cnt->overflow_table) {
-      // the table filled up mid-scan: drop this scan's marks, double the table, run it again
-      VM_TRY(clear_marks(h));
-      VM_TRY(grow_table(h));  // resets every entry's epoch to 0
-      use_table_marks(h);
-      redo = true;
-    } else if (h->h_cnt->overflow_pool) {
-      VM_TRY(clear_marks(h));   // (table mode: the marks are dropped before growing, so a failed grow leaves none)
-      VM_TRY(grow_pool(h, std::min<uint64_t>((uint64_t)h->h_persist->n_entries, (uint64_t)h->h_persist->n_slots + h->h_cnt->n_touched)));
-      // epochs are still the current one: give the re-run a fresh epoch so blocks are re-listed
-      VM_TRY(next_epoch(h));
-      redo = true;
+// Dense mode, marks complete in the window and listed: run the tail, growing the table / the pool
+// and running it again for as long as the device refuses it.  Synchronous (the caller has made
+// sure nothing else is in flight on this handle).  On a capacity error the scan's marks are
+// dropped, so the next scan does not inherit them.
+int run_tail_sync(vmap* h, uint64_t* retries, bool first_attempt_done = false) {
+  for (int guard = 0;; guard++) {
+    if (!(first_attempt_done && guard == 0)) {
+      VM_TRY(launch_tail(h, 0));
+      VM_TRY(read_counters(h));
     }
-    if (!redo) break;
-    if (++retries > 40) return fail(h, VMAP_ERR_CAPACITY, "scan could not be applied after repeated growth");
+    const Counters& c = *h->h_cnt;
+    if (!(c.stall || c.overflow_table || c.overflow_pool)) return VMAP_OK;
+    int gs = VMAP_OK;
+    if (guard >= 40) gs = fail(h, VMAP_ERR_CAPACITY, "scan could not be applied after repeated growth");
+    else if (c.stall & kStallMarks) gs = fail(h, VMAP_ERR_CUDA, "internal: tail run on incomplete marks");
+    else if ((c.stall & kStallTable) || c.overflow_table) gs = grow_table(h);
+    else if ((c.stall & kStallPool) || c.overflow_pool) gs = grow_pool(h, (uint64_t)h->h_persist->n_slots + c.need_slots);
+    // (kStallEarlier alone: the stalled flag was left set by a pipelined scan; cleared below)
+    if (gs != VMAP_OK) {
+      const std::string msg = h->err;
+      clear_window_marks(h);
+      cudaStreamSynchronize(h->stream);
+      h->err = msg;
+      return gs;
+    }
+    ++*retries;
+    VM_CUDA(h, cudaMemsetAsync(&h->m.persist->stalled, 0, sizeof(uint32_t), h->stream));
+    VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->overflow_table, 0, 2 * sizeof(uint32_t), h->stream));   // overflow_table, overflow_pool
+    VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->stall, 0, 3 * sizeof(uint32_t), h->stream));            // stall, need_slots, done_ctas
   }
-  // keep the load factor <= 1/2 so probes stay short
-  while ((uint64_t)h->h_persist->n_entries * 2 > h->table_cap) VM_TRY(grow_table(h));
+}
+
+void fill_stats(vmap* h, uint64_t retries, float ms_total) {
   const Counters& c = *h->h_cnt;
   vmap_scan_stats& s = h->stats;
   s.points_valid = c.points_valid;
@@ -775,6 +781,100 @@ int run_scan(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
   s.resolve_ms = span(1, 2);
   s.walk_ms = h->evk_set[2] ? span(2, 3) : span(0, 3);
   s.update_ms = span(3, 4);
+  h->total_scans++;
+  vmap_scan_stats& t = h->totals;
+  t.points_in += s.points_in; t.points_valid += s.points_valid; t.points_in_range += s.points_in_range;
+  t.rays_cast += s.rays_cast; t.traversals += s.traversals; t.occupied_emitted += s.occupied_emitted;
+  t.unique_free += s.unique_free; t.unique_occupied += s.unique_occupied;
+  t.longest_ray = std::max(t.longest_ray, s.longest_ray);
+  t.blocks_touched += s.blocks_touched; t.blocks_total = s.blocks_total; t.retries += s.retries;
+  t.gpu_ms += s.gpu_ms; t.front_ms += s.front_ms; t.resolve_ms += s.resolve_ms; t.walk_ms += s.walk_ms;
+  t.update_ms += s.update_ms;
+}
+
+// Runs  mark() -> [capture] -> update  with the grow-and-retry protocol, synchronously.
+//   mark() enqueues everything up to and including the kernels that set block masks, into the
+//   mark set h->ms (dense window when `origin` is given and a window is available, else the
+//   table's mask columns).
+template <class Mark>
+int run_scan(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
+  VM_TRY(next_epoch(h));
+  uint64_t retries = 0;
+  float ms_total = 0.f;
+  bool dense = origin && setup_dense_marks(h, origin);
+  if (!dense) use_table_marks(h);
+  for (;;) {
+    VM_TRY(begin_scan_scratch(h, n_points));
+    for (bool& b : h->evk_set) b = false;
+    VM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+    VM_TRY(mark_stage(h, 0));
+    VM_TRY(mark());
+    bool redo = false;
+    if (dense) {
+      // (one host synchronisation in the common case: the tail is enqueued blind; on the device it
+      // refuses itself when the marks or the list turn out to be incomplete)
+      VM_TRY(launch_list(h));
+      VM_TRY(launch_tail(h, 0));
+      VM_TRY(read_counters(h));
+      if (h->h_cnt->overflow_ckpt) {
+        // not every segment got a checkpoint: drop the partial marks, enlarge, run the scan again
+        VM_TRY(clear_window_marks(h));
+        VM_TRY(grow_checkpoints(h));
+        redo = true;
+      } else if (h->h_cnt->overflow_window) {
+        // a voxel outside the window (cannot happen for clipped rays; kept as a safety net):
+        // drop the marks and run this scan through the table's mask columns instead
+        VM_TRY(clear_window_marks(h));
+        h->dense_fallbacks++;
+        dense = false;
+        use_table_marks(h);
+        redo = true;
+      } else if (h->h_cnt->overflow_keys) {
+        // block list too small: the marks are complete and still in the window, only list again
+        VM_TRY(grow_window_list(h, std::max<uint32_t>(h->h_cnt->n_touched + (h->h_cnt->n_touched >> 2), 2 * h->win.list_cap)));
+        h->ms.list = h->win.list; h->ms.locate = h->win.locate; h->ms.list_cap = h->win.list_cap;
+        VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->n_touched, 0, sizeof(uint32_t), h->stream));
+        VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->overflow_keys, 0, sizeof(uint32_t), h->stream));
+        VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->stall, 0, 3 * sizeof(uint32_t), h->stream));
+        VM_TRY(launch_list(h));
+        VM_TRY(launch_tail(h, 0));
+        VM_TRY(read_counters(h));
+        if (h->h_cnt->overflow_keys) return fail(h, VMAP_ERR_CAPACITY, "window block list could not be sized");
+      }
+      if (!redo) {
+        VM_TRY(run_tail_sync(h, &retries, true));
+        VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+        VM_CUDA(h, cudaEventSynchronize(h->ev1));
+      }
+    } else {
+      VM_TRY(launch_tail(h, 0));
+      VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+      VM_TRY(read_counters(h));
+      if (h->h_cnt->overflow_table) {
+        // the table filled up mid-scan: drop this scan's marks, double the table, run it again
+        VM_TRY(clear_marks(h));
+        VM_TRY(grow_table(h));  // resets every entry's epoch to 0
+        use_table_marks(h);
+        redo = true;
+      } else if (h->h_cnt->overflow_pool) {
+        VM_TRY(clear_marks(h));   // (table mode: the marks are dropped before growing, so a failed grow leaves none)
+        VM_TRY(grow_pool(h, std::min<uint64_t>((uint64_t)h->h_persist->n_entries, (uint64_t)h->h_persist->n_slots + h->h_cnt->n_touched)));
+        // epochs are still the current one: give the re-run a fresh epoch so blocks are re-listed
+        VM_TRY(next_epoch(h));
+        redo = true;
+      }
+    }
+    if (!redo) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+      ms_total += ms;
+      break;
+    }
+    if (++retries > 40) return fail(h, VMAP_ERR_CAPACITY, "scan could not be applied after repeated growth");
+  }
+  // keep the load factor <= 1/2 so probes stay short
+  while ((uint64_t)h->h_persist->n_entries * 2 > h->table_cap) VM_TRY(grow_table(h));
+  fill_stats(h, retries, ms_total);
   h->captured = h->capture;
   return VMAP_OK;
 }
@@ -860,20 +960,64 @@ int launch_after_front(vmap* h, size_t n, const Transform& T) {
   return launch_resolve_and_walk(h, n, T);
 }
 
-int insert_cloud_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_dense,
-                        const double Tm[16]) {
-  VM_TRY(flush_app(h));
+// ---------------------------------------------------------------------------------------------
+// scan contexts and pipelined insertion
+// ---------------------------------------------------------------------------------------------
+void swap_ctx(vmap* h) { std::swap(static_cast<ScanCtx&>(*h), h->alt); }
+
+int init_ctx_resources(vmap* h) {   // for the CURRENT context
+  int prio_lo = 0, prio_hi = 0;
+  VM_CUDA(h, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  if (!h->stream) VM_CUDA(h, cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi));
+  if (!h->ev0) VM_CUDA(h, cudaEventCreate(&h->ev0));
+  if (!h->ev1) VM_CUDA(h, cudaEventCreate(&h->ev1));
+  for (auto& e : h->evk)
+    if (!e) VM_CUDA(h, cudaEventCreate(&e));
+  if (!h->ev_done) VM_CUDA(h, cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+  if (!h->ev_h2d) VM_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming));
+  if (!h->h_cnt) {
+    VM_CUDA(h, cudaMallocHost((void**)&h->h_cnt, sizeof(Counters)));
+    std::memset(h->h_cnt, 0, sizeof(Counters));
+  }
+  if (!h->h_persist_snap) {
+    VM_CUDA(h, cudaMallocHost((void**)&h->h_persist_snap, sizeof(Persist)));
+    std::memset(h->h_persist_snap, 0, sizeof(Persist));
+  }
+  // per-scan counters and the segment-count histogram share one allocation (one memset per scan)
+  if (!h->d_cnt) VM_TRY(dev_alloc(h, (void**)&h->d_cnt, sizeof(Counters) + kLenBins * sizeof(uint32_t)));
+  return VMAP_OK;
+}
+
+void free_ctx_resources(vmap* h) {  // of the CURRENT context
+  ScanBuffers& sb = h->sb;
+  cudaFree(sb.world); cudaFree(sb.ray_end); cudaFree(sb.key); cudaFree(sb.flags); cudaFree(sb.rays);
+  cudaFree(sb.len); cudaFree(sb.rank);
+  cudaFree(sb.seg_base); cudaFree(sb.ray_rec); cudaFree(sb.ckpt);
+  cudaFree(sb.first_keys);
+  sb = ScanBuffers{};
+  cudaFree(h->in.p);
+  h->in = DevBuf{};
+  cudaFree(h->d_cnt);
+  h->d_cnt = nullptr;
+  free_window(h);
+  if (h->h_cnt) cudaFreeHost(h->h_cnt);
+  if (h->h_persist_snap) cudaFreeHost(h->h_persist_snap);
+  h->h_cnt = nullptr;
+  h->h_persist_snap = nullptr;
+  cudaEvent_t* evs[] = {&h->ev0, &h->ev1, &h->ev_done, &h->ev_h2d, &h->evk[0], &h->evk[1], &h->evk[2], &h->evk[3], &h->evk[4]};
+  for (cudaEvent_t* e : evs)
+    if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+  if (h->stream) cudaStreamDestroy(h->stream);
+  h->stream = nullptr;
+}
+
+// The classic, synchronous insertion of the cloud staged at d_in (device memory).
+int insert_cloud_sync(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_dense, const double Tm[16]) {
   Transform T;
   fill_transform_matrix(&T, Tm);
   VM_TRY(ensure_scan(h, n));
   h->stats = vmap_scan_stats{};
   h->stats.points_in = n;
-  if (n == 0) {
-    // updateOccupancy on two empty sets: nothing changes
-    h->h_cap_n[0] = h->h_cap_n[1] = 0;
-    h->captured = h->capture;
-    return VMAP_OK;
-  }
   return run_scan(h, n, T.origin, [&]() -> int {
     k_front_cloud<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, d_in, (uint32_t)n,
                                                           (uint32_t)stride, is_dense);
@@ -881,6 +1025,317 @@ int insert_cloud_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride, i
     VM_CUDA(h, cudaGetLastError());
     return launch_after_front(h, n, T);
   });
+}
+
+// Upper bound of the segment checkpoints n rays can need: a clipped ray is at most max_range long,
+// its DDA takes at most the Manhattan distance of its end keys (+3) steps, one segment per
+// kSegSteps steps.
+uint64_t checkpoint_bound(const vmap* h, size_t n) {
+  const double r_vox = h->P.max_range * h->P.res_factor + 2.0;
+  const double per_ray = std::floor((1.7320508075688772 * r_vox + 3.0) / (double)kSegSteps) + 2.0;
+  const double total = per_ray * (double)std::max<size_t>(n, 1);
+  return total < 1.8e19 ? (uint64_t)total : ~0ull;
+}
+
+int ensure_ckpt(vmap* h, uint64_t want) {
+  ScanBuffers& sb = h->sb;
+  if (want <= sb.ckpt_cap) return VMAP_OK;
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  dev_free(h, sb.ckpt, (size_t)sb.ckpt_cap * sizeof(Checkpoint));
+  sb.ckpt = nullptr;
+  sb.ckpt_cap = 0;
+  VM_TRY(dev_alloc(h, (void**)&sb.ckpt, (size_t)want * sizeof(Checkpoint)));
+  sb.ckpt_cap = (uint32_t)want;
+  h->ckpt_want = (size_t)want;
+  return VMAP_OK;
+}
+
+// May this scan go through the pipeline?  (Everything else -- key capture, sort mode, unlimited
+// range, windows over the budget, sharded handles -- takes the synchronous path.)
+bool pipe_eligible(const vmap* h, size_t n) {
+  if (h->pipe_depth <= 0 || h->capture || h->cfg.dedupe_mode != VMAP_DEDUPE_BITMASK) return false;
+  if (h->no_segments || h->shard_world > 1 || h->win.disabled || h->alt.win.disabled) return false;
+  if (!(h->P.max_range >= 0.0) || !std::isfinite(h->P.max_range)) return false;
+  const uint64_t ck = checkpoint_bound(h, n);
+  return ck < 0xFFFFFFFFull && ck * sizeof(Checkpoint) <= (2ull << 30);
+}
+
+int pipe_retire(vmap* h);
+
+// Drain the pipeline.  Returns the first deferred failure (the failing scan was dropped, later
+// scans were still applied).
+int pipe_flush(vmap* h) {
+  int first = VMAP_OK;
+  std::string msg;
+  while (h->pipe_n > 0) {
+    const int st = pipe_retire(h);
+    if (st != VMAP_OK && first == VMAP_OK) { first = st; msg = h->err; }
+  }
+  if (first != VMAP_OK) h->err = msg;
+  return first;
+}
+
+// Quiescent-point work before a pipelined insert: the second context, and map growth ahead of need
+// (a scan that finds too little room is refused on the device and replayed -- correct but slow).
+int pipe_prepare(vmap* h) {
+  if (!h->alt_ready) {
+    swap_ctx(h);
+    h->ctx_id = 1;
+    const int st = init_ctx_resources(h);
+    swap_ctx(h);
+    VM_TRY(st);
+    h->alt_ready = true;
+  }
+  if (!h->copy_stream) {
+    VM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev_stage) VM_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  if (!h->ev_wb) VM_CUDA(h, cudaEventCreateWithFlags(&h->ev_wb, cudaEventDisableTiming));
+  if (h->pipe_grow) {
+    VM_TRY(pipe_flush(h));
+    h->pipe_grow = false;
+    const uint64_t t = h->pipe_touch_max;
+    while (((uint64_t)h->h_persist->n_entries + 6 * t) * 2 > h->table_cap) {
+      if (grow_table(h) != VMAP_OK) { cudaGetLastError(); break; }       // (not fatal here: the refusal path reports real shortages)
+    }
+    uint64_t want = (uint64_t)h->h_persist->n_slots + 6 * t;
+    if (h->cfg.max_blocks) want = std::min<uint64_t>(want, h->cfg.max_blocks);
+    if (want > h->pool_cap && grow_pool(h, want) != VMAP_OK) cudaGetLastError();
+  }
+  return VMAP_OK;
+}
+
+// After a pipelined scan was applied: is the headroom for the next ones getting thin?
+void pipe_watch_headroom(vmap* h, uint32_t n_touched) {
+  h->pipe_touch_max = std::max(h->pipe_touch_max, n_touched);
+  const uint64_t t = h->pipe_touch_max;
+  if (((uint64_t)h->h_persist->n_entries + 3 * t) * 2 > h->table_cap) h->pipe_grow = true;
+  const bool pool_can_grow = !h->cfg.max_blocks || h->pool_cap < h->cfg.max_blocks;
+  if (pool_can_grow && (uint64_t)h->h_persist->n_slots + 3 * t > h->pool_cap) h->pipe_grow = true;
+}
+
+// The current context holds a scan whose tail the device refused; nothing else is in flight.
+int pipe_replay(vmap* h, bool first) {
+  const Counters c = *h->h_cnt;
+  if (first) *h->h_persist = *h->h_persist_snap;   // (a younger scan's snapshot is older than what the replay before it left)
+  VM_CUDA(h, cudaMemsetAsync(&h->m.persist->stalled, 0, sizeof(uint32_t), h->stream));
+  if (c.overflow_window || c.overflow_ckpt || c.overflow_keys) {
+    // the marks are incomplete: drop them and run the whole scan again from its staged input
+    VM_TRY(clear_window_marks(h));
+    VM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return insert_cloud_sync(h, (const uint8_t*)h->in.p, h->meta.n, h->meta.stride, h->meta.is_dense, h->meta.Tm);
+  }
+  // marks, list and touched bitmap are complete: make room, then run the tail until it is admitted
+  while (((uint64_t)h->h_persist->n_entries + c.n_touched) * 2 > h->table_cap) {
+    const int gs = grow_table(h);
+    if (gs != VMAP_OK) {
+      const std::string msg = h->err;
+      clear_window_marks(h);
+      cudaStreamSynchronize(h->stream);
+      h->err = msg;
+      return gs;
+    }
+  }
+  VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->overflow_table, 0, 2 * sizeof(uint32_t), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(&h->d_cnt->stall, 0, 3 * sizeof(uint32_t), h->stream));
+  uint64_t retries = 1;
+  VM_TRY(run_tail_sync(h, &retries));
+  VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  VM_CUDA(h, cudaEventSynchronize(h->ev1));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+  h->stats = vmap_scan_stats{};
+  h->stats.points_in = h->meta.n;
+  fill_stats(h, retries, ms);
+  pipe_watch_headroom(h, h->h_cnt->n_touched);
+  return VMAP_OK;
+}
+
+// Retire the OLDEST scan in flight: wait for it, take its counters, and -- when the device refused
+// its update -- replay it (and the younger scan behind it, which refused itself too).
+int pipe_retire(vmap* h) {
+  if (h->pipe_n <= 0) return VMAP_OK;
+  const bool cur_is_oldest = h->in_flight && (!h->alt.in_flight || h->seq < h->alt.seq);
+  if (!cur_is_oldest) swap_ctx(h);
+  VM_CUDA(h, cudaEventSynchronize(h->ev_done));
+  h->in_flight = false;
+  h->pipe_n--;
+  const Counters& c = *h->h_cnt;
+  if (!(c.stall || c.overflow_table || c.overflow_pool || c.overflow_window || c.overflow_ckpt || c.overflow_keys)) {
+    *h->h_persist = *h->h_persist_snap;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->stats = vmap_scan_stats{};
+    h->stats.points_in = h->meta.n;
+    fill_stats(h, 0, ms);
+    pipe_watch_headroom(h, c.n_touched);
+    return VMAP_OK;
+  }
+  h->pipe_stalls++;
+  const bool younger = h->alt.in_flight;
+  if (younger) VM_CUDA(h, cudaEventSynchronize(h->alt.ev_done));
+  int st = pipe_replay(h, true);
+  if (younger) {
+    swap_ctx(h);
+    h->in_flight = false;
+    h->pipe_n--;
+    const std::string msg = h->err;
+    const int st2 = pipe_replay(h, false);
+    if (st != VMAP_OK) h->err = msg;
+    else st = st2;
+  }
+  return st;
+}
+
+__global__ void __launch_bounds__(256)
+k_writeback(const uint8_t* __restrict__ in, const float* __restrict__ world, uint8_t* __restrict__ out, uint32_t n_words,
+            uint32_t stride) {
+  // the caller's cloud with x, y, z replaced by the world-frame point (every other byte as it came)
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x) {
+    const uint32_t byte = i * 4u, point = byte / stride, off = byte - point * stride;
+    reinterpret_cast<uint32_t*>(out)[i] = off < 12u ? __float_as_uint(world[3u * point + (off >> 2)])
+                                                   : reinterpret_cast<const uint32_t*>(in)[i];
+  }
+}
+
+// The reference leaves the NaN-compacted, world-frame cloud in the caller's buffer
+// (octomap_world.cc:115-119).  `st`: a stream on which the front-end kernel's outputs are ready;
+// d_in: the staged input.  Blocks until the caller's buffer is rewritten.
+int write_back_cloud(vmap* h, cudaStream_t st, const uint8_t* d_in, size_t n, size_t stride, int is_dense,
+                     float* out, size_t* n_out) {
+  if (n_out) *n_out = n;
+  if (!n || (!out && (is_dense || !n_out))) return VMAP_OK;
+  if (is_dense) {
+    if (stride == 12) {
+      VM_CUDA(h, cudaMemcpyAsync(out, h->sb.world, n * 12, cudaMemcpyDeviceToHost, st));
+    } else {
+      const size_t bytes = (n - 1) * stride + 12;
+      if (bytes > h->wb.cap) {   // (only ever used from here, and every use is followed by a synchronisation)
+        dev_free(h, h->wb.p, h->wb.cap);
+        h->wb = DevBuf{};
+        VM_TRY(dev_alloc(h, &h->wb.p, bytes + (bytes >> 2)));
+        h->wb.cap = bytes + (bytes >> 2);
+      }
+      k_writeback<<<g_sm_count(h->device) * 4, 256, 0, st>>>(d_in, h->sb.world, (uint8_t*)h->wb.p, (uint32_t)(bytes / 4), (uint32_t)stride);
+      h->launches++;
+      VM_CUDA(h, cudaGetLastError());
+      VM_CUDA(h, cudaMemcpyAsync(out, h->wb.p, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    VM_CUDA(h, cudaStreamSynchronize(st));
+    return VMAP_OK;
+  }
+  // removeNaNFromPointCloud: order-preserving compaction, done on the host from pinned staging
+  const size_t need = n * 13;
+  if (need > h->wb_host_cap) {
+    if (h->wb_host) cudaFreeHost(h->wb_host);
+    h->wb_host = nullptr;
+    h->wb_host_cap = 0;
+    VM_CUDA(h, cudaMallocHost((void**)&h->wb_host, need + (need >> 2)));
+    h->wb_host_cap = need + (need >> 2);
+  }
+  float* w = reinterpret_cast<float*>(h->wb_host);
+  uint8_t* f = h->wb_host + n * 12;
+  VM_CUDA(h, cudaMemcpyAsync(w, h->sb.world, n * 12, cudaMemcpyDeviceToHost, st));
+  VM_CUDA(h, cudaMemcpyAsync(f, h->sb.flags, n, cudaMemcpyDeviceToHost, st));
+  VM_CUDA(h, cudaStreamSynchronize(st));
+  size_t j = 0;
+  for (size_t i = 0; i < n; i++) {
+    if (!(f[i] & kFlagValid)) continue;
+    if (out) {
+      float* o = reinterpret_cast<float*>(reinterpret_cast<char*>(out) + j * stride);
+      o[0] = w[3 * i]; o[1] = w[3 * i + 1]; o[2] = w[3 * i + 2];
+    }
+    j++;
+  }
+  if (n_out) *n_out = j;
+  return VMAP_OK;
+}
+
+// insertPointcloudIntoMapImpl.  src: the caller's points, in host memory (src_on_host) or on the
+// device.  Pipelined (default): the scan is staged into the free scan context, all of its kernels
+// are enqueued on that context's stream, and the call returns once the caller's buffer has been
+// consumed; up to pipe_depth scans stay in flight, their map updates ordered by events.
+int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, size_t stride, int is_dense,
+                        const double Tm[16], float* wb_out, size_t* wb_n_out) {
+  VM_TRY(flush_rounds(h));
+  if (wb_n_out) *wb_n_out = n;
+  if (n == 0) {
+    // updateOccupancy on two empty sets: nothing changes
+    VM_TRY(pipe_flush(h));
+    h->stats = vmap_scan_stats{};
+    h->h_cap_n[0] = h->h_cap_n[1] = 0;
+    h->captured = h->capture;
+    return VMAP_OK;
+  }
+  const size_t bytes = (n - 1) * stride + 12;
+  bool piped = pipe_eligible(h, n);
+  Transform T;
+  fill_transform_matrix(&T, Tm);
+  if (piped) {
+    VM_TRY(pipe_prepare(h));
+    while (h->pipe_n >= 2) VM_TRY(pipe_retire(h));
+    if (h->in_flight) swap_ctx(h);            // the current context is the free one from here on
+    if (h->epoch >= kEpochMax) VM_TRY(pipe_flush(h));
+    VM_TRY(ensure_scan(h, n));
+    VM_TRY(ensure_ckpt(h, checkpoint_bound(h, n)));
+    piped = setup_dense_marks(h, T.origin);
+    if (piped && h->win.list_cap < h->win.n_blocks) {
+      // a list that can hold every block of the window: the list can never overflow
+      piped = h->win.n_blocks * 8 <= (1ull << 30) && grow_window_list(h, (uint32_t)h->win.n_blocks) == VMAP_OK &&
+              h->win.list_cap >= h->win.n_blocks;
+      h->ms.list = h->win.list; h->ms.locate = h->win.locate; h->ms.list_cap = h->win.list_cap;
+    }
+  }
+  if (!piped) {
+    VM_TRY(pipe_flush(h));
+    const uint8_t* d_in = reinterpret_cast<const uint8_t*>(src);
+    if (src_on_host) {
+      VM_TRY(ensure(h, &h->in, bytes));
+      VM_CUDA(h, cudaMemcpyAsync(h->in.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+      d_in = (const uint8_t*)h->in.p;
+    }
+    VM_TRY(insert_cloud_sync(h, d_in, n, stride, is_dense, Tm));
+    return write_back_cloud(h, h->stream, d_in, n, stride, is_dense, wb_out, wb_n_out);
+  }
+  // ---- pipelined ----
+  VM_TRY(ensure(h, &h->in, bytes));
+  VM_CUDA(h, cudaMemcpyAsync(h->in.p, src, bytes, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+  VM_CUDA(h, cudaEventRecord(h->ev_h2d, h->stream));
+  VM_TRY(next_epoch(h));
+  VM_TRY(begin_scan_scratch(h, n));
+  for (bool& b : h->evk_set) b = false;
+  VM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  VM_TRY(mark_stage(h, 0));
+  k_front_cloud<<<grid_for(n, 256), 256, 0, h->stream>>>(h->P, h->sb, h->d_cnt, T, (const uint8_t*)h->in.p, (uint32_t)n,
+                                                        (uint32_t)stride, is_dense);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  const bool wb = wb_out || (wb_n_out && !is_dense);
+  if (wb) VM_CUDA(h, cudaEventRecord(h->ev_wb, h->stream));
+  VM_TRY(launch_after_front(h, n, T));
+  VM_TRY(launch_list(h));
+  // the ordered half: after the update of the scan before this one
+  if (h->alt.in_flight) VM_CUDA(h, cudaStreamWaitEvent(h->stream, h->alt.ev_done, 0));
+  VM_TRY(launch_tail(h, 1));
+  VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  VM_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaMemcpyAsync(h->h_persist_snap, h->m.persist, sizeof(Persist), cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaEventRecord(h->ev_done, h->stream));
+  h->in_flight = true;
+  h->seq = ++h->pipe_seq;
+  h->pipe_n++;
+  h->meta.n = n;
+  h->meta.stride = stride;
+  h->meta.is_dense = is_dense;
+  std::memcpy(h->meta.Tm, Tm, sizeof(h->meta.Tm));
+  // the caller may reuse its buffer as soon as this call returns
+  VM_CUDA(h, cudaEventSynchronize(h->ev_h2d));
+  if (wb) {
+    VM_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_wb, 0));
+    VM_TRY(write_back_cloud(h, h->copy_stream, (const uint8_t*)h->in.p, n, stride, is_dense, wb_out, wb_n_out));
+  }
+  while (h->pipe_n > h->pipe_depth) VM_TRY(pipe_retire(h));
+  return VMAP_OK;
 }
 
 }  // namespace
@@ -985,23 +1440,14 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
     return false;
   };
   if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return bail(VMAP_ERR_CUDA);
-  {
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (!cuda_ok(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi), "cudaStreamCreate")) return bail(VMAP_ERR_CUDA);
-  }
-  if (!cuda_ok(cudaEventCreate(&h->ev0), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
-  if (!cuda_ok(cudaEventCreate(&h->ev1), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
-  for (auto& e : h->evk)
-    if (!cuda_ok(cudaEventCreate(&e), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
+  if (const char* e = getenv("VMAP_PIPE_DEPTH")) h->pipe_depth = std::min(2, std::max(0, atoi(e)));
+  h->alt.ctx_id = 1;
+  if (init_ctx_resources(h) != VMAP_OK) return bail(VMAP_ERR_CUDA);
   if (!cuda_ok(cudaEventCreate(&h->evr0), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
   if (!cuda_ok(cudaEventCreate(&h->evr1), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
-  if (!cuda_ok(cudaMallocHost((void**)&h->h_cnt, sizeof(Counters)), "cudaMallocHost")) return bail(VMAP_ERR_CUDA);
   if (!cuda_ok(cudaMallocHost((void**)&h->h_persist, sizeof(Persist)), "cudaMallocHost")) return bail(VMAP_ERR_CUDA);
-  std::memset(h->h_cnt, 0, sizeof(Counters));
   std::memset(h->h_persist, 0, sizeof(Persist));
-  // per-scan counters and the segment-count histogram share one allocation (one memset per scan)
-  int s = dev_alloc(h, (void**)&h->d_cnt, sizeof(Counters) + kLenBins * sizeof(uint32_t));
+  int s = VMAP_OK;
   if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_cap_n, 2 * sizeof(uint32_t));
   if (s == VMAP_OK) s = dev_alloc(h, (void**)&h->d_pack_counts_base, (size_t)2 * kMaxBatch * 2 * kMaxRanks * sizeof(uint32_t));
   h->d_pack_counts = h->d_pack_counts_base;
@@ -1015,16 +1461,13 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
 int vmap_destroy(vmap* h) try {
   if (!h) return VMAP_OK;
   cudaSetDevice(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();      // pipelined scans, apply rounds: nothing may be in flight
+  h->pipe_n = 0;
+  h->in_flight = h->alt.in_flight = false;
   free_map(h);
-  ScanBuffers& sb = h->sb;
-  cudaFree(sb.world); cudaFree(sb.ray_end); cudaFree(sb.key); cudaFree(sb.flags); cudaFree(sb.rays);
-  cudaFree(sb.len); cudaFree(sb.rank);
-  cudaFree(sb.seg_base); cudaFree(sb.ray_rec); cudaFree(sb.ckpt);
-  cudaFree(sb.first_keys);
-  cudaFree(h->in.p); cudaFree(h->out.p); cudaFree(h->aux.p);
+  cudaFree(h->out.p); cudaFree(h->aux.p);
   cudaFree(h->cap_free.p); cudaFree(h->cap_occ.p);
-  cudaFree(h->d_cnt); cudaFree(h->d_cap_n);
+  cudaFree(h->d_cap_n);
   vmap_dist_shutdown(h);
   cudaFree(h->pack_inflight.p); cudaFree(h->l2_flush.p); cudaFree(h->d_cnt_app);
   if (h->h_cnt_app) cudaFreeHost(h->h_cnt_app);
@@ -1034,21 +1477,20 @@ int vmap_destroy(vmap* h) try {
   if (h->app_stream) cudaStreamDestroy(h->app_stream);
   cudaFree(h->pack.p); cudaFree(h->recv.p); cudaFree(h->d_pack_counts_base); cudaFree(h->d_count_matrix);
   sort_free(h);
-  free_window(h);
   cudaFree(h->chg0_store); cudaFree(h->chg1_store);
   cudaFree(h->stage[0].p); cudaFree(h->stage[1].p);
+  cudaFree(h->wb.p);
+  if (h->wb_host) cudaFreeHost(h->wb_host);
   for (auto& e : h->ev_stage)
     if (e) cudaEventDestroy(e);
+  if (h->ev_wb) cudaEventDestroy(h->ev_wb);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  if (h->h_cnt) cudaFreeHost(h->h_cnt);
   if (h->h_persist) cudaFreeHost(h->h_persist);
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
-  for (auto& e : h->evk)
-    if (e) cudaEventDestroy(e);
   if (h->evr0) cudaEventDestroy(h->evr0);
   if (h->evr1) cudaEventDestroy(h->evr1);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  free_ctx_resources(h);
+  swap_ctx(h);
+  free_ctx_resources(h);
   delete h;
   return VMAP_OK;
 } catch (...) { return vmap_on_exception(h); }
@@ -1072,6 +1514,11 @@ int vmap_reset(vmap* h) try {
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
   h->epoch = 0;
   h->stats = vmap_scan_stats{};
+  h->totals = vmap_scan_stats{};
+  h->total_scans = 0;
+  h->pipe_touch_max = 0;
+  h->pipe_grow = false;
+  std::memset(h->h_persist, 0, sizeof(Persist));
   h->captured = false;
   return VMAP_OK;
 } catch (...) { return vmap_on_exception(h); }
@@ -1103,7 +1550,7 @@ int vmap_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n, size_t str
   if (!h || (!d_xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
-  return insert_cloud_common(h, reinterpret_cast<const uint8_t*>(d_xyz), n, stride_bytes, 1, T_rowmajor);
+  return insert_cloud_common(h, d_xyz, false, n, stride_bytes, 1, T_rowmajor, nullptr, nullptr);
 } catch (...) { return vmap_on_exception(h); }
 
 int vmap_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_bytes, int is_dense,
@@ -1111,32 +1558,57 @@ int vmap_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_by
   if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
-  if (n_out) *n_out = n;
-  if (n) {
-    const size_t bytes = (n - 1) * stride_bytes + 12;
-    VM_TRY(ensure(h, &h->in, bytes));
-    VM_CUDA(h, cudaMemcpyAsync(h->in.p, xyz, bytes, cudaMemcpyHostToDevice, h->stream));
-  }
-  VM_TRY(insert_cloud_common(h, (const uint8_t*)h->in.p, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor));
-  if (n && (xyz_world_out || (n_out && !is_dense))) {
-    // the reference leaves the NaN-compacted, world-frame cloud in the caller's buffer
-    std::vector<float> w(n * 3);
-    std::vector<uint8_t> f(n);
-    VM_CUDA(h, cudaMemcpyAsync(w.data(), h->sb.world, n * 12, cudaMemcpyDeviceToHost, h->stream));
-    VM_CUDA(h, cudaMemcpyAsync(f.data(), h->sb.flags, n, cudaMemcpyDeviceToHost, h->stream));
-    VM_CUDA(h, cudaStreamSynchronize(h->stream));
-    size_t j = 0;
-    for (size_t i = 0; i < n; i++) {
-      if (!(f[i] & kFlagValid)) continue;
-      if (xyz_world_out) {
-        float* o = reinterpret_cast<float*>(reinterpret_cast<char*>(xyz_world_out) + j * stride_bytes);
-        o[0] = w[3 * i]; o[1] = w[3 * i + 1]; o[2] = w[3 * i + 2];
-      }
-      j++;
-    }
-    if (n_out) *n_out = j;
-  }
-  return VMAP_OK;
+  return insert_cloud_common(h, xyz, true, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor, xyz_world_out, n_out);
+} catch (...) { return vmap_on_exception(h); }
+
+// The scan pipeline from the outside.
+int vmap_flush(vmap* h) try {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  return flush_app(h);
+} catch (...) { return vmap_on_exception(h); }
+
+int vmap_set_pipeline_depth(vmap* h, int depth) try {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  if (depth < 0 || depth > 2) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "pipeline depth must be 0 (synchronous), 1 or 2");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  const int st = flush_app(h);
+  h->pipe_depth = depth;
+  return st;
+} catch (...) { return vmap_on_exception(h); }
+
+int vmap_totals(vmap* h, vmap_scan_stats* sums, uint64_t* n_scans, uint64_t* n_replayed) try {
+  if (!h || !sums) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  const int st = flush_app(h);
+  *sums = h->totals;
+  if (n_scans) *n_scans = h->total_scans;
+  if (n_replayed) *n_replayed = h->pipe_stalls;
+  return st;
+} catch (...) { return vmap_on_exception(h); }
+
+// Timed region on the device: begin drains everything and records an event; end drains again,
+// records a second one and returns the time between them.
+int vmap_region_begin(vmap* h) try {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  const int st = flush_app(h);
+  VM_CUDA(h, cudaDeviceSynchronize());
+  VM_CUDA(h, cudaEventRecord(h->evr0, h->stream));
+  return st;
+} catch (...) { return vmap_on_exception(h); }
+
+int vmap_region_end(vmap* h, double* ms) try {
+  if (!h || !ms) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  const int st = flush_app(h);
+  VM_CUDA(h, cudaDeviceSynchronize());
+  VM_CUDA(h, cudaEventRecord(h->evr1, h->stream));
+  VM_CUDA(h, cudaEventSynchronize(h->evr1));
+  float v = 0.f;
+  VM_CUDA(h, cudaEventElapsedTime(&v, h->evr0, h->evr1));
+  *ms = (double)v;
+  return st;
 } catch (...) { return vmap_on_exception(h); }
 
 static int insert_image_common(vmap* h, const uint8_t* d_img, int rows, int cols, size_t pitch,
@@ -1220,14 +1692,15 @@ int vmap_insert_staged(vmap* h, int is_dense, const double T_rowmajor[16]) try {
   // (the slot is released on every exit path: a failed call must not leave it staged for good)
   struct Release { vmap* h; int k; ~Release() { h->staged[k] = false; } } release{h, k};
   VM_CUDA(h, cudaSetDevice(h->device));
-  VM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_stage[k], 0));
-  return insert_cloud_common(h, (const uint8_t*)h->stage[k].p, h->stage_n[k], h->stage_stride[k], is_dense ? 1 : 0, T_rowmajor);
+  VM_CUDA(h, cudaEventSynchronize(h->ev_stage[k]));   // (the insert picks its own stream: the staged copy must be complete)
+  return insert_cloud_common(h, h->stage[k].p, false, h->stage_n[k], h->stage_stride[k], is_dense ? 1 : 0, T_rowmajor, nullptr, nullptr);
 } catch (...) { return vmap_on_exception(h); }
 
 int vmap_insert_projected(vmap* h, const float* xyz_hw3, int rows, int cols, size_t row_pitch_bytes,
                           const double q_wxyz[4], const double t[3]) try {
   VM_TRY(check_image_args(h, xyz_hw3, rows, cols, row_pitch_bytes, 12, q_wxyz, t));
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   const size_t bytes = (size_t)rows * row_pitch_bytes;
   if (bytes) {
     VM_TRY(ensure(h, &h->in, bytes));
@@ -1269,6 +1742,7 @@ int vmap_insert_disparity(vmap* h, const float* disparity, int rows, int cols, s
   VM_TRY(check_image_args(h, disparity, rows, cols, row_pitch_bytes, 4, q_wxyz, t));
   if (!Q_full_rowmajor) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "null Q");
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   const size_t bytes = (size_t)rows * row_pitch_bytes;
   if (bytes) {
     VM_TRY(ensure(h, &h->in, bytes));
@@ -1285,6 +1759,7 @@ int vmap_reproject(vmap* h, const float* disparity, int rows, int cols, size_t r
   VM_TRY(check_image_args(h, disparity, rows, cols, row_pitch_bytes, 4, qi, ti));
   if (!Q_rowmajor || !xyz_hw3_out) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument");
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   const size_t n = (size_t)rows * cols;
   if (!n) return VMAP_OK;
   const size_t bytes = (size_t)rows * row_pitch_bytes;
@@ -1352,6 +1827,7 @@ int vmap_query_points_dev(vmap* h, const double* d_xyz, size_t n, uint8_t* d_sta
 int vmap_query_points(vmap* h, const double* xyz, size_t n, uint8_t* status) try {
   if (!h || ((!xyz || !status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   if (!n) return VMAP_OK;
   VM_TRY(ensure(h, &h->in, n * 24));
   VM_TRY(ensure(h, &h->out, n));
@@ -1378,6 +1854,7 @@ int vmap_query_lines_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_statu
 int vmap_query_lines(vmap* h, const double* ab, size_t n, uint8_t* status) try {
   if (!h || ((!ab || !status) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
   if (!n) return VMAP_OK;
   VM_TRY(ensure(h, &h->in, n * 48));
   VM_TRY(ensure(h, &h->out, n));
@@ -1385,6 +1862,26 @@ int vmap_query_lines(vmap* h, const double* ab, size_t n, uint8_t* status) try {
   VM_TRY(vmap_query_lines_dev(h, (const double*)h->in.p, n, (uint8_t*)h->out.p));
   VM_CUDA(h, cudaMemcpyAsync(status, h->out.p, n, cudaMemcpyDeviceToHost, h->stream));
   VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return VMAP_OK;
+} catch (...) { return vmap_on_exception(h); }
+
+// vmap_query_lines_dev plus the number of voxels the reference's loop would probe (measurement).
+int vmap_query_lines_probes_dev(vmap* h, const double* d_ab, size_t n, uint8_t* d_status, uint64_t* probes) try {
+  if (!h || ((!d_ab || !d_status) && n) || !probes) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
+  if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many query segments");
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
+  *probes = 0;
+  if (!n) return VMAP_OK;
+  VM_TRY(ensure(h, &h->aux, 16));
+  VM_CUDA(h, cudaMemsetAsync(h->aux.p, 0, 16, h->stream));
+  k_query_lines_probes<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->m, d_ab, (uint32_t)n, d_status, (unsigned long long*)h->aux.p);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  unsigned long long v = 0;
+  VM_CUDA(h, cudaMemcpyAsync(&v, h->aux.p, 8, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  *probes = v;
   return VMAP_OK;
 } catch (...) { return vmap_on_exception(h); }
 
@@ -1585,6 +2082,23 @@ int vmap_export_leaves(vmap* h, uint16_t* keys_k3, float* logodds_out, size_t ca
   return VMAP_OK;
 } catch (...) { return vmap_on_exception(h); }
 
+int vmap_leaf_digest(vmap* h, uint64_t* n_leaves, uint64_t* digest) try {
+  if (!h || !n_leaves || !digest) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(flush_app(h));
+  VM_TRY(ensure(h, &h->aux, 16));
+  VM_CUDA(h, cudaMemsetAsync(h->aux.p, 0, 16, h->stream));
+  k_digest<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->m, (unsigned long long*)h->aux.p);
+  h->launches++;
+  VM_CUDA(h, cudaGetLastError());
+  unsigned long long v[2] = {0, 0};
+  VM_CUDA(h, cudaMemcpyAsync(v, h->aux.p, 16, cudaMemcpyDeviceToHost, h->stream));
+  VM_CUDA(h, cudaStreamSynchronize(h->stream));
+  *n_leaves = v[0];
+  *digest = v[1];
+  return VMAP_OK;
+} catch (...) { return vmap_on_exception(h); }
+
 int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in, size_t n) try {
   if (!h || ((!keys_k3 || !logodds_in) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many leaves");
@@ -1657,9 +2171,13 @@ int vmap_get_changed(vmap* h, uint16_t* keys_k3, uint8_t* occupied, size_t capac
 int vmap_last_scan_stats(const vmap* h, vmap_scan_stats* stats) try {
   if (!h || !stats) return VMAP_ERR_INVALID_ARGUMENT;
   // (an overlapped multi-GPU round still in flight: its apply-side counters arrive with
-  // vmap_dist_flush; the generation-side counters are already final)
+  // vmap_dist_flush; the generation-side counters are already final.)  Pipelined scans are
+  // retired first, so these are the counters of the scan inserted last.
+  vmap* hm = const_cast<vmap*>(h);
+  cudaSetDevice(hm->device);
+  const int st = pipe_flush(hm);
   *stats = h->stats;
-  return VMAP_OK;
+  return st;
 } catch (...) { return vmap_on_exception(const_cast<vmap*>(h)); }
 
 int vmap_set_debug_capture(vmap* h, int enabled) try {

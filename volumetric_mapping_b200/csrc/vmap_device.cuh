@@ -51,6 +51,9 @@ constexpr uint32_t kKeyRayMax = 100000;  // octomap::KeyRay::sizeMax
 struct Persist {            // survives across scans
   uint32_t n_entries;       // occupied hash entries (blocks known to the table)
   uint32_t n_slots;         // pool slots handed out
+  uint32_t stalled;         // pipelined insertion: an earlier scan's update was refused (the map must
+                            // grow first); every later update refuses too until the host has replayed it
+  uint32_t pad;
 };
 
 struct Counters {           // zeroed at the start of every scan
@@ -73,8 +76,15 @@ struct Counters {           // zeroed at the start of every scan
   uint32_t n_keys;          // sort mode: packed keys emitted
   uint32_t n_leaves;        // export
   uint32_t min_disparity_ord;  // ordered-int encoding of the image minimum
-  uint32_t pad;
+  uint32_t stall;           // the scan's update was refused as a whole (kStall* bits); its marks are intact
+  uint32_t need_slots;      // listed blocks that have no pool slot yet (k_locate_blocks)
+  uint32_t done_ctas;       // CTAs of k_locate_blocks that have finished (last one decides about the pool)
+  uint32_t occ_cursor;      // sort mode: occupied keys appended after the free ones
 };
+constexpr uint32_t kStallEarlier = 1u;   // an earlier scan is stalled (Persist::stalled)
+constexpr uint32_t kStallMarks = 2u;     // the marks are incomplete (window / checkpoint / list overflow)
+constexpr uint32_t kStallTable = 4u;     // the table could exceed load 1/2
+constexpr uint32_t kStallPool = 8u;      // not enough free pool slots
 
 struct MapView {
   unsigned long long* keys;

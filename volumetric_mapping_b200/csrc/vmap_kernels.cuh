@@ -667,12 +667,72 @@ __global__ void __launch_bounds__(256) k_list_touched(MarkSet ms, Counters* cnt,
   }
 }
 
-// Table entry of every listed window block (inserted when new).
-__global__ void __launch_bounds__(256) k_locate_blocks(MarkSet ms, MapView m, Counters* cnt) {
-  if (cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
+// Admission of a scan's update, decided ONCE by one thread before anything of the scan touches the
+// map (dense mode: before k_locate_blocks inserts entries).  Refused -- cnt->stall != 0, marks left
+// intact -- when an earlier scan is stalled (the order of the clamped updates must hold), when the
+// marks are incomplete, or when the listed blocks might push the table over load 1/2.  `poison`
+// (pipelined insertion): a refusal also stalls every later scan until the host has replayed it.
+__global__ void k_admit(MarkSet ms, MapView m, Counters* cnt, int poison) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t why = 0;
+  if (m.persist->stalled) why |= kStallEarlier;
+  if (cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) why |= kStallMarks;
+  if (((unsigned long long)m.persist->n_entries + cnt->n_touched) * 2ull > (unsigned long long)m.cap_mask + 1ull) why |= kStallTable;
+  cnt->stall = why;
+  if (why && poison) m.persist->stalled = 1u;
+}
+
+// Table entry of every listed window block (inserted when new).  The last CTA to finish decides,
+// once, whether the pool has a slot for every listed block that lacks one (k_update only reads
+// the verdict).
+__global__ void __launch_bounds__(256) k_locate_blocks(MarkSet ms, MapView m, Counters* cnt, int poison) {
+  if (cnt->stall) return;
   const uint32_t n = cnt->n_touched;
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
-    ms.locate[t] = find_or_insert(m, cnt, window_block_key(ms, ms.list[t]));
+  uint32_t need = 0;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const uint32_t h = find_or_insert(m, cnt, window_block_key(ms, ms.list[t]));
+    ms.locate[t] = h;
+    if (h != kNotFound && m.slot[h] == kUnassigned) ++need;
+  }
+  __shared__ uint32_t s_need;
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) s_need = 0;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) need += __shfl_xor_sync(0xFFFFFFFFu, need, o);
+  if ((threadIdx.x & 31u) == 0 && need) atomicAdd(&s_need, need);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_need) atomicAdd(&cnt->need_slots, s_need);
+    __threadfence();
+    s_last = atomicAdd(&cnt->done_ctas, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    const uint32_t total = *(volatile uint32_t*)&cnt->need_slots;
+    if (*(volatile uint32_t*)&cnt->overflow_table) {
+      cnt->stall |= kStallTable;                      // (probe limit hit: cannot happen below load 1/2)
+      if (poison) m.persist->stalled = 1u;
+    } else if ((unsigned long long)m.persist->n_slots + total > (unsigned long long)m.pool_cap) {
+      cnt->stall |= kStallPool;
+      cnt->overflow_pool = 1u;
+      if (poison) m.persist->stalled = 1u;
+    }
+  }
+}
+
+// Table mode (marks in the table's mask columns, entries already inserted by the walk): the pool
+// verdict by one thread -- at most one new slot per touched block, and (single GPU, where every
+// entry ends up owning a slot) never more than there are entries.
+__global__ void k_admit_pool(MapView m, Counters* cnt) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
+  const uint32_t by_touch = m.persist->n_slots + cnt->n_touched;
+  const uint32_t slots_bound = m.sharded ? by_touch : min(by_touch, m.persist->n_entries);
+  if (slots_bound > m.pool_cap) {
+    cnt->overflow_pool = 1u;
+    cnt->stall |= kStallPool;
+  }
 }
 
 // updateOccupancy on explicit key lists (vmap_apply_keys): mark phase.
@@ -687,7 +747,7 @@ k_mark_keys(MapView m, Counters* cnt, const uint16_t* __restrict__ k3, uint32_t 
 __global__ void __launch_bounds__(256)
 k_capture_keys(MapView m, MarkSet ms, Counters* cnt, uint16_t* __restrict__ free_k3, uint32_t* n_free,
                uint32_t free_cap, uint16_t* __restrict__ occ_k3, uint32_t* n_occ, uint32_t occ_cap) {
-  if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
+  if (cnt->stall || cnt->overflow_table || cnt->overflow_pool || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < cnt->n_touched; t += warps) {
@@ -716,16 +776,12 @@ k_capture_keys(MapView m, MarkSet ms, Counters* cnt, uint16_t* __restrict__ free
 template <int kVariant>
 __global__ void __launch_bounds__(256)
 k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
-  // Abort the whole scan's update (uniformly) when a map structure must grow first.
-  if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) return;
-  // slots after this update: at most one new slot per touched block, and (single GPU, where every
-  // entry ends up owning a slot) never more than there are entries
-  const uint32_t by_touch = m.persist->n_slots + cnt->n_touched;
-  const uint32_t slots_bound = m.sharded ? by_touch : min(by_touch, m.persist->n_entries);
-  if (slots_bound > m.pool_cap) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) cnt->overflow_pool = 1u;
+  // Abort the whole scan's update (uniformly) when a map structure must grow first: the verdict was
+  // reached once, before this launch (k_admit / k_locate_blocks / k_admit_pool), every thread reads
+  // the same flags.
+  if (cnt->stall || cnt->overflow_table || cnt->overflow_pool || cnt->overflow_window || cnt->overflow_ckpt ||
+      cnt->overflow_keys)
     return;
-  }
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_touched = cnt->n_touched;
@@ -828,6 +884,14 @@ k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
   if (threadIdx.x == 0) {
     if (s_stat[0]) atomicAdd(&cnt->unique_free, s_stat[0]);
     if (s_stat[1]) atomicAdd(&cnt->unique_occupied, s_stat[1]);
+  }
+  // The scan is applied: the window's touched bitmap is free for the next scan (nobody in this
+  // kernel reads it -- the blocks come from the list).  A refused update returns before this point,
+  // so its bitmap, list and marks all survive for the replay.
+  if (ms.dense) {
+    const uint32_t n_words = (ms.nx * ms.ny * ms.nz + 31u) >> 5;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x)
+      if (ms.touched_bits[i]) ms.touched_bits[i] = 0u;
   }
 }
 
@@ -952,6 +1016,50 @@ k_export(MapView m, Counters* cnt, uint16_t* __restrict__ k3, float* __restrict_
   }
 }
 
+// Order-independent digest of the map: the 64-bit sum over all known voxels of
+// mix(mix(packed 48-bit key) ^ value bits).  Two maps hold the same leaves with the same float bit
+// patterns iff count and digest agree (up to a 2^-64 collision); used to compare a sharded build
+// with a single-device build without moving the leaves (bench.py, tests).
+__device__ __forceinline__ unsigned long long digest_mix(unsigned long long x) {
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+__global__ void __launch_bounds__(256)
+k_digest(MapView m, unsigned long long* __restrict__ out /* [0] = count, [1] = digest */) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned long long sum = 0, cnt = 0;
+  for (uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h <= m.cap_mask; h += warps) {
+    const unsigned long long w = m.keys[h];
+    if (w == kEmpty) continue;
+    const uint32_t slot = m.slot[h];
+    if (slot == kUnassigned) continue;
+    const unsigned long long b = w >> kEpochBits;
+    const uint32_t bx = (uint32_t)(b & 0x1FFFu) << 3, by = (uint32_t)((b >> 13) & 0x1FFFu) << 3,
+                   bz = (uint32_t)((b >> 26) & 0x1FFFu) << 3;
+    const uint32_t* vox = reinterpret_cast<const uint32_t*>(m.pool) + (size_t)slot * kBlockVoxels;
+    for (int j = 0; j < kMaskWords; j++) {
+      const uint32_t bits = vox[j * 32 + lane];
+      if (bits == kUnknownBits) continue;
+      const uint32_t l = (uint32_t)j * 32u + lane;
+      const unsigned long long key = (unsigned long long)(bx + (l & 7u)) | ((unsigned long long)(by + ((l >> 3) & 7u)) << 16) |
+                                     ((unsigned long long)(bz + (l >> 6)) << 32);
+      sum += digest_mix(digest_mix(key) ^ (unsigned long long)bits);
+      ++cnt;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+  }
+  if (lane == 0 && cnt) {
+    atomicAdd(out, cnt);
+    atomicAdd(out + 1, sum);
+  }
+}
+
 // getChangedPoints (octomap_world.cc:1413-1440): every key of octomap's changed_keys with the
 // CURRENT occupancy of its node; `clear` = resetChangeDetection().  Pass k3 == NULL to count.
 __global__ void __launch_bounds__(256)
@@ -1031,6 +1139,33 @@ k_query_lines(DevParams P, MapView m, const double* __restrict__ ab, uint32_t n,
   // pointEigenToOctomap narrows to float
   status[i] = line_status(P, m, (float)ab[6 * i], (float)ab[6 * i + 1], (float)ab[6 * i + 2],
                           (float)ab[6 * i + 3], (float)ab[6 * i + 4], (float)ab[6 * i + 5]);
+}
+
+// Measurement twin of k_query_lines: same walk, and the number of voxels probed (search() calls of
+// the reference's loop, octomap_world.cc:405-415) summed into *probes -- the `probes` of SURVEY 8d's
+// B_alg = 49 + 12 * probes per segment.
+__global__ void __launch_bounds__(128)
+k_query_lines_probes(DevParams P, MapView m, const double* __restrict__ ab, uint32_t n,
+                     uint8_t* __restrict__ status, unsigned long long* __restrict__ probes) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t mine = 0;
+  if (i < n) {
+    uint8_t st = 0;
+    unsigned long long cached_b = kEmpty;
+    uint32_t cached_h = kNotFound;
+    walk_ray(P, (float)ab[6 * i], (float)ab[6 * i + 1], (float)ab[6 * i + 2], (float)ab[6 * i + 3], (float)ab[6 * i + 4],
+             (float)ab[6 * i + 5], [&](uint32_t kx, uint32_t ky, uint32_t kz) {
+               const unsigned long long b = block_key(kx, ky, kz);
+               if (b != cached_b) { cached_b = b; cached_h = find_block(m, b); }
+               ++mine;
+               const uint8_t s = voxel_status(P, m, cached_h, kx, ky, kz);
+               if (s != 0) { st = s; return false; }
+               return true;
+             });
+    status[i] = st;
+  }
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xFFFFFFFFu, mine, o);
+  if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(probes, (unsigned long long)mine);
 }
 
 // getVisibility (octomap_world.cc:420-449): occupied (or, when asked, unknown) voxels between the

@@ -130,7 +130,7 @@ int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark, B
     // a table-mode generate touches the hash table an in-flight apply is updating: no overlap
     between_done = true;
     VM_TRY(between());
-    VM_TRY(flush_app(h));
+    VM_TRY(flush_rounds(h));
     use_table_marks(h);
   }
   h->packed = false;
@@ -167,7 +167,7 @@ int generate_marks(vmap* h, size_t n_points, const float* origin, Mark&& mark, B
         VM_TRY(clear_window_marks(h));
         h->dense_fallbacks++;
         dense = false;
-        VM_TRY(flush_app(h));
+        VM_TRY(flush_rounds(h));
         use_table_marks(h);
       } else if (h->h_cnt->overflow_keys) {
         VM_TRY(grow_window_list(h, std::max<uint32_t>(h->h_cnt->n_touched + (h->h_cnt->n_touched >> 2), 2 * h->win.list_cap)));
@@ -247,6 +247,7 @@ int pack_marks(vmap* h) {
 template <class Between>
 int shard_generate_common(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_dense,
                           const double Tm[16], uint64_t* counts_out, Between&& between) {
+  VM_TRY(pipe_flush(h));
   Transform T;
   fill_transform_matrix(&T, Tm);
   VM_TRY(ensure_scan(h, std::max<size_t>(n, 1)));
@@ -299,6 +300,8 @@ int shard_apply_lists(vmap* h, const BlockRecord* const* lists, const size_t* co
       k_apply_records<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->m, h->d_cnt, lists[i], (uint32_t)counts[i]);
       h->launches++;
       VM_CUDA(h, cudaGetLastError());
+      k_admit_pool<<<1, 32, 0, h->stream>>>(h->m, h->d_cnt);
+      h->launches++;
       VM_TRY(launch_capture(h));
       VM_TRY(launch_update(h));
     }
@@ -356,6 +359,7 @@ int vmap_shard_generate(vmap* h, const float* xyz, size_t n, size_t stride_bytes
   if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(pipe_flush(h));
   if (n) {
     const size_t bytes = (n - 1) * stride_bytes + 12;
     VM_TRY(ensure(h, &h->in, bytes));
@@ -419,7 +423,7 @@ int vmap_dist_shutdown(vmap* h) try {
   if (h->nccl_comm) {
     cudaSetDevice(h->device);
     h->round_pending = false;   // (a round never exchanged is dropped: vmap_dist_flush is the collective way out)
-    flush_app(h);
+    flush_rounds(h);
     cudaStreamSynchronize(h->stream);
     g_nccl.CommDestroy((NcclComm)h->nccl_comm);
     h->nccl_comm = nullptr;
@@ -488,7 +492,7 @@ static int dist_exchange_and_apply(vmap* h) {
 // Wait for the exchange + apply of the previous round (app_stream) and collect its counters.
 }  // extern "C"
 namespace {
-int flush_app(vmap* h) {
+int flush_rounds(vmap* h) {
   if (h->round_pending && !h->in_collective)
     return fail(h, VMAP_ERR_DIST, "a sharded round awaits its exchange: call vmap_dist_flush on every rank first");
   if (!h->app_pending) return VMAP_OK;
@@ -562,7 +566,7 @@ int complete_round(vmap* h) {
   VM_NCCL(h, g_nccl.AllGather(d_counts, h->d_count_matrix, kRow, kNcclUint32, comm, as));
   VM_CUDA(h, cudaMemcpyAsync(h->h_count_matrix.data(), h->d_count_matrix, (size_t)G * kRow * sizeof(uint32_t), cudaMemcpyDeviceToHost, as));
   VM_CUDA(h, cudaStreamSynchronize(as));
-  VM_TRY(flush_app(h));                         // the round before this one is complete now
+  VM_TRY(flush_rounds(h));                         // the round before this one is complete now
   const double t_b = now_ms();
   auto count = [&](int src, int sub, int dst) -> size_t {
     return h->h_count_matrix[(size_t)src * kRow + (size_t)sub * 2 * kMaxRanks + dst];
@@ -655,7 +659,7 @@ int vmap_dist_flush(vmap* h) try {
     seal_batch(h);                     // ... and a partial batch (every rank has the same one)
     st = complete_round(h);
   }
-  if (st == VMAP_OK) st = flush_app(h);
+  if (st == VMAP_OK) st = flush_rounds(h);
   h->in_collective = false;
   return st;
 } catch (...) { return vmap_on_exception(h); }
@@ -695,7 +699,7 @@ int dist_insert(vmap* h, const uint8_t* d_in, size_t n, size_t stride, int is_de
   if (h->capture) {   // parity hook: synchronous round through the table's mask columns
     seal_batch(h);
     VM_TRY(complete_round(h));
-    VM_TRY(flush_app(h));
+    VM_TRY(flush_rounds(h));
     h->pack_off = 0;
     h->d_pack_counts = h->d_pack_counts_base;
     h->h_pack_counts = h->h_pack_counts_slot[0][0];
@@ -737,6 +741,7 @@ int vmap_dist_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stri
   if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
+  VM_TRY(pipe_flush(h));
   if (n) {
     const size_t bytes = (n - 1) * stride_bytes + 12;
     VM_TRY(ensure(h, &h->in, bytes));

@@ -128,7 +128,7 @@ k_emit_occupied(ScanBuffers sb, Counters* cnt, uint32_t n, unsigned long long* _
   if (i >= n) return;
   if (!(sb.flags[i] & kFlagOcc)) return;
   const unsigned long long k = sb.key[i];
-  const uint32_t pos = n_free + atomicAdd(&cnt->pad, 1u);
+  const uint32_t pos = n_free + atomicAdd(&cnt->occ_cursor, 1u);
   if (pos < cap)
     keys[pos] = morton48((uint32_t)(k & 0xFFFFu), (uint32_t)((k >> 16) & 0xFFFFu), (uint32_t)((k >> 32) & 0xFFFFu)) << 1;
 }

@@ -30,6 +30,25 @@ def owner_of_keys(keys_k3, world):
     return ((b >> np.uint64(40)) % np.uint64(world)).astype(np.int64)
 
 
+def _mix64(x):
+    with np.errstate(over="ignore"):
+        x = x ^ (x >> np.uint64(30)); x = x * np.uint64(0xbf58476d1ce4e5b9)
+        x = x ^ (x >> np.uint64(27)); x = x * np.uint64(0x94d049bb133111eb)
+        x = x ^ (x >> np.uint64(31))
+    return x
+
+
+def leaf_digest(keys_k3, logodds):
+    """Host mirror of vmap_leaf_digest: (count, sum over leaves of mix(mix(key48) ^ value bits)
+    modulo 2^64).  Shard digests add up (modulo 2^64) to the digest of the whole map."""
+    k = np.asarray(keys_k3, dtype=np.uint64).reshape(-1, 3)
+    key = k[:, 0] | (k[:, 1] << np.uint64(16)) | (k[:, 2] << np.uint64(32))
+    bits = np.ascontiguousarray(logodds, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        d = np.add.reduce(_mix64(_mix64(key) ^ bits), dtype=np.uint64) if len(bits) else np.uint64(0)
+    return int(len(bits)), int(d)
+
+
 def broadcast_id(make_id, rank, dist=None, device=None):
     """Rank 0 creates the 128-byte NCCL id, everybody receives it through torch.distributed."""
     import torch

@@ -125,6 +125,32 @@ class OctomapWorld:
         self._check(self._L.vmap_insert_pointcloud_dev(self._h, C.c_void_p(int(data_ptr)), int(n),
                                                        int(stride_bytes), _dptr(Tm)))
 
+    # -- the scan pipeline (include/vmap/vmap.h, "the scan pipeline") ----------------------------
+    def flush(self):
+        """Drain the pipelined scans; deferred failures surface here."""
+        self._check(self._L.vmap_flush(self._h))
+
+    def set_pipeline_depth(self, depth):
+        self._check(self._L.vmap_set_pipeline_depth(self._h, int(depth)))
+
+    def totals(self):
+        """Sums of the per-scan counters since creation / resetMap, plus `scans` and `replayed`."""
+        s = _capi.ScanStats()
+        n, r = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._L.vmap_totals(self._h, C.byref(s), C.byref(n), C.byref(r)))
+        d = s.as_dict()
+        d["scans"], d["replayed"] = int(n.value), int(r.value)
+        return d
+
+    def region_begin(self):
+        self._check(self._L.vmap_region_begin(self._h))
+
+    def region_end(self):
+        """Milliseconds on the device since region_begin (everything drained on both sides)."""
+        ms = C.c_double(0.0)
+        self._check(self._L.vmap_region_end(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def insertProjectedDisparity(self, q_wxyz, t, xyz_hw3):
         """insertProjectedDisparityIntoMapImpl (octomap_world.cc:143-175)."""
         img = np.ascontiguousarray(xyz_hw3, dtype=np.float32)
@@ -396,6 +422,20 @@ class OctomapWorld:
         self._check(self._L.vmap_export_leaves(self._h, k.ctypes.data, v.ctypes.data, n,
                                                C.byref(got)))
         return k[: got.value], v[: got.value]
+
+    def leaf_digest(self):
+        """(number of leaves, order-independent 64-bit digest of (key, value bits)); see
+        sharded.leaf_digest for the host mirror."""
+        n, d = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._L.vmap_leaf_digest(self._h, C.byref(n), C.byref(d)))
+        return int(n.value), int(d.value)
+
+    def getLineStatusProbesDevice(self, ab_ptr, n, status_ptr):
+        """getLineStatusDevice that also returns the total number of voxels probed."""
+        probes = C.c_uint64(0)
+        self._check(self._L.vmap_query_lines_probes_dev(self._h, C.c_void_p(int(ab_ptr)), int(n),
+                                                        C.c_void_p(int(status_ptr)), C.byref(probes)))
+        return int(probes.value)
 
     def import_leaves(self, keys_k3, logodds):
         k = np.ascontiguousarray(keys_k3, dtype=np.uint16).reshape(-1, 3)
