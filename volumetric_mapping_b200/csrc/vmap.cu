@@ -1294,11 +1294,15 @@ int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, si
       VM_CUDA(h, cudaMemcpyAsync(h->in.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
       d_in = (const uint8_t*)h->in.p;
     }
+    if (h->l2_flush_bytes)
+      VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(h->total_scans & 0xFF), h->l2_flush_bytes, h->stream));
     VM_TRY(insert_cloud_sync(h, d_in, n, stride, is_dense, Tm));
     return write_back_cloud(h, h->stream, d_in, n, stride, is_dense, wb_out, wb_n_out);
   }
   // ---- pipelined ----
   VM_TRY(ensure(h, &h->in, bytes));
+  if (h->l2_flush_bytes)   // benchmark hook: no scan finds its map blocks in L2
+    VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(h->pipe_seq & 0xFF), h->l2_flush_bytes, h->stream));
   VM_CUDA(h, cudaMemcpyAsync(h->in.p, src, bytes, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
   VM_CUDA(h, cudaEventRecord(h->ev_h2d, h->stream));
   VM_TRY(next_epoch(h));

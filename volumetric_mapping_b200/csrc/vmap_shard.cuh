@@ -199,6 +199,199 @@ k_apply_update(DevParams P, MapView m, Counters* cnt, const BlockRecord* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-memory exchange (vmap_peer_host.inl).  Every rank owns one MAILBOX in its device memory that
+// all ranks of the box map through CUDA IPC:
+//   * two ROUND buffers (round parity) of block records, packed by this rank's scans and bucketed by
+//     destination, with a header that says where each (sub-scan, destination) bucket is;
+//   * `ready[s]`    -- written by rank s INTO THIS mailbox: the last round rank s has published;
+//   * `consumed[d]` -- written by rank d into this mailbox: the last round of MINE rank d has applied.
+// A rank PUBLISHES a round by one remote store per peer after its pack kernels are done, PULLS the
+// records destined to it straight out of the peers' round buffers while it applies them (the
+// all-to-all is the apply kernel's own loads over NVLink), and tells every peer when it is done
+// with their buffer.  Flags only ever grow; waiting is a bounded spin in a one-warp kernel.
+// ---------------------------------------------------------------------------------------------
+struct RoundHeader {
+  uint32_t round;                               // round number + 1 once the round is sealed
+  uint32_t n_subs;                              // scans of this rank in the round
+  uint32_t fill;                                // records written so far
+  uint32_t status;                              // 0 = fine, 1 = the round buffer overflowed (fatal)
+  uint32_t count[kMaxBatch][kMaxRanks];         // records of sub-scan j for destination d
+  uint32_t offset[kMaxBatch][kMaxRanks];        // first record of that bucket
+};
+struct MailboxHead {
+  RoundHeader hdr[2];
+  uint32_t ready[kMaxRanks];
+  uint32_t consumed[kMaxRanks];
+  uint32_t error;                               // a wait timed out / a peer reported an overflow
+  uint32_t pad[63];
+};
+struct PeerTable {                              // by value into the kernels
+  MailboxHead* head[kMaxRanks];
+  BlockRecord* rec[kMaxRanks];                  // round buffers: rec[s] + parity * capacity
+  uint32_t capacity;                            // records per round buffer
+  uint32_t world, me;
+};
+
+constexpr long long kSpinLimitNs = 20ll * 1000 * 1000 * 1000;   // a peer that is 20 s late is gone
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// Start of a round's first pack: the round buffer of this parity was last used two rounds ago; wait
+// until every rank has applied that round (want = its number + 1; 0 = nothing to wait for), then
+// reset the header.
+__global__ void k_round_open(PeerTable pt, uint32_t parity, uint32_t want) {
+  MailboxHead* mine = pt.head[pt.me];
+  if (threadIdx.x < pt.world && want) {
+    const long long t0 = global_ns();
+    while (ld_flag(&mine->consumed[threadIdx.x]) < want && !ld_flag(&mine->error)) {
+      __nanosleep(256);
+      if (global_ns() - t0 > kSpinLimitNs) { mine->error = 2u; break; }
+    }
+  }
+  __syncthreads();
+  RoundHeader* h = &mine->hdr[parity];
+  if (threadIdx.x == 0) { h->round = 0; h->n_subs = 0; h->fill = 0; h->status = 0; }
+  for (uint32_t i = threadIdx.x; i < kMaxBatch * kMaxRanks; i += blockDim.x) {
+    (&h->count[0][0])[i] = 0;
+    (&h->offset[0][0])[i] = 0;
+  }
+}
+
+// Between k_pack_count and k_pack_write of sub-scan `sub`: bucket offsets inside the round buffer
+// (one thread; counts[] are this sub-scan's per-destination counts).  When the buffer cannot hold
+// them nothing is written, the header says so, and the scan's counters carry overflow_pack.
+__global__ void k_pack_plan(PeerTable pt, uint32_t parity, uint32_t sub, const uint32_t* __restrict__ counts,
+                            Counters* cnt) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  RoundHeader* h = &pt.head[pt.me]->hdr[parity];
+  if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys) { h->status = 2u; return; }
+  uint32_t total = 0;
+  for (uint32_t d = 0; d < pt.world; d++) total += counts[d];
+  if (h->status || (unsigned long long)h->fill + total > pt.capacity) {
+    h->status = 1u;
+    cnt->overflow_pack = total ? total : 1u;
+    return;
+  }
+  uint32_t at = h->fill;
+  for (uint32_t d = 0; d < pt.world; d++) {
+    h->count[sub][d] = counts[d];
+    h->offset[sub][d] = at;
+    at += counts[d];
+  }
+  h->fill = at;
+  h->n_subs = sub + 1u;
+}
+
+// pass 2 of the pack into a round buffer: like k_pack_write, bucket bases taken from the header.
+__global__ void __launch_bounds__(256)
+k_pack_write_round(MapView m, MarkSet ms, Counters* cnt, PeerTable pt, uint32_t parity, uint32_t sub, uint32_t* cursors) {
+  if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys || cnt->overflow_pack) return;
+  __shared__ uint32_t s_base[kMaxRanks];
+  __shared__ uint32_t s_cnt[kMaxRanks];
+  __shared__ uint32_t s_res[kMaxRanks];
+  const RoundHeader* hd = &pt.head[pt.me]->hdr[parity];
+  BlockRecord* out = pt.rec[pt.me] + (size_t)parity * pt.capacity;
+  if (threadIdx.x < pt.world) s_base[threadIdx.x] = hd->offset[sub][threadIdx.x];
+  const uint32_t warps_per_cta = blockDim.x >> 5;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  const uint32_t n_touched = cnt->n_touched;
+  const uint32_t stride = gridDim.x * warps_per_cta;
+  for (uint32_t t0 = blockIdx.x * warps_per_cta; t0 < n_touched; t0 += stride) {   // uniform per CTA
+    if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t t = t0 + warp;
+    uint32_t wv = 0, dest = 0, local = 0;
+    unsigned long long b = 0;
+    uint32_t* src = nullptr;
+    bool have = false;
+    if (t < n_touched) {
+      const uint32_t e = ms.list[t];
+      src = (lane < kMaskWords) ? ms.free_mask + (size_t)e * kMaskWords + lane
+                                : ms.occ_mask + (size_t)e * kMaskWords + lane - kMaskWords;
+      wv = *src;
+      have = __any_sync(0xFFFFFFFFu, wv != 0u);
+      if (have) {
+        b = ms.dense ? window_block_key(ms, e) : (m.keys[e] >> kEpochBits);
+        dest = owner_of(b, pt.world);
+        if (lane == 0) local = atomicAdd(&s_cnt[dest], 1u);
+        local = __shfl_sync(0xFFFFFFFFu, local, 0);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < pt.world && s_cnt[threadIdx.x]) s_res[threadIdx.x] = atomicAdd(cursors + threadIdx.x, s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (have) {
+      if (wv) *src = 0u;
+      BlockRecord* r = out + (s_base[dest] + s_res[dest] + local);
+      if (lane == 0) r->block = b;
+      if (lane < kMaskWords) r->free_mask[lane] = wv;
+      else r->occ_mask[lane - kMaskWords] = wv;
+    }
+    __syncthreads();
+  }
+  // the scan's marks are packed: its touched bitmap is free for the next scan of this context
+  if (ms.dense) {
+    const uint32_t n_words = (ms.nx * ms.ny * ms.nz + 31u) >> 5;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x)
+      if (ms.touched_bits[i]) ms.touched_bits[i] = 0u;
+  }
+}
+
+// Seal round `round` (header of this parity) and tell every rank: one remote store per peer.
+__global__ void k_round_publish(PeerTable pt, uint32_t parity, uint32_t round) {
+  MailboxHead* mine = pt.head[pt.me];
+  if (threadIdx.x == 0) mine->hdr[parity].round = round + 1u;
+  __syncthreads();
+  __threadfence_system();
+  if (threadIdx.x < pt.world) *reinterpret_cast<volatile uint32_t*>(&pt.head[threadIdx.x]->ready[pt.me]) = round + 1u;
+}
+
+// Wait until every rank has published `round`, then collect what they hold for me:
+// out[(j * world + s) * 2] = count, [.. + 1] = offset of (sub-scan j of rank s -> me); out[2 * kMaxBatch *
+// world] = status (0 fine).  One CTA.
+__global__ void k_round_collect(PeerTable pt, uint32_t parity, uint32_t round, uint32_t* __restrict__ out) {
+  MailboxHead* mine = pt.head[pt.me];
+  __shared__ uint32_t s_bad;
+  if (threadIdx.x == 0) s_bad = 0;
+  __syncthreads();
+  if (threadIdx.x < pt.world) {
+    const long long t0 = global_ns();
+    while (ld_flag(&mine->ready[threadIdx.x]) < round + 1u && !ld_flag(&mine->error)) {
+      __nanosleep(256);
+      if (global_ns() - t0 > kSpinLimitNs) { mine->error = 3u; break; }
+    }
+    if (ld_flag(&mine->error)) atomicExch(&s_bad, ld_flag(&mine->error));
+  }
+  __syncthreads();
+  if (!s_bad) {
+    for (uint32_t i = threadIdx.x; i < kMaxBatch * pt.world; i += blockDim.x) {
+      const uint32_t j = i / pt.world, s = i - j * pt.world;
+      const RoundHeader* h = &pt.head[s]->hdr[parity];
+      const uint32_t st = ld_flag(&h->status);
+      if (st) atomicExch(&s_bad, 16u + st);
+      const bool live = j < ld_flag(&h->n_subs);
+      out[2 * i] = live ? ld_flag(&h->count[j][pt.me]) : 0u;
+      out[2 * i + 1] = live ? ld_flag(&h->offset[j][pt.me]) : 0u;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    out[2 * kMaxBatch * pt.world] = s_bad;
+    if (s_bad && !mine->error) mine->error = s_bad;
+  }
+}
+
+// After the round's records have been applied: every peer may reuse the buffer I read from.
+__global__ void k_round_consumed(PeerTable pt, uint32_t round) {
+  __threadfence_system();
+  if (threadIdx.x < pt.world) *reinterpret_cast<volatile uint32_t*>(&pt.head[threadIdx.x]->consumed[pt.me]) = round + 1u;
+}
+
 // Sharded getLineStatus: every rank walks every segment but only probes the voxels it owns;
 // the result is (index of the first non-free owned voxel << 2) | status, 0xFFFFFFFF when none.
 // The global answer is the minimum over ranks (then status = value & 3, or free).
