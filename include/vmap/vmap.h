@@ -369,6 +369,20 @@ VMAP_API int vmap_dist_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t
  * on a second stream while the next round is generated.  Every call that reads the map waits for
  * the round in flight first; vmap_dist_flush does so explicitly. */
 VMAP_API int vmap_dist_flush(vmap* h);
+/* TRANSPORT.  By default vmap_dist_init sets up the PEER-MEMORY transport: every rank's block
+ * records stay in a round buffer in its own device memory, which all ranks of the box map through
+ * CUDA IPC; a round is published with one remote store per peer, and each owner applies the
+ * records straight out of its peers' buffers (the all-to-all is the apply kernel's own NVLink
+ * loads).  Inserts are pipelined like vmap_insert_pointcloud; vmap_dist_flush completes them.
+ * VMAP_DIST_TRANSPORT=nccl (environment), or a rank that cannot map a peer, selects the NCCL
+ * send/recv transport for all ranks instead.  VMAP_DIST_ROUND_RECORDS sizes the round buffers
+ * (default 3 Mi records of 136 bytes, twice per rank).
+ *
+ * vmap_dist_attach_local: `world` handles of ONE process on one device stand for the ranks (tests,
+ * single-GPU development); mailboxes are shared by plain pointers.  Drive the collective calls in
+ * rank order, and flush with vmap_dist_flush_begin on every handle before vmap_dist_flush on any. */
+VMAP_API int vmap_dist_attach_local(vmap** handles, int world, uint64_t records_per_round);
+VMAP_API int vmap_dist_flush_begin(vmap* h);
 /* Scans per rank that share one exchange round (1..8, default 1).  COLLECTIVE setting. */
 VMAP_API int vmap_dist_set_batch(vmap* h, int scans_per_rank);
 /* Benchmark hook: overwrite `bytes` (> L2) of scratch before every round's exchange. 0 = off. */

@@ -1,7 +1,10 @@
-"""torchrun worker for test_nccl_two_ranks_if_two_gpus: builds a sharded map over NCCL and checks
+"""torchrun worker for test_nccl_two_ranks_if_two_gpus: builds a sharded map with one process per
+GPU (peer-memory transport by default, VMAP_DIST_TRANSPORT=nccl for the send/recv one) and checks
 the union of the shards against the oracle (rank 0 gathers the leaves)."""
 import os
 import sys
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream (spin-wait kernels)
 
 import numpy as np
 import torch

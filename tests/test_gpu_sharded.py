@@ -91,6 +91,20 @@ def test_sharded_hdl64_scans_and_queries():
     assert np.array_equal(got_l, ow.getLineStatus(q["segments"]))
 
 
+@pytest.mark.parametrize("G,batch,n_scans", [(2, 1, 5), (3, 2, 10), (4, 4, 19)])
+def test_peer_memory_transport_emulated_on_one_gpu(G, batch, n_scans):
+    """The peer-memory exchange (round buffers, publish / collect / consumed flags, applies that read
+    the peers' buffers) with G handles of one process standing for G ranks; own process because it
+    needs CUDA_DEVICE_MAX_CONNECTIONS set before the CUDA context exists."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "peer_emulation_check.py"), str(G), str(batch),
+                        str(n_scans)], capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0 and "PEER_EMULATION_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-6000:]
+
+
 @pytest.mark.parametrize("batch", [1, 2])
 def test_nccl_two_ranks_if_two_gpus(batch):
     """The real exchange: needs >= 2 GPUs (gpurun --gpus 2); skipped on a 1-GPU box.  batch = scans
@@ -107,7 +121,7 @@ def test_nccl_two_ranks_if_two_gpus(batch):
            os.path.join(root, "tests", "dist_check.py")]
     import signal
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
-                            env=dict(os.environ, DIST_BATCH=str(batch)), start_new_session=True)
+                            env=dict(os.environ, DIST_BATCH=str(batch), VMAP_TRACE="1"), start_new_session=True)
     try:
         stdout, stderr = proc.communicate(timeout=150)
     except subprocess.TimeoutExpired:

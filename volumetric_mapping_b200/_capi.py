@@ -90,6 +90,7 @@ SYMBOLS = [
     "vmap_stage_pointcloud", "vmap_insert_staged",
     "vmap_load_occupied_pointcloud_file", "vmap_insert_occupied_points", "vmap_host_read_pointcloud_file",
     "vmap_leaf_digest", "vmap_query_lines_probes_dev",
+    "vmap_dist_attach_local", "vmap_dist_flush_begin",
     "vmap_flush", "vmap_set_pipeline_depth", "vmap_totals", "vmap_region_begin", "vmap_region_end",
 ]
 
@@ -199,6 +200,8 @@ def lib():
     L.vmap_dist_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.vmap_dist_shutdown.argtypes = [vp]
     L.vmap_dist_flush.argtypes = [vp]
+    L.vmap_dist_flush_begin.argtypes = [vp]
+    L.vmap_dist_attach_local.argtypes = [C.POINTER(vp), C.c_int, C.c_uint64]
     L.vmap_dist_set_batch.argtypes = [vp, C.c_int]
     L.vmap_set_debug_l2_flush.argtypes = [vp, sz]
     L.vmap_dist_insert_pointcloud.argtypes = [vp, vp, sz, sz, C.c_int, dp]

@@ -153,6 +153,21 @@ struct vmap : ScanCtx {
   uint32_t* d_count_matrix = nullptr;         // [world][kMaxBatch][2 * kMaxRanks]
   std::vector<uint32_t> h_count_matrix;
 
+  // peer-memory transport of the sharded build (vmap_peer_host.inl)
+  bool peer_on = false;
+  void* mailbox = nullptr;
+  size_t mailbox_bytes = 0;
+  uint32_t peer_capacity = 0;                 // records per round buffer
+  PeerTable pt{};
+  void* peer_ipc_base[kMaxRanks] = {};        // mappings opened with cudaIpcOpenMemHandle
+  uint32_t* d_round_info = nullptr;           // [2 parities][kRoundInfoWords]
+  uint32_t* h_round_info = nullptr;           // pinned mirror
+  uint32_t* d_sub_counts = nullptr;           // [2 scan contexts][counts + cursors]
+  cudaEvent_t ev_collect[2] = {nullptr, nullptr};
+  uint64_t round_open = 0;                    // number of the round being packed
+  int sub_open = 0;                           // scans packed into it so far
+  uint64_t rounds_published = 0, rounds_applied = 0;
+
   uint64_t dense_fallbacks = 0;
   bool traced = false;        // VMAP_TRACE: the walker selection has been printed
   uint32_t* chg0_store = nullptr;   // change-detection planes (MapView.chg0/1 point here while enabled)
@@ -1061,6 +1076,7 @@ bool pipe_eligible(const vmap* h, size_t n) {
 }
 
 int pipe_retire(vmap* h);
+int peer_retire(vmap* h);   // vmap_peer_host.inl
 
 // Drain the pipeline.  Returns the first deferred failure (the failing scan was dropped, later
 // scans were still applied).
@@ -1155,6 +1171,7 @@ int pipe_replay(vmap* h, bool first) {
 // its update -- replay it (and the younger scan behind it, which refused itself too).
 int pipe_retire(vmap* h) {
   if (h->pipe_n <= 0) return VMAP_OK;
+  if (h->peer_on) return peer_retire(h);
   const bool cur_is_oldest = h->in_flight && (!h->alt.in_flight || h->seq < h->alt.seq);
   if (!cur_is_oldest) swap_ctx(h);
   VM_CUDA(h, cudaEventSynchronize(h->ev_done));
@@ -1346,6 +1363,7 @@ int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, si
 
 #include "vmap_sort_host.inl"
 #include "vmap_shard_host.inl"
+#include "vmap_peer_host.inl"
 
 // =============================================================================================
 // C ABI

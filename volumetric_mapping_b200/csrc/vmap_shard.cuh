@@ -244,7 +244,7 @@ __device__ __forceinline__ uint32_t ld_flag(const uint32_t* p) { return *reinter
 // Start of a round's first pack: the round buffer of this parity was last used two rounds ago; wait
 // until every rank has applied that round (want = its number + 1; 0 = nothing to wait for), then
 // reset the header.
-__global__ void k_round_open(PeerTable pt, uint32_t parity, uint32_t want) {
+__device__ __forceinline__ void wait_consumed(const PeerTable& pt, uint32_t want) {
   MailboxHead* mine = pt.head[pt.me];
   if (threadIdx.x < pt.world && want) {
     const long long t0 = global_ns();
@@ -253,6 +253,14 @@ __global__ void k_round_open(PeerTable pt, uint32_t parity, uint32_t want) {
       if (global_ns() - t0 > kSpinLimitNs) { mine->error = 2u; break; }
     }
   }
+}
+// Flush: wait until every rank has applied my rounds up to number want - 1 (nobody reads my round
+// buffers any more).
+__global__ void k_wait_consumed(PeerTable pt, uint32_t want) { wait_consumed(pt, want); }
+
+__global__ void k_round_open(PeerTable pt, uint32_t parity, uint32_t want) {
+  MailboxHead* mine = pt.head[pt.me];
+  wait_consumed(pt, want);
   __syncthreads();
   RoundHeader* h = &mine->hdr[parity];
   if (threadIdx.x == 0) { h->round = 0; h->n_subs = 0; h->fill = 0; h->status = 0; }

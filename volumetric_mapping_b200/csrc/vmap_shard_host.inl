@@ -384,6 +384,19 @@ int vmap_shard_apply_dev(vmap* h, const void* const* d_record_lists, const size_
   return shard_apply_lists(h, (const BlockRecord* const*)d_record_lists, n_records, n_lists);
 } catch (...) { return vmap_on_exception(h); }
 
+}  // extern "C"
+namespace {
+int peer_alloc_mailbox(vmap* h, uint64_t records_per_round);
+void peer_set_table(vmap* h, int s, void* base);
+uint64_t peer_default_records();
+void peer_release(vmap* h);
+int peer_insert(vmap* h, const void* src, bool src_on_host, size_t n, size_t stride, int is_dense, const double Tm[16]);
+int peer_flush_begin(vmap* h);
+int peer_flush_end(vmap* h);
+int init_app_stream(vmap* h);
+}  // namespace
+extern "C" {
+
 // ---- NCCL-backed collective insertion --------------------------------------------------------
 int vmap_dist_unique_id(uint8_t out128[128]) try {
   if (!out128) return VMAP_ERR_INVALID_ARGUMENT;
@@ -411,7 +424,100 @@ int vmap_dist_init(vmap* h, const uint8_t id128[128], int rank, int world) try {
   NcclComm comm = nullptr;
   VM_NCCL(h, g_nccl.CommInitRank(&comm, world, id, rank));
   h->nccl_comm = comm;
+  // Peer-memory transport (default): every rank allocates its mailbox, the CUDA IPC handles travel
+  // in one all-gather, every rank maps every mailbox; a second all-gather makes the choice
+  // unanimous (one rank that cannot map a peer sends everybody back to the NCCL transport).
+  const char* tr = getenv("VMAP_DIST_TRANSPORT");
+  if (world > 1 && !(tr && std::strcmp(tr, "nccl") == 0)) {
+    int ok = 1;
+    if (init_app_stream(h) != VMAP_OK || peer_alloc_mailbox(h, peer_default_records()) != VMAP_OK) ok = 0;
+    constexpr size_t kSlot = 128;   // sizeof(cudaIpcMemHandle_t) == 64, plus a flag byte
+    static_assert(sizeof(cudaIpcMemHandle_t) <= kSlot - 8, "IPC handle size");
+    uint8_t mine[kSlot] = {0};
+    if (ok) {
+      cudaIpcMemHandle_t hd;
+      if (cudaIpcGetMemHandle(&hd, h->mailbox) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+      else std::memcpy(mine, &hd, sizeof(hd));
+    }
+    mine[kSlot - 1] = (uint8_t)ok;
+    uint8_t* d_x = nullptr;
+    VM_CUDA(h, cudaMalloc((void**)&d_x, (size_t)(world + 1) * kSlot));
+    std::vector<uint8_t> all((size_t)world * kSlot);
+    auto gather = [&]() -> int {
+      VM_CUDA(h, cudaMemcpyAsync(d_x, mine, kSlot, cudaMemcpyHostToDevice, h->stream));
+      VM_NCCL(h, g_nccl.AllGather(d_x, d_x + kSlot, kSlot, kNcclUint8, comm, h->stream));
+      VM_CUDA(h, cudaMemcpyAsync(all.data(), d_x + kSlot, (size_t)world * kSlot, cudaMemcpyDeviceToHost, h->stream));
+      VM_CUDA(h, cudaStreamSynchronize(h->stream));
+      return VMAP_OK;
+    };
+    int st = gather();
+    if (st == VMAP_OK) {
+      for (int s = 0; s < world; s++) ok = ok && all[(size_t)s * kSlot + kSlot - 1];
+      if (ok) {
+        for (int s = 0; s < world && ok; s++) {
+          if (s == rank) { peer_set_table(h, s, h->mailbox); continue; }
+          cudaIpcMemHandle_t hd;
+          std::memcpy(&hd, &all[(size_t)s * kSlot], sizeof(hd));
+          void* base = nullptr;
+          if (cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+          h->peer_ipc_base[s] = base;
+          peer_set_table(h, s, base);
+        }
+      }
+      mine[kSlot - 1] = (uint8_t)ok;
+      st = gather();                       // unanimous?
+      if (st == VMAP_OK)
+        for (int s = 0; s < world; s++) ok = ok && all[(size_t)s * kSlot + kSlot - 1];
+    }
+    cudaFree(d_x);
+    VM_TRY(st);
+    if (ok) {
+      h->pt.capacity = h->peer_capacity;
+      h->pt.world = (uint32_t)world;
+      h->pt.me = (uint32_t)rank;
+      h->peer_on = true;
+    } else {
+      peer_release(h);
+    }
+    if (getenv("VMAP_TRACE")) fprintf(stderr, "[vmap rank %d] sharded transport: %s\n", rank, h->peer_on ? "peer memory (CUDA IPC)" : "NCCL send/recv");
+  }
   return VMAP_OK;
+} catch (...) { return vmap_on_exception(h); }
+
+// One process, several handles on one device standing for `world` ranks (tests and single-GPU
+// development): the mailboxes are mapped by plain pointers instead of CUDA IPC, everything else is
+// the code the multi-process build runs.  Call once, with every handle, before the first insert;
+// drive the handles' collective calls in rank order (vmap_dist_flush_begin on all, then
+// vmap_dist_flush on all).
+int vmap_dist_attach_local(vmap** handles, int world, uint64_t records_per_round) try {
+  if (!handles || world < 1 || world > kMaxRanks) return VMAP_ERR_INVALID_ARGUMENT;
+  for (int r = 0; r < world; r++) {
+    vmap* h = handles[r];
+    if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+    VM_CUDA(h, cudaSetDevice(h->device));
+    VM_TRY(vmap_set_shard(h, r, world));
+    VM_TRY(init_app_stream(h));
+    VM_TRY(peer_alloc_mailbox(h, records_per_round ? records_per_round : peer_default_records()));
+  }
+  for (int r = 0; r < world; r++) {
+    vmap* h = handles[r];
+    for (int s = 0; s < world; s++) peer_set_table(h, s, handles[s]->mailbox);
+    h->pt.capacity = h->peer_capacity;
+    h->pt.world = (uint32_t)world;
+    h->pt.me = (uint32_t)r;
+    h->peer_on = true;
+  }
+  return VMAP_OK;
+} catch (...) { return vmap_on_exception(nullptr); }
+
+int vmap_dist_flush_begin(vmap* h) try {
+  if (!h) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  if (!h->peer_on) return VMAP_OK;
+  h->in_collective = true;
+  const int st = peer_flush_begin(h);
+  h->in_collective = false;
+  return st;
 } catch (...) { return vmap_on_exception(h); }
 
 int vmap_dist_shutdown(vmap* h) try {
@@ -420,6 +526,17 @@ int vmap_dist_shutdown(vmap* h) try {
     fprintf(stderr, "[vmap rank %d] per round (host wall ms): generate+pack %.3f | count allgather + wait for previous apply %.3f | exchange/apply enqueue %.3f | (sync path) %.3f  (%llu rounds)\n",
             h->shard_rank, h->dbg_ms[0] / h->dbg_n, h->dbg_ms[1] / h->dbg_n, h->dbg_ms[2] / h->dbg_n, h->dbg_ms[3] / h->dbg_n,
             (unsigned long long)h->dbg_n);
+  if (h->peer_on || h->mailbox) {
+    cudaSetDevice(h->device);
+    if (h->peer_on && h->app_stream && h->rounds_published) {
+      // nobody may still be reading my round buffers when they are freed: wait (bounded) until every
+      // rank has applied my last round
+      k_wait_consumed<<<1, 64, 0, h->app_stream>>>(h->pt, (uint32_t)h->rounds_published);
+    }
+    cudaDeviceSynchronize();
+    cudaGetLastError();
+    peer_release(h);
+  }
   if (h->nccl_comm) {
     cudaSetDevice(h->device);
     h->round_pending = false;   // (a round never exchanged is dropped: vmap_dist_flush is the collective way out)
@@ -493,6 +610,16 @@ static int dist_exchange_and_apply(vmap* h) {
 }  // extern "C"
 namespace {
 int flush_rounds(vmap* h) {
+  if (h->peer_on) {
+    if ((h->sub_open || h->rounds_applied < h->rounds_published || h->pipe_n) && !h->in_collective)
+      return fail(h, VMAP_ERR_DIST, "sharded scans are still in flight: call vmap_dist_flush on every rank first");
+    if (h->app_pending && !h->in_collective) {   // (left by a flush that failed half-way)
+      VM_CUDA(h, cudaStreamSynchronize(h->app_stream));
+      h->app_pending = false;
+      *h->h_persist = *h->h_persist_app;
+    }
+    return VMAP_OK;
+  }
   if (h->round_pending && !h->in_collective)
     return fail(h, VMAP_ERR_DIST, "a sharded round awaits its exchange: call vmap_dist_flush on every rank first");
   if (!h->app_pending) return VMAP_OK;
@@ -653,6 +780,13 @@ extern "C" {
 int vmap_dist_flush(vmap* h) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
+  if (h->peer_on) {
+    h->in_collective = true;
+    int st = peer_flush_begin(h);
+    const int st2 = peer_flush_end(h);
+    h->in_collective = false;
+    return st != VMAP_OK ? st : st2;
+  }
   h->in_collective = true;
   int st = complete_round(h);          // a sealed round waiting for its exchange
   if (st == VMAP_OK) {
@@ -670,7 +804,7 @@ int vmap_dist_flush(vmap* h) try {
 int vmap_dist_set_batch(vmap* h, int scans_per_rank) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
   if (scans_per_rank < 1 || scans_per_rank > kMaxBatch) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "batch must be 1..8");
-  if (h->pack_sub) return fail(h, VMAP_ERR_DIST, "a batch is under construction: call vmap_dist_flush first");
+  if (h->pack_sub || h->sub_open) return fail(h, VMAP_ERR_DIST, "a batch is under construction: call vmap_dist_flush first");
   h->batch_m = scans_per_rank;
   return VMAP_OK;
 } catch (...) { return vmap_on_exception(h); }
@@ -733,6 +867,12 @@ int vmap_dist_insert_pointcloud_dev(vmap* h, const float* d_xyz, size_t n, size_
   if (!h || (!d_xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
+  if (h->peer_on) {
+    h->in_collective = true;
+    const int st = peer_insert(h, d_xyz, false, n, stride_bytes, 1, T_rowmajor);
+    h->in_collective = false;
+    return st;
+  }
   return dist_insert(h, (const uint8_t*)d_xyz, n, stride_bytes, 1, T_rowmajor);
 } catch (...) { return vmap_on_exception(h); }
 
@@ -741,6 +881,12 @@ int vmap_dist_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stri
   if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
+  if (h->peer_on) {
+    h->in_collective = true;
+    const int st = peer_insert(h, xyz, true, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor);
+    h->in_collective = false;
+    return st;
+  }
   VM_TRY(pipe_flush(h));
   if (n) {
     const size_t bytes = (n - 1) * stride_bytes + 12;

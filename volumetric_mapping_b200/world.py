@@ -376,6 +376,21 @@ class OctomapWorld:
         self._check(self._L.vmap_dist_init(self._h, buf, int(rank), int(world)))
         self._world = int(world)
 
+    @staticmethod
+    def dist_attach_local(worlds, records_per_round=0):
+        """Single-process stand-in for a multi-GPU job: `worlds[r]` becomes rank r of len(worlds)
+        (peer-memory transport with plain pointers; see vmap_dist_attach_local)."""
+        L = _capi.lib()
+        arr = (C.c_void_p * len(worlds))(*[w._h for w in worlds])
+        st = L.vmap_dist_attach_local(arr, len(worlds), int(records_per_round))
+        if st != 0:
+            raise VmapError(st, (L.vmap_last_error(worlds[0]._h) or b"").decode())
+        for w in worlds:
+            w._world = len(worlds)
+
+    def dist_flush_begin(self):
+        self._check(self._L.vmap_dist_flush_begin(self._h))
+
     def dist_flush(self):
         self._check(self._L.vmap_dist_flush(self._h))
 
