@@ -2,21 +2,24 @@
 """bench.py -- the headline benchmark of the scan-insertion hot path.
 
 Metric (BASELINE.json): ray-voxel traversals/s (and scans/s) for Velodyne HDL-64-style scans
-inserted at 0.1 m resolution, 50 m max range.  One STEP = one scan (133,312 points, about
-24.9 M ray-voxel traversals) inserted into the growing map; successive steps use successive
-scans of the synthetic corridor trajectory (scenes.trajectory_scan), so every step has new
-input and new map blocks.
+inserted at 0.1 m resolution, 50 m max range (cfg3).  One STEP = one scan per GPU (133,312 points,
+about 24.9 M ray-voxel traversals) inserted into the growing map; successive steps use successive
+scans of the synthetic corridor trajectory (scenes.trajectory_scan), so every step has new input
+and new map blocks.
 
   python bench.py --gpus N --steps K --warmup W            the CUDA path (this repository)
   python bench.py --impl reference --steps K --warmup W    the reference's CPU algorithm
                                                            (oracle/ restatement, 1 thread)
 
-Per-step timing is done on the device with CUDA events recorded on the library's own stream
-(vmap_scan_stats.gpu_ms, bracketing exactly the scan's kernels); a 256 MiB buffer is
-overwritten between steps so no step starts with its map blocks in L2.  N > 1: one process per
-GPU (torchrun); ONE map, sharded by voxel-block owner over the ranks.  A step is one ROUND of N
-scans: rank r generates scan (step*N + r), block records are exchanged all-to-all over NCCL
-inside the library, and every shard applies the round's scans in order (DESIGN.md "Multi-GPU").
+Timing (every N the same way): the K steps are ONE region on the device -- vmap_region_begin /
+vmap_region_end: everything drained, a CUDA event, the K pipelined inserts, everything drained, a
+second event -- bracketed by a barrier + device synchronisation, maximum over ranks.  A 256 MiB
+buffer is overwritten in-stream before every scan, INSIDE the region, so no scan finds its map
+blocks in L2.  N > 1: one process per GPU (torchrun); ONE map, sharded by voxel-block owner over
+the ranks; rank r generates scan (step*N + r), block records are exchanged through peer memory and
+every shard applies the round's scans in order (DESIGN.md "Multi-GPU").  After the timed region
+the sharded map is compared (leaf count + order-independent digest of (key, log-odds bits)) with a
+single-GPU build of the same scans: "parity" in the JSON line, exit code 3 on a mismatch.
 """
 import argparse
 import ctypes as C
@@ -26,6 +29,8 @@ import subprocess
 import sys
 import threading
 import time
+
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream (spin-wait kernels)
 
 import numpy as np
 
@@ -39,7 +44,9 @@ RESOLUTION = 0.10
 MAX_RANGE = 50.0
 METRIC = "ray_voxel_traversals_per_s"
 UNIT = "traversals/s"
-WORKLOAD = "cfg3: HDL-64-style scan, 64x2083=133312 points, 50 m range, 0.1 m voxels, 1 scan/step"
+WORKLOAD = "cfg3: HDL-64-style scan, 64x2083=133312 points, 50 m range, 0.1 m voxels, 1 scan/step/GPU"
+L2_FLUSH_BYTES = 256 << 20
+MAP_BUILD_RES = 0.05
 
 
 def measured_peak_gbs():
@@ -130,14 +137,6 @@ def oracle_world():
     return oracle.OracleWorld(resolution=RESOLUTION, sensor_max_range=MAX_RANGE)
 
 
-def decimate(scan, d):
-    """Every d-th azimuth firing of the scan (all 64 lasers of the kept firings)."""
-    if d <= 1:
-        return scan["points"]
-    pts = scan["points"].reshape(scenes.HDL64_AZIMUTHS, scenes.HDL64_ELEVATIONS, 3)
-    return np.ascontiguousarray(pts[::d]).reshape(-1, 3)
-
-
 def cpu_baseline_sample(budget_s=20.0):
     """Times the oracle on a bounded sample of the same workload: whole scans of the trajectory
     until about `budget_s` seconds of CPU work are done (at least one scan)."""
@@ -171,27 +170,25 @@ def cpu_baseline_sample(budget_s=20.0):
 
 
 def run_reference(args):
+    """The reference's own (single-threaded) algorithm on the stated config: every step is one FULL
+    cfg3 scan of the same trajectory, inserted into the growing map -- about 6 s of CPU per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     total = args.steps + args.warmup
-    d = max(1, int(np.ceil(total / 12.0)))      # keep the whole run within a few minutes
     ow = oracle_world()
     times, trav = [], 0
     for i in range(total):
         s = scenes.trajectory_scan(i, resolution=RESOLUTION)
-        pts = decimate(s, d)
         t0 = time.perf_counter()
-        ow.insertPointcloud(s["T"], pts)
+        ow.insertPointcloud(s["T"], s["points"])
         dt = time.perf_counter() - t0
         if i >= args.warmup:
             times.append(dt)
             trav += ow.last_scan_stats()["traversals"]
     t = sum(times)
     value = trav / t
-    sample = ("each step = every %d-th azimuth firing (%d of 133312 points) of the step's scan"
-              % (d, decimate(scenes.trajectory_scan(0, resolution=RESOLUTION), d).shape[0])
-              if d > 1 else "each step = one full cfg3 scan")
+    sample = "each step = one full cfg3 scan (133312 points) of the same trajectory"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -217,6 +214,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import volumetric_mapping_b200 as vm
+    from volumetric_mapping_b200 import sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,195 +228,334 @@ def run_b200(args):
 
     K, W = args.steps, args.warmup
     total = K + W
-    # weak scaling: a step is one round of `world` scans of the SAME trajectory and map; rank r
-    # generates scan step*world + r, every shard applies the round in scan order.
-    scans = [scenes.trajectory_scan(rank + world * i, resolution=RESOLUTION) for i in range(total)]
-    n_pts = scans[0]["points"].shape[0]
-    dev_pts = [torch.from_numpy(s["points"]).cuda() for s in scans]
-    pinned = [torch.from_numpy(s["points"]).pin_memory() for s in scans]
-    pinned_np = [p.numpy() for p in pinned]
-    T_c = [(C.c_double * 16)(*np.ascontiguousarray(s["T"], dtype=np.float64).reshape(16)) for s in scans]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(kind):
-        """kind: 'dev' (inputs resident in HBM) or 'host' (pinned host buffers, H2D inside)."""
+    def allmax(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def gather_digest(n, d):
+        """(count, digest) of the whole map: shard digests add up modulo 2^64."""
+        if world == 1:
+            return n, d
+        mine = torch.tensor([n, d - (1 << 64) if d >= (1 << 63) else d], dtype=torch.int64, device="cuda")
+        got = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(got, mine)
+        cnt = sum(int(g[0].item()) for g in got)
+        dg = sum(int(g[1].item()) % (1 << 64) for g in got) % (1 << 64)
+        return cnt, dg
+
+    def make_world(res, blocks):
+        """One map: a single handle at N = 1, a sharded one (peer-memory transport) at N > 1."""
         if world > 1:
-            from volumetric_mapping_b200 import sharded
             sw = sharded.ShardedOctomapWorld(rank, world, local_rank, batch=args.dist_batch,
-                                             resolution=RESOLUTION, sensor_max_range=MAX_RANGE,
-                                             initial_blocks=1 << 18)
-            w = sw.local
-            w.set_debug_l2_flush(256 << 20)   # in-stream L2 flush before every round's apply
-        else:
-            w = vm.OctomapWorld(resolution=RESOLUTION, sensor_max_range=MAX_RANGE,
-                                initial_blocks=1 << 19, device=local_rank)
-        launches0 = None
-        stats, gpu_ms, wall_ms = [], [], []
-        sampler = ClockSampler(local_rank)
-        if kind == "dev" and rank == 0:
-            sampler.start()          # nvidia-smi needs ~100 ms to come up: start before warm-up
-            time.sleep(0.3)
-        t_region = None
-        for i in range(total):
-            if i == W:
-                if world > 1:
-                    w.dist_flush()
-                barrier()
-                launches0 = w.kernel_launches()
-                t_region = time.perf_counter()
-            if world > 1:
-                # rounds are pipelined inside the library (exchange + apply of round k overlap the
-                # generation of round k+1): the timed region is the K rounds as a whole
-                if kind == "dev":
-                    w.dist_insert_pointcloud_device(scans[i]["T"], dev_pts[i].data_ptr(), n_pts)
-                else:
-                    w.dist_insert_pointcloud(scans[i]["T"], pinned_np[i])
-                st = w.last_scan_stats()
-                if i >= W:
-                    stats.append(st)
-                continue
-            flush.fill_(i & 0xFF)            # evict the map from L2 between steps
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            if kind == "dev":
-                w.insertPointcloudDevice(scans[i]["T"], dev_pts[i].data_ptr(), n_pts)
-            else:
-                w.insertPointcloudHostPtr(T_c[i], pinned[i].data_ptr(), n_pts)
-            dt = time.perf_counter() - t0
-            st = w.last_scan_stats()
-            if i >= W:
-                stats.append(st)
-                gpu_ms.append(st["gpu_ms"])
-                wall_ms.append(1e3 * dt)
-        if world > 1:
-            w.dist_flush()
-        barrier()
-        if world > 1:
-            region_ms = 1e3 * (time.perf_counter() - t_region)
-            gpu_ms = wall_ms = [region_ms / K] * K
-        clocks = sampler.stop() if (kind == "dev" and rank == 0) else None
-        launches = w.kernel_launches() - launches0
-        out = {"stats": stats, "gpu_ms": gpu_ms, "wall_ms": wall_ms, "launches": launches,
-               "clocks": clocks, "device_bytes": w.device_bytes()}
-        if kind == "dev" and world == 1:
-            out["queries"] = time_queries(w, total)
-        if world > 1:
+                                             resolution=res, sensor_max_range=MAX_RANGE,
+                                             initial_blocks=blocks)
+            return sw, sw.local
+        w = vm.OctomapWorld(resolution=res, sensor_max_range=MAX_RANGE, initial_blocks=blocks, device=local_rank)
+        return None, w
+
+    def close_world(sw, w):
+        if sw is not None:
             sw.close()
         else:
             w.close()
+
+    def timed_build(res, n_total, n_warm, kind, blocks, stride=12, writeback=False, keep=False, sample_clocks=False):
+        """Inserts scans rank + world * i (i < n_total) of the trajectory at `res`; the first n_warm
+        steps are warm-up, the rest is the timed region.  kind: 'dev' (points resident in HBM),
+        'host' (pinned host points, lean call) or 'dropin' (pageable 16-byte points, in-place
+        world-frame write-back: what the reference-side binding passes)."""
+        scans = [scenes.trajectory_scan(rank + world * i, resolution=res) for i in range(n_total)]
+        n_pts = scans[0]["points"].shape[0]
+        T_c = [(C.c_double * 16)(*np.ascontiguousarray(s["T"], dtype=np.float64).reshape(16)) for s in scans]
+        if kind == "dev":
+            bufs = [torch.from_numpy(s["points"]).cuda() for s in scans]
+        elif kind == "host":
+            bufs = [torch.from_numpy(s["points"]).pin_memory() for s in scans]
+        else:
+            bufs = []
+            for s in scans:      # pcl::PointXYZ: x, y, z, 1.0f -- pageable, like a cloud that came off a message
+                b = np.ones((n_pts, stride // 4), dtype=np.float32)
+                b[:, :3] = s["points"]
+                bufs.append(b)
+        sw, w = make_world(res, blocks)
+        w.set_debug_l2_flush(L2_FLUSH_BYTES)
+        n_out = C.c_size_t(0)
+
+        def insert(i):
+            if world > 1:
+                if kind == "dev":
+                    w.dist_insert_pointcloud_device(scans[i]["T"], bufs[i].data_ptr(), n_pts)
+                else:
+                    w._check(w._L.vmap_dist_insert_pointcloud(w.handle, C.c_void_p(bufs[i].data_ptr()), n_pts, 12, 1, T_c[i]))
+            elif kind == "dev":
+                w._check(w._L.vmap_insert_pointcloud_dev(w.handle, C.c_void_p(bufs[i].data_ptr()), n_pts, 12, T_c[i]))
+            elif kind == "host":
+                w.insertPointcloudHostPtr(T_c[i], bufs[i].data_ptr(), n_pts)
+            else:
+                p = bufs[i].ctypes.data
+                w._check(w._L.vmap_insert_pointcloud(w.handle, p, n_pts, stride, 1, T_c[i], p, C.byref(n_out)))
+
+        def flush():
+            if world > 1:
+                w.dist_flush()
+            else:
+                w.flush()
+
+        sampler = ClockSampler(local_rank)
+        if kind == "dev" and rank == 0 and sample_clocks:
+            sampler.start()          # nvidia-smi needs ~100 ms to come up: start before warm-up
+            time.sleep(0.3)
+        for i in range(n_warm):
+            insert(i)
+        flush()
+        barrier()
+        t_before = w.totals()
+        launches0 = w.kernel_launches()
+        w.region_begin()
+        t0 = time.perf_counter()
+        for i in range(n_warm, n_total):
+            insert(i)
+        flush()
+        ms = w.region_end()
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        t_after = w.totals()
+        clocks = sampler.stop() if (kind == "dev" and rank == 0 and sample_clocks) else None
+        out = {"ms": allmax(ms), "wall_ms": allmax(wall_ms),
+               "traversals": allsum(t_after["traversals"] - t_before["traversals"]),
+               "launches": int(allsum(w.kernel_launches() - launches0)),
+               "replayed": int(allsum(t_after["replayed"])), "n_pts": n_pts, "clocks": clocks,
+               "device_bytes": w.device_bytes(), "steps": n_total - n_warm}
+        out["digest"] = gather_digest(*w.leaf_digest())
+        if keep:
+            out["world"] = (sw, w)
+        else:
+            close_world(sw, w)
         return out
+
+    def single_gpu_digest(res, n_total, blocks):
+        """The same scans, in global order, through vmap_insert_pointcloud_dev on ONE device (the
+        oracle-verified path): what the sharded map must equal."""
+        w = vm.OctomapWorld(resolution=res, sensor_max_range=MAX_RANGE, initial_blocks=blocks, device=local_rank)
+        for g in range(n_total * world):
+            s = scenes.trajectory_scan(g, resolution=res)
+            d = torch.from_numpy(s["points"]).cuda()
+            w.insertPointcloudDevice(s["T"], d.data_ptr(), d.shape[0])
+        out = w.leaf_digest()
+        w.close()
+        return out
+
+    def stage_pass(n_total, n_warm):
+        """Serialised pass (pipeline depth 0, one scan at a time) for the per-stage CUDA-event times
+        the roofline needs; the L2 flush runs in-stream BEFORE each scan's first event."""
+        w = vm.OctomapWorld(resolution=RESOLUTION, sensor_max_range=MAX_RANGE, initial_blocks=1 << 19, device=local_rank)
+        w.set_pipeline_depth(0)
+        w.set_debug_l2_flush(L2_FLUSH_BYTES)
+        stats = []
+        for i in range(n_total):
+            s = scenes.trajectory_scan(i, resolution=RESOLUTION)
+            d = torch.from_numpy(s["points"]).cuda()
+            w.insertPointcloudDevice(s["T"], d.data_ptr(), d.shape[0])
+            if i >= n_warm:
+                stats.append(w.last_scan_stats())
+        w.close()
+        return stats
 
     def time_queries(w, n_scans):
         """cfg5: 1M getLineStatus segments + 1M getCellStatusPoint points against the map just
-        built (device-resident queries, L2 flushed, wall clock around the C ABI call)."""
-        q = scenes.cfg5_queries(bounds=((-45.0, 45.0 + 0.5 * n_scans), (-45.0, 45.0), (-0.5, 4.0)))
-        seg = torch.from_numpy(q["segments"]).cuda()
+        built (device-resident queries, L2 flushed, wall clock around the C ABI call); the same for
+        a HARD subset -- segments that start in known-free space along the trajectory --, the probe
+        count behind B_alg = 49 + 12 * probes per segment, and a 100k subsample checked against the
+        CPU oracle on an oracle-built map of the same scans when that is affordable."""
+        flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        bounds = ((-45.0, 45.0 + 0.5 * n_scans), (-45.0, 45.0), (-0.5, 4.0))
+        q = scenes.cfg5_queries(bounds=bounds)
+        rng = np.random.default_rng(7)
+        m = q["segments"].shape[0]
+        # hard subset: start points 0.3..1.7 m above the ground within 8 m of the sensor path (seen free)
+        a = np.stack([rng.uniform(0.0, 0.5 * n_scans, m), rng.uniform(-8.0, 8.0, m), rng.uniform(0.3, 1.7, m)], axis=1)
+        d = rng.normal(size=(m, 3))
+        d[:, 2] *= 0.15
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        hard = np.concatenate([a, a + d * rng.uniform(2.0, 30.0, (m, 1))], axis=1)
+        out = {}
+        peak, _ = measured_peak_gbs()
+        for name, segs in (("uniform", q["segments"]), ("hard", hard)):
+            seg = torch.from_numpy(np.ascontiguousarray(segs)).cuda()
+            sl = torch.zeros(seg.shape[0], dtype=torch.uint8, device="cuda")
+            best = 1e9
+            for rep in range(4):
+                flush.fill_(rep)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                w.getLineStatusDevice(seg.data_ptr(), seg.shape[0], sl.data_ptr())
+                t1 = time.perf_counter()
+                if rep:
+                    best = min(best, t1 - t0)
+            probes = w.getLineStatusProbesDevice(seg.data_ptr(), seg.shape[0], sl.data_ptr())
+            b_alg = 49 * seg.shape[0] + 12 * probes
+            out[name] = {"segments_per_s": seg.shape[0] / best, "line_ms": 1e3 * best,
+                         "probes_per_segment": probes / seg.shape[0],
+                         "non_free_fraction": float((sl != 0).float().mean().item()),
+                         "roofline": {"bound": "hbm", "algorithmic_bytes": b_alg, "achieved": b_alg / best / 1e9,
+                                      "peak": peak, "unit": "GB/s", "frac": b_alg / best / 1e9 / peak}}
         pts = torch.from_numpy(q["points"]).cuda()
-        sl = torch.zeros(seg.shape[0], dtype=torch.uint8, device="cuda")
         sp = torch.zeros(pts.shape[0], dtype=torch.uint8, device="cuda")
-        best_l, best_p = 1e9, 1e9
+        best_p = 1e9
         for rep in range(4):
-            flush.fill_(rep)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            w.getLineStatusDevice(seg.data_ptr(), seg.shape[0], sl.data_ptr())
-            t1 = time.perf_counter()
             flush.fill_(rep + 7)
             torch.cuda.synchronize()
             t2 = time.perf_counter()
             w.getCellStatusPointDevice(pts.data_ptr(), pts.shape[0], sp.data_ptr())
             t3 = time.perf_counter()
             if rep:
-                best_l, best_p = min(best_l, t1 - t0), min(best_p, t3 - t2)
-        return {"workload": "cfg5: 1M segments (0.5-20 m) + 1M points vs the 0.1 m map of %d scans" % n_scans,
-                "segments_per_s": seg.shape[0] / best_l, "points_per_s": pts.shape[0] / best_p,
-                "line_ms": 1e3 * best_l, "point_ms": 1e3 * best_p,
-                "non_free_fraction": float((sl != 0).float().mean().item())}
+                best_p = min(best_p, t3 - t2)
+        out["points_per_s"] = pts.shape[0] / best_p
+        out["point_ms"] = 1e3 * best_p
+        out["workload"] = ("cfg5: 1M segments (0.5-20 m, uniform in the mapped box) / 1M hard segments (2-30 m, starting in "
+                           "known-free space along the path) + 1M points vs the 0.1 m map of %d scans" % n_scans)
+        # compatibility keys of the round-1 line
+        out["segments_per_s"] = out["uniform"]["segments_per_s"]
+        out["line_ms"] = out["uniform"]["line_ms"]
+        out["non_free_fraction"] = out["uniform"]["non_free_fraction"]
+        return out
 
-    dev = run("dev")
-    host = run("host")
+    def map_build(n_scans):
+        """BASELINE.json config 4, bounded: n_scans consecutive scans per GPU of the 1000-scan trajectory
+        at 0.05 m (about 55 M traversals and 350 k voxel blocks per scan), same timing as the headline."""
+        r = timed_build(MAP_BUILD_RES, n_scans + 3, 3, "dev", 1 << 21)
+        return {"workload": "cfg4 (bounded): %d consecutive scans per GPU of the 1000-scan trajectory at 0.05 m, "
+                            "map sharded over %d GPU(s)" % (n_scans, world),
+                "scans": n_scans * world, "ms_per_step": r["ms"] / n_scans,
+                "scans_per_s": n_scans * world / (r["ms"] * 1e-3),
+                "traversals_per_s": r["traversals"] / (r["ms"] * 1e-3),
+                "traversals_per_scan": r["traversals"] / (n_scans * world),
+                "leaves": r["digest"][0], "replayed": r["replayed"], "device_bytes": r["device_bytes"]}
 
-    trav = sum(s["traversals"] for s in dev["stats"])
-    t_dev = sum(dev["gpu_ms"]) * 1e-3
-    t_host = sum(host["wall_ms"]) * 1e-3
-    trav_host = sum(s["traversals"] for s in host["stats"])
+    # ---- the runs ----
+    dev = timed_build(RESOLUTION, total, W, "dev", 1 << 19, keep=(world == 1), sample_clocks=True)
+    host = timed_build(RESOLUTION, total, W, "host", 1 << 19)
+    parity = None
     if world > 1:
-        # whole-job aggregate: all ranks' traversals over the slowest rank's time
-        tt = torch.tensor([t_dev, t_host], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tv = torch.tensor([trav, trav_host], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tv, op=dist.ReduceOp.SUM)
-        ln = torch.tensor([dev["launches"]], dtype=torch.float64, device="cuda")
-        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
-        t_dev, t_host = tt.tolist()
-        trav, trav_host = tv.tolist()
-        launches = int(ln.item())
-    else:
-        launches = dev["launches"]
+        ref = single_gpu_digest(RESOLUTION, total, 1 << 19) if rank == 0 else (0, 0)
+        parity = {"checked": True, "leaves": dev["digest"][0], "digest": "%016x" % dev["digest"][1],
+                  "single_gpu_leaves": ref[0], "single_gpu_digest": "%016x" % ref[1],
+                  "equal": bool(dev["digest"] == ref and host["digest"] == ref) if rank == 0 else None,
+                  "how": "leaf count and order-independent 64-bit digest of (key, log-odds bits), shards summed, "
+                         "vs a single-GPU vmap_insert_pointcloud_dev build of the same %d scans" % (total * world)}
+    queries = dropin = stages = None
+    if world == 1:
+        sw0, w0 = dev.pop("world")
+        queries = time_queries(w0, total)
+        close_world(sw0, w0)
+        dropin = timed_build(RESOLUTION, total, W, "dropin", 1 << 19, stride=16, writeback=True)
+        stages = stage_pass(min(total, W + 12), W)
+    mb = map_build(args.map_build_scans) if args.map_build_scans > 0 else None
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        st = dev["stats"]
-        # dominant kernel: the DDA walk (K2).  Average launch duration from CUDA events on the
-        # library's stream over the timed region; algorithmic bytes per launch per DESIGN.md.
-        walk_ms = float(np.mean([s["walk_ms"] for s in st]))
-        walk_b = float(np.mean([walk_bytes(s) for s in st]))
-        scan_b = float(np.mean([algorithmic_bytes(s, n_pts) for s in st]))
-        scan_ms = float(np.mean([s["gpu_ms"] for s in st]))
-        ach = walk_b / (walk_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "K2 = k_checkpoints + k_walk_segments (+ list/locate): DDA walk + key-set build",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": walk_b, "avg_launch_ms": walk_ms,
-                    "whole_scan": {"algorithmic_bytes": scan_b, "gpu_ms": scan_ms,
-                                   "achieved": scan_b / (scan_ms * 1e-3) / 1e9,
-                                   "frac": scan_b / (scan_ms * 1e-3) / 1e9 / peak},
-                    "stage_ms": {k: float(np.mean([s[k] for s in st]))
-                                 for k in ("front_ms", "resolve_ms", "walk_ms", "update_ms")}}
-        traffic_file = os.path.join(ROOT, "profiles", "walk_traffic.json")
-        if os.path.exists(traffic_file):
-            try:
-                roofline["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
-            except Exception:
-                pass
+        n_pts = dev["n_pts"]
+        t_dev, t_host = dev["ms"] * 1e-3, host["ms"] * 1e-3
+        roofline = None
+        if stages:
+            # dominant kernel: the DDA walk (K2).  Average duration from CUDA events on the library's
+            # stream in the serialised pass; algorithmic bytes per launch per DESIGN.md.
+            walk_ms = float(np.mean([s["walk_ms"] for s in stages]))
+            walk_b = float(np.mean([walk_bytes(s) for s in stages]))
+            scan_b = float(np.mean([algorithmic_bytes(s, n_pts) for s in stages]))
+            scan_ms = float(np.mean([s["gpu_ms"] for s in stages]))
+            ach = walk_b / (walk_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "K2 = k_checkpoints + k_walk_segments_dilated (+ list): DDA walk + key-set build",
+                        "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": walk_b, "avg_launch_ms": walk_ms,
+                        "measured_in": "serialised pass of %d scans (pipeline depth 0), CUDA events between the kernels" % len(stages),
+                        "whole_scan": {"algorithmic_bytes": scan_b, "gpu_ms": scan_ms,
+                                       "achieved": scan_b / (scan_ms * 1e-3) / 1e9,
+                                       "frac": scan_b / (scan_ms * 1e-3) / 1e9 / peak},
+                        "whole_scan_pipelined": {"algorithmic_bytes": scan_b, "ms": dev["ms"] / K,
+                                                 "achieved": scan_b / (dev["ms"] / K * 1e-3) / 1e9,
+                                                 "frac": scan_b / (dev["ms"] / K * 1e-3) / 1e9 / peak},
+                        "stage_ms": {k: float(np.mean([s[k] for s in stages]))
+                                     for k in ("front_ms", "resolve_ms", "walk_ms", "update_ms")}}
+            traffic_file = os.path.join(ROOT, "profiles", "walk_traffic.json")
+            if os.path.exists(traffic_file):
+                try:
+                    tf = json.load(open(traffic_file))
+                    roofline["traffic"] = tf["dram_bytes_per_launch"]
+                    if tf.get("warp_instructions") and tf.get("kernel_us"):
+                        # the walk is issue / latency bound, not HBM bound: instructions the kernel executes
+                        # against what the 592 SM sub-partitions could issue in its run time
+                        sm_mhz = (dev["clocks"] or {}).get("sm_mhz") or 1965.0
+                        roofline["issue_frac"] = tf["warp_instructions"] / (592 * sm_mhz * 1e6 * tf["kernel_us"] * 1e-6)
+                        roofline["issue_note"] = ("%d warp instructions of the walk kernel (ncu, profiles/) over 592 issue "
+                                                  "ports x SM clock x its %.1f us" % (tf["warp_instructions"], tf["kernel_us"]))
+                except Exception:
+                    pass
         cpu = cpu_baseline_sample() if world == 1 and not args.no_cpu_baseline else None
         line = {
-            "metric": METRIC, "value": trav / t_dev, "unit": UNIT, "n_gpus": world,
+            "metric": METRIC, "value": dev["traversals"] / t_dev, "unit": UNIT, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32/u16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "resolution": RESOLUTION, "max_range": MAX_RANGE,
-                       "points_per_step": n_pts,
-                       "traversals_per_step": trav / K / world,
-                       "l2": ("256 MiB buffer overwritten between steps (L2 flushed)" if world == 1 else
-                              "256 MiB buffer overwritten on the apply stream before every round"),
-                       "timing": ("CUDA events on the library stream around each scan's kernels"
-                                  if world == 1 else "wall clock over the K pipelined rounds, barrier + "
-                                  "device sync on both sides, max over ranks"),
-                       "sharding": ("one map sharded by 8^3-block owner over %d ranks; step = "
-                                    "round of %d scans, NCCL all-to-all of block records once per "
-                                    "%d rounds" % (world, world, args.dist_batch)) if world > 1 else "single GPU"},
+                       "points_per_step": n_pts * world,
+                       "traversals_per_step": dev["traversals"] / K,
+                       "l2": "256 MiB buffer overwritten in-stream before every scan, inside the timed region",
+                       "timing": "one device-timed region over the K pipelined steps (CUDA events after a full drain on "
+                                 "both sides), barrier + device sync around it, max over ranks",
+                       "pipeline": "2 scans in flight per GPU on two scan contexts; map updates ordered by events",
+                       "sharding": ("one map sharded by 8^3-block owner over %d ranks; step = round of %d scans; block "
+                                    "records pulled from the peers' round buffers over NVLink (CUDA IPC), %d scans per "
+                                    "rank per round" % (world, world, args.dist_batch)) if world > 1 else "single GPU"},
             "scans_per_s": K * world / t_dev,
-            "e2e": {"value": trav_host / t_host, "unit": UNIT,
-                    "h2d_bytes_per_step": n_pts * 12, "d2h_bytes_per_step": 80,
-                    "scans_per_s": K * world / t_host,
-                    "how": "vmap_insert_pointcloud (C ABI) on pinned host points; wall clock "
-                           "around each call (H2D copy, 4 kernels, counter read-back)"},
-            "gpu_launches": launches,
+            "e2e": {"value": host["traversals"] / t_host, "unit": UNIT,
+                    "h2d_bytes_per_step": n_pts * 12 * world, "d2h_bytes_per_step": 96 * world,
+                    "scans_per_s": K * world / t_host, "ms_per_step": host["ms"] / K,
+                    "how": "vmap_insert_pointcloud / vmap_dist_insert_pointcloud (C ABI) on pinned host points: H2D copy, "
+                           "kernels and counter read-back of every step inside the same kind of timed region"},
+            "gpu_launches": dev["launches"],
             "clocks": dev["clocks"],
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "queries": dev.get("queries"),
+            "queries": queries,
+            "map_build": mb,
+            "parity": parity,
             "device_bytes": dev["device_bytes"],
+            "scans_replayed_after_growth": dev["replayed"],
         }
+        if dropin:
+            t_d = dropin["ms"] * 1e-3
+            line["e2e_dropin"] = {"value": dropin["traversals"] / t_d, "unit": UNIT,
+                                  "scans_per_s": K / t_d, "ms_per_step": dropin["ms"] / K,
+                                  "h2d_bytes_per_step": n_pts * 16, "d2h_bytes_per_step": n_pts * 16 + 96,
+                                  "how": "what the reference-side binding passes (INTEGRATION.md): pageable pcl::PointXYZ "
+                                         "cloud (16-byte stride), is_dense, in-place world-frame write-back "
+                                         "(octomap_world.cc:115-119) -- every call waits for its own write-back"}
+            line["e2e_dropin"]["same_map_as_lean"] = bool(dropin["digest"] == host["digest"] == dev["digest"])
         print(json.dumps(line))
+    rc = 0
     if world > 1:
+        ok = torch.tensor([1 if (rank != 0 or parity["equal"]) else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        rc = 0 if int(ok.item()) else 3
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 def main():
@@ -428,12 +565,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--dist-batch", type=int, default=4,
+    ap.add_argument("--dist-batch", type=int, default=2,
                     help="N > 1: scans per rank that share one exchange round (1..8)")
+    ap.add_argument("--map-build-scans", type=int, default=32,
+                    help="cfg4 leg: scans per GPU at 0.05 m (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
     if args.impl == "reference":
+        if args.steps == 100 and args.warmup == 5:
+            args.steps, args.warmup = 20, 3       # defaults of the CPU arm: about 2.5 minutes
         return run_reference(args)
     return run_b200(args)
 

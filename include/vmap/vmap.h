@@ -379,8 +379,10 @@ VMAP_API int vmap_dist_flush(vmap* h);
  * (default 3 Mi records of 136 bytes, twice per rank).
  *
  * vmap_dist_attach_local: `world` handles of ONE process on one device stand for the ranks (tests,
- * single-GPU development); mailboxes are shared by plain pointers.  Drive the collective calls in
- * rank order, and flush with vmap_dist_flush_begin on every handle before vmap_dist_flush on any. */
+ * single-GPU development); mailboxes are shared by plain pointers.  Drive every handle from its own
+ * host thread, as if it were a process (a rank's host may block until its peers have made progress).
+ * vmap_dist_flush_begin is the non-blocking first half of vmap_dist_flush (seal + publish a partial
+ * batch). */
 VMAP_API int vmap_dist_attach_local(vmap** handles, int world, uint64_t records_per_round);
 VMAP_API int vmap_dist_flush_begin(vmap* h);
 /* Scans per rank that share one exchange round (1..8, default 1).  COLLECTIVE setting. */

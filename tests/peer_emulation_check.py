@@ -1,5 +1,6 @@
 """Peer-memory transport of the sharded build on ONE GPU: G handles of this process stand for G
-ranks (vmap_dist_attach_local: mailboxes shared by plain pointers instead of CUDA IPC).  Everything
+ranks (vmap_dist_attach_local: mailboxes shared by plain pointers instead of CUDA IPC), each driven
+by its own host thread.  Everything
 else -- pipelined generate on two scan contexts, packing into round buffers, publish / collect /
 consumed flags, applies reading the peers' round buffers, batches, ragged last round, growth of
 table and pool between rounds -- is the code the multi-process build runs.
@@ -7,6 +8,7 @@ Bar: the union of the shards equals the CPU oracle's map bit for bit (order of t
 octomap_world.cc:244-262).       usage: peer_emulation_check.py G batch n_scans [resolution]"""
 import os
 import sys
+import threading
 
 # several spinning one-warp kernels of different handles are resident at once: every stream needs
 # its own hardware queue, or a spinner could sit in front of the kernel it is waiting for
@@ -34,19 +36,36 @@ def main():
     ow.set_faithful_inner_update(False)
     rounds = (n_scans + G - 1) // G
     empty = np.zeros((0, 3), np.float32)
-    for k in range(rounds):
-        for r, w in enumerate(shards):
-            i = k * G + r
-            if i < n_scans:
-                w.dist_insert_pointcloud(scans[i]["T"], scans[i]["points"])
-            else:
-                w.dist_insert_pointcloud(np.eye(4), empty)      # ragged last round: no scan on this rank
+    errors = [None] * G
+
+    def rank_main(r):
+        """What one rank's process does: its scan of every round, then the collective flush."""
+        w = shards[r]
+        try:
+            for k in range(rounds):
+                i = k * G + r
+                if i < n_scans:
+                    w.dist_insert_pointcloud(scans[i]["T"], scans[i]["points"])
+                else:
+                    w.dist_insert_pointcloud(np.eye(4), empty)      # ragged last round: no scan on this rank
+            w.dist_flush()
+        except Exception as e:      # noqa: BLE001
+            errors[r] = e
+
+    # one host thread per rank (ctypes drops the GIL inside the library): a rank's host may block on
+    # its peers -- sizing the table needs the round's counts -- exactly like separate processes do
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(G)]
+    for t in threads:
+        t.start()
     for s in scans:
         ow.insertPointcloud(s["T"], s["points"])
-    for w in shards:
-        w.dist_flush_begin()
-    for w in shards:
-        w.dist_flush()
+    for t in threads:
+        t.join()
+    for r, e in enumerate(errors):
+        if e is not None:
+            print("rank", r, "failed:", repr(e), flush=True)
+    if any(e is not None for e in errors):
+        return 1
     ks, vs, cnt, dig = [], [], 0, 0
     for r, w in enumerate(shards):
         k, v = w.export_leaves()

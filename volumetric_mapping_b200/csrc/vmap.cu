@@ -167,6 +167,8 @@ struct vmap : ScanCtx {
   uint64_t round_open = 0;                    // number of the round being packed
   int sub_open = 0;                           // scans packed into it so far
   uint64_t rounds_published = 0, rounds_applied = 0;
+  bool peer_local = false;                    // vmap_dist_attach_local: the "peers" are handles of this process
+  std::vector<std::pair<void*, size_t>> graveyard;   // device buffers retired while peers may be spinning (see dev_free)
 
   uint64_t dense_fallbacks = 0;
   bool traced = false;        // VMAP_TRACE: the walker selection has been printed
@@ -259,11 +261,25 @@ int dev_alloc(vmap* h, void** p, size_t bytes) {
   h->dev_bytes += bytes;
   return VMAP_OK;
 }
+// cudaFree waits for EVERYTHING on the device.  With the peer-memory transport a one-warp kernel of
+// this handle may be spinning on a flag a peer sets only after this host thread has made progress
+// (and, with vmap_dist_attach_local, the peers' spinners live in this very context), so buffers
+// retired while the transport is on are parked and released at the next quiescent point.
 void dev_free(vmap* h, void* p, size_t bytes) {
-  if (p) {
-    cudaFree(p);
-    h->dev_bytes -= bytes;
+  if (!p) return;
+  if (h->peer_on) {
+    h->graveyard.emplace_back(p, bytes);
+    return;
   }
+  cudaFree(p);
+  h->dev_bytes -= bytes;
+}
+void empty_graveyard(vmap* h) {
+  for (auto& g : h->graveyard) {
+    cudaFree(g.first);
+    h->dev_bytes -= g.second;
+  }
+  h->graveyard.clear();
 }
 int ensure(vmap* h, DevBuf* b, size_t bytes) {
   if (bytes <= b->cap) return VMAP_OK;

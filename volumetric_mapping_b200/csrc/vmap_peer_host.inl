@@ -49,6 +49,8 @@ uint64_t peer_default_records() {
 }
 
 void peer_release(vmap* h) {
+  h->peer_on = false;          // (frees are immediate again: the caller has drained the device)
+  empty_graveyard(h);
   if (!h->mailbox) return;
   for (int s = 0; s < kMaxRanks; s++)
     if (h->peer_ipc_base[s]) { cudaIpcCloseMemHandle(h->peer_ipc_base[s]); h->peer_ipc_base[s] = nullptr; }
@@ -288,6 +290,9 @@ int peer_flush_end(vmap* h) {
       h->stats.blocks_applied = h->app_records;
     }
     if (err) note(fail(h, VMAP_ERR_DIST, "sharded insertion: a rank did not answer in time (mailbox error word set)"));
+    // quiescent: nothing of this rank is in flight and nobody reads its round buffers.  (Not with
+    // vmap_dist_attach_local: the other handles' spinners are kernels of this very context.)
+    if (!h->peer_local) empty_graveyard(h);
   }
   if (first != VMAP_OK) h->err = msg;
   return first;

@@ -487,8 +487,8 @@ int vmap_dist_init(vmap* h, const uint8_t id128[128], int rank, int world) try {
 // One process, several handles on one device standing for `world` ranks (tests and single-GPU
 // development): the mailboxes are mapped by plain pointers instead of CUDA IPC, everything else is
 // the code the multi-process build runs.  Call once, with every handle, before the first insert;
-// drive the handles' collective calls in rank order (vmap_dist_flush_begin on all, then
-// vmap_dist_flush on all).
+// then drive every handle from its OWN host thread (a rank's host blocks on its peers' progress, as
+// separate processes do; one thread driving all handles would wait for work it has not enqueued yet).
 int vmap_dist_attach_local(vmap** handles, int world, uint64_t records_per_round) try {
   if (!handles || world < 1 || world > kMaxRanks) return VMAP_ERR_INVALID_ARGUMENT;
   for (int r = 0; r < world; r++) {
@@ -506,6 +506,7 @@ int vmap_dist_attach_local(vmap** handles, int world, uint64_t records_per_round
     h->pt.world = (uint32_t)world;
     h->pt.me = (uint32_t)r;
     h->peer_on = true;
+    h->peer_local = true;
   }
   return VMAP_OK;
 } catch (...) { return vmap_on_exception(nullptr); }
