@@ -158,6 +158,34 @@ int wc_walk_segmented(double res, double max_free_space, double min_height, cons
       if (mode == 3) {
         if (P.free_filter) walk_slot<true>(P, ms, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], variant, &emitted, &longest);
         else walk_slot<false>(P, ms, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], variant, &emitted, &longest);
+      } else if (mode == 6) {
+        // the shipped walker: queued marks (one "lane": the queue is drained after every 8 steps)
+        uint32_t n_steps = 0;
+        bool active = true;
+        if (jj + 1 < cps[r].size()) n_steps = cps[r][jj + 1].count - cps[r][jj].count;
+        else if (recs[r].n_keys != 0xFFFFFFFFu) n_steps = recs[r].n_keys > cps[r][jj].count ? recs[r].n_keys - cps[r][jj].count : 0u;
+        else active = false;
+        uint32_t qbuf[3 * kQueueSteps];
+        MarkQueue mq;
+        mq.w = qbuf;
+        mq.stride = 1;
+        if (!active) {
+          if (P.free_filter) walk_slot_dilated<true, 0, false, true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest);
+          else walk_slot_dilated<false, 0, false, true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest);
+        } else if (P.free_filter) walk_slot_queued<true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, n_steps, true, mq);
+        else walk_slot_queued<false>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, n_steps, true, mq);
+      } else if (mode == 4 || mode == 5) {
+        // the shipped kernel's counted loop: steps of a non-last segment = next checkpoint's count - this one's
+        // ... of the last one = RayRec::n_keys - this checkpoint's count
+        uint32_t n_inner = 0xFFFFFFFFu;
+        if (jj + 1 < cps[r].size()) n_inner = cps[r][jj + 1].count - cps[r][jj].count;
+        else if (recs[r].n_keys != 0xFFFFFFFFu) n_inner = recs[r].n_keys > cps[r][jj].count ? recs[r].n_keys - cps[r][jj].count : 0u;
+        // mode 5: marks collected per 64-voxel word pair (kWide), what ships
+        if (mode == 5) {
+          if (P.free_filter) walk_slot_dilated<true, 0, false, true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, NearGrid(), n_inner);
+          else walk_slot_dilated<false, 0, false, true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, NearGrid(), n_inner);
+        } else if (P.free_filter) walk_slot_dilated<true, 0>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, NearGrid(), n_inner);
+        else walk_slot_dilated<false, 0>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, NearGrid(), n_inner);
       } else if (P.free_filter) { if (mode == 1) WC_SLOT(true, 1); else WC_SLOT(true, 0); }
       else { if (mode == 1) WC_SLOT(false, 1); else WC_SLOT(false, 0); }
 #undef WC_SLOT

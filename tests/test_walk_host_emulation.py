@@ -65,8 +65,11 @@ def run_both(L, res, origin, ends, max_free=0.0, min_height=0.0, near_limit=48):
     ob, dims = window_for(res, origin, ends)
     n_blocks = int(dims[0]) * int(dims[1]) * int(dims[2])
     out = []
-    modes = ("plain", "seg3", "seg0", "seg1") if max_free else ("plain", "seg3", "seg0", "seg1", "seg2")
-    for which in modes:      # seg3: walk_slot (the default walker); seg0 / seg1: walk_slot_dilated<., mode>; seg2: near-field combining schedule
+    modes = ("plain", "seg3", "seg0", "seg1", "seg4", "seg5", "seg6") if max_free else ("plain", "seg3", "seg0", "seg1", "seg4", "seg5", "seg6", "seg2")
+    # seg3: walk_slot (block addressing); seg0 / seg1: walk_slot_dilated<., mode>; seg4: the same with counted
+    # loops; seg5: counted loops + 64-voxel mask words; seg6: the same with queued marks (walk_slot_queued, what
+    # ships); seg2: near-field combining schedule
+    for which in modes:
         fm = np.zeros(n_blocks * 16, np.uint32)
         tb = np.zeros((n_blocks + 31) // 32, np.uint32)
         stats = np.zeros(5, np.uint64)
@@ -86,7 +89,7 @@ def run_both(L, res, origin, ends, max_free=0.0, min_height=0.0, near_limit=48):
         bad = np.flatnonzero(fa != fb)
         assert bad.size == 0, (bad[:5], fa[bad[:5]], fb[bad[:5]])
         assert np.array_equal(ta, tb_)
-    return sa, out[-1][2] if len(out) == 5 else out[1][2]
+    return sa, out[-1][2] if len(out) == 8 else out[1][2]
 
 
 def lidar_rays(n_elev, n_azim, seed, yaw):

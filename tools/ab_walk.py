@@ -23,7 +23,9 @@ out = {"n_scans": n_scans, "configs": []}
 KEYS = ("walk_ms", "gpu_ms", "update_ms", "front_ms", "resolve_ms")
 
 
-def run(addr, variant, ctas, order=0, n_use=None, reps=3, **params):
+def run(addr, variant, ctas, order=0, counted=1, far_blind=0, n_use=None, reps=3, **params):
+    os.environ["VMAP_WALK_COUNTED"] = str(counted)
+    os.environ["VMAP_WALK_FAR_BLIND"] = str(far_blind)
     os.environ["VMAP_WALK_ADDR"] = str(addr)
     os.environ["VMAP_WALK_VARIANT"] = str(variant)
     os.environ["VMAP_WALK_CTAS"] = str(ctas)
@@ -48,8 +50,10 @@ def run(addr, variant, ctas, order=0, n_use=None, reps=3, **params):
 # (VMAP_WALK_ADDR, near limit, CTAs per SM, VMAP_WALK_ORDER); round-1 results for ADDR 0..4 are in
 # profiles/r01_ab_walk_variants.json -- ADDR 5 (near-field combining) and ORDER 1 (golden-ratio
 # chunk order) have not run on hardware yet
-CONFIGS = [(0, 48, 5, 0), (1, 48, 5, 0), (1, 48, 5, 1), (5, 48, 5, 0), (5, 48, 5, 1), (5, 48, 4, 0), (5, 16, 5, 0),
-           (5, 128, 5, 0), (5, 2, 5, 0), (1, 48, 4, 0)]
+# round 2: + counted loops (VMAP_WALK_COUNTED) and the 64-register build (ADDR 6)
+# + fine-bin ray order (always on) and blind far-field touched REDs (VMAP_WALK_FAR_BLIND)
+CONFIGS = [(0, 48, 5, 0, 1, 0), (7, 48, 5, 0, 1, 0), (9, 48, 5, 0, 1, 0), (8, 48, 4, 0, 1, 0), (9, 32, 5, 0, 1, 0),
+           (9, 64, 5, 0, 1, 0), (9, 48, 6, 0, 1, 0), (9, 48, 4, 0, 1, 0), (8, 48, 5, 0, 1, 0)]
 params = {"max_free_space": 6.0, "min_height_free_space": 0.3} if "--filter" in sys.argv else {}
 base = None
 ok_all = True
@@ -59,7 +63,8 @@ for cfg in CONFIGS:
         base = (counts, k, v)
     same = bool(counts == base[0] and np.array_equal(k, base[1]) and np.array_equal(v, base[2]))
     ok_all = ok_all and same
-    row = {"addr": cfg[0], "near_limit": cfg[1], "ctas": cfg[2], "order": cfg[3], "identical": same, **summary}
+    row = {"addr": cfg[0], "near_limit": cfg[1], "ctas": cfg[2], "order": cfg[3], "counted": cfg[4], "far_blind": cfg[5],
+           "identical": same, **summary}
     out["configs"].append(row)
     print(json.dumps(row), flush=True)
 out["leaves"] = int(len(base[1]))
@@ -71,8 +76,8 @@ if "--oracle" in sys.argv:      # bit-exact leaves against the CPU oracle on the
     ko, vo = ow.export_leaves()
     po = oracle.pack_keys(ko)
     oo = np.argsort(po)
-    for addr in (0, 1, 5):
-        _, _, k, v = run(addr, 48, 5, order=1 if addr else 0, n_use=2, reps=1)
+    for addr in (0, 7, 9):
+        _, _, k, v = run(addr, 48, 5, order=0, counted=1, far_blind=0, n_use=2, reps=1)
         ok = bool(np.array_equal(k, po[oo]) and np.array_equal(v, np.asarray(vo, np.float32).view(np.uint32)[oo]))
         out["oracle_parity_addr%d" % addr] = ok
         ok_all = ok_all and ok

@@ -183,8 +183,9 @@ struct vmap : ScanCtx {
   size_t stage_n[2] = {0, 0}, stage_stride[2] = {0, 0};
   bool staged[2] = {false, false};
   int stage_next = 0;         // slot the next vmap_stage_pointcloud fills
-  int walk_order = 0;     // 1: golden-ratio chunk order in the dilated segment walker (VMAP_WALK_ORDER, experimental)
-  int walk_addr = 1;      // segment walker: 1 dilated window addressing (default), 0 block addressing, 2..5 experiments (VMAP_WALK_ADDR)
+  int walk_order = 2;     // bit 0: golden-ratio chunk order in the dilated segment walker (VMAP_WALK_ORDER, experimental);
+                          // bit 1: counted loops in non-last segments (default; VMAP_WALK_COUNTED=0 turns it off)
+  int walk_addr = 9;      // segment walker: 9 dilated addressing + queued 64-voxel marks (default), 7 unqueued, 1 32-voxel words, 0 block addressing, 5 / 8 experiments (VMAP_WALK_ADDR)
   int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
 
@@ -514,7 +515,7 @@ int begin_scan_scratch(vmap* h, size_t n) {
   // two memsets per scan: counters + histogram (zero), first-index table of fc entries (0xFF:
   // keys [0, fc) followed directly by their indices)
   h->sb.first_idx = reinterpret_cast<uint32_t*>(h->sb.first_keys + fc);
-  VM_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters) + kLenBins * sizeof(uint32_t), h->stream));
+  VM_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters) + kFineBins * sizeof(uint32_t), h->stream));
   VM_CUDA(h, cudaMemsetAsync(h->sb.first_keys, 0xFF, fc * 12, h->stream));
   return VMAP_OK;
 }
@@ -948,8 +949,10 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
     k_checkpoints<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->d_cnt, ox, oy, oz);
     h->launches++;
     const unsigned grid = g_sm_count(h->device) * (unsigned)h->walk_ctas;
-    // VMAP_WALK_ADDR (experimental): 1 dilated addressing, 2 + deferred touched test, 3 dilated at 6 CTAs / SM,
-    // 4 deferred at 6 CTAs / SM, 5 dilated + near-field combining in shared memory
+    // VMAP_WALK_ADDR: 0 block addressing, 1 dilated addressing with 32-voxel mask words (round 1), 5 the same
+    // + near-field combining in shared memory, 7 dilated addressing with 64-voxel words, 9 (default) the same
+    // with queued marks (walk_slot_queued), 8 queued marks built for 4 CTAs / SM.  (Measured and dropped: deferred touched test, 6 CTAs / SM, 64 registers:
+    // profiles/r01_ab_walk_variants.json, r02_ab_walk2.json.)
     const bool dilated = h->walk_addr >= 1 && dilated_window_fits(h->ms.nx, h->ms.ny, h->ms.nz);
     if (!h->traced && getenv("VMAP_TRACE")) {
       h->traced = true;
@@ -957,15 +960,15 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
               dilated ? "dilated" : "block", h->walk_addr, h->ms.nx, h->ms.ny, h->ms.nz, h->ms.x0, h->ms.y0, h->ms.z0,
               (unsigned long long)h->dense_fallbacks);
     }
-#define VMAP_WALK_DIL(F, M, C) k_walk_segments_dilated<F, M, C><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, h->walk_order)
+#define VMAP_WALK_DIL(F, M, C, W) k_walk_segments_dilated<F, M, C, W><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, h->walk_order, dilated_window(h->ms))
     // (with the free-space filter the keys are needed at every step anyway and the block-addressed
     // kernel measured faster: profiles/r01_ab_walk_dilated.json)
     if (dilated && !h->P.free_filter) {
       if (h->walk_addr == 5) k_walk_segments_near<<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, h->walk_order);
-      else if (h->walk_addr == 2) VMAP_WALK_DIL(false, 1, 5);
-      else if (h->walk_addr == 3) VMAP_WALK_DIL(false, 0, 6);
-      else if (h->walk_addr == 4) VMAP_WALK_DIL(false, 1, 6);
-      else VMAP_WALK_DIL(false, 0, 5);
+      else if (h->walk_addr == 1) VMAP_WALK_DIL(false, 0, 5, false);
+      else if (h->walk_addr == 7) VMAP_WALK_DIL(false, 0, 5, true);
+      else if (h->walk_addr == 8) k_walk_segments_queued<false, 4><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms));
+      else k_walk_segments_queued<false, 5><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms));
     }
 #undef VMAP_WALK_DIL
     else if (h->P.free_filter) k_walk_segments<true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
@@ -1015,7 +1018,7 @@ int init_ctx_resources(vmap* h) {   // for the CURRENT context
     std::memset(h->h_persist_snap, 0, sizeof(Persist));
   }
   // per-scan counters and the segment-count histogram share one allocation (one memset per scan)
-  if (!h->d_cnt) VM_TRY(dev_alloc(h, (void**)&h->d_cnt, sizeof(Counters) + kLenBins * sizeof(uint32_t)));
+  if (!h->d_cnt) VM_TRY(dev_alloc(h, (void**)&h->d_cnt, sizeof(Counters) + kFineBins * sizeof(uint32_t)));
   return VMAP_OK;
 }
 
@@ -1464,7 +1467,9 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   if (const char* e = getenv("VMAP_WALK_VARIANT")) h->walk_variant = atoi(e);
   if (const char* e = getenv("VMAP_WALK_ADDR")) h->walk_addr = atoi(e);
   if (const char* e = getenv("VMAP_WALK_CTAS")) h->walk_ctas = std::max(1, atoi(e));
-  if (const char* e = getenv("VMAP_WALK_ORDER")) h->walk_order = atoi(e);
+  if (const char* e = getenv("VMAP_WALK_ORDER")) h->walk_order = (h->walk_order & ~1) | (atoi(e) & 1);
+  if (const char* e = getenv("VMAP_WALK_COUNTED")) h->walk_order = (h->walk_order & ~2) | (atoi(e) ? 2 : 0);
+  if (const char* e = getenv("VMAP_WALK_FAR_BLIND")) h->walk_order = (h->walk_order & ~4) | (atoi(e) ? 4 : 0);
   if (const char* e = getenv("VMAP_NO_SEGMENTS")) h->no_segments = atoi(e);
   if (const char* e = getenv("VMAP_UPDATE_VARIANT")) h->update_variant = atoi(e);
   auto bail = [&](int code) {

@@ -34,7 +34,7 @@ struct ScanBuffers {
   uint32_t* rays;           // [n]   indices of cast rays, longest rays first
   uint32_t* len;            // [n]   DDA steps of the ray (key-space Manhattan distance)
   uint32_t* rank;           // [n]   position of a cast ray inside its length bin
-  uint32_t* len_hist;       // [kLenBins] cast rays per segment-count bin
+  uint32_t* len_hist;       // [kFineBins] cast rays per fine bin (vmap_walk.cuh: fine_bin)
   uint32_t* seg_base;       // [kLenBins + 1] first work slot of every segment level
   RayRec* ray_rec;          // [n]
   Checkpoint* ckpt;         // [ckpt_cap] one per (segment level, ray)
@@ -211,7 +211,7 @@ __device__ __forceinline__ void cta_max_u32(uint32_t* s_acc, uint32_t v) {
 }
 
 __device__ __forceinline__ uint32_t ray_bin(const ScanBuffers& sb, uint32_t i) {
-  return ray_segments(sb.len[i]);
+  return fine_bin(sb.len[i]);
 }
 
 // K1b: skip rule + work list + occupied marks.
@@ -267,15 +267,16 @@ k_resolve(ScanBuffers sb, MapView m, MarkSet ms, Counters* cnt, uint32_t n, int 
 // Cast-ray work list, pass 2: longest rays first (bins in descending order), so that the 32 rays
 // of a warp take about the same number of DDA steps and the longest rays start first.
 __global__ void __launch_bounds__(256) k_order_rays(ScanBuffers sb, uint32_t n) {
-  __shared__ uint32_t off[kLenBins];
+  __shared__ uint32_t off[kFineBins];
   __shared__ uint32_t warp_sum[8];
-  constexpr int kPer = kLenBins / 256;
+  constexpr int kPer = (kFineBins + 255) / 256;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   // thread t owns the kPer bins starting at descending position t * kPer
   uint32_t local[kPer], sum = 0;
 #pragma unroll
   for (int j = 0; j < kPer; j++) {
-    local[j] = sb.len_hist[kLenBins - 1 - (threadIdx.x * kPer + j)];
+    const int pos = threadIdx.x * kPer + j;
+    local[j] = pos < kFineBins ? sb.len_hist[kFineBins - 1 - pos] : 0u;
     sum += local[j];
   }
   uint32_t incl = sum;
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(256) k_order_rays(ScanBuffers sb, uint32_t n) 
   for (uint32_t w2 = 0; w2 < warp; w2++) base += warp_sum[w2];
 #pragma unroll
   for (int j = 0; j < kPer; j++) {
-    off[kLenBins - 1 - (threadIdx.x * kPer + j)] = base;
+    const int pos = threadIdx.x * kPer + j;
+    if (pos < kFineBins) off[kFineBins - 1 - pos] = base;
     base += local[j];
   }
   __syncthreads();
@@ -298,11 +300,13 @@ __global__ void __launch_bounds__(256) k_order_rays(ScanBuffers sb, uint32_t n) 
     sb.rays[off[ray_bin(sb, i)] + sb.rank[i]] = i;
   if (blockIdx.x != 0) return;
   // Work slots of the segment walker, level-major: level j holds one slot for every ray with
-  // more than j segments -- a prefix of the ordered list, off[j] rays long.
-  uint32_t lv[kPer], lsum = 0;
+  // more than j segments -- a prefix of the ordered list, as long as the rays that precede the
+  // highest fine bin of segment count j.
+  constexpr int kLv = kLenBins / 256;
+  uint32_t lv[kLv], lsum = 0;
 #pragma unroll
-  for (int j = 0; j < kPer; j++) {
-    lv[j] = off[threadIdx.x * kPer + j];
+  for (int j = 0; j < kLv; j++) {
+    lv[j] = off[fine_bin_top(threadIdx.x * kLv + j)];
     lsum += lv[j];
   }
   uint32_t linc = lsum;
@@ -316,8 +320,8 @@ __global__ void __launch_bounds__(256) k_order_rays(ScanBuffers sb, uint32_t n) 
   uint32_t lbase = linc - lsum;
   for (uint32_t w2 = 0; w2 < warp; w2++) lbase += warp_sum[w2];
 #pragma unroll
-  for (int j = 0; j < kPer; j++) {
-    sb.seg_base[threadIdx.x * kPer + j] = lbase;
+  for (int j = 0; j < kLv; j++) {
+    sb.seg_base[threadIdx.x * kLv + j] = lbase;
     lbase += lv[j];
   }
   if (threadIdx.x == 255) sb.seg_base[kLenBins] = lbase;
@@ -510,20 +514,22 @@ k_walk_segments(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox
 // stride order instead of level-major order, so that the first-segment slots -- which all mark the
 // same words around the sensor -- are spread over the kernel's run time instead of filling its
 // first wave (marks do not depend on the order).
-template <bool kFilter, int kMode, int kMinCtas>
+template <bool kFilter, int kMode, int kMinCtas, bool kWide>
 __global__ void __launch_bounds__(256, kMinCtas)
 k_walk_segments_dilated(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz,
-                        int variant, int order) {
+                        int variant, int order, DilatedWindow dw) {
+  // (dw = dilated_window(ms), computed by the host: as kernel parameters the axis masks are
+  // constant-bank operands of the step's LOP3s instead of values rebuilt at every step)
   if (cnt->overflow_ckpt) return;
   __shared__ uint32_t base_s[kLenBins + 1];
   for (int k = threadIdx.x; k <= kLenBins; k += blockDim.x) base_s[k] = sb.seg_base[k];
   __syncthreads();
   const uint32_t total = min(base_s[kLenBins], sb.ckpt_cap);
-  const DilatedWindow dw = dilated_window(ms);
   const uint32_t near_limit = (variant == 0) ? 0xFFFFFFFFu : (variant == 2 ? 0u : (uint32_t)variant);
   const uint32_t n_chunks = (total + 255u) >> 8;
   uint32_t stride = 1;
-  if (order == 1 && n_chunks > 2u) {
+  const bool counted = (order & 2) != 0;   // bit 1: non-last segments run a counted loop (VMAP_WALK_COUNTED, default)
+  if ((order & 1) && n_chunks > 2u) {
     stride = (uint32_t)((double)n_chunks * 0.6180339887498949);
     if (stride < 1u) stride = 1u;
     for (;; stride++) {           // a stride coprime to n_chunks visits every chunk exactly once
@@ -544,8 +550,88 @@ k_walk_segments_dilated(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, 
     }
     const Checkpoint cp = sb.ckpt[slot];
     if (cp.count == 0xFFFFFFFFu) continue;
-    walk_slot_dilated<kFilter, kMode>(P, ms, dw, cnt, cp, sb.ray_rec[slot - base_s[lo]], lo, ox, oy, oz, near_limit, &emitted,
-                                      &longest);
+    // steps of a non-last segment = keys emitted up to the next level's checkpoint - up to this one
+    // (level lo + 1 holds a slot for this ray exactly when this is not its last segment)
+    const uint32_t r = slot - base_s[lo];
+    uint32_t n_inner = 0xFFFFFFFFu;
+    // (lo <= kLenBins - 2: a ray has at most kLenBins - 1 segments)
+    const RayRec& rr = sb.ray_rec[r];
+    if (counted) {
+      if (r < base_s[lo + 2] - base_s[lo + 1]) n_inner = sb.ckpt[base_s[lo + 1] + r].count - cp.count;
+      else if (rr.n_keys != 0xFFFFFFFFu) n_inner = rr.n_keys > cp.count ? rr.n_keys - cp.count : 0u;
+    }
+    walk_slot_dilated<kFilter, kMode, false, kWide>(P, ms, dw, cnt, cp, rr, lo, ox, oy, oz, near_limit, &emitted, &longest, NearGrid(),
+                                      n_inner, (order & 4) != 0);
+  }
+  __shared__ uint32_t s_stat[2];
+  __syncthreads();
+  if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+  __syncthreads();
+  cta_add_u32(&s_stat[0], emitted);
+  cta_max_u32(&s_stat[1], longest);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_stat[0]) {
+    atomicAdd(&cnt->traversals, (unsigned long long)s_stat[0]);
+    atomicMax(&cnt->longest_ray, s_stat[1]);
+  }
+}
+
+// K2b, dilated addressing + queued marks (vmap_walk.cuh: walk_slot_queued) -- the default walker.
+// Same slots and marks as k_walk_segments_dilated; the lanes of a warp run one loop nest (every slot
+// knows its step count up front) and drain their parked mask words together.
+template <bool kFilter, int kMinCtas>
+__global__ void __launch_bounds__(256, kMinCtas)
+k_walk_segments_queued(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz, int variant,
+                       DilatedWindow dw) {
+  if (cnt->overflow_ckpt) return;
+  __shared__ uint32_t base_s[kLenBins + 1];
+  __shared__ uint32_t queue_s[3 * kQueueSteps * 256];
+  for (int k = threadIdx.x; k <= kLenBins; k += blockDim.x) base_s[k] = sb.seg_base[k];
+  __syncthreads();
+  const uint32_t total = min(base_s[kLenBins], sb.ckpt_cap);
+  const uint32_t near_limit = (variant == 0) ? 0xFFFFFFFFu : (variant == 2 ? 0u : (uint32_t)variant);
+  MarkQueue mq;
+  mq.w = queue_s + threadIdx.x;
+  mq.stride = 256u;
+  uint32_t emitted = 0, longest = 0;
+  // Work is handed out 32 slots at a time, to whichever warp asks next: with 256-slot chunks dealt
+  // round-robin to the CTAs a third of them got one chunk more than the rest, and the kernel ran its
+  // last third at a quarter of the machine.
+  const uint32_t n_groups = (total + 31u) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (;;) {
+    uint32_t g = 0;
+    if (lane == 0) g = atomicAdd(&cnt->walk_next, 1u);
+    g = __shfl_sync(0xFFFFFFFFu, g, 0);
+    if (g >= n_groups) break;
+    const uint32_t slot = g * 32u + lane;
+    bool active = slot < total;
+    uint32_t lo = 0, r = 0, n_steps = 0;
+    Checkpoint cp;
+    cp.count = 0xFFFFFFFFu;
+    if (active) {
+      uint32_t hi = kLenBins;
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (base_s[mid] <= slot) lo = mid; else hi = mid;
+      }
+      r = slot - base_s[lo];
+      cp = sb.ckpt[slot];
+      active = cp.count != 0xFFFFFFFFu;
+    }
+    const RayRec& rr = sb.ray_rec[r];
+    if (active) {
+      // steps of a non-last segment = keys emitted up to the next level's checkpoint - up to this one
+      // (level lo + 1 holds a slot for this ray exactly when this is not its last segment; lo <= kLenBins - 2)
+      if (r < base_s[lo + 2] - base_s[lo + 1]) n_steps = sb.ckpt[base_s[lo + 1] + r].count - cp.count;
+      else if (rr.n_keys != 0xFFFFFFFFu) n_steps = rr.n_keys > cp.count ? rr.n_keys - cp.count : 0u;
+      else {
+        // (a ray whose key count ray_checkpoints could not bound: walked the plain way, by this lane alone)
+        walk_slot_dilated<kFilter, 0, false, true>(P, ms, dw, cnt, cp, rr, lo, ox, oy, oz, near_limit, &emitted, &longest);
+        active = false;
+      }
+    }
+    walk_slot_queued<kFilter>(P, ms, dw, cnt, cp, rr, lo, ox, oy, oz, near_limit, &emitted, &longest, n_steps, active, mq);
   }
   __shared__ uint32_t s_stat[2];
   __syncthreads();
@@ -587,7 +673,7 @@ k_walk_segments_near(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, flo
   }
   const uint32_t n_chunks = (total + 255u) >> 8;
   uint32_t stride = 1;
-  if (order == 1 && n_chunks > 2u) {
+  if ((order & 1) && n_chunks > 2u) {
     stride = (uint32_t)((double)n_chunks * 0.6180339887498949);
     if (stride < 1u) stride = 1u;
     for (;; stride++) {

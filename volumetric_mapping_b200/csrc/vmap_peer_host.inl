@@ -35,6 +35,14 @@ int peer_alloc_mailbox(vmap* h, uint64_t records_per_round) {
   return VMAP_OK;
 }
 
+// VMAP_TIMING: device time of the apply round that has just been waited for (events on the apply stream)
+void peer_note_apply_time(vmap* h) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, h->ev_app0, h->ev_app1) != cudaSuccess) { cudaGetLastError(); return; }
+  h->dbg_ms[0] += ms;
+  h->dbg_n++;
+}
+
 void peer_set_table(vmap* h, int s, void* base) {
   h->pt.head[s] = reinterpret_cast<MailboxHead*>(base);
   h->pt.rec[s] = reinterpret_cast<BlockRecord*>(reinterpret_cast<char*>(base) + sizeof(MailboxHead));
@@ -115,6 +123,7 @@ int peer_apply_pending(vmap* h) {
       if (h->h_cnt_app->overflow_table || h->h_cnt_app->overflow_pool)
         return fail(h, VMAP_ERR_CAPACITY, "internal: map overflow inside a sharded apply round");
       *h->h_persist = *h->h_persist_app;
+      peer_note_apply_time(h);
       h->totals.unique_free += h->h_cnt_app->unique_free;
       h->totals.unique_occupied += h->h_cnt_app->unique_occupied;
     }
@@ -284,6 +293,7 @@ int peer_flush_end(vmap* h) {
       if (h->h_cnt_app->overflow_table || h->h_cnt_app->overflow_pool)
         note(fail(h, VMAP_ERR_CAPACITY, "internal: map overflow inside a sharded apply round"));
       *h->h_persist = *h->h_persist_app;
+      peer_note_apply_time(h);
       h->totals.unique_free += h->h_cnt_app->unique_free;
       h->totals.unique_occupied += h->h_cnt_app->unique_occupied;
       h->stats.blocks_total = h->h_persist->n_slots;

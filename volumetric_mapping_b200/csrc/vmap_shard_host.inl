@@ -523,10 +523,16 @@ int vmap_dist_flush_begin(vmap* h) try {
 
 int vmap_dist_shutdown(vmap* h) try {
   if (!h) return VMAP_ERR_INVALID_ARGUMENT;
-  if (h->nccl_comm && getenv("VMAP_TIMING") && h->dbg_n)
+  if (h->nccl_comm && !h->peer_on && getenv("VMAP_TIMING") && h->dbg_n)
     fprintf(stderr, "[vmap rank %d] per round (host wall ms): generate+pack %.3f | count allgather + wait for previous apply %.3f | exchange/apply enqueue %.3f | (sync path) %.3f  (%llu rounds)\n",
             h->shard_rank, h->dbg_ms[0] / h->dbg_n, h->dbg_ms[1] / h->dbg_n, h->dbg_ms[2] / h->dbg_n, h->dbg_ms[3] / h->dbg_n,
             (unsigned long long)h->dbg_n);
+  if (h->peer_on && getenv("VMAP_TIMING") && h->total_scans)
+    fprintf(stderr, "[vmap rank %d] peer transport, device ms per scan (events, overlapped with the other scan context): front %.3f resolve %.3f walk+list %.3f pack %.3f | apply per round %.3f (%llu rounds, %llu records) | scans %llu\n",
+            h->shard_rank, h->totals.front_ms / h->total_scans, h->totals.resolve_ms / h->total_scans,
+            h->totals.walk_ms / h->total_scans, h->totals.update_ms / h->total_scans,
+            h->dbg_n ? h->dbg_ms[0] / h->dbg_n : 0.0, (unsigned long long)h->dbg_n, (unsigned long long)h->app_records,
+            (unsigned long long)h->total_scans);
   if (h->peer_on || h->mailbox) {
     cudaSetDevice(h->device);
     if (h->peer_on && h->app_stream && h->rounds_published) {

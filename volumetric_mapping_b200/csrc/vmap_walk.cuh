@@ -28,6 +28,9 @@ struct RayRec {               // per cast ray (index = position in the ordered w
   uint32_t e01, e2s;          // end key: e0 | e1 << 16 ; e2 | step codes << 16 (2 bits per axis: 0, 1 = +1, 2 = -1)
   uint32_t n_seg;
   uint32_t point;             // index of the point / pixel
+  uint32_t n_keys;            // keys the walk emits when neither the end key nor KeyRay's capacity stops it
+                              // first (origin included); 0xFFFFFFFF: not known, the walker tests min(tMax) > length
+  uint32_t pad;
 };
 struct Checkpoint {           // state of the walk at the start of a segment
   double t0, t1, t2;          // tMax
@@ -38,6 +41,30 @@ struct Checkpoint {           // state of the walk at the start of a segment
 
 __device__ __forceinline__ uint32_t ray_segments(uint32_t steps) {
   return min(max(steps / kSegSteps, 1u), (uint32_t)(kLenBins - 1));
+}
+// The ordered ray list is sorted by FINE bin, descending: primary key the segment count (so that
+// level j of the walker's work slots is a prefix of the list), secondary key -- for rays of fewer
+// than kFineSegs segments -- the steps one segment takes, in kFineSub classes, so that the 32 lanes
+// of a warp walk segments of nearly the same length.  MEASURED (profiles/r02_ab_walk3.json, 16
+// classes): the walk got 8 % SLOWER and k_resolve 25 % slower -- lanes that are balanced but no
+// longer neighbours in the scan spread a warp's atomics over more mask words; what bounds the walker
+// is atomic traffic, not idle lanes.  Hence one class (= order by segment count only).
+#ifndef VMAP_FINE_SUB
+#define VMAP_FINE_SUB 1
+#endif
+constexpr int kFineSub = VMAP_FINE_SUB;
+constexpr int kFineSegs = 128;                                   // segment counts below this get sub-bins
+constexpr int kFineBins = kFineSegs * kFineSub + (kLenBins - kFineSegs);
+__device__ __forceinline__ uint32_t fine_bin_top(uint32_t n_seg) {  // highest fine bin of a segment count
+  return n_seg < (uint32_t)kFineSegs ? n_seg * kFineSub + (kFineSub - 1) : (uint32_t)(kFineSegs * kFineSub) + (n_seg - kFineSegs);
+}
+__device__ __forceinline__ uint32_t fine_bin(uint32_t steps) {
+  const uint32_t n_seg = ray_segments(steps);
+  if (n_seg >= (uint32_t)kFineSegs) return (uint32_t)(kFineSegs * kFineSub) + (n_seg - kFineSegs);
+  // one segment: 1 .. 2 * kSegSteps - 1 steps; several: kSegSteps .. < 2 * kSegSteps steps each
+  const uint32_t sub = n_seg == 1u ? min(steps, 2u * kSegSteps - 1u) / (2u * kSegSteps / kFineSub)
+                                   : min((steps / n_seg - kSegSteps) / (kSegSteps / kFineSub), (uint32_t)(kFineSub - 1));
+  return n_seg * kFineSub + sub;
 }
 
 // K2a body.  computeRayKeys' preamble, then the state of the walk at every segment boundary by
@@ -59,6 +86,8 @@ __device__ __forceinline__ void ray_checkpoints(const DevParams& P, float ox, fl
   rr.e2s = w.e2 | (sc << 16);
   rr.n_seg = n_seg;
   rr.point = point;
+  rr.n_keys = 0xFFFFFFFFu;
+  rr.pad = 0;
   *rec = rr;
   uint32_t n0 = 0, n1 = 0, n2 = 0;
   double t0 = w.t0, t1 = w.t1, t2 = w.t2;
@@ -80,6 +109,20 @@ __device__ __forceinline__ void ray_checkpoints(const DevParams& P, float ox, fl
     cp.count = w.live ? 1u + n0 + n1 + n2 : 0xFFFFFFFFu;
     cp.pad = 0;
     if (!put(j, cp)) return;
+  }
+  // computeRayKeys stops after the first step that leaves min(tMax) > length: after k steps min(tMax)
+  // is the (k + 1)-th smallest crossing parameter, so the walk takes max(L, 1) steps, L = crossings
+  // <= length over the three axes, and emits the origin plus every step but the last: max(L, 1) keys
+  // (fewer when it runs into the end key or KeyRay's capacity first -- the walker still tests those).
+  if (w.live && w.dlen > 0.0 && w.dlen < 1e300) {
+    const double past = vmapseq::seq_from_bits(vmapseq::seq_bits(w.dlen) + 1ull);   // t < past  <=>  t <= length
+    const unsigned long long cap = 1ull << 40;
+    unsigned long long L = (unsigned long long)n0 + n1 + n2;
+    if (w.s0) L += vmapseq::seq_advance(&t0, w.dt0, past, cap);
+    if (w.s1) L += vmapseq::seq_advance(&t1, w.dt1, past, cap);
+    if (w.s2) L += vmapseq::seq_advance(&t2, w.dt2, past, cap);
+    if (L < 1ull) L = 1ull;
+    if (L < 0xFFFFFFFFull) rec->n_keys = (uint32_t)L;
   }
 }
 
@@ -208,7 +251,7 @@ __host__ __device__ inline bool dilated_window_fits(uint32_t nx, uint32_t ny, ui
   while ((1u << pz) < nz) pz++;
   return 9u + px + py + pz <= 31u;
 }
-__device__ __forceinline__ DilatedWindow dilated_window(const MarkSet& ms) {
+__host__ __device__ __forceinline__ DilatedWindow dilated_window(const MarkSet& ms) {
   uint32_t px = 0, py = 0;
   while ((1u << px) < ms.nx) px++;
   while ((1u << py) < ms.ny) py++;
@@ -297,11 +340,18 @@ __device__ __forceinline__ void near_flush_word(const MarkSet& ms, const NearGri
 // kMode 1: the touched word is only LOADED at block entry and tested when the ray leaves the
 //          block (or ends), so that the walk never waits for that load.
 // kNear: marks inside `near`'s cube go to the CTA's own bit grid (see NearGrid) instead of the window.
-template <bool kFilter, int kMode = 0, bool kNear = false>
+// kWide: marks are collected per 64-voxel pair of mask words (one 8 x 8 z-slice of the block) and
+//        flushed with one 64-bit RED.OR; a mostly horizontal ray stays in a slice two to three times as
+//        long as in a 32-voxel word, and the number of REDs is what bounds the walker.
+template <bool kWide> struct MaskWord { typedef uint32_t type; };
+template <> struct MaskWord<true> { typedef unsigned long long type; };
+
+template <bool kFilter, int kMode = 0, bool kNear = false, bool kWide = false>
 __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const MarkSet& ms, const DilatedWindow& dw,
                                                   Counters* cnt, const Checkpoint& cp, const RayRec& rr, uint32_t j,
                                                   float ox, float oy, float oz, uint32_t near_limit,
-                                                  uint32_t* emitted, uint32_t* longest, const NearGrid& near = NearGrid()) {
+                                                  uint32_t* emitted, uint32_t* longest, const NearGrid& near = NearGrid(),
+                                                  uint32_t n_inner = 0xFFFFFFFFu, bool far_blind = false) {
   if (cp.count == 0xFFFFFFFFu) return;
   uint32_t c0 = cp.c01 & 0xFFFFu, c1 = cp.c01 >> 16, c2 = cp.c2;
   const uint32_t e0 = rr.e01 & 0xFFFFu, e1 = rr.e01 >> 16, e2 = rr.e2s & 0xFFFFu;
@@ -326,26 +376,36 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
   const bool last = (j + 1 == rr.n_seg);
   uint32_t count = cp.count;
   const uint32_t count0 = count;
-  // cur / bits / seen: as in walk_slot
-  uint32_t cur = 0xFFFFFFFFu, bits = 0, seen = 0;
+  // cur / bits / seen: as in walk_slot (kWide: cur counts 64-bit words)
+  typedef typename MaskWord<kWide>::type Word;
+  constexpr uint32_t kWordShift = kWide ? 6u : 5u;             // address bits below the word index
+  constexpr uint32_t kWordsPerBlock = 512u >> kWordShift;
+  uint32_t cur = 0xFFFFFFFFu;
+  Word bits = 0, seen = 0;
   // kMode 1: touched word of the block in flight as loaded at entry (all ones: nothing pending)
   uint32_t tb_val = 0xFFFFFFFFu, tb_blk = 0;
   // kNear: base word of the current block in the near grid, or kNotFound outside the cube
   uint32_t near_base = kNotFound;
   auto flush = [&]() {
     if (kNear && near_base != kNotFound) {
-      if (bits) atomicOr(near.words + (near_base | (cur & 15u)), bits);
+      if (kWide) {
+        const uint32_t lo = (uint32_t)bits, hi = (uint32_t)((unsigned long long)bits >> 32);
+        if (lo) atomicOr(near.words + (near_base | ((cur & 7u) << 1)), lo);
+        if (hi) atomicOr(near.words + (near_base | ((cur & 7u) << 1) | 1u), hi);
+      } else if (bits) {
+        atomicOr(near.words + (near_base | (cur & 15u)), (uint32_t)bits);
+      }
     } else if (bits & ~seen) {
-      atomicOr(ms.free_mask + cur, bits);
+      atomicOr(reinterpret_cast<Word*>(ms.free_mask) + cur, bits);
     }
   };
   auto emit = [&]() {
     if (kFilter && !free_filter_pass(P, ox, oy, oz, c0, c1, c2)) return;
     const uint32_t a = a0 | a1 | a2;
-    const uint32_t wi = a >> 5;
+    const uint32_t wi = a >> kWordShift;
     if (wi != cur) {
       flush();
-      if ((wi ^ cur) >= 16u) {                       // another block
+      if ((wi ^ cur) >= kWordsPerBlock) {            // another block
         if (kNear) {
           const uint32_t dx = (a0 >> 9) - near.bx0, dy = (a1 >> dw.sh1) - near.by0, dz = (a2 >> dw.sh2) - near.bz0;
           near_base = (dx < kNearBlocks && dy < kNearBlocks && dz < kNearBlocks)
@@ -356,7 +416,12 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
         } else if (kMode == 0) {
           uint32_t* tb = ms.touched_bits + (a >> 14);
           const uint32_t bit = 1u << ((a >> 9) & 31u);
-          if (!(*tb & bit)) atomicOr(tb, bit);
+          // far_blind (VMAP_WALK_FAR_BLIND=1, experiment): beyond the near field the RED goes out without
+          // looking first.  MEASURED: the walk takes TWICE as long (0.19 -> 0.40 ms, profiles/
+          // r02_ab_walk3.json) -- 1.7 M more REDs on a few thousand touched words; same-address atomics
+          // are what the walker waits for, a load that filters them is cheap in comparison.
+          if (far_blind && count >= near_limit) atomicOr(tb, bit);
+          else if (!(*tb & bit)) atomicOr(tb, bit);
         } else {
           if (!((tb_val >> (tb_blk & 31u)) & 1u)) atomicOr(ms.touched_bits + (tb_blk >> 5), 1u << (tb_blk & 31u));
           tb_blk = a >> 9;
@@ -365,9 +430,9 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
       }
       bits = 0;
       cur = wi;
-      seen = (!(kNear && near_base != kNotFound) && count < near_limit) ? ms.free_mask[wi] : 0u;
+      seen = (!(kNear && near_base != kNotFound) && count < near_limit) ? reinterpret_cast<const Word*>(ms.free_mask)[wi] : (Word)0;
     }
-    bits |= 1u << (a & 31u);
+    bits |= (Word)1 << (a & ((1u << kWordShift) - 1u));
   };
   // one DDA step: strict '<' comparisons, ties go to the later axis (computeRayKeys)
   auto step = [&]() {
@@ -391,12 +456,30 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
   const double dlen = rr.dlen;
   const double tau_end = __dmul_rn((double)(j + 1), rr.dtau);
   auto run = [&](auto capped) {
-    if (last) {
+    if (last && n_inner != 0xFFFFFFFFu) {
+      // counted: RayRec::n_keys bounds the keys of the whole walk, so min(tMax) is never compared
+      for (uint32_t k = n_inner; k; --k) {
+        step();
+        if ((a0 | a1 | a2) == a_end) break;                            // cur == end
+        if (decltype(capped)::value && count >= kKeyRayMax - 1u) break;   // KeyRay capacity
+        ++count;
+        emit();
+      }
+    } else if (last) {
       for (;;) {
         step();
         if ((a0 | a1 | a2) == a_end) break;                            // cur == end
         if (all_above(t0, t1, t2, dlen)) break;                        // min(tMax) > length
         if (decltype(capped)::value && count >= kKeyRayMax - 1u) break;   // KeyRay capacity
+        ++count;
+        emit();
+      }
+    } else if (n_inner != 0xFFFFFFFFu) {
+      // the same steps, counted: the next level's checkpoint says how many keys the walk has emitted
+      // when it gets there (ray_checkpoints: count = 1 + steps), so no crossing parameter is compared
+      for (uint32_t k = n_inner; k; --k) {
+        step();
+        if (decltype(capped)::value && count >= kKeyRayMax - 1u) break;
         ++count;
         emit();
       }
@@ -419,6 +502,152 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
   if (kMode == 1 && !((tb_val >> (tb_blk & 31u)) & 1u)) atomicOr(ms.touched_bits + (tb_blk >> 5), 1u << (tb_blk & 31u));
   *emitted += count - count0 + (j == 0 ? 1u : 0u);
   if (last) *longest = max(*longest, count);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b body, dilated addressing, QUEUED marks (the walker that ships).  What costs issue slots in
+// walk_slot_dilated is not the DDA step but the code behind "the ray has entered another mask word":
+// with 32 lanes at different places of their walks some lane takes that branch in nearly every
+// iteration, so the whole warp pays for the flush (RED, block test, touched load + test + RED, near
+// preload) at a handful of active lanes, every step.  Here the branch only PARKS the finished word
+// (word index, 64 bits) in a small per-lane queue in shared memory; after every kQueueSteps steps the
+// warp drains the queues together -- all lanes issue their loads, tests and REDs side by side, one
+// queue entry per pass.  Needs the step count of the slot up front (counted loops: the next level's
+// checkpoint / RayRec::n_keys), so that all lanes of a warp run the same loop nest.
+// Marks are the ones walk_slot_dilated makes (OR is commutative; every parked word's block gets its
+// touched bit); the near-field test "are these bits set already" is done at drain time.
+// WARP-COLLECTIVE: every lane of the warp calls it (`active` false: no slot); q: this lane's queue.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kQueueSteps = 8;                 // steps between drains = queue capacity
+struct MarkQueue {
+  uint32_t* w;        // entry e, word k (0: mask word index | near flag << 31, 1: bits low, 2: bits high) at w[(3 * e + k) * stride]
+  uint32_t stride;
+};
+#if !defined(__CUDA_ARCH__) && defined(VMAP_HOST_EMULATION)
+static inline bool vmap_warp_any(bool p) { return p; }      // one "lane" at a time on the host
+#else
+__device__ __forceinline__ bool vmap_warp_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
+#endif
+
+template <bool kFilter>
+__device__ __forceinline__ void walk_slot_queued(const DevParams& P, const MarkSet& ms, const DilatedWindow& dw, Counters* cnt,
+                                                 const Checkpoint& cp, const RayRec& rr, uint32_t j, float ox, float oy,
+                                                 float oz, uint32_t near_limit, uint32_t* emitted, uint32_t* longest,
+                                                 uint32_t n_steps, bool active, const MarkQueue& q) {
+  uint32_t c0 = 0, c1 = 0, c2 = 0, a0 = 0, a1 = 0, a2 = 0, a_end = 0, k0 = 0, k1 = 0, k2 = 0;
+  int s0 = 0, s1 = 0, s2 = 0;
+  double t0 = 0.0, t1 = 0.0, t2 = 0.0, dt0 = 0.0, dt1 = 0.0, dt2 = 0.0;
+  bool last = false, capped = false;
+  uint32_t count = 0, count0 = 0;
+  if (active && cp.count == 0xFFFFFFFFu) active = false;
+  if (active) {
+    c0 = cp.c01 & 0xFFFFu; c1 = cp.c01 >> 16; c2 = cp.c2;
+    const uint32_t e0 = rr.e01 & 0xFFFFu, e1 = rr.e01 >> 16, e2 = rr.e2s & 0xFFFFu;
+    if (!segment_inside_window(ms, c0, c1, c2, e0, e1, e2)) {   // the host re-runs the scan in table mode
+      atomicExch(&cnt->overflow_window, 1u);
+      active = false;
+    } else {
+      const uint32_t sc = rr.e2s >> 16;
+      const uint32_t sc0 = sc & 3u, sc1 = (sc >> 2) & 3u, sc2 = (sc >> 4) & 3u;
+      k0 = sc0 == 1u ? (0u - dw.m0) : (sc0 == 2u ? 0xFFFFFFFFu : 0u);
+      k1 = sc1 == 1u ? (0u - dw.m1) : (sc1 == 2u ? 0xFFFFFFFFu : 0u);
+      k2 = sc2 == 1u ? (0u - dw.m2) : (sc2 == 2u ? 0xFFFFFFFFu : 0u);
+      s0 = sc0 == 1u ? 1 : (sc0 == 2u ? -1 : 0); s1 = sc1 == 1u ? 1 : (sc1 == 2u ? -1 : 0); s2 = sc2 == 1u ? 1 : (sc2 == 2u ? -1 : 0);
+      const uint32_t wx = (uint32_t)ms.x0 << 3, wy = (uint32_t)ms.y0 << 3, wz = (uint32_t)ms.z0 << 3;
+      a0 = dilate_axis(c0 - wx, 0u, 9u); a1 = dilate_axis(c1 - wy, 3u, dw.sh1); a2 = dilate_axis(c2 - wz, 6u, dw.sh2);
+      a_end = dilate_axis(e0 - wx, 0u, 9u) | dilate_axis(e1 - wy, 3u, dw.sh1) | dilate_axis(e2 - wz, 6u, dw.sh2);
+      t0 = cp.t0; t1 = cp.t1; t2 = cp.t2;
+      dt0 = rr.dt0; dt1 = rr.dt1; dt2 = rr.dt2;
+      last = (j + 1 == rr.n_seg);
+      capped = (rr.n_seg + 1u) * kSegSteps + 4u >= kKeyRayMax - 1u;    // only such rays can reach KeyRay's capacity
+      count = count0 = cp.count;
+    }
+  }
+  uint32_t remaining = active ? n_steps : 0u;
+  uint32_t cur = 0xFFFFFFFFu, cur_near = 0u, nq = 0u, last_blk = 0xFFFFFFFFu;
+  unsigned long long bits = 0ull;
+  auto emit = [&]() {
+    if (kFilter && !free_filter_pass(P, ox, oy, oz, c0, c1, c2)) return;
+    const uint32_t a = a0 | a1 | a2;
+    const uint32_t wi = a >> 6;
+    if (wi != cur) {
+      if (bits) {                                   // park the finished word
+        uint32_t* e = q.w + 3u * nq * q.stride;
+        e[0] = cur | cur_near;
+        e[q.stride] = (uint32_t)bits;
+        e[2u * q.stride] = (uint32_t)(bits >> 32);
+        ++nq;
+      }
+      bits = 0ull;
+      cur = wi;
+      cur_near = count < near_limit ? 0x80000000u : 0u;
+    }
+    bits |= 1ull << (a & 63u);
+  };
+  auto drain = [&]() {
+    for (uint32_t e = 0; vmap_warp_any(e < nq); e++) {
+      if (e < nq) {
+        const uint32_t* ent = q.w + 3u * e * q.stride;
+        const uint32_t cf = ent[0];
+        const unsigned long long b = (unsigned long long)ent[q.stride] | ((unsigned long long)ent[2u * q.stride] << 32);
+        const uint32_t wi = cf & 0x7FFFFFFFu;
+        unsigned long long* w = reinterpret_cast<unsigned long long*>(ms.free_mask) + wi;
+        // near the sensor every ray sets the same voxels: there a RED only goes out for bits not visible yet
+        if (cf >> 31) { if (b & ~*w) atomicOr(w, b); }
+        else atomicOr(w, b);
+        const uint32_t blk = wi >> 3;
+        if (blk != last_blk) {
+          last_blk = blk;
+          uint32_t* tb = ms.touched_bits + (blk >> 5);
+          const uint32_t bit = 1u << (blk & 31u);
+          if (!(*tb & bit)) atomicOr(tb, bit);
+        }
+      }
+    }
+    nq = 0u;
+  };
+  if (active && j == 0) emit();       // the origin voxel belongs to segment 0
+  while (vmap_warp_any(remaining != 0u)) {
+    for (uint32_t s = 0; s < kQueueSteps; s++) {
+      if (remaining) {
+        // one DDA step: strict '<' comparisons, ties go to the later axis (computeRayKeys)
+        const bool a01 = t0 < t1, a02 = t0 < t2, a12 = t1 < t2;
+        const bool d0 = a01 && a02, d1 = !a01 && a12;
+        if (d0) {
+          a0 = (a0 + k0) & dw.m0;
+          t0 = __dadd_rn(t0, dt0);
+          if (kFilter) c0 = (c0 + (uint32_t)s0) & 0xFFFFu;
+        } else if (d1) {
+          a1 = (a1 + k1) & dw.m1;
+          t1 = __dadd_rn(t1, dt1);
+          if (kFilter) c1 = (c1 + (uint32_t)s1) & 0xFFFFu;
+        } else {
+          a2 = (a2 + k2) & dw.m2;
+          t2 = __dadd_rn(t2, dt2);
+          if (kFilter) c2 = (c2 + (uint32_t)s2) & 0xFFFFu;
+        }
+        if ((last && (a0 | a1 | a2) == a_end) || (capped && count >= kKeyRayMax - 1u)) {
+          remaining = 0u;                           // cur == end / KeyRay capacity: this voxel is not emitted
+        } else {
+          ++count;
+          emit();
+          --remaining;
+        }
+      }
+    }
+    drain();
+  }
+  if (bits) {
+    q.w[0] = cur | cur_near;
+    q.w[q.stride] = (uint32_t)bits;
+    q.w[2u * q.stride] = (uint32_t)(bits >> 32);
+    nq = 1u;
+  }
+  drain();
+  if (active) {
+    *emitted += count - count0 + (j == 0 ? 1u : 0u);
+    if (last) *longest = max(*longest, count);
+  }
 }
 
 }  // namespace vmapdev
