@@ -165,15 +165,12 @@ int wc_walk_segmented(double res, double max_free_space, double min_height, cons
         if (jj + 1 < cps[r].size()) n_steps = cps[r][jj + 1].count - cps[r][jj].count;
         else if (recs[r].n_keys != 0xFFFFFFFFu) n_steps = recs[r].n_keys > cps[r][jj].count ? recs[r].n_keys - cps[r][jj].count : 0u;
         else active = false;
-        uint32_t qbuf[3 * kQueueSteps];
-        MarkQueue mq;
-        mq.w = qbuf;
-        mq.stride = 1;
+        uint32_t mq[3 * kQueueSteps];
         if (!active) {
           if (P.free_filter) walk_slot_dilated<true, 0, false, true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest);
           else walk_slot_dilated<false, 0, false, true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest);
-        } else if (P.free_filter) walk_slot_queued<true>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, n_steps, true, mq);
-        else walk_slot_queued<false>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, n_steps, true, mq);
+        } else if (P.free_filter) walk_slot_queued<true, 1u>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, n_steps, true, mq);
+        else walk_slot_queued<false, 1u>(P, ms, dw, &cnt, cps[r][jj], recs[r], jj, origin[0], origin[1], origin[2], near_limit, &emitted, &longest, n_steps, true, mq);
       } else if (mode == 4 || mode == 5) {
         // the shipped kernel's counted loop: steps of a non-last segment = next checkpoint's count - this one's
         // ... of the last one = RayRec::n_keys - this checkpoint's count

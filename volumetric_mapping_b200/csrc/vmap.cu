@@ -163,6 +163,10 @@ struct vmap : ScanCtx {
   uint32_t* d_round_info = nullptr;           // [2 parities][kRoundInfoWords]
   uint32_t* h_round_info = nullptr;           // pinned mirror
   uint32_t* d_sub_counts = nullptr;           // [2 scan contexts][counts + cursors]
+  RecordLists* d_lists = nullptr;             // the round's record lists as the apply kernels see them
+  RecordLists* h_lists = nullptr;             // pinned staging of the same
+  uint32_t* d_located = nullptr;              // table index of every record of the round (k_locate_records)
+  size_t located_cap = 0;
   cudaEvent_t ev_collect[2] = {nullptr, nullptr};
   uint64_t round_open = 0;                    // number of the round being packed
   int sub_open = 0;                           // scans packed into it so far

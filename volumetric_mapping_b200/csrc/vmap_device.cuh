@@ -80,7 +80,6 @@ struct Counters {           // zeroed at the start of every scan
   uint32_t need_slots;      // listed blocks that have no pool slot yet (k_locate_blocks)
   uint32_t done_ctas;       // CTAs of k_locate_blocks that have finished (last one decides about the pool)
   uint32_t occ_cursor;      // sort mode: occupied keys appended after the free ones
-  uint32_t walk_next;       // segment walker: next group of 32 work slots to hand to a warp
 };
 constexpr uint32_t kStallEarlier = 1u;   // an earlier scan is stalled (Persist::stalled)
 constexpr uint32_t kStallMarks = 2u;     // the marks are incomplete (window / checkpoint / list overflow)

@@ -31,6 +31,8 @@ int peer_alloc_mailbox(vmap* h, uint64_t records_per_round) {
   VM_CUDA(h, cudaMallocHost((void**)&h->h_round_info, 2 * kRoundInfoWords * sizeof(uint32_t)));
   std::memset(h->h_round_info, 0, 2 * kRoundInfoWords * sizeof(uint32_t));
   VM_TRY(dev_alloc(h, (void**)&h->d_sub_counts, 2 * 2 * kMaxRanks * sizeof(uint32_t)));
+  VM_TRY(dev_alloc(h, (void**)&h->d_lists, sizeof(RecordLists)));
+  VM_CUDA(h, cudaMallocHost((void**)&h->h_lists, sizeof(RecordLists)));
   for (auto& e : h->ev_collect) VM_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return VMAP_OK;
 }
@@ -66,6 +68,13 @@ void peer_release(vmap* h) {
   h->mailbox = nullptr;
   cudaFree(h->d_round_info); h->d_round_info = nullptr;
   cudaFree(h->d_sub_counts); h->d_sub_counts = nullptr;
+  if (h->d_lists) { cudaFree(h->d_lists); h->dev_bytes -= sizeof(RecordLists); }
+  h->d_lists = nullptr;
+  if (h->h_lists) cudaFreeHost(h->h_lists);
+  h->h_lists = nullptr;
+  if (h->d_located) { cudaFree(h->d_located); h->dev_bytes -= (size_t)h->located_cap * sizeof(uint32_t); }
+  h->d_located = nullptr;
+  h->located_cap = 0;
   if (h->h_round_info) cudaFreeHost(h->h_round_info);
   h->h_round_info = nullptr;
   for (auto& e : h->ev_collect)
@@ -131,15 +140,40 @@ int peer_apply_pending(vmap* h) {
     if ((uint64_t)h->h_persist->n_slots + total > h->pool_cap) VM_TRY(grow_pool(h, (uint64_t)h->h_persist->n_slots + total));
     VM_CUDA(h, cudaMemsetAsync(h->d_cnt_app, 0, sizeof(Counters), as));
     VM_CUDA(h, cudaEventRecord(h->ev_app0, as));
+    // every record of the round is located in one launch (table entry, pool slot), then the lists are
+    // applied one launch each, in scan order = (sub-scan, source rank)
+    RecordLists* hl = h->h_lists;                    // pinned; free again: the apply stream was drained above
+    uint32_t n_lists = 0;
+    hl->first[0] = 0;
     for (int j = 0; j < kMaxBatch; j++)
       for (int s = 0; s < G; s++) {
         const uint32_t cnt = info[2 * (j * G + s)], off = info[2 * (j * G + s) + 1];
         if (!cnt) continue;
-        const BlockRecord* src = h->pt.rec[s] + (size_t)p * h->peer_capacity + off;
+        hl->ptr[n_lists] = h->pt.rec[s] + (size_t)p * h->peer_capacity + off;
+        hl->first[n_lists + 1] = hl->first[n_lists] + cnt;
+        n_lists++;
+      }
+    hl->n_lists = n_lists;
+    if (n_lists) {
+      if (total > h->located_cap) {
+        dev_free(h, h->d_located, (size_t)h->located_cap * sizeof(uint32_t));
+        h->d_located = nullptr;
+        h->located_cap = 0;
+        const size_t want = total + (total >> 2);
+        VM_TRY(dev_alloc(h, (void**)&h->d_located, want * sizeof(uint32_t)));
+        h->located_cap = want;
+      }
+      VM_CUDA(h, cudaMemcpyAsync(h->d_lists, hl, sizeof(RecordLists), cudaMemcpyHostToDevice, as));
+      const unsigned lgrid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)g_sm_count(h->device) * 8);
+      k_locate_records<<<std::max(lgrid, 1u), 256, 0, as>>>(h->m, h->d_cnt_app, h->d_lists, h->d_located);
+      h->launches++;
+      for (uint32_t l = 0; l < n_lists; l++) {
+        const uint32_t cnt = hl->first[l + 1] - hl->first[l];
         const unsigned grid = (unsigned)std::min<size_t>(((size_t)cnt + 7) / 8, (size_t)g_sm_count(h->device) * 8);
-        k_apply_update<<<std::max(grid, 1u), 256, 0, as>>>(h->P, h->m, h->d_cnt_app, src, cnt);
+        k_apply_located<<<std::max(grid, 1u), 256, 0, as>>>(h->P, h->m, h->d_cnt_app, hl->ptr[l], h->d_located + hl->first[l], cnt);
         h->launches++;
       }
+    }
     k_round_consumed<<<1, 64, 0, as>>>(h->pt, (uint32_t)r);
     h->launches++;
     VM_CUDA(h, cudaGetLastError());
@@ -219,7 +253,16 @@ int peer_insert(vmap* h, const void* src, bool src_on_host, size_t n, size_t str
   h->launches++;
   VM_CUDA(h, cudaGetLastError());
   VM_TRY(launch_resolve_and_walk(h, n, T));
-  VM_TRY(launch_list(h));
+  // the touched blocks, listed owner by owner (k_list_by_owner instead of k_list_touched)
+  uint32_t* counts = h->d_sub_counts + (size_t)h->ctx_id * 2 * kMaxRanks;
+  VM_CUDA(h, cudaMemsetAsync(counts, 0, 2 * kMaxRanks * sizeof(uint32_t), h->stream));
+  const uint32_t seg_cap = h->win.list_cap / (uint32_t)h->shard_world;
+  {
+    const unsigned grid = (unsigned)std::min<uint64_t>((h->win.n_words + 255) / 256, (uint64_t)g_sm_count(h->device) * 8);
+    k_list_by_owner<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->ms, h->d_cnt, h->win.n_words, (uint32_t)h->shard_world, seg_cap, counts);
+    h->launches++;
+    VM_CUDA(h, cudaGetLastError());
+  }
   VM_TRY(mark_stage(h, 3));
   // the ordered half: this scan's pack comes after the pack of the scan before it (they share the
   // round buffer's cursor)
@@ -230,19 +273,9 @@ int peer_insert(vmap* h, const void* src, bool src_on_host, size_t n, size_t str
     k_round_open<<<1, 64, 0, h->stream>>>(h->pt, p, r >= 2 ? (uint32_t)(r - 1) : 0u);   // round r-2, stored as number + 1
     h->launches++;
   }
-  uint32_t* counts = h->d_sub_counts + (size_t)h->ctx_id * 2 * kMaxRanks;
-  VM_CUDA(h, cudaMemsetAsync(counts, 0, 2 * kMaxRanks * sizeof(uint32_t), h->stream));
-  PackView pv;
-  pv.records = nullptr;
-  pv.counts = counts;
-  pv.cursors = counts + kMaxRanks;
-  pv.capacity = h->peer_capacity;
-  pv.world = (uint32_t)h->shard_world;
-  const unsigned grid = g_sm_count(h->device) * 8;
-  k_pack_count<<<grid, 256, 0, h->stream>>>(h->m, h->ms, h->d_cnt, pv);
   k_pack_plan<<<1, 32, 0, h->stream>>>(h->pt, p, j, counts, h->d_cnt);
-  k_pack_write_round<<<grid, 256, 0, h->stream>>>(h->m, h->ms, h->d_cnt, h->pt, p, j, pv.cursors);
-  h->launches += 3;
+  k_pack_write_round<<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->ms, h->d_cnt, h->pt, p, j, seg_cap, counts);
+  h->launches += 2;
   VM_CUDA(h, cudaGetLastError());
   VM_TRY(mark_stage(h, 4));
   VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
@@ -256,7 +289,14 @@ int peer_insert(vmap* h, const void* src, bool src_on_host, size_t n, size_t str
   h->meta.is_dense = is_dense;
   std::memcpy(h->meta.Tm, Tm, sizeof(h->meta.Tm));
   h->sub_open++;
+  // VMAP_PEER_SERIAL=1 (measurement only): nothing overlaps, so the stage events time each kernel group alone
+  static const bool serial = getenv("VMAP_PEER_SERIAL") && atoi(getenv("VMAP_PEER_SERIAL"));
+  if (serial) VM_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->sub_open >= h->batch_m) VM_TRY(peer_seal(h));
+  if (serial && h->sub_open == 0) {
+    VM_TRY(peer_apply_pending(h));
+    VM_CUDA(h, cudaStreamSynchronize(h->app_stream));
+  }
   VM_CUDA(h, cudaEventSynchronize(h->ev_h2d));
   return VMAP_OK;
 }

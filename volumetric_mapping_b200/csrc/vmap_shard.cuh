@@ -13,6 +13,7 @@ namespace vmapdev {
 
 constexpr int kMaxRanks = 64;
 constexpr int kMaxBatch = 8;     // scans per rank in one exchange round
+constexpr uint32_t kSlotClaimed = 0xFFFFFFFEu;   // MapView::slot while k_locate_records reserves the block's pool slot
 
 // One touched block of one scan: 8 + 64 + 64 bytes.
 struct __align__(8) BlockRecord {
@@ -158,10 +159,11 @@ k_apply_update(DevParams P, MapView m, Counters* cnt, const BlockRecord* __restr
   const uint32_t lane = threadIdx.x & 31u;
   uint32_t n_free = 0, n_occ = 0;
   for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
-    const BlockRecord* r = rec + i;
+    // a record is 34 words: key (2), free mask (16), occupied mask (16); lane l holds mask word l
+    const uint32_t mask = reinterpret_cast<const uint32_t*>(rec + i)[2 + lane];
     uint32_t slot = kUnassigned;
     if (lane == 0) {
-      const uint32_t h = find_or_insert(m, cnt, r->block);
+      const uint32_t h = find_or_insert(m, cnt, rec[i].block);
       if (h != kNotFound) {
         slot = m.slot[h];
         if (slot == kUnassigned) {
@@ -173,23 +175,107 @@ k_apply_update(DevParams P, MapView m, Counters* cnt, const BlockRecord* __restr
     }
     slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
     if (slot == kUnassigned) continue;
-    uint32_t f = 0, o = 0;
-    if (lane < kMaskWords) {
-      f = r->free_mask[lane];
-      o = r->occ_mask[lane];
-      f &= ~o;
-    }
+    // lanes 0..15: free words with the occupied bits removed (occupied wins); lanes 16..31: occupied words
+    const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, mask, 16);
+    const uint32_t mine = lane < kMaskWords ? (mask & ~other) : mask;
     uint32_t* vox = reinterpret_cast<uint32_t*>(m.pool) + (size_t)slot * kBlockVoxels;
+    uint32_t val[kMaskWords];       // all rows are loaded before the first one is updated: one round trip per block
 #pragma unroll
     for (int j = 0; j < kMaskWords; j++) {
-      const uint32_t fw = __shfl_sync(0xFFFFFFFFu, f, j);
-      const uint32_t ow = __shfl_sync(0xFFFFFFFFu, o, j);
-      if ((fw | ow) == 0u) continue;
+      const uint32_t any = __shfl_sync(0xFFFFFFFFu, mine, j) | __shfl_sync(0xFFFFFFFFu, mine, j + kMaskWords);
+      val[j] = ((any >> lane) & 1u) ? __ldcg(vox + j * 32 + lane) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kMaskWords; j++) {
+      const uint32_t fw = __shfl_sync(0xFFFFFFFFu, mine, j);
+      const uint32_t ow = __shfl_sync(0xFFFFFFFFu, mine, j + kMaskWords);
       const bool is_occ = (ow >> lane) & 1u, is_free = (fw >> lane) & 1u;
-      if (is_occ || is_free) {
-        uint32_t* p = vox + j * 32 + lane;
-        *p = update_leaf(*p, is_occ ? P.hit : P.miss, P.cmin, P.cmax);
+      if (is_occ || is_free) vox[j * 32 + lane] = update_leaf(val[j], is_occ ? P.hit : P.miss, P.cmin, P.cmax);
+      if (lane == 0) { n_free += __popc(fw); n_occ += __popc(ow); }
+    }
+  }
+  if (lane == 0) {
+    if (n_free) atomicAdd(&cnt->unique_free, n_free);
+    if (n_occ) atomicAdd(&cnt->unique_occupied, n_occ);
+  }
+}
+
+// Owner side of the peer-memory transport, in two steps per round:
+//   k_locate_records  ONE launch over every record of the round, one thread per record: looks the block
+//                     up (inserting it when new) and gives it a pool slot; located[] keeps the table
+//                     index.  Order-free: inserting blocks and reserving slots commute.
+//   k_apply_located   one launch per (sub-scan, source rank) list, in scan order, one warp per record:
+//                     all of the block's voxel rows are loaded before the first one is updated.
+struct RecordLists {                               // in device memory, rewritten for every round
+  const BlockRecord* ptr[kMaxBatch * kMaxRanks];
+  uint32_t first[kMaxBatch * kMaxRanks + 1];       // index of every list's first record in located[]
+  uint32_t n_lists;
+};
+
+__global__ void __launch_bounds__(256)
+k_locate_records(MapView m, Counters* cnt, const RecordLists* __restrict__ lists, uint32_t* __restrict__ located) {
+  __shared__ uint32_t s_first[kMaxBatch * kMaxRanks + 1];
+  const uint32_t n_lists = lists->n_lists;
+  for (uint32_t i = threadIdx.x; i <= n_lists; i += blockDim.x) s_first[i] = lists->first[i];
+  __syncthreads();
+  const uint32_t total = s_first[n_lists];
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t g0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; g0 < total; g0 += gridDim.x * blockDim.x) {   // uniform per warp
+    const uint32_t g = g0 + lane;
+    uint32_t h = kNotFound;
+    if (g < total) {
+      uint32_t lo = 0, hi = n_lists;               // list of record g: largest l with first[l] <= g
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_first[mid] <= g) lo = mid; else hi = mid;
       }
+      h = find_or_insert(m, cnt, lists->ptr[lo][g - s_first[lo]].block);
+      // A new block gets its pool slot here.  Several records of the round (different scans) may name
+      // the same new block: the first to swap the claim mark in reserves the slot, the others move on --
+      // k_apply_located reads the slot from the table, after this kernel.
+      if (h != kNotFound && m.slot[h] == kUnassigned && atomicCAS(m.slot + h, kUnassigned, kSlotClaimed) == kUnassigned) {
+        const uint32_t mine = atomicAdd(&m.persist->n_slots, 1u);
+        if (mine < m.pool_cap) {
+          atomicExch(m.slot + h, mine);
+        } else {
+          cnt->overflow_pool = 1u;
+          atomicExch(m.slot + h, kUnassigned);
+        }
+      }
+      located[g] = h;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_apply_located(DevParams P, MapView m, Counters* cnt, const BlockRecord* __restrict__ rec,
+                const uint32_t* __restrict__ located, uint32_t n) {
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t n_free = 0, n_occ = 0;
+  for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const uint32_t h = located[i];
+    if (h == kNotFound) continue;
+    const uint32_t slot = __ldcg(m.slot + h);
+    if (slot >= m.pool_cap) continue;              // (no slot: the pool overflowed, the host reports it)
+    // a record is 34 words: key (2), free mask (16), occupied mask (16); lane l holds mask word l
+    const uint32_t mask = reinterpret_cast<const uint32_t*>(rec + i)[2 + lane];
+    // lanes 0..15: free words with the occupied bits removed (occupied wins); lanes 16..31: occupied words
+    const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, mask, 16);
+    const uint32_t mine = lane < kMaskWords ? (mask & ~other) : mask;
+    uint32_t* vox = reinterpret_cast<uint32_t*>(m.pool) + (size_t)slot * kBlockVoxels;
+    uint32_t val[kMaskWords];
+#pragma unroll
+    for (int j = 0; j < kMaskWords; j++) {
+      const uint32_t any = __shfl_sync(0xFFFFFFFFu, mine, j) | __shfl_sync(0xFFFFFFFFu, mine, j + kMaskWords);
+      val[j] = ((any >> lane) & 1u) ? __ldcg(vox + j * 32 + lane) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < kMaskWords; j++) {
+      const uint32_t fw = __shfl_sync(0xFFFFFFFFu, mine, j);
+      const uint32_t ow = __shfl_sync(0xFFFFFFFFu, mine, j + kMaskWords);
+      const bool is_occ = (ow >> lane) & 1u, is_free = (fw >> lane) & 1u;
+      if (is_occ || is_free) vox[j * 32 + lane] = update_leaf(val[j], is_occ ? P.hit : P.miss, P.cmin, P.cmax);
       if (lane == 0) { n_free += __popc(fw); n_occ += __popc(ow); }
     }
   }
@@ -270,9 +356,48 @@ __global__ void k_round_open(PeerTable pt, uint32_t parity, uint32_t want) {
   }
 }
 
-// Between k_pack_count and k_pack_write of sub-scan `sub`: bucket offsets inside the round buffer
-// (one thread; counts[] are this sub-scan's per-destination counts).  When the buffer cannot hold
-// them nothing is written, the header says so, and the scan's counters carry overflow_pack.
+// Peer-memory pack, step 1 (replaces k_list_touched): compact the window's touched bitmap into ONE LIST
+// PER OWNER -- owner d's blocks at ms.list[d * seg_cap ...], counts[d] of them -- so that the records
+// can be written one warp per block with no further bookkeeping.  A CTA takes 256 bitmap words at a
+// time: its blocks are counted per owner in shared memory, the owners' list space is reserved with one
+// global atomic per owner per CTA pass, positions inside the reservation come from shared cursors.
+// (Round 2, first version: a count pass, and a write pass that reserved space with a returning atomic
+// on `world` hot addresses per 8 blocks -- the pack took longer than the K4 update it replaces.)
+__global__ void __launch_bounds__(256)
+k_list_by_owner(MarkSet ms, Counters* cnt, uint32_t n_words, uint32_t world, uint32_t seg_cap, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t s_cnt[kMaxRanks];
+  __shared__ uint32_t s_cur[kMaxRanks];
+  for (uint32_t wbase = blockIdx.x * blockDim.x; wbase < n_words; wbase += gridDim.x * blockDim.x) {   // uniform per CTA
+    if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t wi = wbase + threadIdx.x;
+    const uint32_t v = wi < n_words ? ms.touched_bits[wi] : 0u;
+    for (uint32_t rest = v; rest; rest &= rest - 1u) {
+      const uint32_t e = wi * 32u + (uint32_t)(__ffs(rest) - 1);
+      atomicAdd(&s_cnt[owner_of(window_block_key(ms, e), world)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world) s_cur[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(counts + threadIdx.x, s_cnt[threadIdx.x]) : 0u;
+    if (threadIdx.x == 0) {
+      uint32_t total = 0;
+      for (uint32_t d = 0; d < world; d++) total += s_cnt[d];
+      if (total) atomicAdd(&cnt->n_touched, total);
+    }
+    __syncthreads();
+    for (uint32_t rest = v; rest; rest &= rest - 1u) {
+      const uint32_t e = wi * 32u + (uint32_t)(__ffs(rest) - 1);
+      const uint32_t d = owner_of(window_block_key(ms, e), world);
+      const uint32_t pos = atomicAdd(&s_cur[d], 1u);
+      if (pos < seg_cap) ms.list[(size_t)d * seg_cap + pos] = e;
+      else atomicExch(&cnt->overflow_keys, 1u);   // an owner's share of the list is full (sizing error: the host reports it)
+    }
+    __syncthreads();
+  }
+}
+
+// Step 2 (one thread): bucket offsets of sub-scan `sub` inside the round buffer from counts[].  When the
+// buffer cannot hold the records nothing is written, the header says so, and the scan's counters carry
+// overflow_pack.
 __global__ void k_pack_plan(PeerTable pt, uint32_t parity, uint32_t sub, const uint32_t* __restrict__ counts,
                             Counters* cnt) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -295,59 +420,44 @@ __global__ void k_pack_plan(PeerTable pt, uint32_t parity, uint32_t sub, const u
   h->n_subs = sub + 1u;
 }
 
-// pass 2 of the pack into a round buffer: like k_pack_write, bucket bases taken from the header.
+// Step 3: one warp per listed block, owner by owner: the block's 128 bytes of masks become its record
+// in the owner's bucket of the round buffer (same position as in the owner's list) and are cleared.
 __global__ void __launch_bounds__(256)
-k_pack_write_round(MapView m, MarkSet ms, Counters* cnt, PeerTable pt, uint32_t parity, uint32_t sub, uint32_t* cursors) {
+k_pack_write_round(MarkSet ms, Counters* cnt, PeerTable pt, uint32_t parity, uint32_t sub, uint32_t seg_cap,
+                   const uint32_t* __restrict__ counts) {
   if (cnt->overflow_table || cnt->overflow_window || cnt->overflow_ckpt || cnt->overflow_keys || cnt->overflow_pack) return;
-  __shared__ uint32_t s_base[kMaxRanks];
-  __shared__ uint32_t s_cnt[kMaxRanks];
-  __shared__ uint32_t s_res[kMaxRanks];
+  __shared__ uint32_t s_first[kMaxRanks + 1];     // global record index of every owner's first block
+  __shared__ uint32_t s_off[kMaxRanks];           // first record of every owner's bucket
   const RoundHeader* hd = &pt.head[pt.me]->hdr[parity];
+  if (threadIdx.x == 0) {
+    uint32_t at = 0;
+    for (uint32_t d = 0; d < pt.world; d++) { s_first[d] = at; at += counts[d]; }
+    s_first[pt.world] = at;
+  }
+  if (threadIdx.x < pt.world) s_off[threadIdx.x] = hd->offset[sub][threadIdx.x];
+  __syncthreads();
   BlockRecord* out = pt.rec[pt.me] + (size_t)parity * pt.capacity;
-  if (threadIdx.x < pt.world) s_base[threadIdx.x] = hd->offset[sub][threadIdx.x];
-  const uint32_t warps_per_cta = blockDim.x >> 5;
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  const uint32_t n_touched = cnt->n_touched;
-  const uint32_t stride = gridDim.x * warps_per_cta;
-  for (uint32_t t0 = blockIdx.x * warps_per_cta; t0 < n_touched; t0 += stride) {   // uniform per CTA
-    if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t t = t0 + warp;
-    uint32_t wv = 0, dest = 0, local = 0;
-    unsigned long long b = 0;
-    uint32_t* src = nullptr;
-    bool have = false;
-    if (t < n_touched) {
-      const uint32_t e = ms.list[t];
-      src = (lane < kMaskWords) ? ms.free_mask + (size_t)e * kMaskWords + lane
-                                : ms.occ_mask + (size_t)e * kMaskWords + lane - kMaskWords;
-      wv = *src;
-      have = __any_sync(0xFFFFFFFFu, wv != 0u);
-      if (have) {
-        b = ms.dense ? window_block_key(ms, e) : (m.keys[e] >> kEpochBits);
-        dest = owner_of(b, pt.world);
-        if (lane == 0) local = atomicAdd(&s_cnt[dest], 1u);
-        local = __shfl_sync(0xFFFFFFFFu, local, 0);
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x < pt.world && s_cnt[threadIdx.x]) s_res[threadIdx.x] = atomicAdd(cursors + threadIdx.x, s_cnt[threadIdx.x]);
-    __syncthreads();
-    if (have) {
-      if (wv) *src = 0u;
-      BlockRecord* r = out + (s_base[dest] + s_res[dest] + local);
-      if (lane == 0) r->block = b;
-      if (lane < kMaskWords) r->free_mask[lane] = wv;
-      else r->occ_mask[lane - kMaskWords] = wv;
-    }
-    __syncthreads();
+  const uint32_t total = s_first[pt.world];
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < total; g += warps) {
+    uint32_t d = 0;
+    while (g >= s_first[d + 1]) d++;
+    const uint32_t i = g - s_first[d];
+    const uint32_t e = ms.list[(size_t)d * seg_cap + i];
+    uint32_t* src = (lane < kMaskWords) ? ms.free_mask + (size_t)e * kMaskWords + lane
+                                        : ms.occ_mask + (size_t)e * kMaskWords + lane - kMaskWords;
+    const uint32_t wv = *src;
+    if (wv) *src = 0u;
+    BlockRecord* r = out + (s_off[d] + i);
+    if (lane == 0) r->block = window_block_key(ms, e);
+    if (lane < kMaskWords) r->free_mask[lane] = wv;
+    else r->occ_mask[lane - kMaskWords] = wv;
   }
   // the scan's marks are packed: its touched bitmap is free for the next scan of this context
-  if (ms.dense) {
-    const uint32_t n_words = (ms.nx * ms.ny * ms.nz + 31u) >> 5;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x)
-      if (ms.touched_bits[i]) ms.touched_bits[i] = 0u;
-  }
+  const uint32_t n_words = (ms.nx * ms.ny * ms.nz + 31u) >> 5;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x)
+    if (ms.touched_bits[i]) ms.touched_bits[i] = 0u;
 }
 
 // Seal round `round` (header of this parity) and tell every rank: one remote store per peer.

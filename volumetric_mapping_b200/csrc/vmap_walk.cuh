@@ -519,22 +519,21 @@ __device__ __forceinline__ void walk_slot_dilated(const DevParams& P, const Mark
 // WARP-COLLECTIVE: every lane of the warp calls it (`active` false: no slot); q: this lane's queue.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kQueueSteps = 8;                 // steps between drains = queue capacity
-struct MarkQueue {
-  uint32_t* w;        // entry e, word k (0: mask word index | near flag << 31, 1: bits low, 2: bits high) at w[(3 * e + k) * stride]
-  uint32_t stride;
-};
 #if !defined(__CUDA_ARCH__) && defined(VMAP_HOST_EMULATION)
 static inline bool vmap_warp_any(bool p) { return p; }      // one "lane" at a time on the host
 #else
 __device__ __forceinline__ bool vmap_warp_any(bool p) { return __any_sync(0xFFFFFFFFu, p) != 0; }
 #endif
 
-template <bool kFilter>
+// q: this lane's queue; entry e, word k (0: index of the 64-bit mask word, 1: bits 0..31, 2: bits 32..63)
+// at q[(3 * e + k) * kQStride] (kQStride = threads per CTA on the device: conflict-free banks).
+template <bool kFilter, uint32_t kQStride>
 __device__ __forceinline__ void walk_slot_queued(const DevParams& P, const MarkSet& ms, const DilatedWindow& dw, Counters* cnt,
                                                  const Checkpoint& cp, const RayRec& rr, uint32_t j, float ox, float oy,
                                                  float oz, uint32_t near_limit, uint32_t* emitted, uint32_t* longest,
-                                                 uint32_t n_steps, bool active, const MarkQueue& q) {
-  uint32_t c0 = 0, c1 = 0, c2 = 0, a0 = 0, a1 = 0, a2 = 0, a_end = 0, k0 = 0, k1 = 0, k2 = 0;
+                                                 uint32_t n_steps, bool active, uint32_t* q) {
+  uint32_t c0 = 0, c1 = 0, c2 = 0, a0 = 0, a1 = 0, a2 = 0, k0 = 0, k1 = 0, k2 = 0;
+  uint32_t a_stop = 0xFFFFFFFFu;                    // address of the end voxel in a ray's last segment, else none
   int s0 = 0, s1 = 0, s2 = 0;
   double t0 = 0.0, t1 = 0.0, t2 = 0.0, dt0 = 0.0, dt1 = 0.0, dt2 = 0.0;
   bool last = false, capped = false;
@@ -555,45 +554,46 @@ __device__ __forceinline__ void walk_slot_queued(const DevParams& P, const MarkS
       s0 = sc0 == 1u ? 1 : (sc0 == 2u ? -1 : 0); s1 = sc1 == 1u ? 1 : (sc1 == 2u ? -1 : 0); s2 = sc2 == 1u ? 1 : (sc2 == 2u ? -1 : 0);
       const uint32_t wx = (uint32_t)ms.x0 << 3, wy = (uint32_t)ms.y0 << 3, wz = (uint32_t)ms.z0 << 3;
       a0 = dilate_axis(c0 - wx, 0u, 9u); a1 = dilate_axis(c1 - wy, 3u, dw.sh1); a2 = dilate_axis(c2 - wz, 6u, dw.sh2);
-      a_end = dilate_axis(e0 - wx, 0u, 9u) | dilate_axis(e1 - wy, 3u, dw.sh1) | dilate_axis(e2 - wz, 6u, dw.sh2);
       t0 = cp.t0; t1 = cp.t1; t2 = cp.t2;
       dt0 = rr.dt0; dt1 = rr.dt1; dt2 = rr.dt2;
       last = (j + 1 == rr.n_seg);
+      // (a voxel address has at most 31 bits -- dilated_window_fits -- so all ones never matches)
+      if (last) a_stop = dilate_axis(e0 - wx, 0u, 9u) | dilate_axis(e1 - wy, 3u, dw.sh1) | dilate_axis(e2 - wz, 6u, dw.sh2);
       capped = (rr.n_seg + 1u) * kSegSteps + 4u >= kKeyRayMax - 1u;    // only such rays can reach KeyRay's capacity
       count = count0 = cp.count;
     }
   }
+  const bool any_capped = vmap_warp_any(capped);    // warp-uniform: the per-step capacity test is compiled out of the common loop
   uint32_t remaining = active ? n_steps : 0u;
-  uint32_t cur = 0xFFFFFFFFu, cur_near = 0u, nq = 0u, last_blk = 0xFFFFFFFFu;
-  unsigned long long bits = 0ull;
-  auto emit = [&]() {
+  uint32_t cur = 0xFFFFFFFFu, lo = 0u, hi = 0u;      // 64-bit mask word in flight and the bits collected for it
+  uint32_t* qp = q;                                  // next free queue entry
+  uint32_t last_blk = 0xFFFFFFFFu;
+  auto emit = [&](uint32_t a) {
     if (kFilter && !free_filter_pass(P, ox, oy, oz, c0, c1, c2)) return;
-    const uint32_t a = a0 | a1 | a2;
     const uint32_t wi = a >> 6;
     if (wi != cur) {
-      if (bits) {                                   // park the finished word
-        uint32_t* e = q.w + 3u * nq * q.stride;
-        e[0] = cur | cur_near;
-        e[q.stride] = (uint32_t)bits;
-        e[2u * q.stride] = (uint32_t)(bits >> 32);
-        ++nq;
+      if (cur != 0xFFFFFFFFu) {                     // park the finished word
+        qp[0] = cur;
+        qp[kQStride] = lo;
+        qp[2u * kQStride] = hi;
+        qp += 3u * kQStride;
       }
-      bits = 0ull;
+      lo = 0u; hi = 0u;
       cur = wi;
-      cur_near = count < near_limit ? 0x80000000u : 0u;
     }
-    bits |= 1ull << (a & 63u);
+    const uint32_t bit = 1u << (a & 31u);
+    if (a & 32u) hi |= bit; else lo |= bit;
   };
   auto drain = [&]() {
-    for (uint32_t e = 0; vmap_warp_any(e < nq); e++) {
-      if (e < nq) {
-        const uint32_t* ent = q.w + 3u * e * q.stride;
-        const uint32_t cf = ent[0];
-        const unsigned long long b = (unsigned long long)ent[q.stride] | ((unsigned long long)ent[2u * q.stride] << 32);
-        const uint32_t wi = cf & 0x7FFFFFFFu;
+    // near the sensor every ray sets the same voxels: there a RED only goes out for bits not visible
+    // yet.  Decided per drain from the lane's key count (the entries are at most kQueueSteps keys old).
+    const bool near = count < near_limit + kQueueSteps;
+    for (const uint32_t* e = q; vmap_warp_any(e < qp); e += 3u * kQStride) {
+      if (e < qp) {
+        const uint32_t wi = e[0];
+        const unsigned long long b = (unsigned long long)e[kQStride] | ((unsigned long long)e[2u * kQStride] << 32);
         unsigned long long* w = reinterpret_cast<unsigned long long*>(ms.free_mask) + wi;
-        // near the sensor every ray sets the same voxels: there a RED only goes out for bits not visible yet
-        if (cf >> 31) { if (b & ~*w) atomicOr(w, b); }
+        if (near) { if (b & ~*w) atomicOr(w, b); }
         else atomicOr(w, b);
         const uint32_t blk = wi >> 3;
         if (blk != last_blk) {
@@ -604,10 +604,11 @@ __device__ __forceinline__ void walk_slot_queued(const DevParams& P, const MarkS
         }
       }
     }
-    nq = 0u;
+    qp = q;
   };
-  if (active && j == 0) emit();       // the origin voxel belongs to segment 0
+  if (active && j == 0) emit(a0 | a1 | a2);       // the origin voxel belongs to segment 0
   while (vmap_warp_any(remaining != 0u)) {
+#pragma unroll 2
     for (uint32_t s = 0; s < kQueueSteps; s++) {
       if (remaining) {
         // one DDA step: strict '<' comparisons, ties go to the later axis (computeRayKeys)
@@ -626,22 +627,25 @@ __device__ __forceinline__ void walk_slot_queued(const DevParams& P, const MarkS
           t2 = __dadd_rn(t2, dt2);
           if (kFilter) c2 = (c2 + (uint32_t)s2) & 0xFFFFu;
         }
-        if ((last && (a0 | a1 | a2) == a_end) || (capped && count >= kKeyRayMax - 1u)) {
-          remaining = 0u;                           // cur == end / KeyRay capacity: this voxel is not emitted
+        const uint32_t a = a0 | a1 | a2;
+        bool stop = a == a_stop;                                          // cur == end: this voxel is not emitted
+        if (any_capped) stop = stop || (capped && count >= kKeyRayMax - 1u);   // KeyRay capacity
+        if (stop) {
+          remaining = 0u;
         } else {
-          ++count;
-          emit();
           --remaining;
+          ++count;
+          emit(a);
         }
       }
     }
     drain();
   }
-  if (bits) {
-    q.w[0] = cur | cur_near;
-    q.w[q.stride] = (uint32_t)bits;
-    q.w[2u * q.stride] = (uint32_t)(bits >> 32);
-    nq = 1u;
+  if (cur != 0xFFFFFFFFu) {
+    qp[0] = cur;
+    qp[kQStride] = lo;
+    qp[2u * kQStride] = hi;
+    qp += 3u * kQStride;
   }
   drain();
   if (active) {
