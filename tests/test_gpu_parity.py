@@ -429,6 +429,61 @@ def test_cfg5_style_queries_on_hdl64_map():
     assert set(g.tolist()) == {0, 1}        # treat_unknown_as_occupied folds unknown into 1
 
 
+def test_bench_query_workloads_vs_oracle_subsample():
+    """The two segment workloads bench.py times (uniform in the mapped box; "hard": starting in known-free space
+    along the sensor path), 100k segments each, on a map of trajectory scans -- statuses against the oracle, and
+    the probe counter behind the query roofline against the oracle's key counts."""
+    import torch
+    n_scans = 3
+    gw = vm.OctomapWorld(resolution=0.1, sensor_max_range=50.0)
+    ow = oracle.OracleWorld(resolution=0.1, sensor_max_range=50.0)
+    ow.set_faithful_inner_update(False)
+    for i in range(n_scans):
+        s = scenes.trajectory_scan(i, resolution=0.1)
+        gw.insertPointcloudFast(s["T"], s["points"])
+        ow.insertPointcloud(s["T"], s["points"])
+    m = 100000
+    q = scenes.cfg5_queries(n_segments=m, n_points=m, bounds=((-45.0, 45.0 + 0.5 * n_scans), (-45.0, 45.0), (-0.5, 4.0)))
+    rng = np.random.default_rng(7)
+    a = np.stack([rng.uniform(0.0, 0.5 * n_scans, m), rng.uniform(-8.0, 8.0, m), rng.uniform(0.3, 1.7, m)], axis=1)
+    d = rng.normal(size=(m, 3))
+    d[:, 2] *= 0.15
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    hard = np.concatenate([a, a + d * rng.uniform(2.0, 30.0, (m, 1))], axis=1)
+    for name, segs in (("uniform", q["segments"]), ("hard", hard)):
+        g, o = gw.getLineStatus(segs), ow.getLineStatus(segs)
+        assert np.array_equal(g, o), name
+        seg = torch.from_numpy(np.ascontiguousarray(segs)).cuda()
+        st = torch.zeros(m, dtype=torch.uint8, device="cuda")
+        probes = gw.getLineStatusProbesDevice(seg.data_ptr(), m, st.data_ptr())
+        assert np.array_equal(st.cpu().numpy(), o), name
+        assert probes >= int((o == 0).sum())          # a free segment probes at least its one voxel
+    # the hard subset really walks: a good share of its segments cross free space and end free
+    assert (ow.getLineStatus(hard) == 0).mean() > 0.2
+    assert np.array_equal(gw.getCellStatusPoint(q["points"]), ow.getCellStatusPoint(q["points"]))
+
+
+def test_walker_variants_build_the_same_map(monkeypatch):
+    """Every segment-walker variant (block addressing, dilated 32- / 64-voxel words, queued marks) must leave the
+    same map bit for bit; the default (queued) one is also what every other test in this file runs."""
+    scans = [scenes.trajectory_scan(5 * i, resolution=0.2) for i in range(2)]
+    ref = None
+    for addr in ("0", "1", "7", "9", "8"):
+        monkeypatch.setenv("VMAP_WALK_ADDR", addr)
+        w = vm.OctomapWorld(resolution=0.2, sensor_max_range=50.0)
+        stats = []
+        for s in scans:
+            w.insertPointcloud(s["T"], s["points"])
+            st = w.last_scan_stats()
+            stats.append((st["traversals"], st["unique_free"], st["unique_occupied"], st["longest_ray"]))
+        dg = (w.leaf_digest(), stats)
+        w.close()
+        if ref is None:
+            ref = dg
+        assert dg == ref, addr
+    monkeypatch.delenv("VMAP_WALK_ADDR")
+
+
 # ---------------------------------------------------------------------------------------
 # BASELINE.json full sizes: cfg4 against the oracle (one scan), and size-independent
 # properties where the oracle would take too long

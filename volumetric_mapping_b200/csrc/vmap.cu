@@ -165,6 +165,7 @@ struct vmap : ScanCtx {
   uint32_t* d_sub_counts = nullptr;           // [2 scan contexts][counts + cursors]
   RecordLists* d_lists = nullptr;             // the round's record lists as the apply kernels see them
   RecordLists* h_lists = nullptr;             // pinned staging of the same
+  cudaEvent_t ev_split[4] = {nullptr, nullptr, nullptr, nullptr};   // VMAP_PEER_SERIAL + VMAP_TIMING: per-kernel times of the apply
   uint32_t* d_located = nullptr;              // table index of every record of the round (k_locate_records)
   size_t located_cap = 0;
   cudaEvent_t ev_collect[2] = {nullptr, nullptr};

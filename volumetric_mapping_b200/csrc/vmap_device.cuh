@@ -80,6 +80,7 @@ struct Counters {           // zeroed at the start of every scan
   uint32_t need_slots;      // listed blocks that have no pool slot yet (k_locate_blocks)
   uint32_t done_ctas;       // CTAs of k_locate_blocks that have finished (last one decides about the pool)
   uint32_t occ_cursor;      // sort mode: occupied keys appended after the free ones
+  uint32_t round_blocks;    // sharded apply: distinct blocks named by the round's records
 };
 constexpr uint32_t kStallEarlier = 1u;   // an earlier scan is stalled (Persist::stalled)
 constexpr uint32_t kStallMarks = 2u;     // the marks are incomplete (window / checkpoint / list overflow)

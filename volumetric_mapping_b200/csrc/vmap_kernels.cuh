@@ -863,7 +863,7 @@ k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t n_touched = cnt->n_touched;
-  uint32_t n_free = 0, n_occ = 0;
+  uint32_t n_free = 0, n_occ = 0, lane_free = 0, lane_occ = 0;
   for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_touched; t += warps) {
     uint32_t e, h;
     listed_block(ms, m, t, &e, &h);
@@ -937,6 +937,10 @@ k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
         }
       }
     } else {
+      // (statistics: every lane counts its own mask word once per block instead of lane 0 counting
+      // every row -- the row loop is what the kernel's issue slots go to)
+      lane_free += __popc(f);
+      lane_occ += __popc(o);
 #pragma unroll
       for (int j = 0; j < kMaskWords; j++) {
         const uint32_t fw = __shfl_sync(0xFFFFFFFFu, f, j);
@@ -947,10 +951,15 @@ k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
           uint32_t* p = vox + j * 32 + lane;
           *p = update_leaf(*p, is_occ ? P.hit : P.miss, P.cmin, P.cmax);
         }
-        if (lane == 0) { n_free += __popc(fw); n_occ += __popc(ow); }
       }
     }
   }
+  for (int o2 = 16; o2 > 0; o2 >>= 1) {
+    lane_free += __shfl_xor_sync(0xFFFFFFFFu, lane_free, o2);
+    lane_occ += __shfl_xor_sync(0xFFFFFFFFu, lane_occ, o2);
+  }
+  n_free += lane_free;
+  n_occ += lane_occ;
   __shared__ uint32_t s_stat[2];
   if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
   __syncthreads();

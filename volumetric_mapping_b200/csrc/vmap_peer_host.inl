@@ -155,23 +155,60 @@ int peer_apply_pending(vmap* h) {
       }
     hl->n_lists = n_lists;
     if (n_lists) {
-      if (total > h->located_cap) {
+      // round-fused apply (k_apply_round) for up to 32 lists, list by list beyond that; VMAP_PEER_FUSED=0 forces the latter
+      static const bool fused_ok = !(getenv("VMAP_PEER_FUSED") && atoi(getenv("VMAP_PEER_FUSED")) == 0);
+      const bool fused = fused_ok && n_lists <= 32;
+      const size_t need = fused ? 3 * total + total * n_lists : total;     // located | round_blocks | bcount | bucket
+      if (need > h->located_cap) {
         dev_free(h, h->d_located, (size_t)h->located_cap * sizeof(uint32_t));
         h->d_located = nullptr;
         h->located_cap = 0;
-        const size_t want = total + (total >> 2);
+        const size_t want = need + (need >> 2);
         VM_TRY(dev_alloc(h, (void**)&h->d_located, want * sizeof(uint32_t)));
         h->located_cap = want;
       }
+      uint32_t* d_round_blocks = h->d_located + total;
+      uint32_t* d_bcount = h->d_located + 2 * total;
+      uint32_t* d_bucket = h->d_located + 3 * total;
       VM_CUDA(h, cudaMemcpyAsync(h->d_lists, hl, sizeof(RecordLists), cudaMemcpyHostToDevice, as));
+      if (fused) {
+        // m.touched (the table-mode block list, unused by sharded handles' scans) serves as "index of this
+        // block among the round's blocks": all ones = not seen yet in this round
+        VM_CUDA(h, cudaMemsetAsync(h->m.touched, 0xFF, h->table_cap * sizeof(uint32_t), as));
+        VM_CUDA(h, cudaMemsetAsync(d_bcount, 0, total * sizeof(uint32_t), as));
+      }
+      static const bool split = getenv("VMAP_PEER_SERIAL") && atoi(getenv("VMAP_PEER_SERIAL")) && getenv("VMAP_TIMING");
+      if (split) {
+        for (auto& e : h->ev_split)
+          if (!e) VM_CUDA(h, cudaEventCreate(&e));
+        VM_CUDA(h, cudaEventRecord(h->ev_split[0], as));
+      }
       const unsigned lgrid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)g_sm_count(h->device) * 8);
-      k_locate_records<<<std::max(lgrid, 1u), 256, 0, as>>>(h->m, h->d_cnt_app, h->d_lists, h->d_located);
+      k_locate_records<<<std::max(lgrid, 1u), 256, 0, as>>>(h->m, h->d_cnt_app, h->d_lists, h->d_located, fused ? d_round_blocks : nullptr);
       h->launches++;
-      for (uint32_t l = 0; l < n_lists; l++) {
-        const uint32_t cnt = hl->first[l + 1] - hl->first[l];
-        const unsigned grid = (unsigned)std::min<size_t>(((size_t)cnt + 7) / 8, (size_t)g_sm_count(h->device) * 8);
-        k_apply_located<<<std::max(grid, 1u), 256, 0, as>>>(h->P, h->m, h->d_cnt_app, hl->ptr[l], h->d_located + hl->first[l], cnt);
-        h->launches++;
+      if (split) VM_CUDA(h, cudaEventRecord(h->ev_split[1], as));
+      if (fused) {
+        k_bucket_records<<<(unsigned)((total + 255) / 256), 256, 0, as>>>(h->m, h->d_located, (uint32_t)total, n_lists, d_bcount, d_bucket);
+        if (split) VM_CUDA(h, cudaEventRecord(h->ev_split[2], as));
+        const unsigned grid = (unsigned)std::min<size_t>((total + 7) / 8, (size_t)g_sm_count(h->device) * 8);
+        k_apply_round<<<std::max(grid, 1u), 256, 0, as>>>(h->P, h->m, h->d_cnt_app, h->d_lists, d_round_blocks, d_bcount, d_bucket);
+        h->launches += 2;
+        if (split) {
+          VM_CUDA(h, cudaEventRecord(h->ev_split[3], as));
+          VM_CUDA(h, cudaEventSynchronize(h->ev_split[3]));
+          for (int k = 0; k < 3; k++) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev_split[k], h->ev_split[k + 1]);
+            h->dbg_ms[1 + k] += ms;
+          }
+        }
+      } else {
+        for (uint32_t l = 0; l < n_lists; l++) {
+          const uint32_t cnt = hl->first[l + 1] - hl->first[l];
+          const unsigned grid = (unsigned)std::min<size_t>(((size_t)cnt + 7) / 8, (size_t)g_sm_count(h->device) * 8);
+          k_apply_located<<<std::max(grid, 1u), 256, 0, as>>>(h->P, h->m, h->d_cnt_app, hl->ptr[l], h->d_located + hl->first[l], cnt);
+          h->launches++;
+        }
       }
     }
     k_round_consumed<<<1, 64, 0, as>>>(h->pt, (uint32_t)r);

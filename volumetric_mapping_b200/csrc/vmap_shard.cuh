@@ -212,8 +212,12 @@ struct RecordLists {                               // in device memory, rewritte
   uint32_t n_lists;
 };
 
+// round_blocks != nullptr (round-fused apply, below): the first record of the round that names a block
+// also registers it -- m.touched[h] (all ones before the launch) becomes the block's index in
+// round_blocks[], cnt->round_blocks counts them.
 __global__ void __launch_bounds__(256)
-k_locate_records(MapView m, Counters* cnt, const RecordLists* __restrict__ lists, uint32_t* __restrict__ located) {
+k_locate_records(MapView m, Counters* cnt, const RecordLists* __restrict__ lists, uint32_t* __restrict__ located,
+                 uint32_t* __restrict__ round_blocks) {
   __shared__ uint32_t s_first[kMaxBatch * kMaxRanks + 1];
   const uint32_t n_lists = lists->n_lists;
   for (uint32_t i = threadIdx.x; i <= n_lists; i += blockDim.x) s_first[i] = lists->first[i];
@@ -243,8 +247,98 @@ k_locate_records(MapView m, Counters* cnt, const RecordLists* __restrict__ lists
         }
       }
       located[g] = h;
+      if (round_blocks && h != kNotFound && atomicCAS(m.touched + h, kUnassigned, kSlotClaimed) == kUnassigned) {
+        const uint32_t b = atomicAdd(&cnt->round_blocks, 1u);
+        round_blocks[b] = h;
+        atomicExch(m.touched + h, b);
+      }
     }
   }
+}
+
+// Round-fused apply.  Consecutive scans touch nearly the same blocks, and a round brings a block up to
+// n_lists records (one per scan): applying the lists one launch after the other reads and writes every
+// such block n_lists times -- that traffic is what bounds the apply.  Instead the round's records are
+// grouped by block (k_bucket_records: bucket[b * n_lists + k] = record index, any order) and ONE warp per
+// block (k_apply_round) loads the block's 512 voxels into registers once, applies the block's records in
+// scan order (record indices are laid out list by list, so ascending index = scan order:
+// octomap_world.cc:244-262 per voxel), and writes the rows that changed back once.
+__global__ void __launch_bounds__(256)
+k_bucket_records(MapView m, const uint32_t* __restrict__ located, uint32_t total, uint32_t n_lists,
+                 uint32_t* __restrict__ bcount, uint32_t* __restrict__ bucket) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= total) return;
+  const uint32_t h = located[g];
+  if (h == kNotFound) return;
+  const uint32_t b = __ldcg(m.touched + h);
+  const uint32_t pos = atomicAdd(bcount + b, 1u);
+  if (pos < n_lists) bucket[(size_t)b * n_lists + pos] = g;     // (always: a block appears at most once per list)
+}
+
+__global__ void __launch_bounds__(256)
+k_apply_round(DevParams P, MapView m, Counters* cnt, const RecordLists* __restrict__ lists,
+              const uint32_t* __restrict__ round_blocks, const uint32_t* __restrict__ bcount,
+              const uint32_t* __restrict__ bucket) {
+  __shared__ uint32_t s_first[kMaxBatch * kMaxRanks + 1];
+  const uint32_t n_lists = lists->n_lists;            // <= 32 (the host takes the list-by-list path otherwise)
+  for (uint32_t i = threadIdx.x; i <= n_lists; i += blockDim.x) s_first[i] = lists->first[i];
+  __syncthreads();
+  const uint32_t n_blocks = cnt->round_blocks;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t n_marks = 0;
+  auto record_words = [&](uint32_t g) -> const uint32_t* {
+    uint32_t lo = 0, hi = n_lists;                     // list of record g: largest l with first[l] <= g
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (s_first[mid] <= g) lo = mid; else hi = mid;
+    }
+    return reinterpret_cast<const uint32_t*>(lists->ptr[lo] + (g - s_first[lo]));
+  };
+  for (uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < n_blocks; b += warps) {
+    const uint32_t h = round_blocks[b];
+    const uint32_t n = min(bcount[b], n_lists);
+    const uint32_t slot = __ldcg(m.slot + h);
+    if (slot >= m.pool_cap) continue;                  // (no slot: the pool overflowed, the host reports it)
+    // lane k holds record k of the bucket; its rank among them = its place in scan order
+    const uint32_t g_mine = lane < n ? bucket[(size_t)b * n_lists + lane] : 0xFFFFFFFFu;
+    uint32_t rank = 0;
+    for (uint32_t k = 0; k < n; k++) rank += __shfl_sync(0xFFFFFFFFu, g_mine, k) < g_mine ? 1u : 0u;
+    uint32_t* vox = reinterpret_cast<uint32_t*>(m.pool) + (size_t)slot * kBlockVoxels;
+    uint32_t val[kMaskWords];
+#pragma unroll
+    for (int j = 0; j < kMaskWords; j++) val[j] = __ldcg(vox + j * 32 + lane);
+    uint32_t dirty = 0;                                // rows with at least one marked voxel (warp-uniform)
+    // the first record's masks are requested now, every later one while its predecessor is applied
+    uint32_t src = (uint32_t)__ffs(__ballot_sync(0xFFFFFFFFu, lane < n && rank == 0u)) - 1u;
+    uint32_t nx_mask = record_words(__shfl_sync(0xFFFFFFFFu, g_mine, src))[2 + lane];
+    for (uint32_t r = 0; r < n; r++) {
+      const uint32_t mask = nx_mask;
+      if (r + 1 < n) {
+        src = (uint32_t)__ffs(__ballot_sync(0xFFFFFFFFu, lane < n && rank == r + 1u)) - 1u;
+        nx_mask = record_words(__shfl_sync(0xFFFFFFFFu, g_mine, src))[2 + lane];
+      }
+      // lanes 0..15: free words with the occupied bits removed (occupied wins); lanes 16..31: occupied words
+      const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, mask, 16);
+      const uint32_t mine = lane < kMaskWords ? (mask & ~other) : mask;
+      n_marks += __popc(mine);                         // lanes 0..15 count free voxels, lanes 16..31 occupied ones
+#pragma unroll
+      for (int j = 0; j < kMaskWords; j++) {
+        const uint32_t fw = __shfl_sync(0xFFFFFFFFu, mine, j);
+        const uint32_t ow = __shfl_sync(0xFFFFFFFFu, mine, j + kMaskWords);
+        if ((fw | ow) == 0u) continue;
+        dirty |= 1u << j;
+        const bool is_occ = (ow >> lane) & 1u, is_free = (fw >> lane) & 1u;
+        if (is_occ || is_free) val[j] = update_leaf(val[j], is_occ ? P.hit : P.miss, P.cmin, P.cmax);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaskWords; j++)
+      if ((dirty >> j) & 1u) vox[j * 32 + lane] = val[j];
+  }
+  for (int o = 8; o > 0; o >>= 1) n_marks += __shfl_xor_sync(0xFFFFFFFFu, n_marks, o);   // sums within each half warp
+  if (lane == 0 && n_marks) atomicAdd(&cnt->unique_free, n_marks);
+  if (lane == kMaskWords && n_marks) atomicAdd(&cnt->unique_occupied, n_marks);
 }
 
 __global__ void __launch_bounds__(256)

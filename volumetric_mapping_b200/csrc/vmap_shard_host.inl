@@ -528,10 +528,11 @@ int vmap_dist_shutdown(vmap* h) try {
             h->shard_rank, h->dbg_ms[0] / h->dbg_n, h->dbg_ms[1] / h->dbg_n, h->dbg_ms[2] / h->dbg_n, h->dbg_ms[3] / h->dbg_n,
             (unsigned long long)h->dbg_n);
   if (h->peer_on && getenv("VMAP_TIMING") && h->total_scans)
-    fprintf(stderr, "[vmap rank %d] peer transport, device ms per scan (events, overlapped with the other scan context): front %.3f resolve %.3f walk+list %.3f pack %.3f | apply per round %.3f (%llu rounds, %llu records) | scans %llu\n",
+    fprintf(stderr, "[vmap rank %d] peer transport, device ms per scan (events, overlapped with the other scan context): front %.3f resolve %.3f walk+list %.3f pack %.3f | apply per round %.3f (locate %.3f bucket %.3f apply %.3f) (%llu rounds, %llu records) | scans %llu\n",
             h->shard_rank, h->totals.front_ms / h->total_scans, h->totals.resolve_ms / h->total_scans,
             h->totals.walk_ms / h->total_scans, h->totals.update_ms / h->total_scans,
-            h->dbg_n ? h->dbg_ms[0] / h->dbg_n : 0.0, (unsigned long long)h->dbg_n, (unsigned long long)h->app_records,
+            h->dbg_n ? h->dbg_ms[0] / h->dbg_n : 0.0, h->dbg_n ? h->dbg_ms[1] / h->dbg_n : 0.0, h->dbg_n ? h->dbg_ms[2] / h->dbg_n : 0.0,
+            h->dbg_n ? h->dbg_ms[3] / h->dbg_n : 0.0, (unsigned long long)h->dbg_n, (unsigned long long)h->app_records,
             (unsigned long long)h->total_scans);
   if (h->peer_on || h->mailbox) {
     cudaSetDevice(h->device);
