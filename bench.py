@@ -481,7 +481,7 @@ def run_b200(args):
             scan_b = float(np.mean([algorithmic_bytes(s, n_pts) for s in stages]))
             scan_ms = float(np.mean([s["gpu_ms"] for s in stages]))
             ach = walk_b / (walk_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": "K2 = k_checkpoints + k_walk_segments_dilated (+ list): DDA walk + key-set build",
+            roofline = {"bound": "hbm", "kernel": "K2 = k_checkpoints + k_walk_segments_queued (+ list): DDA walk + key-set build",
                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                         "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": walk_b, "avg_launch_ms": walk_ms,

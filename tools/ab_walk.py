@@ -52,8 +52,8 @@ def run(addr, variant, ctas, order=0, counted=1, far_blind=0, n_use=None, reps=3
 # chunk order) have not run on hardware yet
 # round 2: + counted loops (VMAP_WALK_COUNTED) and the 64-register build (ADDR 6)
 # + fine-bin ray order (always on) and blind far-field touched REDs (VMAP_WALK_FAR_BLIND)
-CONFIGS = [(0, 48, 5, 0, 1, 0), (7, 48, 5, 0, 1, 0), (9, 48, 5, 0, 1, 0), (8, 48, 4, 0, 1, 0), (9, 32, 5, 0, 1, 0),
-           (9, 64, 5, 0, 1, 0), (9, 48, 6, 0, 1, 0), (9, 48, 4, 0, 1, 0), (8, 48, 5, 0, 1, 0)]
+CONFIGS = [(0, 48, 5, 0, 1, 0), (7, 48, 5, 0, 1, 0), (9, 48, 5, 0, 1, 0), (10, 48, 5, 0, 1, 0), (9, 64, 5, 0, 1, 0),
+           (10, 64, 5, 0, 1, 0), (9, 48, 5, 0, 1, 0), (10, 48, 5, 0, 1, 0)]
 params = {"max_free_space": 6.0, "min_height_free_space": 0.3} if "--filter" in sys.argv else {}
 base = None
 ok_all = True
@@ -76,7 +76,7 @@ if "--oracle" in sys.argv:      # bit-exact leaves against the CPU oracle on the
     ko, vo = ow.export_leaves()
     po = oracle.pack_keys(ko)
     oo = np.argsort(po)
-    for addr in (0, 7, 9):
+    for addr in (0, 9, 10):
         _, _, k, v = run(addr, 48, 5, order=0, counted=1, far_blind=0, n_use=2, reps=1)
         ok = bool(np.array_equal(k, po[oo]) and np.array_equal(v, np.asarray(vo, np.float32).view(np.uint32)[oo]))
         out["oracle_parity_addr%d" % addr] = ok

@@ -188,13 +188,6 @@ struct vmap : ScanCtx {
   size_t stage_n[2] = {0, 0}, stage_stride[2] = {0, 0};
   bool staged[2] = {false, false};
   int stage_next = 0;         // slot the next vmap_stage_pointcloud fills
-  // pipelined inserts from host memory: the caller's points leave for one of two device buffers on the copy
-  // stream at the very start of the call, before the call waits for a free scan context (early_h2d)
-  DevBuf early[2];
-  cudaEvent_t ev_early[2] = {nullptr, nullptr};        // the H2D copy into the slot is complete
-  cudaEvent_t ev_early_used[2] = {nullptr, nullptr};   // the slot has been copied on into a scan context
-  bool early_used_set[2] = {false, false};
-  int early_next = 0;
   int walk_order = 2;     // bit 0: golden-ratio chunk order in the dilated segment walker (VMAP_WALK_ORDER, experimental);
                           // bit 1: counted loops in non-last segments (default; VMAP_WALK_COUNTED=0 turns it off)
   int walk_addr = 9;      // segment walker: 9 dilated addressing + queued 64-voxel marks (default), 7 unqueued, 1 32-voxel words, 0 block addressing, 5 / 8 experiments (VMAP_WALK_ADDR)
@@ -979,8 +972,9 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
       if (h->walk_addr == 5) k_walk_segments_near<<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, h->walk_order);
       else if (h->walk_addr == 1) VMAP_WALK_DIL(false, 0, 5, false);
       else if (h->walk_addr == 7) VMAP_WALK_DIL(false, 0, 5, true);
-      else if (h->walk_addr == 8) k_walk_segments_queued<false, 4><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms));
-      else k_walk_segments_queued<false, 5><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms));
+      else if (h->walk_addr == 8) k_walk_segments_queued<false, 4, false><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms));
+      else if (h->walk_addr == 10) k_walk_segments_queued<false, 5, true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms));
+      else k_walk_segments_queued<false, 5, false><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms));
     }
 #undef VMAP_WALK_DIL
     else if (h->P.free_filter) k_walk_segments<true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
@@ -1299,39 +1293,6 @@ int write_back_cloud(vmap* h, cudaStream_t st, const uint8_t* d_in, size_t n, si
   return VMAP_OK;
 }
 
-// Host-memory source of a pipelined insert: start the H2D copy NOW, on the copy stream, into the next
-// early slot -- before the call blocks on the oldest scan in flight -- so that the copy (60 us for a
-// 1.6 MB scan over PCIe) is off the scan's own critical path.  Returns the slot.
-int early_h2d(vmap* h, const void* src, size_t bytes, int* slot_out) {
-  const int e = h->early_next;
-  h->early_next = e ^ 1;
-  for (int k = 0; k < 2; k++) {
-    if (!h->ev_early[k]) VM_CUDA(h, cudaEventCreateWithFlags(&h->ev_early[k], cudaEventDisableTiming));
-    if (!h->ev_early_used[k]) VM_CUDA(h, cudaEventCreateWithFlags(&h->ev_early_used[k], cudaEventDisableTiming));
-  }
-  if (bytes > h->early[e].cap) {
-    // (rare: nothing may still read the old buffer)
-    VM_CUDA(h, cudaStreamSynchronize(h->copy_stream));
-    if (h->alt.stream) VM_CUDA(h, cudaStreamSynchronize(h->alt.stream));
-    VM_TRY(ensure(h, &h->early[e], bytes));
-    h->early_used_set[e] = false;
-  }
-  // the slot's previous content was copied on into a scan context two inserts ago
-  if (h->early_used_set[e]) VM_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_early_used[e], 0));
-  VM_CUDA(h, cudaMemcpyAsync(h->early[e].p, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
-  VM_CUDA(h, cudaEventRecord(h->ev_early[e], h->copy_stream));
-  *slot_out = e;
-  return VMAP_OK;
-}
-// ... and the scan context's side of it: its own copy of the points (a refused scan is replayed from there).
-int early_take(vmap* h, int e, size_t bytes) {
-  VM_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_early[e], 0));
-  VM_CUDA(h, cudaMemcpyAsync(h->in.p, h->early[e].p, bytes, cudaMemcpyDeviceToDevice, h->stream));
-  VM_CUDA(h, cudaEventRecord(h->ev_early_used[e], h->stream));
-  h->early_used_set[e] = true;
-  return VMAP_OK;
-}
-
 // insertPointcloudIntoMapImpl.  src: the caller's points, in host memory (src_on_host) or on the
 // device.  Pipelined (default): the scan is staged into the free scan context, all of its kernels
 // are enqueued on that context's stream, and the call returns once the caller's buffer has been
@@ -1352,10 +1313,8 @@ int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, si
   bool piped = pipe_eligible(h, n);
   Transform T;
   fill_transform_matrix(&T, Tm);
-  int early = -1;
   if (piped) {
     VM_TRY(pipe_prepare(h));
-    if (src_on_host) VM_TRY(early_h2d(h, src, bytes, &early));
     while (h->pipe_n >= 2) VM_TRY(pipe_retire(h));
     if (h->in_flight) swap_ctx(h);            // the current context is the free one from here on
     if (h->epoch >= kEpochMax) VM_TRY(pipe_flush(h));
@@ -1371,7 +1330,6 @@ int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, si
   }
   if (!piped) {
     VM_TRY(pipe_flush(h));
-    if (early >= 0) VM_CUDA(h, cudaEventSynchronize(h->ev_early[early]));   // (the early copy still reads the caller's buffer)
     const uint8_t* d_in = reinterpret_cast<const uint8_t*>(src);
     if (src_on_host) {
       VM_TRY(ensure(h, &h->in, bytes));
@@ -1387,8 +1345,7 @@ int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, si
   VM_TRY(ensure(h, &h->in, bytes));
   if (h->l2_flush_bytes)   // benchmark hook: no scan finds its map blocks in L2
     VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(h->pipe_seq & 0xFF), h->l2_flush_bytes, h->stream));
-  if (early >= 0) VM_TRY(early_take(h, early, bytes));
-  else VM_CUDA(h, cudaMemcpyAsync(h->in.p, src, bytes, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+  VM_CUDA(h, cudaMemcpyAsync(h->in.p, src, bytes, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
   VM_CUDA(h, cudaEventRecord(h->ev_h2d, h->stream));
   VM_TRY(next_epoch(h));
   VM_TRY(begin_scan_scratch(h, n));
@@ -1418,7 +1375,7 @@ int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, si
   h->meta.is_dense = is_dense;
   std::memcpy(h->meta.Tm, Tm, sizeof(h->meta.Tm));
   // the caller may reuse its buffer as soon as this call returns
-  VM_CUDA(h, cudaEventSynchronize(early >= 0 ? h->ev_early[early] : h->ev_h2d));
+  VM_CUDA(h, cudaEventSynchronize(h->ev_h2d));
   if (wb) {
     VM_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_wb, 0));
     VM_TRY(write_back_cloud(h, h->copy_stream, (const uint8_t*)h->in.p, n, stride, is_dense, wb_out, wb_n_out));
@@ -1571,11 +1528,6 @@ int vmap_destroy(vmap* h) try {
   sort_free(h);
   cudaFree(h->chg0_store); cudaFree(h->chg1_store);
   cudaFree(h->stage[0].p); cudaFree(h->stage[1].p);
-  cudaFree(h->early[0].p); cudaFree(h->early[1].p);
-  for (int k = 0; k < 2; k++) {
-    if (h->ev_early[k]) cudaEventDestroy(h->ev_early[k]);
-    if (h->ev_early_used[k]) cudaEventDestroy(h->ev_early_used[k]);
-  }
   cudaFree(h->wb.p);
   if (h->wb_host) cudaFreeHost(h->wb_host);
   for (auto& e : h->ev_stage)
@@ -1655,9 +1607,7 @@ int vmap_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stride_by
   if (!h || (!xyz && n) || !T_rowmajor) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "stride_bytes must be a multiple of 4 and >= 12");
   VM_CUDA(h, cudaSetDevice(h->device));
-  const int st = insert_cloud_common(h, xyz, true, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor, xyz_world_out, n_out);
-  if (st != VMAP_OK && h->copy_stream) cudaStreamSynchronize(h->copy_stream);   // (an early copy may still read the caller's buffer)
-  return st;
+  return insert_cloud_common(h, xyz, true, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor, xyz_world_out, n_out);
 } catch (...) { return vmap_on_exception(h); }
 
 // The scan pipeline from the outside.

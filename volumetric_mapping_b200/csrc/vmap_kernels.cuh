@@ -579,7 +579,7 @@ k_walk_segments_dilated(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, 
 // K2b, dilated addressing + queued marks (vmap_walk.cuh: walk_slot_queued) -- the default walker.
 // Same slots and marks as k_walk_segments_dilated; the lanes of a warp run one loop nest (every slot
 // knows its step count up front) and drain their parked mask words together.
-template <bool kFilter, int kMinCtas>
+template <bool kFilter, int kMinCtas, bool kBranchFree>
 __global__ void __launch_bounds__(256, kMinCtas)
 k_walk_segments_queued(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz, int variant,
                        DilatedWindow dw) {
@@ -623,7 +623,7 @@ k_walk_segments_queued(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, f
         active = false;
       }
     }
-    walk_slot_queued<kFilter, 256u>(P, ms, dw, cnt, cp, rr, lo, ox, oy, oz, near_limit, &emitted, &longest, n_steps, active, mq);
+    walk_slot_queued<kFilter, 256u, kBranchFree>(P, ms, dw, cnt, cp, rr, lo, ox, oy, oz, near_limit, &emitted, &longest, n_steps, active, mq);
   }
   __shared__ uint32_t s_stat[2];
   __syncthreads();

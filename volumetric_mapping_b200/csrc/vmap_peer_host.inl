@@ -253,8 +253,6 @@ int peer_insert(vmap* h, const void* src, bool src_on_host, size_t n, size_t str
   if (h->capture) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "key capture is not available with the peer-memory transport (VMAP_DIST_TRANSPORT=nccl)");
   VM_TRY(init_app_stream(h));
   VM_TRY(pipe_prepare(h));
-  int early = -1;
-  if (n && src_on_host) VM_TRY(early_h2d(h, src, (n - 1) * stride + 12, &early));   // (see insert_cloud_common)
   while (h->pipe_n >= 2) VM_TRY(peer_retire(h));
   if (h->in_flight) swap_ctx(h);
   if (h->epoch >= kEpochMax) {
@@ -277,8 +275,7 @@ int peer_insert(vmap* h, const void* src, bool src_on_host, size_t n, size_t str
   if (n) {
     const size_t bytes = (n - 1) * stride + 12;
     VM_TRY(ensure(h, &h->in, bytes));
-    if (early >= 0) VM_TRY(early_take(h, early, bytes));
-    else VM_CUDA(h, cudaMemcpyAsync(h->in.p, src, bytes, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+    VM_CUDA(h, cudaMemcpyAsync(h->in.p, src, bytes, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
   }
   VM_CUDA(h, cudaEventRecord(h->ev_h2d, h->stream));
   if (h->l2_flush_bytes)
@@ -337,7 +334,7 @@ int peer_insert(vmap* h, const void* src, bool src_on_host, size_t n, size_t str
     VM_TRY(peer_apply_pending(h));
     VM_CUDA(h, cudaStreamSynchronize(h->app_stream));
   }
-  VM_CUDA(h, cudaEventSynchronize(early >= 0 ? h->ev_early[early] : h->ev_h2d));
+  VM_CUDA(h, cudaEventSynchronize(h->ev_h2d));
   return VMAP_OK;
 }
 

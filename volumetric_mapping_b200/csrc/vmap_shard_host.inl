@@ -892,7 +892,6 @@ int vmap_dist_insert_pointcloud(vmap* h, const float* xyz, size_t n, size_t stri
   if (h->peer_on) {
     h->in_collective = true;
     const int st = peer_insert(h, xyz, true, n, stride_bytes, is_dense ? 1 : 0, T_rowmajor);
-    if (st != VMAP_OK && h->copy_stream) cudaStreamSynchronize(h->copy_stream);   // (an early copy may still read the caller's buffer)
     h->in_collective = false;
     return st;
   }

@@ -527,7 +527,7 @@ __device__ __forceinline__ bool vmap_warp_any(bool p) { return __any_sync(0xFFFF
 
 // q: this lane's queue; entry e, word k (0: index of the 64-bit mask word, 1: bits 0..31, 2: bits 32..63)
 // at q[(3 * e + k) * kQStride] (kQStride = threads per CTA on the device: conflict-free banks).
-template <bool kFilter, uint32_t kQStride>
+template <bool kFilter, uint32_t kQStride, bool kBranchFree = false>
 __device__ __forceinline__ void walk_slot_queued(const DevParams& P, const MarkSet& ms, const DilatedWindow& dw, Counters* cnt,
                                                  const Checkpoint& cp, const RayRec& rr, uint32_t j, float ox, float oy,
                                                  float oz, uint32_t near_limit, uint32_t* emitted, uint32_t* longest,
@@ -610,7 +610,33 @@ __device__ __forceinline__ void walk_slot_queued(const DevParams& P, const MarkS
   while (vmap_warp_any(remaining != 0u)) {
 #pragma unroll 2
     for (uint32_t s = 0; s < kQueueSteps; s++) {
-      if (remaining) {
+      if (kBranchFree) {
+        // One DDA step written without branches (selects become predicated instructions; the only branch
+        // left in a step is "the voxel lies in another mask word").  MEASURED against the branchy form
+        // below: see profiles/README.md (round 2, "branch-free step").
+        const bool act = remaining != 0u;
+        const bool a01 = t0 < t1, a02 = t0 < t2, a12 = t1 < t2;
+        const bool d0 = act && a01 && a02;
+        const bool d1 = act && !a01 && a12;
+        const bool d2 = act && !(a01 && a02) && !(!a01 && a12);
+        a0 = d0 ? ((a0 + k0) & dw.m0) : a0;
+        a1 = d1 ? ((a1 + k1) & dw.m1) : a1;
+        a2 = d2 ? ((a2 + k2) & dw.m2) : a2;
+        t0 = d0 ? __dadd_rn(t0, dt0) : t0;
+        t1 = d1 ? __dadd_rn(t1, dt1) : t1;
+        t2 = d2 ? __dadd_rn(t2, dt2) : t2;
+        if (kFilter) {
+          c0 = d0 ? ((c0 + (uint32_t)s0) & 0xFFFFu) : c0;
+          c1 = d1 ? ((c1 + (uint32_t)s1) & 0xFFFFu) : c1;
+          c2 = d2 ? ((c2 + (uint32_t)s2) & 0xFFFFu) : c2;
+        }
+        const uint32_t a = a0 | a1 | a2;
+        bool go = act && a != a_stop;                                       // cur == end: this voxel is not emitted
+        if (any_capped) go = go && !(capped && count >= kKeyRayMax - 1u);   // KeyRay capacity
+        remaining = go ? remaining - 1u : 0u;
+        count += go ? 1u : 0u;
+        if (go) emit(a);
+      } else if (remaining) {
         // one DDA step: strict '<' comparisons, ties go to the later axis (computeRayKeys)
         const bool a01 = t0 < t1, a02 = t0 < t2, a12 = t1 < t2;
         const bool d0 = a01 && a02, d1 = !a01 && a12;
