@@ -195,8 +195,10 @@ def run_reference(args):
         "ms_per_step": 1e3 * t / max(1, len(times)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64/f32/u16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "resolution": RESOLUTION, "max_range": MAX_RANGE,
+                   "points_per_step": int(s["points"].shape[0]), "traversals_per_step": trav / max(1, len(times)),
                    "path": "oracle/ C++ restatement of OctomapWorld (reference is unbuildable "
-                           "here: octomap/PCL/OpenCV/Eigen absent), 1 thread like the reference"},
+                           "here: octomap/PCL/OpenCV/Eigen absent), 1 thread like the reference; every step "
+                           "is one full scan of the same trajectory the CUDA arm inserts"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
                          "sample": sample, "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
