@@ -180,7 +180,10 @@ struct vmap : ScanCtx {
   uint32_t* chg0_store = nullptr;   // change-detection planes (MapView.chg0/1 point here while enabled)
   uint32_t* chg1_store = nullptr;
   int walk_variant = 48;  // near-field limit of the walker's read-before-RED filter (VMAP_WALK_VARIANT)
-  int walk_ctas = 5;      // CTAs per SM of the segment walker's grid = resident CTAs at 48 registers (VMAP_WALK_CTAS)
+  int walk_ctas = 0;      // CTAs per SM of the segment walker's grid (VMAP_WALK_CTAS); 0 = 5 (all that fit at 48 registers) for a
+                          // scan that runs alone, 4 for a pipelined scan: the fifth slot per SM is what lets the other scan's
+                          // short kernels run beside the walk (pipelined 0.263 -> 0.251 ms per scan, alone 0.378 -> 0.393)
+  bool walk_overlaps = false;   // the scan being enqueued shares the device with another scan in flight
   // vmap_stage_pointcloud / vmap_insert_staged: two device staging buffers filled on their own stream
   DevBuf stage[2];
   cudaStream_t copy_stream = nullptr;
@@ -835,6 +838,7 @@ void fill_stats(vmap* h, uint64_t retries, float ms_total) {
 //   table's mask columns).
 template <class Mark>
 int run_scan(vmap* h, size_t n_points, const float* origin, Mark&& mark) {
+  h->walk_overlaps = false;
   VM_TRY(next_epoch(h));
   uint64_t retries = 0;
   float ms_total = 0.f;
@@ -953,7 +957,7 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
     // K2a + K2b: exact checkpoints, then one thread per ray segment
     k_checkpoints<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->d_cnt, ox, oy, oz);
     h->launches++;
-    const unsigned grid = g_sm_count(h->device) * (unsigned)h->walk_ctas;
+    const unsigned grid = g_sm_count(h->device) * (unsigned)(h->walk_ctas > 0 ? h->walk_ctas : (h->walk_overlaps ? 4 : 5));
     // VMAP_WALK_ADDR: 0 block addressing, 1 dilated addressing with 32-voxel mask words (round 1), 5 the same
     // + near-field combining in shared memory, 7 dilated addressing with 64-voxel words, 9 (default) the same
     // with queued marks (walk_slot_queued), 8 queued marks built for 4 CTAs / SM.  (Measured and dropped: deferred touched test, 6 CTAs / SM, 64 registers:
@@ -1342,6 +1346,7 @@ int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, si
     return write_back_cloud(h, h->stream, d_in, n, stride, is_dense, wb_out, wb_n_out);
   }
   // ---- pipelined ----
+  h->walk_overlaps = true;
   VM_TRY(ensure(h, &h->in, bytes));
   if (h->l2_flush_bytes)   // benchmark hook: no scan finds its map blocks in L2
     VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(h->pipe_seq & 0xFF), h->l2_flush_bytes, h->stream));

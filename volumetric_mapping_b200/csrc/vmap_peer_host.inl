@@ -280,6 +280,7 @@ int peer_insert(vmap* h, const void* src, bool src_on_host, size_t n, size_t str
   VM_CUDA(h, cudaEventRecord(h->ev_h2d, h->stream));
   if (h->l2_flush_bytes)
     VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(h->pipe_seq & 0xFF), h->l2_flush_bytes, h->stream));
+  h->walk_overlaps = true;
   VM_TRY(next_epoch(h));
   VM_TRY(begin_scan_scratch(h, n1));
   for (bool& b : h->evk_set) b = false;
