@@ -95,9 +95,9 @@ __device__ __forceinline__ void ray_checkpoints(const DevParams& P, float ox, fl
     if (j > 0) {
       const double tau = __dmul_rn((double)j, rr.dtau);
       const unsigned long long cap = 1ull << 40;
-      if (w.s0) n0 += (uint32_t)vmapseq::seq_advance_near(&t0, w.dt0, tau, cap);
-      if (w.s1) n1 += (uint32_t)vmapseq::seq_advance_near(&t1, w.dt1, tau, cap);
-      if (w.s2) n2 += (uint32_t)vmapseq::seq_advance_near(&t2, w.dt2, tau, cap);
+      if (w.s0) n0 += (uint32_t)vmapseq::seq_advance(&t0, w.dt0, tau, cap);
+      if (w.s1) n1 += (uint32_t)vmapseq::seq_advance(&t1, w.dt1, tau, cap);
+      if (w.s2) n2 += (uint32_t)vmapseq::seq_advance(&t2, w.dt2, tau, cap);
     }
     Checkpoint cp;
     cp.t0 = t0; cp.t1 = t1; cp.t2 = t2;
@@ -118,9 +118,9 @@ __device__ __forceinline__ void ray_checkpoints(const DevParams& P, float ox, fl
     const double past = vmapseq::seq_from_bits(vmapseq::seq_bits(w.dlen) + 1ull);   // t < past  <=>  t <= length
     const unsigned long long cap = 1ull << 40;
     unsigned long long L = (unsigned long long)n0 + n1 + n2;
-    if (w.s0) L += vmapseq::seq_advance_near(&t0, w.dt0, past, cap);
-    if (w.s1) L += vmapseq::seq_advance_near(&t1, w.dt1, past, cap);
-    if (w.s2) L += vmapseq::seq_advance_near(&t2, w.dt2, past, cap);
+    if (w.s0) L += vmapseq::seq_advance(&t0, w.dt0, past, cap);
+    if (w.s1) L += vmapseq::seq_advance(&t1, w.dt1, past, cap);
+    if (w.s2) L += vmapseq::seq_advance(&t2, w.dt2, past, cap);
     if (L < 1ull) L = 1ull;
     if (L < 0xFFFFFFFFull) rec->n_keys = (uint32_t)L;
   }
