@@ -160,3 +160,4 @@ def test_very_long_rays_at_fine_resolution(lib):
     ends = np.array([[120.0, 0.3, 0.01], [110.0, -0.2, 0.02], [-117.0, 0.2, 0.01], [-121.0, 0.1, 0.0]], np.float32)
     sa, sb = run_both(lib, res, o, ends)
     assert int(sa[1]) > 59000 and int(sb[3]) > 1500
+

@@ -195,6 +195,9 @@ struct vmap : ScanCtx {
                           // bit 1: counted loops in non-last segments (default; VMAP_WALK_COUNTED=0 turns it off)
   int walk_addr = 9;      // segment walker: 9 dilated addressing + queued 64-voxel marks (default), 7 unqueued, 1 32-voxel words, 0 block addressing, 5 / 8 experiments (VMAP_WALK_ADDR)
   int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
+  int pdl = 123;          // VMAP_PDL: programmatic dependent launch along the scan's kernel chain (bit mask kPdl*; default: all but the walker)
+  int stage_marks = -1;   // VMAP_STAGE_MARKS: 1 always, 0 never, unset: synchronous scans only
+  int helpers = 1;        // VMAP_HELPERS: 1 folded helper chain (k_resolve_fold, k_checkpoints_pts), 0 round 1's
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
 
   // parity hook
@@ -486,6 +489,7 @@ int ensure_scan(vmap* h, size_t n) {
   dev_free(h, sb.len, oc * 4);
   dev_free(h, sb.rank, oc * 4);
   dev_free(h, sb.seg_base, (kLenBins + 1) * 4);
+  dev_free(h, sb.bin_off, kFineBins * 4);
   dev_free(h, sb.ray_rec, oc * sizeof(RayRec));
   dev_free(h, sb.ckpt, (size_t)sb.ckpt_cap * sizeof(Checkpoint));
   dev_free(h, sb.first_keys, ofc * 12);
@@ -502,6 +506,7 @@ int ensure_scan(vmap* h, size_t n) {
   VM_TRY(dev_alloc(h, (void**)&sb.rank, cap * 4));
   sb.len_hist = reinterpret_cast<uint32_t*>(h->d_cnt + 1);
   VM_TRY(dev_alloc(h, (void**)&sb.seg_base, (kLenBins + 1) * 4));
+  VM_TRY(dev_alloc(h, (void**)&sb.bin_off, kFineBins * 4));
   VM_TRY(dev_alloc(h, (void**)&sb.ray_rec, cap * sizeof(RayRec)));
   {
     const size_t cc = std::max<size_t>(cap * 8, h->ckpt_want);
@@ -538,9 +543,31 @@ int read_counters(vmap* h) {
 // Stage marks for vmap_scan_stats.{front,resolve,walk,update}_ms: 0 = scan start, 1 = after the
 // front-end kernel, 2 = after resolve, 3 = after the walk (key-set complete), 4 = after update.
 int mark_stage(vmap* h, int i) {
+  // (an event between two kernels keeps the second from launching programmatically: pipelined scans
+  // record no stage marks unless VMAP_STAGE_MARKS=1 -- their stage times read 0)
+  if (h->stage_marks == 0 || (h->stage_marks < 0 && h->walk_overlaps)) return VMAP_OK;
   VM_CUDA(h, cudaEventRecord(h->evk[i], h->stream));
   h->evk_set[i] = true;
   return VMAP_OK;
+}
+
+// Launch with the programmatic-serialization attribute (vmap_device.cuh: pdl_wait / pdl_launch): ONLY for kernels
+// that call pdl_wait() before they touch global memory.  h->pdl == 0 (VMAP_PDL=0): an ordinary launch.
+enum { kPdlResolve = 1, kPdlCkpt = 2, kPdlWalk = 4, kPdlList = 8, kPdlAdmit = 16, kPdlLocate = 32, kPdlUpdate = 64 };
+template <class... KArgs, class... Args>
+cudaError_t launch_chain(const vmap* h, int which, void (*kernel)(KArgs...), unsigned grid, unsigned block, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (h->pdl & which) ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
 unsigned grid_for(size_t n, unsigned block) { return (unsigned)std::max<size_t>(1, (n + block - 1) / block); }
@@ -693,9 +720,8 @@ bool setup_dense_marks(vmap* h, const float origin[3]) {
 
 int launch_list(vmap* h) {
   const unsigned grid = (unsigned)std::min<uint64_t>((h->win.n_words + 255) / 256, (uint64_t)g_sm_count(h->device) * 8);
-  k_list_touched<<<std::max(grid, 1u), 256, 0, h->stream>>>(h->ms, h->d_cnt, h->win.n_words);
+  VM_CUDA(h, launch_chain(h, kPdlList, k_list_touched, std::max(grid, 1u), 256, h->ms, h->d_cnt, h->win.n_words));
   h->launches++;
-  VM_CUDA(h, cudaGetLastError());
   return VMAP_OK;
 }
 
@@ -727,10 +753,9 @@ int launch_capture(vmap* h) {
 }
 
 int launch_update(vmap* h) {
-  if (h->update_variant == 1) k_update<1><<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->P, h->m, h->ms, h->d_cnt);
-  else k_update<0><<<g_sm_count(h->device) * 8, 256, 0, h->stream>>>(h->P, h->m, h->ms, h->d_cnt);
+  if (h->update_variant == 1) VM_CUDA(h, launch_chain(h, kPdlUpdate, k_update<1>, g_sm_count(h->device) * 8, 256, h->P, h->m, h->ms, h->d_cnt));
+  else VM_CUDA(h, launch_chain(h, kPdlUpdate, k_update<0>, g_sm_count(h->device) * 8, 256, h->P, h->m, h->ms, h->d_cnt));
   h->launches++;
-  VM_CUDA(h, cudaGetLastError());
   return VMAP_OK;
 }
 
@@ -741,8 +766,8 @@ int launch_update(vmap* h) {
 // poison != 0 (pipelined insertion): a refusal also stalls every later tail (Persist::stalled).
 int launch_tail(vmap* h, int poison) {
   if (h->ms.dense) {
-    k_admit<<<1, 32, 0, h->stream>>>(h->ms, h->m, h->d_cnt, poison);
-    k_locate_blocks<<<g_sm_count(h->device) * 4, 256, 0, h->stream>>>(h->ms, h->m, h->d_cnt, poison);
+    VM_CUDA(h, launch_chain(h, kPdlAdmit, k_admit, 1, 32, h->ms, h->m, h->d_cnt, poison));
+    VM_CUDA(h, launch_chain(h, kPdlLocate, k_locate_blocks, g_sm_count(h->device) * 4, 256, h->ms, h->m, h->d_cnt, poison));
     h->launches += 2;
   } else {
     k_admit_pool<<<1, 32, 0, h->stream>>>(h->m, h->d_cnt);
@@ -947,15 +972,24 @@ void fill_transform_quat(Transform* T, const double q[4], const double t[3]) {
 // K1b + K2 of the bitmask mode (everything after the front-end kernel).
 int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
   VM_TRY(mark_stage(h, 1));
-  k_resolve<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, h->m, h->ms, h->d_cnt, (uint32_t)n, 1);
-  k_order_rays<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, (uint32_t)n);
-  h->launches += 2;
+  // VMAP_HELPERS=1 (default): k_resolve_fold -> k_checkpoints_pts (no k_order_rays launch, no ordered ray
+  // list); 0: round 1's chain k_resolve -> k_order_rays -> k_checkpoints
+  const bool fold = h->helpers >= 1 && h->ms.dense && !h->no_segments;
+  if (fold) {
+    VM_CUDA(h, launch_chain(h, kPdlResolve, k_resolve_fold, grid_for(n, 256), 256, h->sb, h->m, h->ms, h->d_cnt, (uint32_t)n, 1));
+    h->launches++;
+  } else {
+    k_resolve<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, h->m, h->ms, h->d_cnt, (uint32_t)n, 1);
+    k_order_rays<<<grid_for(n, 256), 256, 0, h->stream>>>(h->sb, (uint32_t)n);
+    h->launches += 2;
+  }
   VM_CUDA(h, cudaGetLastError());
   VM_TRY(mark_stage(h, 2));
   const float ox = T.origin[0], oy = T.origin[1], oz = T.origin[2];
   if (h->ms.dense && !h->no_segments) {
     // K2a + K2b: exact checkpoints, then one thread per ray segment
-    k_checkpoints<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->d_cnt, ox, oy, oz);
+    if (fold) VM_CUDA(h, launch_chain(h, kPdlCkpt, k_checkpoints_pts, grid_for(n, 256), 256, h->P, h->sb, h->d_cnt, ox, oy, oz));
+    else k_checkpoints<<<grid_for(n, 128), 128, 0, h->stream>>>(h->P, h->sb, h->d_cnt, ox, oy, oz);
     h->launches++;
     const unsigned grid = g_sm_count(h->device) * (unsigned)(h->walk_ctas > 0 ? h->walk_ctas : (h->walk_overlaps ? 4 : 5));
     // VMAP_WALK_ADDR: 0 block addressing, 1 dilated addressing with 32-voxel mask words (round 1), 5 the same
@@ -978,7 +1012,7 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
       else if (h->walk_addr == 7) VMAP_WALK_DIL(false, 0, 5, true);
       else if (h->walk_addr == 8) k_walk_segments_queued<false, 4, false><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms));
       else if (h->walk_addr == 10) k_walk_segments_queued<false, 5, true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms));
-      else k_walk_segments_queued<false, 5, false><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms));
+      else VM_CUDA(h, launch_chain(h, kPdlWalk, k_walk_segments_queued<false, 5, false>, grid, 256, h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant, dilated_window(h->ms)));
     }
 #undef VMAP_WALK_DIL
     else if (h->P.free_filter) k_walk_segments<true><<<grid, 256, 0, h->stream>>>(h->P, h->sb, h->ms, h->d_cnt, ox, oy, oz, h->walk_variant);
@@ -1036,7 +1070,7 @@ void free_ctx_resources(vmap* h) {  // of the CURRENT context
   ScanBuffers& sb = h->sb;
   cudaFree(sb.world); cudaFree(sb.ray_end); cudaFree(sb.key); cudaFree(sb.flags); cudaFree(sb.rays);
   cudaFree(sb.len); cudaFree(sb.rank);
-  cudaFree(sb.seg_base); cudaFree(sb.ray_rec); cudaFree(sb.ckpt);
+  cudaFree(sb.seg_base); cudaFree(sb.bin_off); cudaFree(sb.ray_rec); cudaFree(sb.ckpt);
   cudaFree(sb.first_keys);
   sb = ScanBuffers{};
   cudaFree(h->in.p);
@@ -1483,6 +1517,9 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   if (const char* e = getenv("VMAP_WALK_FAR_BLIND")) h->walk_order = (h->walk_order & ~4) | (atoi(e) ? 4 : 0);
   if (const char* e = getenv("VMAP_NO_SEGMENTS")) h->no_segments = atoi(e);
   if (const char* e = getenv("VMAP_UPDATE_VARIANT")) h->update_variant = atoi(e);
+  if (const char* e = getenv("VMAP_HELPERS")) h->helpers = atoi(e);
+  if (const char* e = getenv("VMAP_PDL")) h->pdl = atoi(e);
+  if (const char* e = getenv("VMAP_STAGE_MARKS")) h->stage_marks = atoi(e) != 0;
   auto bail = [&](int code) {
     g_create_error = h->err;
     vmap_destroy(h);

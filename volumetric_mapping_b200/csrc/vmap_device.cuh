@@ -56,6 +56,22 @@ struct Persist {            // survives across scans
   uint32_t pad;
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization
+// attribute may become resident while its predecessor in the stream is still running; pdl_wait()
+// blocks until that predecessor has completed and its memory is visible (a no-op for an ordinary
+// launch), pdl_launch() lets the successor's CTAs in early.  Every kernel of the scan chain calls
+// pdl_wait() before it touches global memory.
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_launch() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 struct Counters {           // zeroed at the start of every scan
   unsigned long long traversals;
   uint32_t points_valid;
@@ -81,6 +97,8 @@ struct Counters {           // zeroed at the start of every scan
   uint32_t done_ctas;       // CTAs of k_locate_blocks that have finished (last one decides about the pool)
   uint32_t occ_cursor;      // sort mode: occupied keys appended after the free ones
   uint32_t round_blocks;    // sharded apply: distinct blocks named by the round's records
+  uint32_t done_resolve;    // CTAs of k_resolve_fold that have finished (last one builds bin_off / seg_base)
+  uint32_t done_list;       // CTAs of k_list_touched that have finished (last one decides the admission)
 };
 constexpr uint32_t kStallEarlier = 1u;   // an earlier scan is stalled (Persist::stalled)
 constexpr uint32_t kStallMarks = 2u;     // the marks are incomplete (window / checkpoint / list overflow)

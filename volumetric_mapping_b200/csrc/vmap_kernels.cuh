@@ -36,6 +36,7 @@ struct ScanBuffers {
   uint32_t* rank;           // [n]   position of a cast ray inside its length bin
   uint32_t* len_hist;       // [kFineBins] cast rays per fine bin (vmap_walk.cuh: fine_bin)
   uint32_t* seg_base;       // [kLenBins + 1] first work slot of every segment level
+  uint32_t* bin_off;        // [kFineBins] first list position of every fine bin (k_resolve_fold)
   RayRec* ray_rec;          // [n]
   Checkpoint* ckpt;         // [ckpt_cap] one per (segment level, ray)
   uint32_t ckpt_cap;
@@ -81,7 +82,7 @@ __device__ __forceinline__ uint32_t first_lookup(const ScanBuffers& sb, unsigned
 // Common tail of the three front-ends: classify world point `p` of index i.
 __device__ __forceinline__ void classify_point(const DevParams& P, const ScanBuffers& sb,
                                                Counters* cnt, const float* origin, uint32_t i,
-                                               float px, float py, float pz) {
+                                               float px, float py, float pz, uint32_t* s_acc = nullptr) {
   sb.world[3 * i + 0] = px;
   sb.world[3 * i + 1] = py;
   sb.world[3 * i + 2] = pz;
@@ -99,8 +100,9 @@ __device__ __forceinline__ void classify_point(const DevParams& P, const ScanBuf
   const unsigned act = __activemask();
   const unsigned in_b = __ballot_sync(act, in_range);
   if ((threadIdx.x & 31u) == (uint32_t)(__ffs(act) - 1)) {
-    atomicAdd(&cnt->points_valid, (uint32_t)__popc(act));
-    if (in_b) atomicAdd(&cnt->points_in_range, (uint32_t)__popc(in_b));
+    // (s_acc: the CTA's own pair of counters in shared memory -- the caller adds them to the scan's once)
+    atomicAdd(s_acc ? s_acc : &cnt->points_valid, (uint32_t)__popc(act));
+    if (in_b) atomicAdd(s_acc ? s_acc + 1 : &cnt->points_in_range, (uint32_t)__popc(in_b));
   }
 }
 
@@ -108,18 +110,30 @@ __device__ __forceinline__ void classify_point(const DevParams& P, const ScanBuf
 __global__ void __launch_bounds__(256)
 k_front_cloud(DevParams P, ScanBuffers sb, Counters* cnt, Transform T, const uint8_t* __restrict__ in,
               uint32_t n, uint32_t stride, int is_dense) {
+  pdl_launch();
+  // statistics: one pair of global atomics per CTA (thousands of per-warp atomics on one address
+  // serialise in the L2 and show up as a tail on a kernel this short)
+  __shared__ uint32_t s_acc[2];
+  if (threadIdx.x < 2) s_acc[threadIdx.x] = 0u;
+  __syncthreads();
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* p = reinterpret_cast<const float*>(in + (size_t)i * stride);
-  const float fx = p[0], fy = p[1], fz = p[2];
-  if (!is_dense && !(isfinite(fx) && isfinite(fy) && isfinite(fz))) {
-    sb.flags[i] = 0;
-    sb.world[3 * i] = fx; sb.world[3 * i + 1] = fy; sb.world[3 * i + 2] = fz;
-    return;
+  if (i < n) {
+    const float* p = reinterpret_cast<const float*>(in + (size_t)i * stride);
+    const float fx = p[0], fy = p[1], fz = p[2];
+    if (!is_dense && !(isfinite(fx) && isfinite(fy) && isfinite(fz))) {
+      sb.flags[i] = 0;
+      sb.world[3 * i] = fx; sb.world[3 * i + 1] = fy; sb.world[3 * i + 2] = fz;
+    } else {
+      float wx, wy, wz;
+      matrix_transform(T, fx, fy, fz, &wx, &wy, &wz);
+      classify_point(P, sb, cnt, T.origin, i, wx, wy, wz, s_acc);
+    }
   }
-  float wx, wy, wz;
-  matrix_transform(T, fx, fy, fz, &wx, &wy, &wz);
-  classify_point(P, sb, cnt, T.origin, i, wx, wy, wz);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_acc[0]) atomicAdd(&cnt->points_valid, s_acc[0]);
+    if (s_acc[1]) atomicAdd(&cnt->points_in_range, s_acc[1]);
+  }
 }
 
 __device__ __forceinline__ void projected_point(const DevParams& P, const ScanBuffers& sb,
@@ -264,11 +278,11 @@ k_resolve(ScanBuffers sb, MapView m, MarkSet ms, Counters* cnt, uint32_t n, int 
   }
 }
 
-// Cast-ray work list, pass 2: longest rays first (bins in descending order), so that the 32 rays
-// of a warp take about the same number of DDA steps and the longest rays start first.
-__global__ void __launch_bounds__(256) k_order_rays(ScanBuffers sb, uint32_t n) {
-  __shared__ uint32_t off[kFineBins];
-  __shared__ uint32_t warp_sum[8];
+// Descending exclusive prefix of the fine-bin histogram (a CTA of 256 threads): off_s[b] = number of
+// cast rays in bins above b, i.e. the position of bin b's first ray in the ordered list (longest
+// rays first, so that the 32 rays of a warp take about the same number of DDA steps).
+template <bool kGlobalSource = true>
+__device__ __forceinline__ void cta_bin_offsets(const uint32_t* len_hist, uint32_t* off_s, uint32_t* warp_sum) {
   constexpr int kPer = (kFineBins + 255) / 256;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   // thread t owns the kPer bins starting at descending position t * kPer
@@ -276,7 +290,7 @@ __global__ void __launch_bounds__(256) k_order_rays(ScanBuffers sb, uint32_t n) 
 #pragma unroll
   for (int j = 0; j < kPer; j++) {
     const int pos = threadIdx.x * kPer + j;
-    local[j] = pos < kFineBins ? sb.len_hist[kFineBins - 1 - pos] : 0u;
+    local[j] = pos < kFineBins ? (kGlobalSource ? __ldcg(len_hist + (kFineBins - 1 - pos)) : len_hist[kFineBins - 1 - pos]) : 0u;
     sum += local[j];
   }
   uint32_t incl = sum;
@@ -291,22 +305,21 @@ __global__ void __launch_bounds__(256) k_order_rays(ScanBuffers sb, uint32_t n) 
 #pragma unroll
   for (int j = 0; j < kPer; j++) {
     const int pos = threadIdx.x * kPer + j;
-    if (pos < kFineBins) off[kFineBins - 1 - pos] = base;
+    if (pos < kFineBins) off_s[kFineBins - 1 - pos] = base;
     base += local[j];
   }
   __syncthreads();
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && (sb.flags[i] & kFlagCast))
-    sb.rays[off[ray_bin(sb, i)] + sb.rank[i]] = i;
-  if (blockIdx.x != 0) return;
-  // Work slots of the segment walker, level-major: level j holds one slot for every ray with
-  // more than j segments -- a prefix of the ordered list, as long as the rays that precede the
-  // highest fine bin of segment count j.
+}
+// Work slots of the segment walker, level-major: level j holds one slot for every ray with more
+// than j segments -- a prefix of the ordered list, as long as the rays that precede the highest
+// fine bin of segment count j.  (CTA of 256 threads; off_s from cta_bin_offsets.)
+__device__ __forceinline__ void cta_seg_base(const uint32_t* off_s, uint32_t* warp_sum, uint32_t* seg_base) {
   constexpr int kLv = kLenBins / 256;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint32_t lv[kLv], lsum = 0;
 #pragma unroll
   for (int j = 0; j < kLv; j++) {
-    lv[j] = off[fine_bin_top(threadIdx.x * kLv + j)];
+    lv[j] = off_s[fine_bin_top(threadIdx.x * kLv + j)];
     lsum += lv[j];
   }
   uint32_t linc = lsum;
@@ -321,10 +334,116 @@ __global__ void __launch_bounds__(256) k_order_rays(ScanBuffers sb, uint32_t n) 
   for (uint32_t w2 = 0; w2 < warp; w2++) lbase += warp_sum[w2];
 #pragma unroll
   for (int j = 0; j < kLv; j++) {
-    sb.seg_base[threadIdx.x * kLv + j] = lbase;
+    seg_base[threadIdx.x * kLv + j] = lbase;
     lbase += lv[j];
   }
-  if (threadIdx.x == 255) sb.seg_base[kLenBins] = lbase;
+  if (threadIdx.x == 255) seg_base[kLenBins] = lbase;
+}
+
+// K1b for the segment walker's chain: k_resolve with the work-list bookkeeping folded in.
+//   * position inside a bin: one shared-memory counter per bin and CTA (warp-aggregated), then ONE
+//     global atomic per populated bin and CTA -- k_resolve's per-warp returning atomics on a dozen
+//     hot histogram words were 45 % of its stall samples (profiles/README.md, round 2);
+//   * the CTA also leaves its own cast rays, longest first, in sb.rays[256 * blockIdx.x ...] (padded
+//     with kNoRay): k_checkpoints_pts runs CTA for CTA over these lists, so its warps get rays of
+//     about the same segment count without a globally ordered list;
+//   * the last CTA to finish turns the finished histogram into sb.bin_off (first list position of
+//     every bin) and sb.seg_base, so no k_order_rays launch follows: a ray's position in the ordered
+//     list is bin_off[bin] + rank.
+constexpr uint32_t kNoRay = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(256)
+k_resolve_fold(ScanBuffers sb, MapView m, MarkSet ms, Counters* cnt, uint32_t n, int mark_occupied) {
+  __shared__ uint32_t s_hist[kFineBins];     // the CTA's rays per bin, then their first position inside the bin
+  __shared__ uint32_t s_off[kFineBins];      // rays of the CTA in higher bins
+  __shared__ uint32_t s_stat[3];
+  __shared__ uint32_t warp_sum[8];
+  __shared__ bool s_last;
+  for (int k = threadIdx.x; k < kFineBins; k += 256) s_hist[k] = 0u;
+  if (threadIdx.x < 3) s_stat[threadIdx.x] = 0u;
+  pdl_wait();
+  pdl_launch();
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane_ = threadIdx.x & 31u;
+  bool cast = false, occ = false;
+  unsigned long long key = 0;
+  uint32_t f = 0;
+  if (i < n) {
+    f = sb.flags[i];
+    if (f & kFlagValid) {
+      key = sb.key[i];
+      const uint32_t first = first_lookup(sb, key);
+      const bool rb = (f & kFlagRange) && (f & kFlagBound);
+      cast = rb ? (i == first) : (i < first);
+      occ = rb && cast;
+    }
+  }
+  if (occ) {
+    if (mark_occupied && ms.dense)
+      mark_voxel_dense(ms, cnt, ms.occ_mask, (uint32_t)(key & 0xFFFFu), (uint32_t)((key >> 16) & 0xFFFFu),
+                       (uint32_t)((key >> 32) & 0xFFFFu));
+    else if (mark_occupied)
+      mark_voxel(m, cnt, m.occ_mask, (uint32_t)(key & 0xFFFFu), (uint32_t)((key >> 16) & 0xFFFFu),
+                 (uint32_t)((key >> 32) & 0xFFFFu));
+    else
+      f |= 8u;   // kFlagOcc
+  }
+  const unsigned cast_b = __ballot_sync(0xFFFFFFFFu, cast);
+  uint32_t bin = 0, local = 0;
+  if (cast) {
+    sb.flags[i] = (uint8_t)(f | kFlagCast);
+    bin = ray_bin(sb, i);
+    const unsigned peers = __match_any_sync(cast_b, bin);
+    const int leader = __ffs(peers) - 1;
+    if (lane_ == (uint32_t)leader) local = atomicAdd(&s_hist[bin], (uint32_t)__popc(peers));
+    local = __shfl_sync(peers, local, leader) + __popc(peers & ((1u << lane_) - 1u));
+  }
+  const unsigned occ_b = __ballot_sync(0xFFFFFFFFu, occ);
+  if (lane_ == 0 && cast_b) {
+    atomicAdd(&s_stat[0], (uint32_t)__popc(cast_b));
+    if (occ_b) atomicAdd(&s_stat[1], (uint32_t)__popc(occ_b));
+  }
+  __syncthreads();
+  cta_bin_offsets<false>(s_hist, s_off, warp_sum);
+  // the CTA's share of every populated bin -> its first position inside the bin
+  for (int k = threadIdx.x; k < kFineBins; k += 256) {
+    const uint32_t c = s_hist[k];
+    if (c) s_hist[k] = atomicAdd(sb.len_hist + k, c);
+  }
+  __syncthreads();
+  if (cast) {
+    sb.rank[i] = s_hist[bin] + local;
+    sb.rays[blockIdx.x * 256u + s_off[bin] + local] = i;
+  }
+  if (threadIdx.x >= s_stat[0]) sb.rays[blockIdx.x * 256u + threadIdx.x] = kNoRay;
+  if (threadIdx.x == 0) {
+    if (s_stat[0]) {
+      atomicAdd(&cnt->n_rays, s_stat[0]);
+      atomicAdd(&cnt->rays_cast, s_stat[0]);
+    }
+    if (s_stat[1]) atomicAdd(&cnt->occupied_emitted, s_stat[1]);
+    __threadfence();
+    s_last = atomicAdd(&cnt->done_resolve, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  cta_bin_offsets(sb.len_hist, s_hist, warp_sum);
+  for (int k = threadIdx.x; k < kFineBins; k += 256) sb.bin_off[k] = s_hist[k];
+  cta_seg_base(s_hist, warp_sum, sb.seg_base);
+}
+
+// Cast-ray work list, pass 2 (walkers that read the ordered list sb.rays: table mode, k_walk_dense,
+// sort mode; the segment walker's chain gets its positions from k_resolve_fold instead).
+__global__ void __launch_bounds__(256) k_order_rays(ScanBuffers sb, uint32_t n) {
+  __shared__ uint32_t off[kFineBins];
+  __shared__ uint32_t warp_sum[8];
+  cta_bin_offsets(sb.len_hist, off, warp_sum);
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (sb.flags[i] & kFlagCast))
+    sb.rays[off[ray_bin(sb, i)] + sb.rank[i]] = i;
+  if (blockIdx.x != 0) return;
+  cta_seg_base(off, warp_sum, sb.seg_base);
 }
 
 // K2: one thread per cast ray.  Every visited voxel is one bit of its block's 512-bit free mask
@@ -466,6 +585,34 @@ k_checkpoints(DevParams P, ScanBuffers sb, Counters* cnt, float ox, float oy, fl
                   });
 }
 
+// K2a of the folded chain: CTA b takes the rays k_resolve_fold's CTA b left in sb.rays[256 b ...]
+// (its cast rays, longest first), one thread per ray; the ray's position in the ordered list is
+// bin_off[bin] + rank.
+// (Three lanes per ray -- one per axis, checkpoints assembled with shuffles -- was built and measured:
+// 42 us instead of 25, the three axes take different paths through seq_advance and serialise inside
+// the warp.  Rays taken in point order instead of longest first: +14 us, a warp then waits for its
+// longest ray.  profiles/README.md, round 2.)
+__global__ void __launch_bounds__(256)
+k_checkpoints_pts(DevParams P, ScanBuffers sb, Counters* cnt, float ox, float oy, float oz) {
+  pdl_wait();
+  const uint32_t i = sb.rays[blockIdx.x * 256u + threadIdx.x];
+  if (i != kNoRay) {
+    const uint32_t steps = sb.len[i];
+    const uint32_t r = sb.bin_off[fine_bin(steps)] + sb.rank[i];
+    ray_checkpoints(P, ox, oy, oz, sb.ray_end[3 * i], sb.ray_end[3 * i + 1], sb.ray_end[3 * i + 2], steps, i,
+                    &sb.ray_rec[r], [&](uint32_t j, const Checkpoint& cp) {
+                      const uint32_t slot = sb.seg_base[j] + r;
+                      if (slot >= sb.ckpt_cap) {
+                        atomicExch(&cnt->overflow_ckpt, 1u);
+                        return false;
+                      }
+                      sb.ckpt[slot] = cp;
+                      return true;
+                    });
+  }
+  pdl_launch();
+}
+
 // K2b: one thread per (segment level, ray) work slot, level-major so that the lanes of a warp
 // walk neighbouring rays at the same depth.  Segment j performs the DDA steps whose crossing
 // parameter is in [j, j+1) * dtau and emits the voxels those steps enter (segment 0 also the
@@ -583,6 +730,7 @@ template <bool kFilter, int kMinCtas, bool kBranchFree>
 __global__ void __launch_bounds__(256, kMinCtas)
 k_walk_segments_queued(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, float ox, float oy, float oz, int variant,
                        DilatedWindow dw) {
+  pdl_wait();
   if (cnt->overflow_ckpt) return;
   __shared__ uint32_t base_s[kLenBins + 1];
   __shared__ uint32_t queue_s[3 * kQueueSteps * 256];
@@ -625,6 +773,7 @@ k_walk_segments_queued(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, f
     }
     walk_slot_queued<kFilter, 256u, kBranchFree>(P, ms, dw, cnt, cp, rr, lo, ox, oy, oz, near_limit, &emitted, &longest, n_steps, active, mq);
   }
+  pdl_launch();
   __shared__ uint32_t s_stat[2];
   __syncthreads();
   if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
@@ -717,6 +866,8 @@ k_walk_segments_near(DevParams P, ScanBuffers sb, MarkSet ms, Counters* cnt, flo
 
 // Compact the window's touched bitmap into the block list (cnt->n_touched entries).
 __global__ void __launch_bounds__(256) k_list_touched(MarkSet ms, Counters* cnt, uint32_t n_words) {
+  pdl_wait();
+  pdl_launch();
   const uint32_t lane = threadIdx.x & 31u;
   for (uint32_t wbase = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; wbase < n_words;
        wbase += gridDim.x * blockDim.x) {
@@ -751,6 +902,8 @@ __global__ void __launch_bounds__(256) k_list_touched(MarkSet ms, Counters* cnt,
 // marks are incomplete, or when the listed blocks might push the table over load 1/2.  `poison`
 // (pipelined insertion): a refusal also stalls every later scan until the host has replayed it.
 __global__ void k_admit(MarkSet ms, MapView m, Counters* cnt, int poison) {
+  pdl_wait();
+  pdl_launch();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   uint32_t why = 0;
   if (m.persist->stalled) why |= kStallEarlier;
@@ -764,6 +917,8 @@ __global__ void k_admit(MarkSet ms, MapView m, Counters* cnt, int poison) {
 // once, whether the pool has a slot for every listed block that lacks one (k_update only reads
 // the verdict).
 __global__ void __launch_bounds__(256) k_locate_blocks(MarkSet ms, MapView m, Counters* cnt, int poison) {
+  pdl_wait();
+  pdl_launch();
   if (cnt->stall) return;
   const uint32_t n = cnt->n_touched;
   uint32_t need = 0;
@@ -854,6 +1009,7 @@ k_capture_keys(MapView m, MarkSet ms, Counters* cnt, uint16_t* __restrict__ free
 template <int kVariant>
 __global__ void __launch_bounds__(256)
 k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
+  pdl_wait();
   // Abort the whole scan's update (uniformly) when a map structure must grow first: the verdict was
   // reached once, before this launch (k_admit / k_locate_blocks / k_admit_pool), every thread reads
   // the same flags.

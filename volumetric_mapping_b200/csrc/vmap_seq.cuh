@@ -90,9 +90,22 @@ VMAP_HD uint64_t seq_advance(double* t_io, double dt, double tau, uint64_t max_s
     const uint64_t bt = seq_bits(tau);
     const bool tau_here = (tau > 0 && bt <= top);     // tau > t3 here, so it is in this binade
     const uint64_t lim = tau_here ? bt - 1 : top;
-    // one division, done in double (both operands < 2^52 are exact) and corrected exactly
+    // one division: only an ESTIMATE of num / q is needed -- the two loops below correct it exactly.
+    // Quotients below 2^20 (every DDA: j is a step count) take a single-precision estimate (one
+    // MUFU.RCP + one multiply on the device instead of the ~40-instruction IEEE double division:
+    // relative error < 2^-21, so the estimate is off by at most one); anything larger takes the
+    // double division (both operands < 2^52 are exact).
     const uint64_t num = lim - b3;
-    uint64_t j = (uint64_t)((double)num / (double)q);
+    uint64_t j;
+    if ((num >> 20) < q) {
+#if defined(__CUDA_ARCH__)
+      j = (uint64_t)__float2uint_rz(__fdividef(__ull2float_rz(num), __ull2float_rn(q)));
+#else
+      j = (uint64_t)(uint32_t)((float)num / (float)q);
+#endif
+    } else {
+      j = (uint64_t)((double)num / (double)q);
+    }
     while (j * q > num) --j;
     while ((j + 1) * q <= num) ++j;
     if (tau_here && b3 + (j + 1) * q <= top) ++j;     // step onto the first element >= tau
