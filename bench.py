@@ -518,10 +518,14 @@ def run_b200(args):
             "config": {"workload": WORKLOAD, "resolution": RESOLUTION, "max_range": MAX_RANGE,
                        "points_per_step": n_pts * world,
                        "traversals_per_step": dev["traversals"] / K,
-                       "l2": "256 MiB buffer overwritten in-stream before every scan, inside the timed region",
+                       "l2": ("256 MiB buffer overwritten in-stream inside the timed region, once per scan: between the "
+                              "previous scan's map update and this scan's (no update finds its blocks in L2)" if world == 1 else
+                              "256 MiB buffer overwritten in-stream before every scan's generate, inside the timed region"),
                        "timing": "one device-timed region over the K pipelined steps (CUDA events after a full drain on "
                                  "both sides), barrier + device sync around it, max over ranks",
-                       "pipeline": "2 scans in flight per GPU on two scan contexts; map updates ordered by events",
+                       "pipeline": ("2 scans in flight when an insert call returns, three scan contexts (the next scan's front "
+                                    "half is queued while the host waits); map updates ordered by events" if world == 1 else
+                                    "2 scans in flight per GPU on two scan contexts; map updates ordered by events"),
                        "sharding": ("one map sharded by 8^3-block owner over %d ranks; step = round of %d scans; block "
                                     "records pulled from the peers' round buffers over NVLink (CUDA IPC), %d scans per "
                                     "rank per round" % (world, world, args.dist_batch)) if world > 1 else "single GPU"},

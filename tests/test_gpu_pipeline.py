@@ -1,5 +1,6 @@
-"""Pipelined scan insertion (include/vmap/vmap.h, "the scan pipeline"): up to two scans in flight on
-two scan contexts, map updates ordered by events, refusals on the device replayed by the host.
+"""Pipelined scan insertion (include/vmap/vmap.h, "the scan pipeline"): up to two scans in flight when a
+call returns, on three scan contexts (two with VMAP_PIPE_CTX=2), map updates ordered by events, refusals on
+the device replayed by the host.
 Bar: whatever the depth and however often the map has to grow under the pipeline, the leaves equal
 the CPU oracle's bit for bit (octomap_world.cc:110-141, 238-264 called scan after scan)."""
 import numpy as np
@@ -23,12 +24,13 @@ def hdl_scans(n, res):
     return [scenes.trajectory_scan(3 * i, resolution=res) for i in range(n)]
 
 
-@pytest.mark.parametrize("depth", [0, 1, 2])
-def test_pipelined_build_equals_oracle_with_growth_under_the_pipeline(depth):
+@pytest.mark.parametrize("depth,contexts", [(0, 3), (1, 3), (2, 3), (2, 2)])
+def test_pipelined_build_equals_oracle_with_growth_under_the_pipeline(depth, contexts, monkeypatch):
     """initial_blocks = 64: the first scans do not fit, their updates are refused on the device
-    (table, then pool), the scan behind them refuses itself, and the host replays both in order."""
+    (table, then pool), the scans behind them refuse themselves, and the host replays them all in order."""
     params = dict(resolution=0.2, sensor_max_range=50.0)
-    scans = hdl_scans(6, 0.2)
+    scans = hdl_scans(7, 0.2)
+    monkeypatch.setenv("VMAP_PIPE_CTX", str(contexts))
     gw = vm.OctomapWorld(initial_blocks=64, **params)
     gw.set_pipeline_depth(depth)
     ow = oracle.OracleWorld(**params)

@@ -46,7 +46,9 @@ KEYS = ("gpu_ms", "front_ms", "resolve_ms", "walk_ms", "update_ms")
 COUNTS = ("traversals", "unique_free", "unique_occupied", "longest_ray", "rays_cast", "occupied_emitted", "blocks_touched")
 
 
-def make(helpers, pdl, marks):
+def make(helpers, pdl, marks, ctx=3, flush_at=1):
+    os.environ["VMAP_FLUSH_AT"] = str(flush_at)
+    os.environ["VMAP_PIPE_CTX"] = str(ctx)
     os.environ["VMAP_HELPERS"] = str(helpers)
     os.environ["VMAP_PDL"] = str(pdl)
     if marks is None:
@@ -74,8 +76,8 @@ def run_sync(helpers, pdl, marks, reps=3, flush=0):
     return summary, counts, dg
 
 
-def run_pipe(helpers, pdl, marks, flush, warm=4, reps=3):
-    w = make(helpers, pdl, marks)
+def run_pipe(helpers, pdl, marks, ctx, flush, warm=4, reps=3, flush_at=1):
+    w = make(helpers, pdl, marks, ctx, flush_at)
     w.set_pipeline_depth(2)
     w.set_debug_l2_flush(flush)
     best = None
@@ -99,7 +101,9 @@ base = None
 ok = True
 # every configuration is visited `rounds` times in turn (clock / thermal drift hits all alike); medians over the visits
 rounds = 3
-SYNC = [(0, 0, None), (1, 0, None), (1, 123, None), (0, 0, 0), (1, 0, 0), (1, 123, 0), (1, 127, 0)]
+SYNC = [(0, 0, None), (1, 123, None), (0, 0, 0), (1, 123, 0)]
+if "--quick" in sys.argv:
+    SYNC = SYNC[:2]
 acc = {c: [] for c in SYNC}
 for _ in range(rounds):
     for cfg in SYNC:
@@ -113,7 +117,7 @@ for cfg in SYNC:
            **{k: round(float(np.median([a[k] for a in acc[cfg]])), 5) for k in KEYS}}
     out["sync"].append(row)
     print(json.dumps(row), flush=True)
-PIPE = [(0, 0, None), (1, 0, None), (1, 123, None), (1, 127, None)]
+PIPE = [(0, 0, None, 2), (1, 123, None, 3)]   # (helpers, pdl, marks, scan contexts)
 for flush in (0, 256 << 20):
     accp = {c: [] for c in PIPE}
     for _ in range(rounds):
@@ -122,10 +126,23 @@ for flush in (0, 256 << 20):
             ok = ok and dg == base[1]
             accp[cfg].append(ms)
     for cfg in PIPE:
-        row = {"helpers": cfg[0], "pdl": cfg[1], "flush_mb": flush >> 20, "ms_per_scan": round(float(np.median(accp[cfg])), 5),
+        row = {"helpers": cfg[0], "pdl": cfg[1], "contexts": cfg[3], "flush_mb": flush >> 20, "ms_per_scan": round(float(np.median(accp[cfg])), 5),
                "min": min(accp[cfg]), "max": max(accp[cfg])}
         out["pipelined"].append(row)
         print(json.dumps(row), flush=True)
+# where and how the benchmark's L2 flush runs (three contexts, folded helpers)
+out["flush_placement"] = []
+FL = [(0,), (1,)]
+accf = {c: [] for c in FL}
+for _ in range(rounds):
+    for c in FL:
+        ms, dg, rep = run_pipe(1, 123, None, 3, 256 << 20, reps=2, flush_at=c[0])
+        ok = ok and dg == base[1]
+        accf[c].append(ms)
+for c in FL:
+    row = {"flush_at": c[0], "ms_per_scan": round(float(np.median(accf[c])), 5), "min": min(accf[c]), "max": max(accf[c])}
+    out["flush_placement"].append(row)
+    print(json.dumps(row), flush=True)
 print(json.dumps({"all_identical": ok}), flush=True)
 
 if "--oracle" in sys.argv:

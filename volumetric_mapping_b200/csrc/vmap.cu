@@ -91,6 +91,9 @@ struct vmap : ScanCtx {
   cudaEvent_t evr0 = nullptr, evr1 = nullptr;  // timed region (vmap_region_begin / _end)
   ScanCtx alt;                   // the other scan context (created on the first pipelined insert)
   bool alt_ready = false;
+  ScanCtx alt2;                  // a third one (single-GPU pipelined insertion, VMAP_PIPE_CTX=3): the next scan's front half
+  bool alt2_ready = false;       // can be enqueued while two scans are still in flight, so the device never waits for the host
+  int pipe_ctx = 3;              // scan contexts the single-GPU pipeline rotates through (2 or 3)
   int pipe_depth = 2;            // scans that may stay in flight when an insert call returns (0 = synchronous)
   int pipe_n = 0;                // scans in flight
   uint64_t pipe_seq = 0;
@@ -197,6 +200,7 @@ struct vmap : ScanCtx {
   int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
   int pdl = 123;          // VMAP_PDL: programmatic dependent launch along the scan's kernel chain (bit mask kPdl*; default: all but the walker)
   int stage_marks = -1;   // VMAP_STAGE_MARKS: 1 always, 0 never, unset: synchronous scans only
+  int flush_at = 1;       // VMAP_FLUSH_AT: where a pipelined scan runs the benchmark's L2 flush (0 scan start, 1 before its update)
   int helpers = 1;        // VMAP_HELPERS: 1 folded helper chain (k_resolve_fold, k_checkpoints_pts), 0 round 1's
   int no_segments = 0;    // experiments (VMAP_NO_SEGMENTS): one thread per whole ray
 
@@ -1042,6 +1046,18 @@ int launch_after_front(vmap* h, size_t n, const Transform& T) {
 // scan contexts and pipelined insertion
 // ---------------------------------------------------------------------------------------------
 void swap_ctx(vmap* h) { std::swap(static_cast<ScanCtx&>(*h), h->alt); }
+void swap_ctx2(vmap* h) { std::swap(static_cast<ScanCtx&>(*h), h->alt2); }
+// the context (other than the current one) whose scan in flight is the oldest / the newest; null: none in flight
+ScanCtx* other_in_flight(vmap* h, bool newest) {
+  ScanCtx* best = nullptr;
+  for (ScanCtx* c : {&h->alt, &h->alt2})
+    if (c->in_flight && (!best || (newest ? c->seq > best->seq : c->seq < best->seq))) best = c;
+  return best;
+}
+void make_current(vmap* h, ScanCtx* c) {
+  if (c == &h->alt) swap_ctx(h);
+  else if (c == &h->alt2) swap_ctx2(h);
+}
 
 int init_ctx_resources(vmap* h) {   // for the CURRENT context
   int prio_lo = 0, prio_hi = 0;
@@ -1132,7 +1148,7 @@ int ensure_ckpt(vmap* h, uint64_t want) {
 // range, windows over the budget, sharded handles -- takes the synchronous path.)
 bool pipe_eligible(const vmap* h, size_t n) {
   if (h->pipe_depth <= 0 || h->capture || h->cfg.dedupe_mode != VMAP_DEDUPE_BITMASK) return false;
-  if (h->no_segments || h->shard_world > 1 || h->win.disabled || h->alt.win.disabled) return false;
+  if (h->no_segments || h->shard_world > 1 || h->win.disabled || h->alt.win.disabled || h->alt2.win.disabled) return false;
   if (!(h->P.max_range >= 0.0) || !std::isfinite(h->P.max_range)) return false;
   const uint64_t ck = checkpoint_bound(h, n);
   return ck < 0xFFFFFFFFull && ck * sizeof(Checkpoint) <= (2ull << 30);
@@ -1156,7 +1172,7 @@ int pipe_flush(vmap* h) {
 
 // Quiescent-point work before a pipelined insert: the second context, and map growth ahead of need
 // (a scan that finds too little room is refused on the device and replayed -- correct but slow).
-int pipe_prepare(vmap* h) {
+int pipe_prepare(vmap* h, bool third = false) {
   if (!h->alt_ready) {
     swap_ctx(h);
     h->ctx_id = 1;
@@ -1164,6 +1180,14 @@ int pipe_prepare(vmap* h) {
     swap_ctx(h);
     VM_TRY(st);
     h->alt_ready = true;
+  }
+  if (third && !h->alt2_ready) {
+    swap_ctx2(h);
+    h->ctx_id = 2;
+    const int st = init_ctx_resources(h);
+    swap_ctx2(h);
+    VM_TRY(st);
+    h->alt2_ready = true;
   }
   if (!h->copy_stream) {
     VM_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
@@ -1174,10 +1198,10 @@ int pipe_prepare(vmap* h) {
     VM_TRY(pipe_flush(h));
     h->pipe_grow = false;
     const uint64_t t = h->pipe_touch_max;
-    while (((uint64_t)h->h_persist->n_entries + 6 * t) * 2 > h->table_cap) {
+    while (((uint64_t)h->h_persist->n_entries + 8 * t) * 2 > h->table_cap) {
       if (grow_table(h) != VMAP_OK) { cudaGetLastError(); break; }       // (not fatal here: the refusal path reports real shortages)
     }
-    uint64_t want = (uint64_t)h->h_persist->n_slots + 6 * t;
+    uint64_t want = (uint64_t)h->h_persist->n_slots + 8 * t;
     if (h->cfg.max_blocks) want = std::min<uint64_t>(want, h->cfg.max_blocks);
     if (want > h->pool_cap && grow_pool(h, want) != VMAP_OK) cudaGetLastError();
   }
@@ -1188,9 +1212,10 @@ int pipe_prepare(vmap* h) {
 void pipe_watch_headroom(vmap* h, uint32_t n_touched) {
   h->pipe_touch_max = std::max(h->pipe_touch_max, n_touched);
   const uint64_t t = h->pipe_touch_max;
-  if (((uint64_t)h->h_persist->n_entries + 3 * t) * 2 > h->table_cap) h->pipe_grow = true;
+  // (up to three scans are in flight behind the counters this is decided on)
+  if (((uint64_t)h->h_persist->n_entries + 4 * t) * 2 > h->table_cap) h->pipe_grow = true;
   const bool pool_can_grow = !h->cfg.max_blocks || h->pool_cap < h->cfg.max_blocks;
-  if (pool_can_grow && (uint64_t)h->h_persist->n_slots + 3 * t > h->pool_cap) h->pipe_grow = true;
+  if (pool_can_grow && (uint64_t)h->h_persist->n_slots + 4 * t > h->pool_cap) h->pipe_grow = true;
 }
 
 // The current context holds a scan whose tail the device refused; nothing else is in flight.
@@ -1235,8 +1260,10 @@ int pipe_replay(vmap* h, bool first) {
 int pipe_retire(vmap* h) {
   if (h->pipe_n <= 0) return VMAP_OK;
   if (h->peer_on) return peer_retire(h);
-  const bool cur_is_oldest = h->in_flight && (!h->alt.in_flight || h->seq < h->alt.seq);
-  if (!cur_is_oldest) swap_ctx(h);
+  {
+    ScanCtx* oldest = other_in_flight(h, false);
+    if (oldest && (!h->in_flight || oldest->seq < h->seq)) make_current(h, oldest);
+  }
   VM_CUDA(h, cudaEventSynchronize(h->ev_done));
   h->in_flight = false;
   h->pipe_n--;
@@ -1251,12 +1278,14 @@ int pipe_retire(vmap* h) {
     pipe_watch_headroom(h, c.n_touched);
     return VMAP_OK;
   }
+  // refused on the device: every younger scan in flight has refused itself too (Persist::stalled);
+  // wait for them all, then replay in scan order
   h->pipe_stalls++;
-  const bool younger = h->alt.in_flight;
-  if (younger) VM_CUDA(h, cudaEventSynchronize(h->alt.ev_done));
+  for (ScanCtx* y : {&h->alt, &h->alt2})
+    if (y->in_flight) VM_CUDA(h, cudaEventSynchronize(y->ev_done));
   int st = pipe_replay(h, true);
-  if (younger) {
-    swap_ctx(h);
+  while (ScanCtx* y = other_in_flight(h, false)) {
+    make_current(h, y);
     h->in_flight = false;
     h->pipe_n--;
     const std::string msg = h->err;
@@ -1265,6 +1294,15 @@ int pipe_retire(vmap* h) {
     else st = st2;
   }
   return st;
+}
+
+// Benchmark hook (vmap_set_debug_l2_flush): overwrite a buffer larger than the L2 so that what follows finds
+// nothing of the map in it.  (A kernel of our own with one light CTA per SM, meant to run beside another scan's
+// walk, measured SLOWER than the memset node: 0.224 vs 0.205 ms per pipelined scan, profiles/README.md.)
+int enqueue_l2_flush(vmap* h, cudaStream_t st, uint64_t tag) {
+  if (!h->l2_flush_bytes) return VMAP_OK;
+  VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(tag & 0xFF), h->l2_flush_bytes, st));
+  return VMAP_OK;
 }
 
 __global__ void __launch_bounds__(256)
@@ -1352,9 +1390,13 @@ int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, si
   Transform T;
   fill_transform_matrix(&T, Tm);
   if (piped) {
-    VM_TRY(pipe_prepare(h));
-    while (h->pipe_n >= 2) VM_TRY(pipe_retire(h));
-    if (h->in_flight) swap_ctx(h);            // the current context is the free one from here on
+    const int n_ctx = h->pipe_depth >= 2 && h->pipe_ctx >= 3 ? 3 : 2;
+    VM_TRY(pipe_prepare(h, n_ctx == 3));
+    while (h->pipe_n >= n_ctx) VM_TRY(pipe_retire(h));
+    if (h->in_flight) {                       // the current context is a free one from here on
+      if (!h->alt.in_flight) swap_ctx(h);
+      else swap_ctx2(h);
+    }
     if (h->epoch >= kEpochMax) VM_TRY(pipe_flush(h));
     VM_TRY(ensure_scan(h, n));
     VM_TRY(ensure_ckpt(h, checkpoint_bound(h, n)));
@@ -1374,16 +1416,17 @@ int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, si
       VM_CUDA(h, cudaMemcpyAsync(h->in.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
       d_in = (const uint8_t*)h->in.p;
     }
-    if (h->l2_flush_bytes)
-      VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(h->total_scans & 0xFF), h->l2_flush_bytes, h->stream));
+    VM_TRY(enqueue_l2_flush(h, h->stream, h->total_scans));
     VM_TRY(insert_cloud_sync(h, d_in, n, stride, is_dense, Tm));
     return write_back_cloud(h, h->stream, d_in, n, stride, is_dense, wb_out, wb_n_out);
   }
   // ---- pipelined ----
   h->walk_overlaps = true;
   VM_TRY(ensure(h, &h->in, bytes));
-  if (h->l2_flush_bytes)   // benchmark hook: no scan finds its map blocks in L2
-    VM_CUDA(h, cudaMemsetAsync(h->l2_flush.p, (int)(h->pipe_seq & 0xFF), h->l2_flush_bytes, h->stream));
+  // benchmark hook: no scan finds its map blocks in L2.  VMAP_FLUSH_AT=0: at the start of the scan (round 2's
+  // placement -- the update of the scan before may still run after it); 1 (default): in the ordered half, between
+  // the previous scan's update and this one's
+  if (h->flush_at == 0) VM_TRY(enqueue_l2_flush(h, h->stream, h->pipe_seq));
   VM_CUDA(h, cudaMemcpyAsync(h->in.p, src, bytes, src_on_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
   VM_CUDA(h, cudaEventRecord(h->ev_h2d, h->stream));
   VM_TRY(next_epoch(h));
@@ -1400,7 +1443,8 @@ int insert_cloud_common(vmap* h, const void* src, bool src_on_host, size_t n, si
   VM_TRY(launch_after_front(h, n, T));
   VM_TRY(launch_list(h));
   // the ordered half: after the update of the scan before this one
-  if (h->alt.in_flight) VM_CUDA(h, cudaStreamWaitEvent(h->stream, h->alt.ev_done, 0));
+  if (ScanCtx* prev = other_in_flight(h, true)) VM_CUDA(h, cudaStreamWaitEvent(h->stream, prev->ev_done, 0));
+  if (h->flush_at != 0) VM_TRY(enqueue_l2_flush(h, h->stream, h->pipe_seq));
   VM_TRY(launch_tail(h, 1));
   VM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
   VM_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
@@ -1518,6 +1562,7 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   if (const char* e = getenv("VMAP_NO_SEGMENTS")) h->no_segments = atoi(e);
   if (const char* e = getenv("VMAP_UPDATE_VARIANT")) h->update_variant = atoi(e);
   if (const char* e = getenv("VMAP_HELPERS")) h->helpers = atoi(e);
+  if (const char* e = getenv("VMAP_FLUSH_AT")) h->flush_at = atoi(e);
   if (const char* e = getenv("VMAP_PDL")) h->pdl = atoi(e);
   if (const char* e = getenv("VMAP_STAGE_MARKS")) h->stage_marks = atoi(e) != 0;
   auto bail = [&](int code) {
@@ -1533,6 +1578,8 @@ int vmap_create(const vmap_params* params, const vmap_config* config, vmap** out
   if (!cuda_ok(cudaSetDevice(dev), "cudaSetDevice")) return bail(VMAP_ERR_CUDA);
   if (const char* e = getenv("VMAP_PIPE_DEPTH")) h->pipe_depth = std::min(2, std::max(0, atoi(e)));
   h->alt.ctx_id = 1;
+  h->alt2.ctx_id = 2;
+  if (const char* e = getenv("VMAP_PIPE_CTX")) h->pipe_ctx = std::min(3, std::max(2, atoi(e)));
   if (init_ctx_resources(h) != VMAP_OK) return bail(VMAP_ERR_CUDA);
   if (!cuda_ok(cudaEventCreate(&h->evr0), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
   if (!cuda_ok(cudaEventCreate(&h->evr1), "cudaEventCreate")) return bail(VMAP_ERR_CUDA);
@@ -1554,7 +1601,7 @@ int vmap_destroy(vmap* h) try {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();      // pipelined scans, apply rounds: nothing may be in flight
   h->pipe_n = 0;
-  h->in_flight = h->alt.in_flight = false;
+  h->in_flight = h->alt.in_flight = h->alt2.in_flight = false;
   free_map(h);
   cudaFree(h->out.p); cudaFree(h->aux.p);
   cudaFree(h->cap_free.p); cudaFree(h->cap_occ.p);
@@ -1581,6 +1628,8 @@ int vmap_destroy(vmap* h) try {
   if (h->evr1) cudaEventDestroy(h->evr1);
   free_ctx_resources(h);
   swap_ctx(h);
+  free_ctx_resources(h);
+  swap_ctx2(h);
   free_ctx_resources(h);
   delete h;
   return VMAP_OK;
