@@ -525,7 +525,8 @@ def run_b200(args):
                                  "both sides), barrier + device sync around it, max over ranks",
                        "pipeline": ("2 scans in flight when an insert call returns, three scan contexts (the next scan's front "
                                     "half is queued while the host waits); map updates ordered by events" if world == 1 else
-                                    "2 scans in flight per GPU on two scan contexts; map updates ordered by events"),
+                                    "up to 3 generated scans in flight per GPU on three scan contexts; packs ordered by events, "
+                                    "applies on their own stream"),
                        "sharding": ("one map sharded by 8^3-block owner over %d ranks; step = round of %d scans; block "
                                     "records pulled from the peers' round buffers over NVLink (CUDA IPC), %d scans per "
                                     "rank per round" % (world, world, args.dist_batch)) if world > 1 else "single GPU"},

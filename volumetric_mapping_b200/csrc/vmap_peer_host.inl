@@ -2,7 +2,7 @@
 // vmap_shard_host.inl).  Same partitioning and ordering as the NCCL path (rank r generates the
 // r-th scan of every round, every owner applies a round's scans in scan order), but nothing is sent:
 //
-//   generate  scan k runs through the scan pipeline's two contexts (K1..K2 on its own window);
+//   generate  scan k runs through the scan pipeline's three contexts (K1..K2 on its own window);
 //             its touched blocks are packed into this rank's ROUND BUFFER of the round's parity,
 //             bucketed by owner, bucket offsets kept in a device-side header (vmap_shard.cuh).
 //   publish   after the round's last pack: one remote store per peer (k_round_publish).
@@ -30,7 +30,7 @@ int peer_alloc_mailbox(vmap* h, uint64_t records_per_round) {
   VM_TRY(dev_alloc(h, (void**)&h->d_round_info, 2 * kRoundInfoWords * sizeof(uint32_t)));
   VM_CUDA(h, cudaMallocHost((void**)&h->h_round_info, 2 * kRoundInfoWords * sizeof(uint32_t)));
   std::memset(h->h_round_info, 0, 2 * kRoundInfoWords * sizeof(uint32_t));
-  VM_TRY(dev_alloc(h, (void**)&h->d_sub_counts, 2 * 2 * kMaxRanks * sizeof(uint32_t)));
+  VM_TRY(dev_alloc(h, (void**)&h->d_sub_counts, 3 * 2 * kMaxRanks * sizeof(uint32_t)));   // one set per scan context
   VM_TRY(dev_alloc(h, (void**)&h->d_lists, sizeof(RecordLists)));
   VM_CUDA(h, cudaMallocHost((void**)&h->h_lists, sizeof(RecordLists)));
   for (auto& e : h->ev_collect) VM_CUDA(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -86,8 +86,10 @@ void peer_release(vmap* h) {
 // are in the round buffer; only its counters are taken and its failure flags turned into errors.
 int peer_retire(vmap* h) {
   if (h->pipe_n <= 0) return VMAP_OK;
-  const bool cur_is_oldest = h->in_flight && (!h->alt.in_flight || h->seq < h->alt.seq);
-  if (!cur_is_oldest) swap_ctx(h);
+  {
+    ScanCtx* oldest = other_in_flight(h, false);
+    if (oldest && (!h->in_flight || oldest->seq < h->seq)) make_current(h, oldest);
+  }
   VM_CUDA(h, cudaEventSynchronize(h->ev_done));
   h->in_flight = false;
   h->pipe_n--;
@@ -235,6 +237,7 @@ int peer_seal(vmap* h) {
   // after the round's packs (the two scan contexts' streams; earlier sub-scans precede these in stream order)
   if (h->in_flight) VM_CUDA(h, cudaStreamWaitEvent(as, h->ev_done, 0));
   if (h->alt.in_flight) VM_CUDA(h, cudaStreamWaitEvent(as, h->alt.ev_done, 0));
+  if (h->alt2.in_flight) VM_CUDA(h, cudaStreamWaitEvent(as, h->alt2.ev_done, 0));
   k_round_publish<<<1, 64, 0, as>>>(h->pt, p, (uint32_t)r);
   k_round_collect<<<1, 128, 0, as>>>(h->pt, p, (uint32_t)r, h->d_round_info + p * kRoundInfoWords);
   h->launches += 2;
@@ -252,9 +255,13 @@ int peer_seal(vmap* h) {
 int peer_insert(vmap* h, const void* src, bool src_on_host, size_t n, size_t stride, int is_dense, const double Tm[16]) {
   if (h->capture) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "key capture is not available with the peer-memory transport (VMAP_DIST_TRANSPORT=nccl)");
   VM_TRY(init_app_stream(h));
-  VM_TRY(pipe_prepare(h));
-  while (h->pipe_n >= 2) VM_TRY(peer_retire(h));
-  if (h->in_flight) swap_ctx(h);
+  const int n_ctx = h->pipe_ctx >= 3 ? 3 : 2;      // scan contexts the generate side rotates through
+  VM_TRY(pipe_prepare(h, n_ctx == 3));
+  while (h->pipe_n >= n_ctx) VM_TRY(peer_retire(h));
+  if (h->in_flight) {                               // the current context is a free one from here on
+    if (!h->alt.in_flight) swap_ctx(h);
+    else swap_ctx2(h);
+  }
   if (h->epoch >= kEpochMax) {
     while (h->pipe_n > 0) VM_TRY(peer_retire(h));
   }
@@ -304,7 +311,7 @@ int peer_insert(vmap* h, const void* src, bool src_on_host, size_t n, size_t str
   VM_TRY(mark_stage(h, 3));
   // the ordered half: this scan's pack comes after the pack of the scan before it (they share the
   // round buffer's cursor)
-  if (h->alt.in_flight) VM_CUDA(h, cudaStreamWaitEvent(h->stream, h->alt.ev_done, 0));
+  if (ScanCtx* prev = other_in_flight(h, true)) VM_CUDA(h, cudaStreamWaitEvent(h->stream, prev->ev_done, 0));
   const uint64_t r = h->round_open;
   const uint32_t p = (uint32_t)(r & 1u), j = (uint32_t)h->sub_open;
   if (j == 0) {
