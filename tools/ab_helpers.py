@@ -46,7 +46,11 @@ KEYS = ("gpu_ms", "front_ms", "resolve_ms", "walk_ms", "update_ms")
 COUNTS = ("traversals", "unique_free", "unique_occupied", "longest_ray", "rays_cast", "occupied_emitted", "blocks_touched")
 
 
+EXTRA = {}                 # further environment switches for the worlds made next
+
+
 def make(helpers, pdl, marks, ctx=3, flush_at=1):
+    os.environ.update(EXTRA)
     os.environ["VMAP_FLUSH_AT"] = str(flush_at)
     os.environ["VMAP_PIPE_CTX"] = str(ctx)
     os.environ["VMAP_HELPERS"] = str(helpers)
@@ -96,6 +100,7 @@ def run_pipe(helpers, pdl, marks, ctx, flush, warm=4, reps=3, flush_at=1):
     return round(best, 5), dg, rep
 
 
+# ---- main (tools/ab_cosched.py executes everything above this line) ----
 out = {"n_scans": n_scans, "res": res, "sync": [], "pipelined": []}
 base = None
 ok = True
@@ -104,6 +109,7 @@ rounds = 3
 SYNC = [(0, 0, None), (1, 123, None), (0, 0, 0), (1, 123, 0)]
 if "--quick" in sys.argv:
     SYNC = SYNC[:2]
+    PIPE_SKIP = True
 acc = {c: [] for c in SYNC}
 for _ in range(rounds):
     for cfg in SYNC:
@@ -142,6 +148,27 @@ for _ in range(rounds):
 for c in FL:
     row = {"flush_at": c[0], "ms_per_scan": round(float(np.median(accf[c])), 5), "min": min(accf[c]), "max": max(accf[c])}
     out["flush_placement"].append(row)
+    print(json.dumps(row), flush=True)
+# K4 variants: k_update<0> (row by row) vs k_update_mlp (rows in flight together, blocks pipelined)
+out["update_variants"] = []
+accu = {v: {"sync": [], "sync_flush": [], "pipe": [], "pipe_flush": []} for v in (0, 2)}
+for _ in range(rounds):
+    for v in (0, 2):
+        EXTRA["VMAP_UPDATE_VARIANT"] = str(v)
+        s0, counts, dg = run_sync(1, 123, None, reps=2)
+        ok = ok and counts == base[0] and dg == base[1]
+        s1, counts, dg = run_sync(1, 123, None, reps=2, flush=256 << 20)
+        ok = ok and counts == base[0] and dg == base[1]
+        accu[v]["sync"].append(s0["update_ms"]); accu[v]["sync_flush"].append(s1["update_ms"])
+        for key, fl in (("pipe", 0), ("pipe_flush", 256 << 20)):
+            ms, dg, rep = run_pipe(1, 123, None, 3, fl, reps=2)
+            ok = ok and dg == base[1]
+            accu[v][key].append(ms)
+EXTRA.pop("VMAP_UPDATE_VARIANT", None)
+for v in (0, 2):
+    row = {"update_variant": v, "update_ms_sync": float(np.median(accu[v]["sync"])), "update_ms_sync_flushed": float(np.median(accu[v]["sync_flush"])),
+           "pipelined_ms": float(np.median(accu[v]["pipe"])), "pipelined_flushed_ms": float(np.median(accu[v]["pipe_flush"]))}
+    out["update_variants"].append(row)
     print(json.dumps(row), flush=True)
 print(json.dumps({"all_identical": ok}), flush=True)
 

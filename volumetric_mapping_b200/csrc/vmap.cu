@@ -197,7 +197,7 @@ struct vmap : ScanCtx {
   int walk_order = 2;     // bit 0: golden-ratio chunk order in the dilated segment walker (VMAP_WALK_ORDER, experimental);
                           // bit 1: counted loops in non-last segments (default; VMAP_WALK_COUNTED=0 turns it off)
   int walk_addr = 9;      // segment walker: 9 dilated addressing + queued 64-voxel marks (default), 7 unqueued, 1 32-voxel words, 0 block addressing, 5 / 8 experiments (VMAP_WALK_ADDR)
-  int update_variant = 0; // experiments (VMAP_UPDATE_VARIANT)
+  int update_variant = 2; // K4: 2 k_update_mlp (default; rows in flight together, blocks pipelined), 0 k_update<0> (row by row; also what change detection uses), 1 experiment (VMAP_UPDATE_VARIANT)
   int pdl = 123;          // VMAP_PDL: programmatic dependent launch along the scan's kernel chain (bit mask kPdl*; default: all but the walker)
   int stage_marks = -1;   // VMAP_STAGE_MARKS: 1 always, 0 never, unset: synchronous scans only
   int flush_at = 1;       // VMAP_FLUSH_AT: where a pipelined scan runs the benchmark's L2 flush (0 scan start, 1 before its update)
@@ -757,7 +757,15 @@ int launch_capture(vmap* h) {
 }
 
 int launch_update(vmap* h) {
-  if (h->update_variant == 1) VM_CUDA(h, launch_chain(h, kPdlUpdate, k_update<1>, g_sm_count(h->device) * 8, 256, h->P, h->m, h->ms, h->d_cnt));
+  if (h->update_variant == 2 && h->m.chg0 == nullptr) {
+    static int per_sm = 0;      // CTAs of k_update_mlp resident per SM
+    if (!per_sm) {
+      int v = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_update_mlp, 256, 0) != cudaSuccess || v < 1) { cudaGetLastError(); v = 4; }
+      per_sm = v;
+    }
+    VM_CUDA(h, launch_chain(h, kPdlUpdate, k_update_mlp, g_sm_count(h->device) * (unsigned)per_sm, 256, h->P, h->m, h->ms, h->d_cnt));
+  } else if (h->update_variant == 1) VM_CUDA(h, launch_chain(h, kPdlUpdate, k_update<1>, g_sm_count(h->device) * 8, 256, h->P, h->m, h->ms, h->d_cnt));
   else VM_CUDA(h, launch_chain(h, kPdlUpdate, k_update<0>, g_sm_count(h->device) * 8, 256, h->P, h->m, h->ms, h->d_cnt));
   h->launches++;
   return VMAP_OK;

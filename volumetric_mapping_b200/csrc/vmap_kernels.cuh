@@ -1138,6 +1138,96 @@ k_update(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
   }
 }
 
+// K4 with the memory accesses of a block in flight together (the default without change detection).
+// k_update<0> walks a block row by row -- load, update, store -- so a warp has ONE 128-byte load in
+// flight at a time and sixteen dependent round trips per block (85 % warps active, 20 warps stalled on
+// long scoreboard per issued instruction, ~55 % of the HBM time for the traffic it moves).  Here a warp
+//   * keeps the list entry of the block after next and the masks + pool slot of the next block in
+//     registers while it works on the current one (two-deep software pipeline over its blocks), and
+//   * issues the loads of every marked row of the current block before the first update.
+// Launched with as many CTAs as are resident at once (the register count is what it is).
+__global__ void __launch_bounds__(256)
+k_update_mlp(DevParams P, MapView m, MarkSet ms, Counters* cnt) {
+  pdl_wait();
+  if (cnt->stall || cnt->overflow_table || cnt->overflow_pool || cnt->overflow_window || cnt->overflow_ckpt ||
+      cnt->overflow_keys)
+    return;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t n_touched = cnt->n_touched;
+  uint32_t lane_free = 0, lane_occ = 0;
+  uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // stage A: list entry; stage B: masks (cleared as they are read) + pool slot
+  uint32_t eA = 0, hA = 0, eB = 0, hB = 0, fB = 0, oB = 0, slotB = 0;
+  auto stage_a = [&](uint32_t tt) {
+    if (tt < n_touched) listed_block(ms, m, tt, &eA, &hA);
+  };
+  auto stage_b = [&](uint32_t tt) {       // from the entry in (eA, hA)
+    eB = eA; hB = hA; fB = 0; oB = 0; slotB = 0;
+    if (tt >= n_touched) return;
+    if (lane < kMaskWords) {
+      uint32_t* pf = ms.free_mask + (size_t)eB * kMaskWords + lane;
+      uint32_t* po = ms.occ_mask + (size_t)eB * kMaskWords + lane;
+      fB = *pf; oB = *po;
+      if (fB) *pf = 0u;
+      if (oB) *po = 0u;
+      fB &= ~oB;  // occupied wins (octomap_world.cc:252-254)
+    }
+    if (lane == 0) slotB = m.slot[hB];
+  };
+  stage_a(t);
+  stage_b(t);
+  stage_a(t + warps);
+  for (; t < n_touched; t += warps) {
+    const uint32_t f = fB, o = oB, h = hB;
+    uint32_t slot = slotB;
+    stage_b(t + warps);
+    stage_a(t + 2u * warps);
+    const uint32_t rows = __ballot_sync(0xFFFFFFFFu, (f | o) != 0u);   // bit j: row j has marks (lanes >= 16 hold 0)
+    if (!rows) continue;   // e.g. every voxel filtered out
+    if (lane == 0 && slot == kUnassigned) {
+      slot = atomicAdd(&m.persist->n_slots, 1u);
+      m.slot[h] = slot;
+    }
+    slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+    uint32_t* vox = reinterpret_cast<uint32_t*>(m.pool) + (size_t)slot * kBlockVoxels;
+    uint32_t val[kMaskWords];
+#pragma unroll
+    for (int j = 0; j < kMaskWords; j++) val[j] = ((rows >> j) & 1u) ? __ldcg(vox + j * 32 + lane) : 0u;
+    lane_free += __popc(f);
+    lane_occ += __popc(o);
+#pragma unroll
+    for (int j = 0; j < kMaskWords; j++) {
+      if (!((rows >> j) & 1u)) continue;
+      const uint32_t fw = __shfl_sync(0xFFFFFFFFu, f, j);
+      const uint32_t ow = __shfl_sync(0xFFFFFFFFu, o, j);
+      const bool is_occ = (ow >> lane) & 1u, is_free = (fw >> lane) & 1u;
+      if (is_occ || is_free) vox[j * 32 + lane] = update_leaf(val[j], is_occ ? P.hit : P.miss, P.cmin, P.cmax);
+    }
+  }
+  for (int o2 = 16; o2 > 0; o2 >>= 1) {
+    lane_free += __shfl_xor_sync(0xFFFFFFFFu, lane_free, o2);
+    lane_occ += __shfl_xor_sync(0xFFFFFFFFu, lane_occ, o2);
+  }
+  __shared__ uint32_t s_stat[2];
+  if (threadIdx.x < 2) s_stat[threadIdx.x] = 0;
+  __syncthreads();
+  if (lane == 0) {
+    if (lane_free) atomicAdd(&s_stat[0], lane_free);
+    if (lane_occ) atomicAdd(&s_stat[1], lane_occ);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_stat[0]) atomicAdd(&cnt->unique_free, s_stat[0]);
+    if (s_stat[1]) atomicAdd(&cnt->unique_occupied, s_stat[1]);
+  }
+  if (ms.dense) {   // (as in k_update: the window's touched bitmap is free for the next scan)
+    const uint32_t n_words = (ms.nx * ms.ny * ms.nz + 31u) >> 5;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x)
+      if (ms.touched_bits[i]) ms.touched_bits[i] = 0u;
+  }
+}
+
 // Drop this scan's marks (used when a scan has to be re-run after a grow).
 __global__ void __launch_bounds__(256) k_clear_masks(MapView m, MarkSet ms, Counters* cnt) {
   const uint32_t total = cnt->n_touched * kMaskWords;
