@@ -400,6 +400,10 @@ VMAP_API void* vmap_stream(vmap* h);
 VMAP_API uint64_t vmap_kernel_launches(const vmap* h);
 /* Device memory currently held by the handle, bytes. */
 VMAP_API uint64_t vmap_device_bytes(const vmap* h);
+/* Duration of the segment walker's launch (K2b, computeRayKeys + KeySet inserts: octomap_world.cc:188-190, 214-216)
+ * in the last SYNCHRONOUS scan (pipeline depth 0), CUDA events directly around that one launch; 0 when the scan
+ * recorded no stage marks.  bench.py's roofline divides the walk's algorithmic bytes by this. */
+VMAP_API double vmap_last_walk_kernel_ms(const vmap* h);
 
 #ifdef __cplusplus
 }

@@ -78,7 +78,7 @@ SYMBOLS = [
     "vmap_query_points", "vmap_query_points_dev", "vmap_query_lines", "vmap_query_lines_dev",
     "vmap_leaf_count", "vmap_export_leaves", "vmap_import_leaves", "vmap_last_scan_stats",
     "vmap_set_debug_capture", "vmap_debug_last_scan_keys", "vmap_logodds_constants",
-    "vmap_stream", "vmap_kernel_launches", "vmap_device_bytes",
+    "vmap_stream", "vmap_kernel_launches", "vmap_device_bytes", "vmap_last_walk_kernel_ms",
     "vmap_set_shard", "vmap_shard_owner", "vmap_shard_record_bytes", "vmap_shard_generate",
     "vmap_shard_generate_dev", "vmap_shard_records", "vmap_shard_apply_dev",
     "vmap_shard_query_points_dev", "vmap_shard_query_lines_dev", "vmap_dist_unique_id",
@@ -155,6 +155,8 @@ def lib():
     L.vmap_kernel_launches.restype = C.c_uint64
     L.vmap_device_bytes.argtypes = [vp]
     L.vmap_device_bytes.restype = C.c_uint64
+    L.vmap_last_walk_kernel_ms.argtypes = [vp]
+    L.vmap_last_walk_kernel_ms.restype = C.c_double
     u64p = C.POINTER(C.c_uint64)
     L.vmap_tree_size.argtypes = [vp, C.c_int, C.POINTER(sz)]
     L.vmap_leaf_digest.argtypes = [vp, u64p, u64p]

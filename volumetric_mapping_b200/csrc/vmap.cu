@@ -63,6 +63,9 @@ struct ScanCtx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // per-kernel timing marks
   bool evk_set[5] = {false, false, false, false, false};
+  cudaEvent_t evw[2] = {nullptr, nullptr};   // around the segment walker's launch alone (synchronous scans with stage marks)
+  bool evw_set = false;
+  float walk_kernel_ms = 0.f;                // ... its duration in the last such scan
   ScanBuffers sb{};
   size_t scan_cap = 0;
   size_t first_cap = 0;
@@ -854,6 +857,9 @@ void fill_stats(vmap* h, uint64_t retries, float ms_total) {
     if (cudaEventElapsedTime(&v, h->evk[a], h->evk[b]) != cudaSuccess) { cudaGetLastError(); return 0.0; }
     return (double)v;
   };
+  h->walk_kernel_ms = 0.f;
+  if (h->evw_set && cudaEventElapsedTime(&h->walk_kernel_ms, h->evw[0], h->evw[1]) != cudaSuccess) { cudaGetLastError(); h->walk_kernel_ms = 0.f; }
+  h->evw_set = false;
   s.front_ms = span(0, 1);
   s.resolve_ms = span(1, 2);
   s.walk_ms = h->evk_set[2] ? span(2, 3) : span(0, 3);
@@ -1009,6 +1015,8 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
     // with queued marks (walk_slot_queued), 8 queued marks built for 4 CTAs / SM.  (Measured and dropped: deferred touched test, 6 CTAs / SM, 64 registers:
     // profiles/r01_ab_walk_variants.json, r02_ab_walk2.json.)
     const bool dilated = h->walk_addr >= 1 && dilated_window_fits(h->ms.nx, h->ms.ny, h->ms.nz);
+    h->evw_set = h->evk_set[2];      // stage marks are being recorded for this scan: time the walker's launch alone as well
+    if (h->evw_set) VM_CUDA(h, cudaEventRecord(h->evw[0], h->stream));
     if (!h->traced && getenv("VMAP_TRACE")) {
       h->traced = true;
       fprintf(stderr, "[vmap] segment walker: %s addressing (mode %d), window %u x %u x %u blocks at (%d, %d, %d), fallbacks so far %llu\n",
@@ -1038,6 +1046,7 @@ int launch_resolve_and_walk(vmap* h, size_t n, const Transform& T) {
   }
   h->launches++;
   VM_CUDA(h, cudaGetLastError());
+  if (h->ms.dense && !h->no_segments && h->evw_set) VM_CUDA(h, cudaEventRecord(h->evw[1], h->stream));
   return VMAP_OK;
 }
 
@@ -1075,6 +1084,8 @@ int init_ctx_resources(vmap* h) {   // for the CURRENT context
   if (!h->ev1) VM_CUDA(h, cudaEventCreate(&h->ev1));
   for (auto& e : h->evk)
     if (!e) VM_CUDA(h, cudaEventCreate(&e));
+  for (auto& e : h->evw)
+    if (!e) VM_CUDA(h, cudaEventCreate(&e));
   if (!h->ev_done) VM_CUDA(h, cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
   if (!h->ev_h2d) VM_CUDA(h, cudaEventCreateWithFlags(&h->ev_h2d, cudaEventDisableTiming));
   if (!h->h_cnt) {
@@ -1106,7 +1117,7 @@ void free_ctx_resources(vmap* h) {  // of the CURRENT context
   if (h->h_persist_snap) cudaFreeHost(h->h_persist_snap);
   h->h_cnt = nullptr;
   h->h_persist_snap = nullptr;
-  cudaEvent_t* evs[] = {&h->ev0, &h->ev1, &h->ev_done, &h->ev_h2d, &h->evk[0], &h->evk[1], &h->evk[2], &h->evk[3], &h->evk[4]};
+  cudaEvent_t* evs[] = {&h->ev0, &h->ev1, &h->ev_done, &h->ev_h2d, &h->evk[0], &h->evk[1], &h->evk[2], &h->evk[3], &h->evk[4], &h->evw[0], &h->evw[1]};
   for (cudaEvent_t* e : evs)
     if (*e) { cudaEventDestroy(*e); *e = nullptr; }
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -2359,6 +2370,7 @@ int vmap_logodds_constants(const vmap* h, float out5[5]) try {
 void* vmap_stream(vmap* h) { return h ? (void*)h->stream : nullptr; }
 uint64_t vmap_kernel_launches(const vmap* h) { return h ? h->launches : 0; }
 uint64_t vmap_device_bytes(const vmap* h) { return h ? h->dev_bytes : 0; }
+double vmap_last_walk_kernel_ms(const vmap* h) { return h ? (double)h->walk_kernel_ms : 0.0; }
 
 }  // extern "C"
 

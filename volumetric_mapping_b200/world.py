@@ -529,6 +529,10 @@ class OctomapWorld:
     def stream(self):
         return int(self._L.vmap_stream(self._h) or 0)
 
+    def last_walk_kernel_ms(self):
+        """Duration of the segment walker's launch alone in the last synchronous scan (0: not recorded)."""
+        return float(self._L.vmap_last_walk_kernel_ms(self._h))
+
     def kernel_launches(self):
         return int(self._L.vmap_kernel_launches(self._h))
 
