@@ -137,6 +137,12 @@ def oracle_world():
     return oracle.OracleWorld(resolution=RESOLUTION, sensor_max_range=MAX_RANGE)
 
 
+def oracle_world_for(params):
+    import oracle  # test infrastructure; legal here (bench.py cpu_baseline leg)
+    oracle.build()
+    return oracle.OracleWorld(**params)
+
+
 def cpu_baseline_sample(budget_s=20.0):
     """Times the oracle on a bounded sample of the same workload: whole scans of the trajectory
     until about `budget_s` seconds of CPU work are done (at least one scan)."""
@@ -440,6 +446,91 @@ def run_b200(args):
         out["non_free_fraction"] = out["uniform"]["non_free_fraction"]
         return out
 
+    def time_queries_sharded(sw, n_scans):
+        """cfg5 on the SHARDED map (N > 1): every GPU assembles a read-only replica of the whole map
+        (ShardedOctomapWorld.replicate: leaves exported on the device, NCCL broadcasts over NVLink,
+        imported in place), then the 1M uniform segments / 1M points are dealt over the ranks in equal
+        slices and the statuses all-gathered -- wall clock around the collective call, max over ranks;
+        the digest of the replica is compared with the sum of the shards'."""
+        t0 = time.perf_counter()
+        leaves = sw.replicate()
+        torch.cuda.synchronize()
+        t_rep = allmax(time.perf_counter() - t0)
+        rep_ok = bool(gather_digest(*sw.local.leaf_digest()) == sw.replica.leaf_digest())
+        bounds = ((-45.0, 45.0 + 0.5 * n_scans), (-45.0, 45.0), (-0.5, 4.0))
+        q = scenes.cfg5_queries(bounds=bounds)
+        seg = torch.from_numpy(np.ascontiguousarray(q["segments"])).cuda()
+        pts = torch.from_numpy(np.ascontiguousarray(q["points"])).cuda()
+        flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+        best_l = best_p = 1e9
+        for rep in range(4):
+            flush.fill_(rep)
+            barrier()
+            t0 = time.perf_counter()
+            sl = sw.getLineStatusSliced(seg)
+            torch.cuda.synchronize()
+            dt = allmax(time.perf_counter() - t0)
+            if rep:
+                best_l = min(best_l, dt)
+        for rep in range(4):
+            flush.fill_(rep + 9)
+            barrier()
+            t0 = time.perf_counter()
+            sw.getCellStatusPointSliced(pts)
+            torch.cuda.synchronize()
+            dt = allmax(time.perf_counter() - t0)
+            if rep:
+                best_p = min(best_p, dt)
+        return {"mode": "read-only replica per GPU + segment slices (SURVEY 8(e)); statuses all-gathered to every rank",
+                "replicate_ms": 1e3 * t_rep, "replica_leaves": leaves, "replica_equals_shards": rep_ok,
+                "segments_per_s": seg.shape[0] / best_l, "line_ms": 1e3 * best_l,
+                "points_per_s": pts.shape[0] / best_p, "point_ms": 1e3 * best_p,
+                "non_free_fraction": float((sl != 0).float().mean().item()),
+                "workload": "cfg5: 1M uniform segments (0.5-20 m) + 1M points vs the sharded 0.1 m map of %d scans" % n_scans}
+
+    def small_configs(with_cpu):
+        """BASELINE.json configs 1 and 2 (the reference's own CPU-runnable cases): ONE insertion of the
+        config's input into an empty 0.15 m map through the reference-facing call with host buffers
+        (vmap_insert_pointcloud with write-back / vmap_insert_disparity), wall clock around call +
+        drain, median of 9 after 3 warm-ups (resetMap between repetitions, outside the clock); the
+        oracle's time for the same single insertion beside it."""
+        out = {}
+        c1, c2 = scenes.cfg1_pointcloud(), scenes.cfg2_disparity()
+        for name, s in (("cfg1", c1), ("cfg2", c2)):
+            w = vm.OctomapWorld(device=local_rank, **s["params"])
+
+            def one(world_obj, s=s, name=name):
+                if name == "cfg1":
+                    world_obj.insertPointcloud(s["T"], s["points"])
+                else:
+                    world_obj.insertDisparityImage(s["q"], s["t"], s["disparity"], s["Q"], s["full_image_size"][0])
+            times = []
+            for rep in range(12):
+                w.resetMap()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                one(w)
+                w.flush()
+                times.append(time.perf_counter() - t0)
+            st = w.last_scan_stats()
+            leaves = w.leaf_count()
+            w.close()
+            t = float(np.median(times[3:]))
+            out[name] = {"ms_per_insert": 1e3 * t, "traversals": int(st["traversals"]), "rays_cast": int(st["rays_cast"]),
+                         "traversals_per_s": st["traversals"] / t, "leaves": int(leaves)}
+            if with_cpu:
+                ow = oracle_world_for(s["params"])
+                t0 = time.perf_counter()
+                one(ow)
+                tc = time.perf_counter() - t0
+                ost = ow.last_scan_stats()
+                out[name]["cpu_ms"] = 1e3 * tc
+                out[name]["cpu_traversals_per_s"] = ost["traversals"] / tc
+                out[name]["same_traversals_as_cpu"] = bool(int(ost["traversals"]) == int(st["traversals"]))
+        out["workload"] = ("cfg1: 10k-point cloud, 0.15 m, 5 m range; cfg2: 480x640 disparity image through Q, 0.15 m, 5 m range; "
+                           "one insertion into an empty map, host buffers, wall clock around call + drain")
+        return out
+
     def map_build(n_scans):
         """BASELINE.json config 4, bounded: n_scans consecutive scans per GPU of the 1000-scan trajectory
         at 0.05 m (about 55 M traversals and 350 k voxel blocks per scan), same timing as the headline."""
@@ -453,7 +544,15 @@ def run_b200(args):
                 "leaves": r["digest"][0], "replayed": r["replayed"], "device_bytes": r["device_bytes"]}
 
     # ---- the runs ----
-    dev = timed_build(RESOLUTION, total, W, "dev", 1 << 19, keep=(world == 1), sample_clocks=True)
+    dev = timed_build(RESOLUTION, total, W, "dev", 1 << 19, keep=True, sample_clocks=True)
+    queries_sharded = None
+    if world > 1:
+        sw0, w0 = dev.pop("world")
+        try:
+            queries_sharded = time_queries_sharded(sw0, total * world)
+        except Exception as e:          # reported in the line, never hides the headline
+            queries_sharded = {"error": repr(e)[:300]}
+        close_world(sw0, w0)
     host = timed_build(RESOLUTION, total, W, "host", 1 << 19)
     parity = None
     if world > 1:
@@ -463,13 +562,14 @@ def run_b200(args):
                   "equal": bool(dev["digest"] == ref and host["digest"] == ref) if rank == 0 else None,
                   "how": "leaf count and order-independent 64-bit digest of (key, log-odds bits), shards summed, "
                          "vs a single-GPU vmap_insert_pointcloud_dev build of the same %d scans" % (total * world)}
-    queries = dropin = stages = None
+    queries = dropin = stages = small = None
     if world == 1:
         sw0, w0 = dev.pop("world")
         queries = time_queries(w0, total)
         close_world(sw0, w0)
         dropin = timed_build(RESOLUTION, total, W, "dropin", 1 << 19, stride=16, writeback=True)
         stages = stage_pass(min(total, W + 12), W)
+        small = small_configs(with_cpu=(rank == 0 and not args.no_cpu_baseline))
     mb = map_build(args.map_build_scans) if args.map_build_scans > 0 else None
 
     if rank == 0:
@@ -545,7 +645,9 @@ def run_b200(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "queries": queries,
+            "queries_sharded": queries_sharded,
             "map_build": mb,
+            "small_configs": small,
             "parity": parity,
             "device_bytes": dev["device_bytes"],
             "scans_replayed_after_growth": dev["replayed"],

@@ -251,6 +251,14 @@ VMAP_API int vmap_export_leaves(vmap* h, uint16_t* keys_k3, float* logodds, size
 VMAP_API int vmap_leaf_digest(vmap* h, uint64_t* n_leaves, uint64_t* digest);
 /* Inverse (loadOctomapFromFile / setOctomapFromMsg feed): sets leaf values, no clamping. */
 VMAP_API int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds, size_t n);
+/* Both with DEVICE buffers (memory of the handle's GPU), no host round trip: how a read-only
+ * replica of a sharded map is assembled on every GPU for query batches (SURVEY 8(e) "gather then
+ * query on every GPU over a segment slice"; the reference's queries, octomap_world.cc:346-360 and
+ * :395-418, see one whole tree). */
+VMAP_API int vmap_export_leaves_dev(vmap* h, uint16_t* d_keys_k3, float* d_logodds, size_t capacity,
+                                    size_t* n);
+VMAP_API int vmap_import_leaves_dev(vmap* h, const uint16_t* d_keys_k3, const float* d_logodds,
+                                    size_t n);
 
 /* On-demand export to octomap's tree form, built on the host from the finest-level leaves:
  * canonical pruned tree (8 equal leaf children collapse; inner value = max of children). */

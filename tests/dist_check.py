@@ -45,6 +45,11 @@ def main():
     sl = torch.zeros(seg.shape[0], dtype=torch.uint8, device="cuda")
     w.local.dist_query_points_device(pts.data_ptr(), pts.shape[0], sp.data_ptr())
     w.local.dist_query_lines_device(seg.data_ptr(), seg.shape[0], sl.data_ptr())
+    # the sliced query mode: a read-only replica of the whole map on every GPU, queries dealt over the ranks
+    n_rep = w.replicate()
+    sp2 = w.getCellStatusPointSliced(pts)
+    sl2 = w.getLineStatusSliced(seg)
+    rep_n, rep_d = w.replica.leaf_digest()
     # gather leaves on rank 0
     packed = torch.from_numpy(oracle.pack_keys(k).astype(np.int64)).cuda()
     vals = torch.from_numpy(v.view(np.int32).copy()).cuda()
@@ -71,7 +76,10 @@ def main():
         p0 = oracle.pack_keys(k0); o0 = np.argsort(p0)
         ok = (np.array_equal(allk[o], p0[o0]) and np.array_equal(allv[o], v0.view(np.uint32)[o0])
               and np.array_equal(sp.cpu().numpy(), ow.getCellStatusPoint(q["points"]))
-              and np.array_equal(sl.cpu().numpy(), ow.getLineStatus(q["segments"])))
+              and np.array_equal(sl.cpu().numpy(), ow.getLineStatus(q["segments"]))
+              and n_rep == allk.shape[0] and (rep_n, rep_d) == sharded.leaf_digest(k0, v0)
+              and np.array_equal(sp2.cpu().numpy(), sp.cpu().numpy())
+              and np.array_equal(sl2.cpu().numpy(), sl.cpu().numpy()))
         print("DIST_CHECK_OK" if ok else "DIST_CHECK_MISMATCH", allk.shape[0], flush=True)
     dist.barrier()
     w.close()

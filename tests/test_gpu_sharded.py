@@ -91,6 +91,48 @@ def test_sharded_hdl64_scans_and_queries():
     assert np.array_equal(got_l, ow.getLineStatus(q["segments"]))
 
 
+def test_replica_of_the_shards_equals_the_oracle_map_and_answers_queries():
+    """The sliced query mode's replica (SURVEY 8(e) "gather then query on every GPU over a segment
+    slice"): the shards' leaves move device to device (vmap_export_leaves_dev /
+    vmap_import_leaves_dev) into one single-GPU map, which must equal the oracle's map bit for bit
+    and answer getCellStatusPoint / getLineStatus like it."""
+    import torch
+    G = 3
+    params = dict(resolution=0.2, sensor_max_range=50.0)
+    scans = [scenes.trajectory_scan(3 * i, resolution=0.2) for i in range(4)]
+    shards, ow = run_rounds(G, scans, params)
+    rep = sharded.build_replica(shards, initial_blocks=64)        # small on purpose: table and pool grow in the import
+    n_sum = sum(w.leaf_digest()[0] for w in shards)
+    d_sum = sum(w.leaf_digest()[1] for w in shards) % (1 << 64)
+    assert rep.leaf_digest() == (n_sum, d_sum)
+    gk, gv = leaves_packed(*rep.export_leaves())
+    ok, ov = leaves_packed(*ow.export_leaves())
+    assert np.array_equal(gk, ok) and np.array_equal(gv, ov)
+    q = scenes.cfg5_queries(n_segments=60000, n_points=60000)
+    pts = torch.from_numpy(q["points"]).cuda()
+    seg = torch.from_numpy(q["segments"]).cuda()
+    want_p, want_l = ow.getCellStatusPoint(q["points"]), ow.getLineStatus(q["segments"])
+    got_p = torch.zeros(pts.shape[0], dtype=torch.uint8, device="cuda")
+    got_l = torch.zeros(seg.shape[0], dtype=torch.uint8, device="cuda")
+    for r in range(G):                   # every "rank" answers its slice on the replica
+        lo, hi = sharded.query_slice(pts.shape[0], r, G)
+        rep.getCellStatusPointDevice(pts[lo:hi].data_ptr(), hi - lo, got_p[lo:].data_ptr())
+        lo, hi = sharded.query_slice(seg.shape[0], r, G)
+        rep.getLineStatusDevice(seg[lo:hi].data_ptr(), hi - lo, got_l[lo:].data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(got_p.cpu().numpy(), want_p)
+    assert np.array_equal(got_l.cpu().numpy(), want_l)
+    # capacity too small: an error, nothing written past the buffer
+    small = torch.zeros(6 * 8, dtype=torch.uint8, device="cuda")
+    smallv = torch.zeros(8, dtype=torch.float32, device="cuda")
+    with pytest.raises(vm.VmapError):
+        rep.export_leaves_device(small.data_ptr(), smallv.data_ptr(), 8)
+    empty = vm.OctomapWorld(**params)
+    assert empty.export_leaves_device(0, 0, 0) == 0
+    empty.import_leaves_device(0, 0, 0)
+    assert empty.leaf_count() == 0
+
+
 @pytest.mark.parametrize("G,batch,n_scans", [(2, 1, 5), (3, 2, 10), (4, 4, 19)])
 def test_peer_memory_transport_emulated_on_one_gpu(G, batch, n_scans):
     """The peer-memory exchange (round buffers, publish / collect / consumed flags, applies that read

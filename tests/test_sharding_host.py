@@ -41,6 +41,17 @@ def test_scan_dealing_covers_all_scans_in_round_order():
         assert order == list(range(n))
 
 
+def test_query_slices_partition_the_batch():
+    for n in (0, 1, 7, 8, 9, 1000, 1_000_003):
+        for world in (1, 2, 3, 8):
+            cuts = [sharded.query_slice(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(lo <= hi for lo, hi in cuts)
+            assert all(cuts[r][1] == cuts[r + 1][0] for r in range(world - 1))
+            per = (n + world - 1) // world
+            assert all(hi - lo <= per for lo, hi in cuts)
+
+
 def test_id_broadcast_over_gloo_world_size_2():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517",

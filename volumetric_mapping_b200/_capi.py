@@ -91,6 +91,7 @@ SYMBOLS = [
     "vmap_load_occupied_pointcloud_file", "vmap_insert_occupied_points", "vmap_host_read_pointcloud_file",
     "vmap_leaf_digest", "vmap_query_lines_probes_dev",
     "vmap_dist_attach_local", "vmap_dist_flush_begin",
+    "vmap_export_leaves_dev", "vmap_import_leaves_dev",
     "vmap_flush", "vmap_set_pipeline_depth", "vmap_totals", "vmap_region_begin", "vmap_region_end",
 ]
 
@@ -145,6 +146,8 @@ def lib():
     L.vmap_leaf_count.argtypes = [vp, C.POINTER(sz)]
     L.vmap_export_leaves.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
     L.vmap_import_leaves.argtypes = [vp, vp, vp, sz]
+    L.vmap_export_leaves_dev.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+    L.vmap_import_leaves_dev.argtypes = [vp, vp, vp, sz]
     L.vmap_last_scan_stats.argtypes = [vp, C.POINTER(ScanStats)]
     L.vmap_set_debug_capture.argtypes = [vp, C.c_int]
     L.vmap_debug_last_scan_keys.argtypes = [vp, vp, sz, C.POINTER(sz), vp, sz, C.POINTER(sz)]

@@ -2241,6 +2241,21 @@ int vmap_export_leaves(vmap* h, uint16_t* keys_k3, float* logodds_out, size_t ca
   return VMAP_OK;
 } catch (...) { return vmap_on_exception(h); }
 
+// The same leaves straight into the caller's DEVICE buffers (no host round trip): the feed of a
+// read-only replica on another GPU (volumetric_mapping_b200.sharded.ShardedOctomapWorld.replicate).
+int vmap_export_leaves_dev(vmap* h, uint16_t* d_keys_k3, float* d_logodds, size_t capacity, size_t* n) try {
+  if (!h || !n) return VMAP_ERR_INVALID_ARGUMENT;
+  VM_CUDA(h, cudaSetDevice(h->device));
+  size_t total = 0;
+  VM_TRY(count_leaves(h, nullptr, nullptr, 0, &total));
+  *n = total;
+  if (total == 0) return VMAP_OK;
+  if (capacity < total || !d_keys_k3 || !d_logodds) return fail(h, VMAP_ERR_BUFFER_TOO_SMALL, "export buffers too small; *n holds the leaf count");
+  if (total > 0xFFFFFFFFull) return fail(h, VMAP_ERR_CAPACITY, "too many leaves for one export");
+  size_t again = 0;
+  return count_leaves(h, d_keys_k3, d_logodds, (uint32_t)total, &again);
+} catch (...) { return vmap_on_exception(h); }
+
 int vmap_leaf_digest(vmap* h, uint64_t* n_leaves, uint64_t* digest) try {
   if (!h || !n_leaves || !digest) return VMAP_ERR_INVALID_ARGUMENT;
   VM_CUDA(h, cudaSetDevice(h->device));
@@ -2258,22 +2273,28 @@ int vmap_leaf_digest(vmap* h, uint64_t* n_leaves, uint64_t* digest) try {
   return VMAP_OK;
 } catch (...) { return vmap_on_exception(h); }
 
-int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in, size_t n) try {
+static int import_leaves_common(vmap* h, const uint16_t* keys_k3, const float* logodds_in, size_t n, bool on_device) {
   if (!h || ((!keys_k3 || !logodds_in) && n)) return h ? fail(h, VMAP_ERR_INVALID_ARGUMENT, "null argument") : VMAP_ERR_INVALID_ARGUMENT;
   if (n > 0x7FFFFFFFull) return fail(h, VMAP_ERR_INVALID_ARGUMENT, "too many leaves");
   VM_CUDA(h, cudaSetDevice(h->device));
   VM_TRY(flush_app(h));
   if (!n) return VMAP_OK;
-  VM_TRY(ensure(h, &h->in, n * 6));
-  VM_TRY(ensure(h, &h->aux, n * 4));
-  VM_CUDA(h, cudaMemcpyAsync(h->in.p, keys_k3, n * 6, cudaMemcpyHostToDevice, h->stream));
-  VM_CUDA(h, cudaMemcpyAsync(h->aux.p, logodds_in, n * 4, cudaMemcpyHostToDevice, h->stream));
+  const uint16_t* d_k3 = keys_k3;
+  const float* d_val = logodds_in;
+  if (!on_device) {
+    VM_TRY(ensure(h, &h->in, n * 6));
+    VM_TRY(ensure(h, &h->aux, n * 4));
+    VM_CUDA(h, cudaMemcpyAsync(h->in.p, keys_k3, n * 6, cudaMemcpyHostToDevice, h->stream));
+    VM_CUDA(h, cudaMemcpyAsync(h->aux.p, logodds_in, n * 4, cudaMemcpyHostToDevice, h->stream));
+    d_k3 = (const uint16_t*)h->in.p;
+    d_val = (const float*)h->aux.p;
+  }
   for (int attempt = 0; attempt < 40; attempt++) {
     VM_TRY(next_epoch(h));
     VM_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(Counters), h->stream));
-    k_touch_keys<<<grid_for(n, 256), 256, 0, h->stream>>>(h->m, h->d_cnt, (const uint16_t*)h->in.p, (uint32_t)n);
+    k_touch_keys<<<grid_for(n, 256), 256, 0, h->stream>>>(h->m, h->d_cnt, d_k3, (uint32_t)n);
     k_assign_slots<<<grid_for(h->table_cap, 256), 256, 0, h->stream>>>(h->m, h->d_cnt);
-    k_write_leaves<<<grid_for(n, 256), 256, 0, h->stream>>>(h->m, h->d_cnt, (const uint16_t*)h->in.p, (const float*)h->aux.p, (uint32_t)n);
+    k_write_leaves<<<grid_for(n, 256), 256, 0, h->stream>>>(h->m, h->d_cnt, d_k3, d_val, (uint32_t)n);
     h->launches += 3;
     VM_CUDA(h, cudaGetLastError());
     VM_TRY(read_counters(h));
@@ -2289,6 +2310,15 @@ int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in
     return VMAP_OK;
   }
   return fail(h, VMAP_ERR_CAPACITY, "import could not be applied after repeated growth");
+}
+
+int vmap_import_leaves(vmap* h, const uint16_t* keys_k3, const float* logodds_in, size_t n) try {
+  return import_leaves_common(h, keys_k3, logodds_in, n, false);
+} catch (...) { return vmap_on_exception(h); }
+
+// Leaves that already sit in device memory (of this GPU): read in place.
+int vmap_import_leaves_dev(vmap* h, const uint16_t* d_keys_k3, const float* d_logodds, size_t n) try {
+  return import_leaves_common(h, d_keys_k3, d_logodds, n, true);
 } catch (...) { return vmap_on_exception(h); }
 
 // OctomapWorld::getChangedPoints (octomap_world.cc:1413-1440): the keys octomap's change detection

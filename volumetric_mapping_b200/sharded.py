@@ -17,6 +17,13 @@ def scans_of_rank(n_scans, rank, world):
     return [k * world + rank if k * world + rank < n_scans else -1 for k in range(rounds)]
 
 
+def query_slice(n, rank, world):
+    """[lo, hi) of n batched queries that rank `rank` answers in the sliced query mode (equal
+    contiguous slices, the last ones may be short or empty)."""
+    per = (n + world - 1) // world
+    return min(rank * per, n), min((rank + 1) * per, n)
+
+
 def owner_of_keys(keys_k3, world):
     """Owner rank of each key (host mirror of vmap_shard_owner, vectorised)."""
     k = np.asarray(keys_k3, dtype=np.uint64).reshape(-1, 3) >> np.uint64(3)
@@ -49,6 +56,27 @@ def leaf_digest(keys_k3, logodds):
     return int(len(bits)), int(d)
 
 
+def build_replica(shards, device=-1, **kw):
+    """Non-collective form of ShardedOctomapWorld.replicate for shards that live in ONE process on
+    one GPU (the single-GPU emulation of the sharded path): a new single-GPU OctomapWorld holding the
+    union of the shards' leaves, moved device to device."""
+    import torch
+    counts = [w.leaf_count() for w in shards]
+    total = sum(counts)
+    keys = torch.empty(6 * max(total, 1), dtype=torch.uint8, device="cuda")       # 3 x uint16 per leaf
+    vals = torch.empty(max(total, 1), dtype=torch.float32, device="cuda")
+    lo = 0
+    for w, c in zip(shards, counts):
+        if c:
+            assert w.export_leaves_device(keys[6 * lo:].data_ptr(), vals[lo:].data_ptr(), c) == c
+        lo += c
+    torch.cuda.synchronize()
+    rep = OctomapWorld(params=shards[0].getOctomapParameters(), device=device, **kw)
+    if total:
+        rep.import_leaves_device(keys.data_ptr(), vals.data_ptr(), total)
+    return rep
+
+
 def broadcast_id(make_id, rank, dist=None, device=None):
     """Rank 0 creates the 128-byte NCCL id, everybody receives it through torch.distributed."""
     import torch
@@ -67,6 +95,8 @@ class ShardedOctomapWorld:
     def __init__(self, rank, world, device, batch=1, **kw):
         import torch.distributed as dist
         self.rank, self.world = rank, world
+        self._device = device
+        self.replica = None
         self.local = OctomapWorld(device=device, **kw)
         import torch
         ident = broadcast_id(OctomapWorld.dist_unique_id, rank, dist,
@@ -83,6 +113,79 @@ class ShardedOctomapWorld:
         self.local.dist_insert_pointcloud(T if T is not None else np.eye(4),
                                           xyz if xyz is not None else np.zeros((0, 3), np.float32))
 
+    # -- queries that scale: a read-only replica per GPU, segments sliced over the ranks ------------
+    # ("gather then query on every GPU over a segment slice".  The collective queries
+    # vmap_dist_query_* need no replica but make every rank walk every segment.)
+    def replicate(self):
+        """COLLECTIVE.  Every rank ends up with a read-only single-GPU copy of the WHOLE map
+        (self.replica): each shard exports its leaves into its slice of one device buffer
+        (vmap_export_leaves_dev), the slices travel by NCCL broadcast over NVLink, and the buffer is
+        imported in place (vmap_import_leaves_dev).  Call again after further insertions."""
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self._device)
+        self.local.dist_flush()
+        mine = self.local.leaf_count()
+        counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(self.world)]
+        dist.all_gather(counts, torch.tensor([mine], dtype=torch.int64, device=dev))
+        counts = [int(c.item()) for c in counts]
+        offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        total = int(offs[-1])
+        keys = torch.empty(6 * max(total, 1), dtype=torch.uint8, device=dev)      # 3 x uint16 per leaf
+        vals = torch.empty(max(total, 1), dtype=torch.float32, device=dev)
+        lo = int(offs[self.rank])
+        if mine:
+            got = self.local.export_leaves_device(keys[6 * lo:].data_ptr(), vals[lo:].data_ptr(), mine)
+            assert got == mine
+        torch.cuda.synchronize(dev)
+        for r in range(self.world):
+            a, b = int(offs[r]), int(offs[r + 1])
+            if b > a:
+                dist.broadcast(keys[6 * a:6 * b], src=r)
+                dist.broadcast(vals[a:b], src=r)
+        torch.cuda.synchronize(dev)
+        if self.replica is not None:
+            self.replica.close()
+        blocks = 1
+        while blocks * 64 < total:        # a block rarely holds fewer than 64 known voxels; grows on demand anyway
+            blocks *= 2
+        self.replica = OctomapWorld(params=self.local.getOctomapParameters(), device=self._device,
+                                    initial_blocks=max(blocks, 1 << 10))
+        if total:
+            self.replica.import_leaves_device(keys.data_ptr(), vals.data_ptr(), total)
+        return total
+
+    def slice_of(self, n):
+        """[lo, hi) of n queries that this rank answers."""
+        return query_slice(n, self.rank, self.world)
+
+    def _sliced(self, call, q, n):
+        import torch
+        import torch.distributed as dist
+        if self.replica is None:
+            raise RuntimeError("replicate() first")
+        per = (n + self.world - 1) // self.world
+        out = torch.zeros(per * self.world, dtype=torch.uint8, device=q.device)
+        lo, hi = self.slice_of(n)
+        if hi > lo:
+            call(q[lo:hi].data_ptr(), hi - lo, out[lo:].data_ptr())
+        torch.cuda.synchronize(q.device)
+        dist.all_gather_into_tensor(out, out[self.rank * per:(self.rank + 1) * per].clone())
+        return out[:n]
+
+    def getLineStatusSliced(self, segments):
+        """COLLECTIVE.  getLineStatus (octomap_world.cc:395-418) for an (n, 6) float64 CUDA tensor that
+        every rank holds: rank r walks segments [r*per, (r+1)*per) on its replica; all ranks get all n
+        statuses (uint8 CUDA tensor)."""
+        return self._sliced(self.replica.getLineStatusDevice, segments, segments.shape[0])
+
+    def getCellStatusPointSliced(self, points):
+        """COLLECTIVE.  getCellStatusPoint (octomap_world.cc:346-360), sliced the same way."""
+        return self._sliced(self.replica.getCellStatusPointDevice, points, points.shape[0])
+
     def close(self):
+        if self.replica is not None:
+            self.replica.close()
+            self.replica = None
         self.local.dist_shutdown()
         self.local.close()

@@ -438,6 +438,17 @@ class OctomapWorld:
                                                C.byref(got)))
         return k[: got.value], v[: got.value]
 
+    def export_leaves_device(self, keys_ptr, logodds_ptr, capacity):
+        """Leaves straight into device buffers (capacity x 3 uint16 keys, capacity float32 values) of
+        this handle's GPU; returns the leaf count (VMAP_ERR_BUFFER_TOO_SMALL when capacity is too small)."""
+        n = C.c_size_t(0)
+        self._check(self._L.vmap_export_leaves_dev(self._h, C.c_void_p(int(keys_ptr)), C.c_void_p(int(logodds_ptr)),
+                                                   int(capacity), C.byref(n)))
+        return int(n.value)
+
+    def import_leaves_device(self, keys_ptr, logodds_ptr, n):
+        self._check(self._L.vmap_import_leaves_dev(self._h, C.c_void_p(int(keys_ptr)), C.c_void_p(int(logodds_ptr)), int(n)))
+
     def leaf_digest(self):
         """(number of leaves, order-independent 64-bit digest of (key, value bits)); see
         sharded.leaf_digest for the host mirror."""
