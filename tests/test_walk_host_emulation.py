@@ -33,11 +33,14 @@ LIB = os.path.join(NATIVE, "libwalk_check.so")
 def lib():
     deps = [SRC, os.path.join(NATIVE, "cuda_host_shim.h")] + [os.path.join(CSRC, f) for f in
                                                                ("vmap_device.cuh", "vmap_seq.cuh", "vmap_walk.cuh")]
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+    # VMAP_TEST_SEG_STEPS=N: the same checks for another segment length (tools/ab_segsteps.py variants)
+    seg = os.environ.get("VMAP_TEST_SEG_STEPS")
+    out = LIB if not seg else os.path.join(NATIVE, "libwalk_check_seg%d.so" % int(seg))
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
-                               "-DVMAP_HOST_EMULATION", "-include", os.path.join(NATIVE, "cuda_host_shim.h"),
-                               "-x", "c++", SRC, "-o", LIB])
-    L = C.CDLL(LIB)
+                               "-DVMAP_HOST_EMULATION"] + (["-DVMAP_SEG_STEPS=%d" % int(seg)] if seg else []) +
+                              ["-include", os.path.join(NATIVE, "cuda_host_shim.h"), "-x", "c++", SRC, "-o", out])
+    L = C.CDLL(out)
     vp = C.c_void_p
     L.wc_ray_keys.argtypes = [C.c_double, vp, vp, vp, C.c_uint32]
     L.wc_ray_keys.restype = C.c_uint32
