@@ -3,6 +3,7 @@
 // Exits non-zero when a hand-derived known answer (tests/test_oracle_insertion.py) is not met.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <sstream>
 
 #include "volumetric_mapping_b200/octomap_world.h"
@@ -90,6 +91,33 @@ int main() {
   EXPECT(other.loadOctomapFromFile("/tmp/vmap_demo.bt"));
   std::ostringstream bt2;
   EXPECT(other.writeOctomapToBinaryConst(bt2) && bt2.str() == bt.str());
+  // the two message forms (octomap_world.cc:820-844): binary = the .bt node stream without its header,
+  // full = OcTree::writeData; a world of another resolution takes the message's
+  OctomapMsg bin_msg, full_msg;
+  EXPECT(world.getOctomapBinaryMsg(&bin_msg) && bin_msg.binary && bin_msg.id == "OcTree" && bin_msg.resolution == 0.1);
+  EXPECT(!bin_msg.data.empty() && bin_msg.data.size() < bt.str().size());
+  EXPECT(std::memcmp(bin_msg.data.data(), bt.str().data() + (bt.str().size() - bin_msg.data.size()), bin_msg.data.size()) == 0);
+  OctomapWorld from_bin;                       // 0.15 m by default
+  from_bin.setOctomapFromMsg(bin_msg);
+  EXPECT(from_bin.getResolution() == 0.1);
+  std::ostringstream bt3;
+  EXPECT(from_bin.writeOctomapToBinaryConst(bt3) && bt3.str() == bt.str());
+  EXPECT(world.getOctomapFullMsg(&full_msg) && !full_msg.binary && full_msg.resolution == 0.1);
+  OctomapWorld from_full;
+  from_full.setOctomapFromMsg(full_msg);
+  EXPECT(from_full.getResolution() == 0.1);
+  OctomapMsg full_again;
+  EXPECT(from_full.getOctomapFullMsg(&full_again) && full_again.data == full_msg.data);
+  std::vector<OcTreeKey> keys2;
+  std::vector<float> lo2;
+  world.exportLeaves(&keys, &lo);
+  from_full.exportLeaves(&keys2, &lo2);
+  EXPECT(keys2.size() == keys.size() && !keys.empty());
+  // box edits: setOccupied writes the clamping maximum, setFree the minimum (octomap_world.cc:497-523)
+  world.setOccupied(Vector3d(2.05, 2.05, 2.05), Vector3d(0.3, 0.3, 0.3));
+  EXPECT(world.getCellStatusPoint(Vector3d(2.05, 2.05, 2.05)) == WorldBase::kOccupied);
+  world.setFree(Vector3d(2.05, 2.05, 2.05), Vector3d(0.3, 0.3, 0.3));
+  EXPECT(world.getCellStatusPoint(Vector3d(2.05, 2.05, 2.05)) == WorldBase::kFree);
   world.resetMap();
   world.exportLeaves(&keys, &lo);
   EXPECT(keys.empty());

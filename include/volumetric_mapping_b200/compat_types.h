@@ -31,6 +31,12 @@ using OcTreeKey = octomap::OcTreeKey;
 using KeySet = octomap::KeySet;
 }  // namespace compat
 }  // namespace volumetric_mapping
+#include <octomap_msgs/Octomap.h>
+namespace volumetric_mapping {
+namespace compat {
+using OctomapMsg = octomap_msgs::Octomap;
+}  // namespace compat
+}  // namespace volumetric_mapping
 #else
 
 #include <stddef.h>
@@ -38,6 +44,7 @@ using KeySet = octomap::KeySet;
 
 #include <cmath>
 #include <memory>
+#include <string>
 #include <unordered_set>
 #include <vector>
 
@@ -158,6 +165,14 @@ struct OcTreeKey {   // octomap::OcTreeKey
   };
 };
 typedef std::unordered_set<OcTreeKey, OcTreeKey::KeyHash> KeySet;
+
+struct OctomapMsg {   // octomap_msgs::Octomap without the ROS header: what binaryMapToMsg / fullMapToMsg fill
+  bool binary;
+  std::string id;
+  double resolution;
+  std::vector<int8_t> data;
+  OctomapMsg() : binary(false), resolution(0.0) {}
+};
 
 }  // namespace compat
 }  // namespace volumetric_mapping

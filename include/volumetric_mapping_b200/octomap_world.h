@@ -6,6 +6,8 @@
 #ifndef VOLUMETRIC_MAPPING_B200_OCTOMAP_WORLD_H_
 #define VOLUMETRIC_MAPPING_B200_OCTOMAP_WORLD_H_
 
+#include <cstdio>
+#include <cstring>
 #include <ostream>
 #include <iostream>
 #include <stdexcept>
@@ -19,6 +21,7 @@ namespace volumetric_mapping {
 
 using compat::KeySet;
 using compat::OcTreeKey;
+using compat::OctomapMsg;
 
 // octomap_world.h:43-52
 enum BoundHandling { kDefault, kIncludePartialBoxes, kIgnorePartialBoxes };
@@ -223,7 +226,11 @@ class OctomapWorld : public WorldBase {
 
   // octomap_world.cc:846-856.  writeOctomapToFile thresholds the live map like
   // OcTree::writeBinary(filename) does (toMaxLikelihood + prune before writing).
-  bool loadOctomapFromFile(const std::string& filename) { return vmap_load_bt(handle_, filename.c_str()) == VMAP_OK; }
+  bool loadOctomapFromFile(const std::string& filename) {
+    const bool ok = vmap_load_bt(handle_, filename.c_str()) == VMAP_OK;
+    refreshResolution();
+    return ok;
+  }
   bool writeOctomapToFile(const std::string& filename) { return vmap_write_bt(handle_, filename.c_str(), 1) == VMAP_OK; }
   // OctomapManager::loadOctomapCallback's .pcd / .ply branch (octomap_manager.cc:313-344): the
   // file's points become occupied keys, the free set stays empty.
@@ -238,6 +245,43 @@ class OctomapWorld : public WorldBase {
     s.write(reinterpret_cast<const char*>(buf.data()), (std::streamsize)n);
     return s.good();
   }
+  // octomap_world.cc:820-825: octomap_msgs::binaryMapToMsg -- id, resolution and the ".bt" node stream
+  // WITHOUT its text header (OcTree::writeBinaryData) as the payload.
+  bool getOctomapBinaryMsg(OctomapMsg* msg) const {
+    if (!msg) throw std::invalid_argument("getOctomapBinaryMsg: null message");
+    size_t n = 0;
+    if (vmap_serialize_bt(handle_, nullptr, 0, &n) != VMAP_OK) return false;
+    std::vector<uint8_t> buf(n ? n : 1);
+    if (vmap_serialize_bt(handle_, buf.data(), buf.size(), &n) != VMAP_OK) return false;
+    static const char kData[] = "\ndata\n";
+    size_t body = n;
+    for (size_t i = 0; i + 6 <= n; i++)
+      if (std::memcmp(buf.data() + i, kData, 6) == 0) { body = i + 6; break; }
+    msg->binary = true;
+    msg->id = "OcTree";
+    msg->resolution = params_.resolution;
+    msg->data.assign(reinterpret_cast<const int8_t*>(buf.data()) + body, reinterpret_cast<const int8_t*>(buf.data()) + n);
+    return true;
+  }
+  // octomap_world.cc:826-831: octomap_msgs::fullMapToMsg -- OcTree::writeData as the payload.
+  bool getOctomapFullMsg(OctomapMsg* msg) const {
+    if (!msg) throw std::invalid_argument("getOctomapFullMsg: null message");
+    size_t n = 0;
+    if (vmap_serialize_ot(handle_, 0, nullptr, 0, &n) != VMAP_OK) return false;
+    std::vector<uint8_t> buf(n ? n : 1);
+    if (vmap_serialize_ot(handle_, 0, buf.data(), buf.size(), &n) != VMAP_OK) return false;
+    msg->binary = false;
+    msg->id = "OcTree";
+    msg->resolution = params_.resolution;
+    msg->data.assign(reinterpret_cast<const int8_t*>(buf.data()), reinterpret_cast<const int8_t*>(buf.data()) + n);
+    return true;
+  }
+  // octomap_world.cc:833-839
+  void setOctomapFromMsg(const OctomapMsg& msg) {
+    if (msg.binary) setOctomapFromBinaryMsg(msg);
+    else setOctomapFromFullMsg(msg);
+  }
+
   // octree_->prune(); octree_->size()
   size_t getNumNodesPruned() const {
     size_t n = 0;
@@ -284,9 +328,52 @@ class OctomapWorld : public WorldBase {
                                 Q_full.m, full_image_size.x(), sensor_to_world.quaternion_wxyz(), t.v));
   }
 
+  // octomap_world.cc:781-818: manually affect the probabilities of areas within a bounding box
+  // (protected in the reference as well; setFree / setOccupied pass the clamping thresholds).
+  void setLogOddsBoundingBox(const Vector3d& position, const Vector3d& bounding_box_size, double log_odds_value,
+                             const BoundHandling& insertion_method = kDefault) {
+    check(vmap_set_log_odds_bbox(handle_, position.v, 1, bounding_box_size.v, log_odds_value, insertion_method));
+  }
+  void setLogOddsBoundingBox(const std::vector<Vector3d>& positions, const Vector3d& bounding_box_size,
+                             double log_odds_value, const BoundHandling& insertion_method = kDefault) {
+    if (positions.empty()) return;
+    std::vector<double> xyz(3 * positions.size());
+    for (size_t i = 0; i < positions.size(); i++) {
+      xyz[3 * i] = positions[i].x(); xyz[3 * i + 1] = positions[i].y(); xyz[3 * i + 2] = positions[i].z();
+    }
+    check(vmap_set_log_odds_bbox(handle_, xyz.data(), positions.size(), bounding_box_size.v, log_odds_value, insertion_method));
+  }
+  // octomap_world.cc:841-844 (binaryMsgToMap): the payload is the node stream of a ".bt" file; the tree takes
+  // the message's resolution.
+  void setOctomapFromBinaryMsg(const OctomapMsg& msg) {
+    char head[160];
+    const int n_head = std::snprintf(head, sizeof(head), "# Octomap OcTree binary file\nid OcTree\nsize %zu\nres %.17g\ndata\n",
+                                     msg.data.empty() ? (size_t)0 : (size_t)1, msg.resolution);
+    std::vector<uint8_t> buf(head, head + n_head);
+    buf.insert(buf.end(), reinterpret_cast<const uint8_t*>(msg.data.data()),
+               reinterpret_cast<const uint8_t*>(msg.data.data()) + msg.data.size());
+    if (vmap_deserialize_bt(handle_, buf.data(), buf.size()) != VMAP_OK) std::cerr << "Could not read the binary octomap message!\n";
+    refreshResolution();
+  }
+  // octomap_world.cc:845-848 (fullMsgToMap): OcTree::readData on a tree of the message's resolution.
+  void setOctomapFromFullMsg(const OctomapMsg& msg) {
+    if (msg.resolution != params_.resolution) {     // a new tree of that resolution
+      params_.resolution = msg.resolution;
+      setOctomapParameters(params_);
+    }
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(msg.data.data());
+    const uint8_t none = 0;
+    if (vmap_deserialize_ot(handle_, 0, msg.data.empty() ? &none : p, msg.data.size()) != VMAP_OK)
+      std::cerr << "Could not read the full octomap message!\n";
+  }
+
   OctomapParameters params_;
 
  private:
+  void refreshResolution() {     // a loaded stream brings its own resolution
+    vmap_params p;
+    if (vmap_get_params(handle_, &p) == VMAP_OK) params_.resolution = p.resolution;
+  }
   static vmap_params toC(const OctomapParameters& q) {
     vmap_params p;
     vmap_default_params(&p);
